@@ -1,0 +1,89 @@
+/* libb2s - C ABI of the B200-native batched rigid-body engine (one environment per warp, sm_100a).
+ *
+ * Every entry point replaces one call the reference makes into its third-party engine through
+ * `robosuite/utils/binding_utils.py` (the `MjSim` shim, SURVEY.md section 8b "Seam 1"), batched over n_env
+ * independent environments.  All array arguments are DEVICE pointers unless the name ends in `_host`.
+ * Return value: 0 on success, negative error code otherwise; `b2s_last_error()` returns a thread-local message
+ * (the Python layer maps codes to the exception types of `robosuite/utils/errors.py`).
+ * A handle is not thread-safe (matches the reference: one MjSim per env per process, binding_utils.py:1059).
+ */
+#ifndef B2S_H
+#define B2S_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b2s_sim b2s_sim;
+
+enum { B2S_OK = 0, B2S_ERR_ARG = -1, B2S_ERR_CUDA = -2, B2S_ERR_MODEL = -3, B2S_ERR_UNSUPPORTED = -4 };
+enum { B2S_F32 = 0, B2S_F64 = 1, B2S_I32 = 2 };
+/* controller kinds for the fused control step (controller_config "type", controllers/parts/controller_factory.py:145) */
+enum { B2S_CTRL_NONE = 0, B2S_CTRL_OSC_POSE = 1, B2S_CTRL_JOINT_VELOCITY = 2 };
+
+/* MjSim.from_xml_string (binding_utils.py:1074-1087): `model_blob` is the flat compiled model produced by
+ * robosuite_b200.mjcf.compiler.pack_model (host memory).  precision: B2S_F32 (production) or B2S_F64 (debug). */
+int b2s_create(const void* model_blob_host, size_t nbytes, int n_env, int device, int precision, b2s_sim** out);
+/* MjSim.free (binding_utils.py:1186-1192) */
+void b2s_destroy(b2s_sim* sim);
+const char* b2s_last_error(void);
+/* all device work of this handle is enqueued on `cuda_stream` (a cudaStream_t); default: the legacy default stream */
+int b2s_set_stream(b2s_sim* sim, void* cuda_stream);
+
+/* MjSim.reset -> mj_resetData (binding_utils.py:1089-1091); env_mask: n_env bytes on device (non-zero = reset) or NULL */
+int b2s_reset(b2s_sim* sim, const uint8_t* env_mask);
+/* MjSim.forward -> mj_forward (binding_utils.py:1093-1095) */
+int b2s_forward(b2s_sim* sim);
+/* MjSim.step1 / step2 -> mj_step1 / mj_step2 (binding_utils.py:1101-1107); ctrl is read between them */
+int b2s_step1(b2s_sim* sim);
+int b2s_step2(b2s_sim* sim);
+/* MjSim.step -> mj_step (binding_utils.py:1097-1099), repeated n_substeps times inside one kernel with ctrl held */
+int b2s_step(b2s_sim* sim, int n_substeps);
+
+/* Named device arrays, leading dimension n_env: qpos qvel qacc qacc_warmstart ctrl time xpos xquat xmat
+ * site_xpos site_xmat geom_xpos geom_xmat qM(dense nv x nv) qfrc_bias qfrc_passive qfrc_actuator qfrc_constraint
+ * actuator_force ncon contact_geom contact_dist contact_pos contact_frame nefc efc_force warn ...
+ * (the attributes the reference touches).  dtype is B2S_F32/F64/I32. */
+int b2s_array(b2s_sim* sim, const char* name, void** dev_ptr, int* dtype, int* ndim, int64_t shape[4]);
+
+/* MjData.get_site_jacp/jacr (binding_utils.py:826-852): jacp/jacr are [n_env,3,nv] device buffers (either may be NULL);
+ * valid after b2s_forward/b2s_step1. */
+int b2s_jac_site(b2s_sim* sim, int site_id, void* jacp, void* jacr);
+
+/* Fused control step = MujocoEnv.step's substep loop (environments/base.py:494-505):
+ * n_substeps x { step1 ; controller(action) -> ctrl ; step2 } in ONE kernel with state resident on chip.
+ * Configure once with b2s_ctrl_config (fields of controllers/config/default/parts/osc_pose.json + robot indices),
+ * then call b2s_env_step(action[n_env, action_dim]) per control step.  obs_out[n_env, obs_dim] may be NULL. */
+typedef struct {
+  int kind;            /* B2S_CTRL_* */
+  int action_dim;      /* arm dims + gripper dims */
+  int n_arm;           /* number of arm joints (7) */
+  int arm_dof[8];      /* dof (= qvel) index of each arm joint */
+  int arm_qpos[8];
+  int arm_act[8];      /* actuator index of each arm joint */
+  int eef_site;        /* ref_name site id */
+  int base_site;       /* "{prefix}{part}_center" site id (controller origin) */
+  int n_grip;          /* gripper actuators (2) */
+  int grip_act[4];
+  double grip_sign[4]; /* format_action signs (models/grippers/panda_gripper.py:55-57) */
+  double grip_speed;   /* 0.2 per policy step */
+  double kp[6], damping_ratio[6];
+  double input_max[6], input_min[6], output_max[6], output_min[6];
+  double null_kp;      /* nullspace_torques joint_kp (control_utils.py:7-40), 10 */
+  int uncouple_pos_ori;
+  int n_obs_site;      /* sites appended to obs (task layer) - reserved */
+} b2s_ctrl_cfg;
+int b2s_ctrl_config(b2s_sim* sim, const b2s_ctrl_cfg* cfg);
+/* controller.reset_goal + update_initial_joints (osc.py:520-544) for masked envs (NULL = all); needs a prior forward */
+int b2s_ctrl_reset(b2s_sim* sim, const uint8_t* env_mask);
+int b2s_env_step(b2s_sim* sim, const void* action, int n_substeps);
+
+/* number of kernels this handle has launched since creation (bench.py "gpu_launches") */
+int64_t b2s_launch_count(const b2s_sim* sim);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,480 @@
+// libb2s: C ABI + host side of the batched engine (model upload, workspace layout, kernel launches).
+// Entry points are declared in include/b2s.h; each cites the reference call it replaces.
+#include "../../include/b2s.h"
+#include "b2s_kernel.cuh"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(B2S_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(e_)); } while (0)
+
+// ------------------------------------------------------------------------------------------------ blob reader
+struct BlobRec { char name[48]; int32_t dtype, ndim, shape[4]; int64_t off, nbytes; };
+struct Blob {
+  const char* p; size_t n;
+  const BlobRec* find(const char* name) const {
+    int64_t cnt; memcpy(&cnt, p + 8, 8);
+    const BlobRec* r = (const BlobRec*)(p + 16);
+    for (int64_t i = 0; i < cnt; i++) if (!strcmp(r[i].name, name)) return r + i;
+    return nullptr;
+  }
+  bool has(const char* name) const { return find(name) != nullptr; }
+  const double* f64(const char* name, int64_t* count = nullptr) const {
+    const BlobRec* r = find(name);
+    if (!r || r->dtype != 0) throw std::string("model blob: missing f64 field ") + name;
+    if (count) *count = r->nbytes / 8;
+    return (const double*)(p + r->off);
+  }
+  const int* i32(const char* name, int64_t* count = nullptr) const {
+    const BlobRec* r = find(name);
+    if (!r || r->dtype != 1) throw std::string("model blob: missing i32 field ") + name;
+    if (count) *count = r->nbytes / 4;
+    return (const int*)(p + r->off);
+  }
+  int scalar_i(const char* name) const { return i32(name)[0]; }
+  double scalar_f(const char* name) const { return f64(name)[0]; }
+};
+
+// ------------------------------------------------------------------------------------------------ sim object
+struct ArrayInfo { void* ptr; int dtype; int ndim; int64_t shape[4]; };
+
+struct b2s_sim {
+  int n_env = 0, device = 0, precision = B2S_F32;
+  cudaStream_t stream = 0;
+  std::vector<void*> allocs;
+  std::map<std::string, ArrayInfo> arrays;
+  WSLayout L{};
+  DModel<float> mf{};
+  DModel<double> md{};
+  DState<float> sf{};
+  DState<double> sd{};
+  CtrlCfgDev ctrl{};
+  int has_ctrl = 0;
+  int wpb = 4;          // warps (environments) per block
+  size_t smem_bytes = 0;
+  int64_t launches = 0;
+  int nq = 0, nv = 0, nu = 0, nbody = 0, ngeom = 0, nsite = 0, maxcon = 0, maxefc = 0;
+  std::vector<double> qpos0;
+  std::vector<int> site_bodyid;
+};
+
+template <typename T> static T* dev_upload(b2s_sim* s, const std::vector<T>& h) {
+  T* d = nullptr;
+  size_t n = h.size() ? h.size() : 1;
+  if (cudaMalloc(&d, n * sizeof(T)) != cudaSuccess) throw std::string("cudaMalloc failed");
+  s->allocs.push_back(d);
+  if (h.size()) cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+  return d;
+}
+template <typename R> static const R* up_f(b2s_sim* s, const Blob& b, const char* name) {
+  int64_t n; const double* p = b.f64(name, &n);
+  std::vector<R> h(n);
+  for (int64_t i = 0; i < n; i++) h[i] = (R)p[i];
+  return dev_upload(s, h);
+}
+static const int* up_i(b2s_sim* s, const Blob& b, const char* name) {
+  int64_t n; const int* p = b.i32(name, &n);
+  std::vector<int> h(p, p + n);
+  return dev_upload(s, h);
+}
+template <typename R> static const R* up_vec(b2s_sim* s, const std::vector<double>& v) {
+  std::vector<R> h(v.size());
+  for (size_t i = 0; i < v.size(); i++) h[i] = (R)v[i];
+  return dev_upload(s, h);
+}
+
+static void h_quat2mat(double* M, const double* q) {
+  double w = q[0], x = q[1], y = q[2], z = q[3];
+  M[0] = w * w + x * x - y * y - z * z; M[1] = 2 * (x * y - w * z); M[2] = 2 * (x * z + w * y);
+  M[3] = 2 * (x * y + w * z); M[4] = w * w - x * x + y * y - z * z; M[5] = 2 * (y * z - w * x);
+  M[6] = 2 * (x * z - w * y); M[7] = 2 * (y * z + w * x); M[8] = w * w - x * x - y * y + z * z;
+}
+static void h_qmul(double* r, const double* a, const double* b) {
+  double w = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
+  double x = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
+  double y = a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1];
+  double z = a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0];
+  r[0] = w; r[1] = x; r[2] = y; r[3] = z;
+}
+
+template <typename R> static void build_model(b2s_sim* s, const Blob& b, DModel<R>& m) {
+  m.nq = b.scalar_i("nq"); m.nv = b.scalar_i("nv"); m.nu = b.scalar_i("nu"); m.nbody = b.scalar_i("nbody");
+  m.njnt = b.scalar_i("njnt"); m.ngeom = b.scalar_i("ngeom"); m.nsite = b.scalar_i("nsite"); m.npair = b.scalar_i("npair");
+  m.nmocap = b.scalar_i("nmocap");
+  m.timestep = (R)b.scalar_f("opt_timestep"); m.impratio = (R)b.scalar_f("opt_impratio");
+  m.density = (R)b.scalar_f("opt_density"); m.viscosity = (R)b.scalar_f("opt_viscosity");
+  m.tolerance = (R)b.scalar_f("opt_tolerance"); m.meaninertia = (R)b.scalar_f("stat_meaninertia");
+  m.iterations = b.scalar_i("opt_iterations"); m.ls_iterations = b.scalar_i("opt_ls_iterations");
+  const double* grav = b.f64("opt_gravity");
+  for (int k = 0; k < 3; k++) m.gravity[k] = (R)grav[k];
+  if (b.scalar_i("opt_cone") != 1) throw std::string("only elliptic friction cones are implemented (reference models set cone=elliptic)");
+  if (m.nv > 64) throw std::string("nv > 64 not supported");
+  int nb = m.nbody, nv = m.nv, nj = m.njnt, ng = m.ngeom;
+  const int* parent = b.i32("body_parentid");
+  const int* jntnum = b.i32("body_jntnum");
+  const int* jntadr = b.i32("body_jntadr");
+  const int* dofnum = b.i32("body_dofnum");
+  const int* dofadr = b.i32("body_dofadr");
+  const int* weld = b.i32("body_weldid");
+  const int* jtype = b.i32("jnt_type");
+  const int* jdofadr = b.i32("jnt_dofadr");
+  const int* dofjnt = b.i32("dof_jntid");
+  const int* dofpar = b.i32("dof_parentid");
+  const int* dofbody = b.i32("dof_bodyid");
+  // one joint per body (free joints included); ball joints unsupported
+  std::vector<int> body_jntid(nb, -1), depth(nb, 0), sub_end(nb, 0);
+  for (int i = 0; i < nb; i++) {
+    if (jntnum[i] > 1) throw std::string("bodies with more than one joint are not supported");
+    if (jntnum[i] == 1) { body_jntid[i] = jntadr[i]; if (jtype[jntadr[i]] == JNT_BALL) throw std::string("ball joints are not supported"); }
+  }
+  int maxdepth = 0;
+  for (int i = 1; i < nb; i++) {
+    depth[i] = weld[i] == 0 ? 0 : depth[parent[i]] + 1;
+    if (depth[i] > maxdepth) maxdepth = depth[i];
+  }
+  for (int i = nb - 1; i >= 0; i--) {
+    if (sub_end[i] < i + 1) sub_end[i] = i + 1;
+    if (i > 0 && sub_end[parent[i]] < sub_end[i]) sub_end[parent[i]] = sub_end[i];
+  }
+  m.maxdepth = maxdepth;
+  // static world poses
+  std::vector<double> xpos0(3 * nb, 0.0), xquat0(4 * nb, 0.0);
+  const double* bpos = b.f64("body_pos");
+  const double* bquat = b.f64("body_quat");
+  xquat0[0] = 1;
+  for (int i = 1; i < nb; i++) {
+    if (weld[i] != 0) { xquat0[4 * i] = 1; continue; }
+    double Mp[9];
+    h_quat2mat(Mp, &xquat0[4 * parent[i]]);
+    for (int r = 0; r < 3; r++)
+      xpos0[3 * i + r] = xpos0[3 * parent[i] + r] + Mp[3 * r] * bpos[3 * i] + Mp[3 * r + 1] * bpos[3 * i + 1] + Mp[3 * r + 2] * bpos[3 * i + 2];
+    h_qmul(&xquat0[4 * i], &xquat0[4 * parent[i]], bquat + 4 * i);
+  }
+  // dof tables
+  std::vector<int> dkind(nv), cddstart(nv), fl_dof, lim_jnt;
+  const double* floss = b.f64("dof_frictionloss");
+  for (int i = 0; i < nv; i++) {
+    int j = dofjnt[i], k = i - jdofadr[j];
+    if (jtype[j] == JNT_FREE) {
+      dkind[i] = k < 3 ? DK_FREE_T : DK_FREE_R;
+      cddstart[i] = k < 3 ? -1 : jdofadr[j] + 2;  // rotational axes: velocity of the three translations only
+    } else {
+      dkind[i] = jtype[j] == JNT_SLIDE ? DK_SLIDE : DK_HINGE;
+      cddstart[i] = dofpar[i];
+    }
+    if (floss[i] > 0) fl_dof.push_back(i);
+  }
+  const int* jlim = b.i32("jnt_limited");
+  for (int j = 0; j < nj; j++)
+    if (jlim[j] && (jtype[j] == JNT_SLIDE || jtype[j] == JNT_HINGE)) lim_jnt.push_back(j);
+  m.nfl = (int)fl_dof.size(); m.nlim = (int)lim_jnt.size();
+  std::vector<unsigned long long> dofmask(nb, 0ull);
+  for (int i = 1; i < nb; i++) {
+    dofmask[i] = dofmask[parent[i]];
+    for (int d = 0; d < dofnum[i]; d++) dofmask[i] |= 1ull << (dofadr[i] + d);
+  }
+  std::vector<int> ment_i, ment_j;
+  for (int i = 0; i < nv; i++)
+    for (int j = i; j >= 0; j = dofpar[j]) { ment_i.push_back(i); ment_j.push_back(j); }
+  m.nment = (int)ment_i.size();
+  // colliding geoms
+  const int* pair = b.i32("pair_geom");
+  std::vector<int> cgid(ng, -1), cg;
+  for (int p = 0; p < m.npair; p++)
+    for (int k = 0; k < 2; k++) { int g = pair[2 * p + k]; if (cgid[g] < 0) cgid[g] = 1; }
+  for (int g = 0; g < ng; g++) if (cgid[g] > 0) { cgid[g] = (int)cg.size(); cg.push_back(g); }
+  m.ncg = (int)cg.size();
+  const int* condim = b.i32("geom_condim");
+  int maxdim = 1;
+  for (int g : cg) if (condim[g] > maxdim) maxdim = condim[g];
+  m.hc_stride = maxdim * maxdim;
+  m.maxcon = s->maxcon; m.maxefc = s->maxefc;
+
+  m.body_parentid = up_i(s, b, "body_parentid"); m.body_jntid = dev_upload(s, body_jntid);
+  m.body_dofnum = up_i(s, b, "body_dofnum"); m.body_dofadr = up_i(s, b, "body_dofadr"); m.body_weldid = up_i(s, b, "body_weldid");
+  m.body_subtree_end = dev_upload(s, sub_end); m.body_depth = dev_upload(s, depth);
+  m.body_pos = up_f<R>(s, b, "body_pos"); m.body_quat = up_f<R>(s, b, "body_quat"); m.body_ipos = up_f<R>(s, b, "body_ipos");
+  m.body_iquat = up_f<R>(s, b, "body_iquat"); m.body_mass = up_f<R>(s, b, "body_mass"); m.body_inertia = up_f<R>(s, b, "body_inertia");
+  m.body_invweight0 = up_f<R>(s, b, "body_invweight0");
+  m.body_xpos0 = up_vec<R>(s, xpos0); m.body_xquat0 = up_vec<R>(s, xquat0);
+  m.jnt_type = up_i(s, b, "jnt_type"); m.jnt_qposadr = up_i(s, b, "jnt_qposadr"); m.jnt_dofadr = up_i(s, b, "jnt_dofadr");
+  m.jnt_bodyid = up_i(s, b, "jnt_bodyid"); m.jnt_limited = up_i(s, b, "jnt_limited");
+  m.jnt_pos = up_f<R>(s, b, "jnt_pos"); m.jnt_axis = up_f<R>(s, b, "jnt_axis"); m.jnt_range = up_f<R>(s, b, "jnt_range");
+  m.jnt_solref = up_f<R>(s, b, "jnt_solref"); m.jnt_solimp = up_f<R>(s, b, "jnt_solimp"); m.qpos0 = up_f<R>(s, b, "qpos0");
+  m.dof_bodyid = up_i(s, b, "dof_bodyid"); m.dof_jntid = up_i(s, b, "dof_jntid"); m.dof_parentid = up_i(s, b, "dof_parentid");
+  m.dof_kind = dev_upload(s, dkind); m.dof_cddstart = dev_upload(s, cddstart); m.fl_dof = dev_upload(s, fl_dof);
+  m.lim_jnt = dev_upload(s, lim_jnt); m.body_dofmask = dev_upload(s, dofmask);
+  m.dof_armature = up_f<R>(s, b, "dof_armature"); m.dof_damping = up_f<R>(s, b, "dof_damping");
+  m.dof_frictionloss = up_f<R>(s, b, "dof_frictionloss"); m.dof_solref = up_f<R>(s, b, "dof_solref");
+  m.dof_solimp = up_f<R>(s, b, "dof_solimp"); m.dof_invweight0 = up_f<R>(s, b, "dof_invweight0");
+  m.ment_i = dev_upload(s, ment_i); m.ment_j = dev_upload(s, ment_j);
+  m.geom_type = up_i(s, b, "geom_type"); m.geom_bodyid = up_i(s, b, "geom_bodyid"); m.geom_condim = up_i(s, b, "geom_condim");
+  m.geom_dataid = up_i(s, b, "geom_dataid"); m.geom_priority = up_i(s, b, "geom_priority");
+  m.geom_cgid = dev_upload(s, cgid); m.cg_geom = dev_upload(s, cg);
+  m.geom_size = up_f<R>(s, b, "geom_size"); m.geom_pos = up_f<R>(s, b, "geom_pos"); m.geom_quat = up_f<R>(s, b, "geom_quat");
+  m.geom_friction = up_f<R>(s, b, "geom_friction"); m.geom_solmix = up_f<R>(s, b, "geom_solmix");
+  m.geom_solref = up_f<R>(s, b, "geom_solref"); m.geom_solimp = up_f<R>(s, b, "geom_solimp");
+  m.geom_rbound = up_f<R>(s, b, "geom_rbound"); m.geom_aabb = up_f<R>(s, b, "geom_aabb");
+  m.pair_geom = up_i(s, b, "pair_geom");
+  m.mesh_vertadr = up_i(s, b, "mesh_vertadr"); m.mesh_vertnum = up_i(s, b, "mesh_vertnum"); m.mesh_vert = up_f<R>(s, b, "mesh_vert");
+  m.site_bodyid = up_i(s, b, "site_bodyid"); m.site_pos = up_f<R>(s, b, "site_pos"); m.site_quat = up_f<R>(s, b, "site_quat");
+  m.act_trnid = up_i(s, b, "actuator_trnid"); m.act_ctrllimited = up_i(s, b, "actuator_ctrllimited");
+  m.act_forcelimited = up_i(s, b, "actuator_forcelimited"); m.act_biastype = up_i(s, b, "actuator_biastype");
+  m.act_ctrlrange = up_f<R>(s, b, "actuator_ctrlrange"); m.act_forcerange = up_f<R>(s, b, "actuator_forcerange");
+  {
+    int64_t n; const double* g6 = b.f64("actuator_gear", &n);
+    std::vector<double> g1(m.nu);
+    for (int i = 0; i < m.nu; i++) g1[i] = g6[6 * i];
+    m.act_gear = up_vec<R>(s, g1);
+  }
+  m.act_gainprm = up_f<R>(s, b, "actuator_gainprm"); m.act_biasprm = up_f<R>(s, b, "actuator_biasprm");
+}
+
+template <typename T> static T* dev_zeros(b2s_sim* s, size_t n) {
+  T* d = nullptr;
+  if (n == 0) n = 1;
+  if (cudaMalloc(&d, n * sizeof(T)) != cudaSuccess) throw std::string("cudaMalloc failed");
+  cudaMemset(d, 0, n * sizeof(T));
+  s->allocs.push_back(d);
+  return d;
+}
+template <typename R> struct DT;
+template <> struct DT<float> { static const int code = B2S_F32; };
+template <> struct DT<double> { static const int code = B2S_F64; };
+
+template <typename R>
+static R* state_arr(b2s_sim* s, const char* name, int64_t d1, int64_t d2 = 0, int64_t d3 = 0) {
+  size_t per = (size_t)(d1 ? d1 : 1) * (d2 ? d2 : 1) * (d3 ? d3 : 1);
+  R* p = dev_zeros<R>(s, (size_t)s->n_env * per);
+  ArrayInfo a{p, DT<R>::code, 1 + (d1 > 0) + (d2 > 0) + (d3 > 0), {s->n_env, d1, d2, d3}};
+  if (d1 == 0) a.ndim = 1;
+  s->arrays[name] = a;
+  return p;
+}
+static int* state_arr_i(b2s_sim* s, const char* name, int64_t d1, int64_t d2 = 0) {
+  size_t per = (size_t)(d1 ? d1 : 1) * (d2 ? d2 : 1);
+  int* p = dev_zeros<int>(s, (size_t)s->n_env * per);
+  ArrayInfo a{p, B2S_I32, 1 + (d1 > 0) + (d2 > 0), {s->n_env, d1, d2, 0}};
+  s->arrays[name] = a;
+  return p;
+}
+
+template <typename R> static void build_state(b2s_sim* s, const DModel<R>& m, DState<R>& st) {
+  st.n_env = s->n_env;
+  int nq = m.nq, nv = m.nv, nu = m.nu, nb = m.nbody, ng = m.ngeom, ns = m.nsite, mc = m.maxcon, me = m.maxefc;
+  st.qpos = state_arr<R>(s, "qpos", nq); st.qvel = state_arr<R>(s, "qvel", nv); st.qacc = state_arr<R>(s, "qacc", nv);
+  st.qacc_ws = state_arr<R>(s, "qacc_warmstart", nv); st.ctrl = state_arr<R>(s, "ctrl", nu); st.time = state_arr<R>(s, "time", 0);
+  st.xpos = state_arr<R>(s, "xpos", nb, 3); st.xquat = state_arr<R>(s, "xquat", nb, 4); st.xmat = state_arr<R>(s, "xmat", nb, 9);
+  st.site_xpos = state_arr<R>(s, "site_xpos", ns, 3); st.site_xmat = state_arr<R>(s, "site_xmat", ns, 9);
+  st.geom_xpos = state_arr<R>(s, "geom_xpos", ng, 3); st.geom_xmat = state_arr<R>(s, "geom_xmat", ng, 9);
+  st.qM = state_arr<R>(s, "qM", nv, nv); st.qfrc_bias = state_arr<R>(s, "qfrc_bias", nv);
+  st.qfrc_passive = state_arr<R>(s, "qfrc_passive", nv); st.qfrc_actuator = state_arr<R>(s, "qfrc_actuator", nv);
+  st.qfrc_constraint = state_arr<R>(s, "qfrc_constraint", nv); st.qfrc_smooth = state_arr<R>(s, "qfrc_smooth", nv);
+  st.qacc_smooth = state_arr<R>(s, "qacc_smooth", nv); st.actuator_force = state_arr<R>(s, "actuator_force", nu);
+  st.cdof = state_arr<R>(s, "cdof", nv, 6);
+  st.ncon = state_arr_i(s, "ncon", 0); st.contact_geom = state_arr_i(s, "contact_geom", mc, 2);
+  st.contact_dim = state_arr_i(s, "contact_dim", mc); st.nefc = state_arr_i(s, "nefc", 0);
+  st.efc_type = state_arr_i(s, "efc_type", me); st.warn = state_arr_i(s, "warn", 0); st.solver_niter = state_arr_i(s, "solver_niter", 0);
+  st.contact_dist = state_arr<R>(s, "contact_dist", mc); st.contact_pos = state_arr<R>(s, "contact_pos", mc, 3);
+  st.contact_frame = state_arr<R>(s, "contact_frame", mc, 9); st.contact_friction = state_arr<R>(s, "contact_friction", mc, 3);
+  st.contact_solref = nullptr; st.contact_solimp = nullptr;
+  st.efc_J = state_arr<R>(s, "efc_J", me, nv); st.efc_force = state_arr<R>(s, "efc_force", me);
+  st.efc_aref = state_arr<R>(s, "efc_aref", me); st.efc_D = state_arr<R>(s, "efc_D", me); st.efc_R = state_arr<R>(s, "efc_R", me);
+  st.goal_pos = state_arr<R>(s, "ctrl_goal_pos", 3); st.goal_ori = state_arr<R>(s, "ctrl_goal_ori", 9);
+  st.init_qpos_arm = state_arr<R>(s, "ctrl_initial_joint", 8); st.grip_state = state_arr<R>(s, "ctrl_grip_state", 4);
+  st.ctrl_torque = state_arr<R>(s, "ctrl_torque", 8);
+  st.action = nullptr;
+}
+
+static void build_layout(b2s_sim* s, int nq, int nv, int nu, int nb, int ncg, int ns, int mc, int me, int hc_stride) {
+  WSLayout& L = s->L;
+  int o = 0;
+  auto take = [&](int n) { int r = o; o += (n + 1) & ~1; return r; };  // keep 8-byte alignment for fp32 builds
+  L.qpos = take(nq); L.qvel = take(nv); L.qacc = take(nv); L.qacc_ws = take(nv); L.ctrl = take(nu);
+  L.xpos = take(3 * nb); L.xquat = take(4 * nb); L.xmat = take(9 * nb); L.xipos = take(3 * nb);
+  L.cdof = take(6 * nv); L.cdofdot = take(6 * nv); L.cinert = take(10 * nb); L.cvel = take(6 * nb);
+  L.frne = take(6 * nb); L.ffl = take(6 * nb);
+  L.M = take(nv * nv); L.H = take(nv * nv);
+  L.bias = take(nv); L.passive = take(nv); L.qact = take(nv); L.qsmooth = take(nv); L.qaccs = take(nv); L.qcon = take(nv);
+  L.gpos = take(3 * ncg); L.gmat = take(9 * ncg); L.spos = take(3 * ns); L.smat = take(9 * ns);
+  L.c_pos = take(3 * mc); L.c_frame = take(9 * mc); L.c_dist = take(mc); L.c_fric = take(3 * mc);
+  L.c_solref = 0; L.c_solimp = 0;
+  L.c_mu = take(mc); L.c_int = take(5 * mc);
+  L.J = take(me * nv); L.e_D = take(me); L.e_R = take(me); L.e_aref = take(me); L.e_jar = take(me); L.e_jv = take(me);
+  L.e_force = take(me); L.e_floss = take(me); L.e_int = take(2 * me);
+  L.Ma = take(nv); L.grad = take(nv); L.search = take(nv); L.Mv = take(nv);
+  int sc = 10 * nb;
+  int epa = 128 + 9 * EPA_MAXV + 4 * EPA_MAXF + EPA_MAXF + 8;
+  if (epa > sc) sc = epa;
+  int hs = me + hc_stride * mc;
+  if (hs > sc) sc = hs;
+  L.scratch_size = sc;
+  L.scratch = take(sc);
+  L.total = o;
+}
+
+// ------------------------------------------------------------------------------------------------ API
+extern "C" {
+
+const char* b2s_last_error(void) { return g_err.c_str(); }
+
+int b2s_create(const void* blob_host, size_t nbytes, int n_env, int device, int precision, b2s_sim** out) {
+  if (!blob_host || !out || n_env <= 0) return fail(B2S_ERR_ARG, "b2s_create: bad argument");
+  if (nbytes < 16 || memcmp(blob_host, "B2SMODEL", 8) != 0) return fail(B2S_ERR_MODEL, "b2s_create: not a model blob");
+  if (precision != B2S_F32 && precision != B2S_F64) return fail(B2S_ERR_ARG, "b2s_create: precision must be B2S_F32 or B2S_F64");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(B2S_ERR_CUDA, "b2s_create: no CUDA device available (this library has no CPU fallback)");
+  CUDA_TRY(cudaSetDevice(device));
+  b2s_sim* s = new b2s_sim();
+  s->n_env = n_env; s->device = device; s->precision = precision;
+  Blob b{(const char*)blob_host, nbytes};
+  try {
+    s->nq = b.scalar_i("nq"); s->nv = b.scalar_i("nv"); s->nu = b.scalar_i("nu"); s->nbody = b.scalar_i("nbody");
+    s->ngeom = b.scalar_i("ngeom"); s->nsite = b.scalar_i("nsite");
+    s->maxcon = b.has("opt_maxcon") ? b.scalar_i("opt_maxcon") : 32;
+    s->maxefc = b.has("opt_maxefc") ? b.scalar_i("opt_maxefc") : 96;
+    if (s->maxcon > 64) throw std::string("opt_maxcon > 64 not supported");
+    const double* q0 = b.f64("qpos0");
+    s->qpos0.assign(q0, q0 + s->nq);
+    const int* sb = b.i32("site_bodyid");
+    s->site_bodyid.assign(sb, sb + s->nsite);
+    int ncg, hcs;
+    if (precision == B2S_F32) { build_model(s, b, s->mf); build_state(s, s->mf, s->sf); ncg = s->mf.ncg; hcs = s->mf.hc_stride; }
+    else { build_model(s, b, s->md); build_state(s, s->md, s->sd); ncg = s->md.ncg; hcs = s->md.hc_stride; }
+    build_layout(s, s->nq, s->nv, s->nu, s->nbody, ncg, s->nsite, s->maxcon, s->maxefc, hcs);
+  } catch (const std::string& e) {
+    b2s_destroy(s);
+    return fail(B2S_ERR_MODEL, "b2s_create: " + e);
+  }
+  size_t rsz = precision == B2S_F32 ? 4 : 8;
+  size_t per_warp = (size_t)s->L.total * rsz;
+  int wpb = 4;
+  while (wpb > 1 && per_warp * wpb > 227 * 1024) wpb--;
+  if (per_warp > 227 * 1024) { b2s_destroy(s); return fail(B2S_ERR_UNSUPPORTED, "model workspace exceeds shared memory"); }
+  const char* env_wpb = getenv("B2S_WARPS_PER_BLOCK");
+  if (env_wpb) { int v = atoi(env_wpb); if (v >= 1 && per_warp * v <= 227 * 1024) wpb = v; }
+  s->wpb = wpb;
+  s->smem_bytes = per_warp * wpb;
+  cudaError_t e1 = precision == B2S_F32
+                       ? cudaFuncSetAttribute(step_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes)
+                       : cudaFuncSetAttribute(step_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes);
+  if (e1 != cudaSuccess) { std::string msg = cudaGetErrorString(e1); b2s_destroy(s); return fail(B2S_ERR_CUDA, "cudaFuncSetAttribute: " + msg); }
+  *out = s;
+  int rc = b2s_reset(s, nullptr);
+  if (rc != 0) { b2s_destroy(s); *out = nullptr; return rc; }
+  return B2S_OK;
+}
+
+void b2s_destroy(b2s_sim* s) {
+  if (!s) return;
+  cudaSetDevice(s->device);
+  for (void* p : s->allocs) cudaFree(p);
+  delete s;
+}
+
+int b2s_set_stream(b2s_sim* s, void* stream) {
+  if (!s) return fail(B2S_ERR_ARG, "null handle");
+  s->stream = (cudaStream_t)stream;
+  return B2S_OK;
+}
+
+int64_t b2s_launch_count(const b2s_sim* s) { return s ? s->launches : 0; }
+
+int b2s_array(b2s_sim* s, const char* name, void** dev_ptr, int* dtype, int* ndim, int64_t shape[4]) {
+  if (!s || !name) return fail(B2S_ERR_ARG, "b2s_array: bad argument");
+  auto it = s->arrays.find(name);
+  if (it == s->arrays.end()) return fail(B2S_ERR_ARG, std::string("b2s_array: unknown array '") + name + "'");
+  if (dev_ptr) *dev_ptr = it->second.ptr;
+  if (dtype) *dtype = it->second.dtype;
+  if (ndim) *ndim = it->second.ndim;
+  if (shape) for (int k = 0; k < 4; k++) shape[k] = it->second.shape[k];
+  return B2S_OK;
+}
+
+static int launch(b2s_sim* s, int phases, int nsub) {
+  CUDA_TRY(cudaSetDevice(s->device));
+  int blocks = (s->n_env + s->wpb - 1) / s->wpb;
+  CtrlCfgDev cc = s->ctrl;
+  if (s->precision == B2S_F32)
+    step_kernel<float><<<blocks, s->wpb * 32, s->smem_bytes, s->stream>>>(s->mf, s->sf, s->L, cc, phases, nsub);
+  else
+    step_kernel<double><<<blocks, s->wpb * 32, s->smem_bytes, s->stream>>>(s->md, s->sd, s->L, cc, phases, nsub);
+  s->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return B2S_OK;
+}
+
+int b2s_reset(b2s_sim* s, const uint8_t* mask) {
+  if (!s) return fail(B2S_ERR_ARG, "null handle");
+  CUDA_TRY(cudaSetDevice(s->device));
+  if (s->precision == B2S_F32) reset_kernel<float><<<(s->n_env + 127) / 128, 128, 0, s->stream>>>(s->mf, s->sf, mask);
+  else reset_kernel<double><<<(s->n_env + 127) / 128, 128, 0, s->stream>>>(s->md, s->sd, mask);
+  s->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return B2S_OK;
+}
+
+int b2s_forward(b2s_sim* s) { return s ? launch(s, PH_STEP1 | PH_STEP2 | PH_NOINTEGRATE | PH_EXPORT, 1) : fail(B2S_ERR_ARG, "null handle"); }
+int b2s_step1(b2s_sim* s) { return s ? launch(s, PH_STEP1 | PH_EXPORT, 1) : fail(B2S_ERR_ARG, "null handle"); }
+int b2s_step2(b2s_sim* s) { return s ? launch(s, PH_STEP1 | PH_STEP2 | PH_EXPORT, 1) : fail(B2S_ERR_ARG, "null handle"); }
+int b2s_step(b2s_sim* s, int n) {
+  if (!s || n < 1) return fail(B2S_ERR_ARG, "b2s_step: bad argument");
+  return launch(s, PH_STEP1 | PH_STEP2, n);
+}
+
+int b2s_jac_site(b2s_sim* s, int site_id, void* jacp, void* jacr) {
+  if (!s || site_id < 0 || site_id >= s->nsite) return fail(B2S_ERR_ARG, "b2s_jac_site: bad argument");
+  CUDA_TRY(cudaSetDevice(s->device));
+  int threads = 128, blocks = (s->n_env * s->nv + threads - 1) / threads;
+  if (s->precision == B2S_F32) jac_site_kernel<float><<<blocks, threads, 0, s->stream>>>(s->mf, s->sf, site_id, (float*)jacp, (float*)jacr);
+  else jac_site_kernel<double><<<blocks, threads, 0, s->stream>>>(s->md, s->sd, site_id, (double*)jacp, (double*)jacr);
+  s->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return B2S_OK;
+}
+
+int b2s_ctrl_config(b2s_sim* s, const b2s_ctrl_cfg* c) {
+  if (!s || !c) return fail(B2S_ERR_ARG, "b2s_ctrl_config: bad argument");
+  if (c->kind != B2S_CTRL_OSC_POSE && c->kind != B2S_CTRL_NONE) return fail(B2S_ERR_UNSUPPORTED, "controller kind not implemented");
+  if (c->n_arm > 8 || c->n_grip > 4) return fail(B2S_ERR_ARG, "b2s_ctrl_config: too many joints");
+  CtrlCfgDev& d = s->ctrl;
+  d.kind = c->kind; d.action_dim = c->action_dim; d.n_arm = c->n_arm; d.eef_site = c->eef_site; d.base_site = c->base_site;
+  d.n_grip = c->n_grip; d.uncouple = c->uncouple_pos_ori;
+  for (int i = 0; i < 8; i++) { d.arm_dof[i] = c->arm_dof[i]; d.arm_qpos[i] = c->arm_qpos[i]; d.arm_act[i] = c->arm_act[i]; }
+  for (int i = 0; i < 4; i++) { d.grip_act[i] = c->grip_act[i]; d.grip_sign[i] = c->grip_sign[i]; }
+  d.grip_speed = c->grip_speed; d.null_kp = c->null_kp;
+  for (int i = 0; i < 6; i++) {
+    d.kp[i] = c->kp[i]; d.kd[i] = 2.0 * sqrt(c->kp[i]) * c->damping_ratio[i];
+    d.input_max[i] = c->input_max[i]; d.input_min[i] = c->input_min[i];
+    d.output_max[i] = c->output_max[i]; d.output_min[i] = c->output_min[i];
+  }
+  s->has_ctrl = c->kind != B2S_CTRL_NONE;
+  return B2S_OK;
+}
+
+int b2s_ctrl_reset(b2s_sim* s, const uint8_t* mask) {
+  if (!s || !s->has_ctrl) return fail(B2S_ERR_ARG, "b2s_ctrl_reset: controller not configured");
+  CUDA_TRY(cudaSetDevice(s->device));
+  int threads = 128, blocks = (s->n_env + threads - 1) / threads;
+  CtrlCfgDev cc = s->ctrl;
+  if (s->precision == B2S_F32) ctrl_reset_kernel<float><<<blocks, threads, 0, s->stream>>>(s->mf, s->sf, cc, mask);
+  else ctrl_reset_kernel<double><<<blocks, threads, 0, s->stream>>>(s->md, s->sd, cc, mask);
+  s->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return B2S_OK;
+}
+
+int b2s_env_step(b2s_sim* s, const void* action, int nsub) {
+  if (!s || !s->has_ctrl || !action || nsub < 1) return fail(B2S_ERR_ARG, "b2s_env_step: bad argument / controller not configured");
+  if (s->precision == B2S_F32) s->sf.action = (const float*)action; else s->sd.action = (const double*)action;
+  return launch(s, PH_STEP1 | PH_STEP2 | PH_CTRL | PH_EXPORT, nsub);
+}
+
+}  // extern "C"

@@ -1,0 +1,157 @@
+// Kernels: the fused per-warp step kernel (n_substeps x {step1, controller, step2} with state resident in shared
+// memory), reset, and small support kernels.  See include/b2s.h for the reference calls each launch replaces.
+#pragma once
+#include "b2s_ctrl.cuh"
+
+template <typename R> DEV void load_row(R* dst, const R* src, int n, int lane) {
+  for (int i = lane; i < n; i += 32) dst[i] = src[i];
+}
+
+template <typename R>
+DEV void export_step1(const Eng<R>& e, const DState<R>& s, int env, int ncon, int nefc) {
+  const DModel<R>& m = e.m;
+  const WSLayout& L = e.L;
+  int lane = e.lane;
+  size_t E = env;
+  load_row(s.xpos + E * 3 * m.nbody, e.p(L.xpos), 3 * m.nbody, lane);
+  load_row(s.xquat + E * 4 * m.nbody, e.p(L.xquat), 4 * m.nbody, lane);
+  load_row(s.xmat + E * 9 * m.nbody, e.p(L.xmat), 9 * m.nbody, lane);
+  load_row(s.site_xpos + E * 3 * m.nsite, e.p(L.spos), 3 * m.nsite, lane);
+  load_row(s.site_xmat + E * 9 * m.nsite, e.p(L.smat), 9 * m.nsite, lane);
+  for (int k = lane; k < m.ncg; k += 32) {
+    int g = m.cg_geom[k];
+    for (int q = 0; q < 3; q++) s.geom_xpos[(E * m.ngeom + g) * 3 + q] = e.p(L.gpos)[3 * k + q];
+    for (int q = 0; q < 9; q++) s.geom_xmat[(E * m.ngeom + g) * 9 + q] = e.p(L.gmat)[9 * k + q];
+  }
+  load_row(s.qM + E * m.nv * m.nv, e.p(L.M), m.nv * m.nv, lane);
+  load_row(s.cdof + E * 6 * m.nv, e.p(L.cdof), 6 * m.nv, lane);
+  load_row(s.qfrc_bias + E * m.nv, e.p(L.bias), m.nv, lane);
+  load_row(s.qfrc_passive + E * m.nv, e.p(L.passive), m.nv, lane);
+  const int* cint = e.pi(L.c_int);
+  for (int c = lane; c < m.maxcon; c += 32) {
+    bool v = c < ncon;
+    s.contact_geom[(E * m.maxcon + c) * 2] = v ? cint[5 * c] : -1;
+    s.contact_geom[(E * m.maxcon + c) * 2 + 1] = v ? cint[5 * c + 1] : -1;
+    s.contact_dim[E * m.maxcon + c] = v ? cint[5 * c + 2] : 0;
+    s.contact_dist[E * m.maxcon + c] = v ? e.p(L.c_dist)[c] : R(0);
+    for (int q = 0; q < 3; q++) s.contact_pos[(E * m.maxcon + c) * 3 + q] = v ? e.p(L.c_pos)[3 * c + q] : R(0);
+    for (int q = 0; q < 9; q++) s.contact_frame[(E * m.maxcon + c) * 9 + q] = v ? e.p(L.c_frame)[9 * c + q] : R(0);
+    for (int q = 0; q < 3; q++) s.contact_friction[(E * m.maxcon + c) * 3 + q] = v ? e.p(L.c_fric)[3 * c + q] : R(0);
+  }
+  for (int r = lane; r < m.maxefc; r += 32) {
+    bool v = r < nefc;
+    s.efc_type[E * m.maxefc + r] = v ? e.pi(L.e_int)[2 * r] : 0;
+    s.efc_aref[E * m.maxefc + r] = v ? e.p(L.e_aref)[r] : R(0);
+    s.efc_D[E * m.maxefc + r] = v ? e.p(L.e_D)[r] : R(0);
+    s.efc_R[E * m.maxefc + r] = v ? e.p(L.e_R)[r] : R(0);
+  }
+  for (int k = lane; k < nefc * m.nv; k += 32) s.efc_J[E * m.maxefc * m.nv + k] = e.p(L.J)[k];
+  if (lane == 0) { s.ncon[env] = ncon; s.nefc[env] = nefc; }
+}
+
+template <typename R>
+DEV void export_step2(const Eng<R>& e, const DState<R>& s, int env, int nefc, int niter) {
+  const DModel<R>& m = e.m;
+  const WSLayout& L = e.L;
+  int lane = e.lane;
+  size_t E = env;
+  load_row(s.qfrc_actuator + E * m.nv, e.p(L.qact), m.nv, lane);
+  load_row(s.qfrc_smooth + E * m.nv, e.p(L.qsmooth), m.nv, lane);
+  load_row(s.qacc_smooth + E * m.nv, e.p(L.qaccs), m.nv, lane);
+  load_row(s.qfrc_constraint + E * m.nv, e.p(L.qcon), m.nv, lane);
+  for (int r = lane; r < m.maxefc; r += 32) s.efc_force[E * m.maxefc + r] = r < nefc ? e.p(L.e_force)[r] : R(0);
+  if (lane == 0) s.solver_niter[env] = niter;
+}
+
+template <typename R>
+__global__ void step_kernel(const __grid_constant__ DModel<R> m, const __grid_constant__ DState<R> s,
+                            const __grid_constant__ WSLayout L, const __grid_constant__ CtrlCfgDev cc, int phases, int nsub) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  R* smem = reinterpret_cast<R*>(smem_raw);
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  int env = blockIdx.x * wpb + warp;
+  if (env >= s.n_env) return;
+  Eng<R> e(m, L, smem + (size_t)warp * L.total, lane);
+  size_t E = env;
+  load_row(e.p(L.qpos), s.qpos + E * m.nq, m.nq, lane);
+  load_row(e.p(L.qvel), s.qvel + E * m.nv, m.nv, lane);
+  load_row(e.p(L.qacc), s.qacc + E * m.nv, m.nv, lane);
+  load_row(e.p(L.qacc_ws), s.qacc_ws + E * m.nv, m.nv, lane);
+  load_row(e.p(L.ctrl), s.ctrl + E * m.nu, m.nu, lane);
+  R time = s.time[env];
+  CtrlState<R> cs;
+  if (phases & PH_CTRL) ctrl_load(e, s, cc, cs, env);
+  __syncwarp();
+  int warn = 0;
+  for (int sub = 0; sub < nsub; sub++) {
+    int ncon = 0, nefc = 0, niter = 0;
+    if (phases & PH_STEP1) {
+      e.kinematics();
+      e.velocity();
+      e.crb();
+      ncon = collide(e, warn);
+      nefc = make_constraint(e, ncon, warn);
+      if ((phases & PH_EXPORT) && sub == nsub - 1) export_step1(e, s, env, ncon, nefc);
+    }
+    if (phases & PH_CTRL) ctrl_run(e, s, cc, cs, env, sub == 0);
+    if (phases & PH_STEP2) {
+      bool ex = (phases & PH_EXPORT) && sub == nsub - 1;
+      e.actuation(ex ? s.actuator_force + E * m.nu : nullptr);
+      if (e.acceleration()) warn |= 1;
+      niter = solve(e, nefc, ncon, warn);
+      if (ex) export_step2(e, s, env, nefc, niter);
+      if (!(phases & PH_NOINTEGRATE)) {
+        if (e.euler(&time)) warn |= 2;
+      }
+    }
+    __syncwarp();
+  }
+  // write back
+  for (int i = lane; i < m.nq; i += 32) s.qpos[E * m.nq + i] = e.p(L.qpos)[i];
+  for (int i = lane; i < m.nv; i += 32) {
+    s.qvel[E * m.nv + i] = e.p(L.qvel)[i];
+    s.qacc[E * m.nv + i] = e.p(L.qacc)[i];
+    s.qacc_ws[E * m.nv + i] = e.p(L.qacc_ws)[i];
+  }
+  if (phases & PH_CTRL) {
+    for (int i = lane; i < m.nu; i += 32) s.ctrl[E * m.nu + i] = e.p(L.ctrl)[i];
+    ctrl_store(e, s, cc, cs, env);
+  }
+  if (lane == 0) { s.time[env] = time; s.warn[env] |= warn; }
+}
+
+template <typename R>
+__global__ void reset_kernel(const __grid_constant__ DModel<R> m, const __grid_constant__ DState<R> s, const uint8_t* mask) {
+  int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= s.n_env) return;
+  if (mask && !mask[env]) return;
+  size_t E = env;
+  for (int i = 0; i < m.nq; i++) s.qpos[E * m.nq + i] = m.qpos0[i];
+  for (int i = 0; i < m.nv; i++) { s.qvel[E * m.nv + i] = 0; s.qacc[E * m.nv + i] = 0; s.qacc_ws[E * m.nv + i] = 0; }
+  for (int i = 0; i < m.nu; i++) s.ctrl[E * m.nu + i] = 0;
+  s.time[env] = 0;
+  s.warn[env] = 0;
+}
+
+// translational / rotational Jacobian of a site from the exported cdof and site_xpos (valid after forward/step1)
+template <typename R>
+__global__ void jac_site_kernel(const __grid_constant__ DModel<R> m, const __grid_constant__ DState<R> s, int site, R* jacp, R* jacr) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= s.n_env * m.nv) return;
+  int env = idx / m.nv, i = idx % m.nv;
+  size_t E = env;
+  int body = m.site_bodyid[site];
+  bool on = (m.body_dofmask[body] >> i) & 1ull;
+  const R* cd = s.cdof + (E * m.nv + i) * 6;
+  const R* pos = s.site_xpos + (E * m.nsite + site) * 3;
+  R t[3] = {0, 0, 0}, w[3] = {0, 0, 0};
+  if (on) {
+    v3cross(t, cd, pos);
+    t[0] += cd[3]; t[1] += cd[4]; t[2] += cd[5];
+    w[0] = cd[0]; w[1] = cd[1]; w[2] = cd[2];
+  }
+  for (int r = 0; r < 3; r++) {
+    if (jacp) jacp[(E * 3 + r) * m.nv + i] = t[r];
+    if (jacr) jacr[(E * 3 + r) * m.nv + i] = w[r];
+  }
+}

@@ -1,0 +1,96 @@
+// Device-side model / workspace descriptors of the batched engine (one environment per warp).
+// The field set mirrors what the reference reads from the engine through binding_utils.MjModel / MjData
+// (robosuite/utils/binding_utils.py:252-1056); layouts are this repo's own.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define B2S_FULL 0xffffffffu
+
+enum { JNT_FREE = 0, JNT_BALL = 1, JNT_SLIDE = 2, JNT_HINGE = 3 };
+enum { G_PLANE = 0, G_HFIELD, G_SPHERE, G_CAPSULE, G_ELLIPSOID, G_CYLINDER, G_BOX, G_MESH };
+enum { C_FRICTION = 1, C_LIMIT = 3, C_FRICTIONLESS = 5, C_ELLIPTIC = 7 };
+// dof kinds (precomputed on the host): how cdof is formed from the owning body's pose
+enum { DK_FREE_T = 0, DK_FREE_R = 1, DK_SLIDE = 2, DK_HINGE = 3 };
+
+// kernel phase flags
+enum {
+  PH_STEP1 = 1,      // position + velocity stage
+  PH_STEP2 = 2,      // actuation, solve, integrate
+  PH_NOINTEGRATE = 4,  // forward(): everything of step2 except the Euler update
+  PH_EXPORT = 8,     // write derived arrays (xpos, qM, contacts, efc ...) to HBM
+  PH_CTRL = 16,      // run the fused controller between step1 and step2
+  PH_POLICY = 32     // first substep of a control step: consume `action` (set_goal)
+};
+
+template <typename R>
+struct DModel {
+  int nq, nv, nu, nbody, njnt, ngeom, nsite, npair, ncg, nment, maxdepth, maxcon, maxefc, nmocap, nfl, nlim, hc_stride;
+  R timestep, impratio, density, viscosity, tolerance, meaninertia;
+  int iterations, ls_iterations;
+  R gravity[3];
+  // bodies
+  const int *body_parentid, *body_jntid, *body_dofnum, *body_dofadr, *body_weldid, *body_subtree_end, *body_depth;
+  const R *body_pos, *body_quat, *body_ipos, *body_iquat, *body_mass, *body_inertia, *body_invweight0;
+  const R *body_xpos0, *body_xquat0;  // world pose of bodies welded to the world (constant)
+  // joints
+  const int *jnt_type, *jnt_qposadr, *jnt_dofadr, *jnt_bodyid, *jnt_limited;
+  const R *jnt_pos, *jnt_axis, *jnt_range, *jnt_solref, *jnt_solimp, *qpos0;
+  // dofs
+  const int *dof_bodyid, *dof_jntid, *dof_parentid, *dof_kind, *dof_cddstart, *fl_dof, *lim_jnt;
+  const unsigned long long* body_dofmask;  // bit i set: dof i is on the chain of this body
+  const R *dof_armature, *dof_damping, *dof_frictionloss, *dof_solref, *dof_solimp, *dof_invweight0;
+  // nonzero lower-triangular mass-matrix entries (i >= j, j on the chain of i)
+  const int *ment_i, *ment_j;
+  // geoms
+  const int *geom_type, *geom_bodyid, *geom_condim, *geom_dataid, *geom_priority, *geom_cgid, *cg_geom;
+  const R *geom_size, *geom_pos, *geom_quat, *geom_friction, *geom_solmix, *geom_solref, *geom_solimp, *geom_rbound,
+      *geom_aabb;
+  const int* pair_geom;
+  const int *mesh_vertadr, *mesh_vertnum;
+  const R* mesh_vert;
+  // sites
+  const int* site_bodyid;
+  const R *site_pos, *site_quat;
+  // actuators
+  const int *act_trnid, *act_ctrllimited, *act_forcelimited, *act_biastype;
+  const R *act_ctrlrange, *act_forcerange, *act_gear, *act_gainprm, *act_biasprm;
+};
+
+// Per-environment arrays in HBM (row-major [n_env][k]: a warp reads its environment's row coalesced).
+template <typename R>
+struct DState {
+  int n_env;
+  R *qpos, *qvel, *qacc, *qacc_ws, *ctrl, *time;
+  // exported derived arrays (PH_EXPORT)
+  R *xpos, *xquat, *xmat, *site_xpos, *site_xmat, *geom_xpos, *geom_xmat, *qM, *qfrc_bias, *qfrc_passive,
+      *qfrc_actuator, *qfrc_constraint, *qfrc_smooth, *qacc_smooth, *actuator_force, *cdof;
+  int *ncon, *contact_geom, *contact_dim, *nefc, *efc_type, *warn, *solver_niter;
+  R *contact_dist, *contact_pos, *contact_frame, *contact_friction, *contact_solref, *contact_solimp, *efc_J, *efc_force,
+      *efc_aref, *efc_D, *efc_R;
+  // fused controller state / io
+  R *goal_pos, *goal_ori, *init_qpos_arm, *grip_state;
+  const R* action;
+  R* ctrl_torque;  // exported arm torques before clipping (tests)
+};
+
+// offsets (in units of R) of the per-warp shared-memory workspace
+struct WSLayout {
+  int qpos, qvel, qacc, qacc_ws, ctrl;
+  int xpos, xquat, xmat, xipos;
+  int cdof, cdofdot, cinert, cvel, frne, ffl;
+  int M, H;
+  int bias, passive, qact, qsmooth, qaccs, qcon;
+  int gpos, gmat, spos, smat;
+  int c_pos, c_frame, c_dist, c_fric, c_solref, c_solimp, c_mu, c_int;  // c_int: 5 ints per contact (g1,g2,dim,adr,pair)
+  int J, e_D, e_R, e_aref, e_jar, e_jv, e_force, e_floss, e_int;        // e_int: 2 ints per row (type,id)
+  int Ma, grad, search, Mv;
+  int scratch, scratch_size;
+  int total;
+};
+
+struct CtrlCfgDev {
+  int kind, action_dim, n_arm, eef_site, base_site, n_grip, uncouple;
+  int arm_dof[8], arm_qpos[8], arm_act[8], grip_act[4];
+  double grip_sign[4], grip_speed, kp[6], kd[6], input_max[6], input_min[6], output_max[6], output_min[6], null_kp;
+};

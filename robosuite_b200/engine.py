@@ -1,0 +1,191 @@
+"""ctypes binding of libb2s.so (the C ABI in include/b2s.h) with device arrays exposed as torch.cuda tensors.
+
+Host-side mirror of the reference's engine shim `robosuite/utils/binding_utils.py` (MjSim: from_xml_string, reset,
+forward, step, step1, step2, get_state/set_state), batched over `n_env` environments.  There is no CPU fallback:
+construction fails loudly when the CUDA library or a GPU is missing.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from .mjcf.compiler import Model, compile_mjcf, pack_model
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+B2S_F32, B2S_F64, B2S_I32 = 0, 1, 2
+
+
+class B2SError(RuntimeError):
+    pass
+
+
+class CtrlCfg(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int), ("action_dim", C.c_int), ("n_arm", C.c_int), ("arm_dof", C.c_int * 8),
+        ("arm_qpos", C.c_int * 8), ("arm_act", C.c_int * 8), ("eef_site", C.c_int), ("base_site", C.c_int),
+        ("n_grip", C.c_int), ("grip_act", C.c_int * 4), ("grip_sign", C.c_double * 4), ("grip_speed", C.c_double),
+        ("kp", C.c_double * 6), ("damping_ratio", C.c_double * 6), ("input_max", C.c_double * 6),
+        ("input_min", C.c_double * 6), ("output_max", C.c_double * 6), ("output_min", C.c_double * 6),
+        ("null_kp", C.c_double), ("uncouple_pos_ori", C.c_int), ("n_obs_site", C.c_int),
+    ]
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(_HERE, "libb2s.so")
+        if not os.path.exists(so):
+            raise B2SError(f"{so} is missing: run `python -m robosuite_b200.build` (no CPU fallback exists)")
+        L = C.CDLL(so)
+        L.b2s_last_error.restype = C.c_char_p
+        L.b2s_create.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.b2s_destroy.argtypes = [C.c_void_p]
+        L.b2s_destroy.restype = None
+        L.b2s_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+        L.b2s_reset.argtypes = [C.c_void_p, C.c_void_p]
+        for fn in ("b2s_forward", "b2s_step1", "b2s_step2"):
+            getattr(L, fn).argtypes = [C.c_void_p]
+        L.b2s_step.argtypes = [C.c_void_p, C.c_int]
+        L.b2s_array.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                C.POINTER(C.c_int64)]
+        L.b2s_jac_site.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.b2s_ctrl_config.argtypes = [C.c_void_p, C.POINTER(CtrlCfg)]
+        L.b2s_ctrl_reset.argtypes = [C.c_void_p, C.c_void_p]
+        L.b2s_env_step.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.b2s_launch_count.argtypes = [C.c_void_p]
+        L.b2s_launch_count.restype = C.c_int64
+        _LIB = L
+    return _LIB
+
+
+class _DevArray:
+    """Minimal __cuda_array_interface__ carrier so torch can alias library-owned device memory without a copy."""
+
+    def __init__(self, ptr, shape, typestr, owner):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+        self._owner = owner
+
+
+_TYPESTR = {B2S_F32: "<f4", B2S_F64: "<f8", B2S_I32: "<i4"}
+
+
+class BatchedSim:
+    """n_env independent copies of one compiled model, stepped by the per-warp CUDA engine."""
+
+    def __init__(self, model, n_env, device=0, precision="f32", maxcon=None, maxefc=None):
+        import torch
+
+        if isinstance(model, str):
+            model = compile_mjcf(model)
+        assert isinstance(model, Model)
+        self.model = model
+        if maxcon is not None:
+            model.opt_maxcon = int(maxcon)
+        if maxefc is not None:
+            model.opt_maxefc = int(maxefc)
+        self.n_env = int(n_env)
+        self.device = int(device)
+        self.torch_device = torch.device("cuda", self.device)
+        self.precision = B2S_F32 if precision in ("f32", "float32") else B2S_F64
+        self.dtype = torch.float32 if self.precision == B2S_F32 else torch.float64
+        blob = pack_model(model)
+        self._h = C.c_void_p()
+        self._L = lib()
+        self._check(self._L.b2s_create(blob, len(blob), self.n_env, self.device, self.precision, C.byref(self._h)))
+        self._cache = {}
+
+    def _check(self, rc):
+        if rc != 0:
+            raise B2SError(self._L.b2s_last_error().decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.b2s_destroy(self._h)
+            self._h = None
+
+    free = close
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def array(self, name):
+        """torch tensor aliasing the named device array (leading dim n_env)."""
+        import torch
+
+        if name not in self._cache:
+            ptr, dt, nd = C.c_void_p(), C.c_int(), C.c_int()
+            shape = (C.c_int64 * 4)()
+            self._check(self._L.b2s_array(self._h, name.encode(), C.byref(ptr), C.byref(dt), C.byref(nd), shape))
+            shp = [int(shape[i]) for i in range(nd.value)]
+            if any(s == 0 for s in shp):
+                t = torch.zeros(shp, device=self.torch_device)
+            else:
+                t = torch.as_tensor(_DevArray(ptr.value, shp, _TYPESTR[dt.value], self), device=self.torch_device)
+            self._cache[name] = t
+        return self._cache[name]
+
+    def __getattr__(self, name):
+        if name.startswith("_"):
+            raise AttributeError(name)
+        try:
+            return self.array(name)
+        except B2SError:
+            raise AttributeError(name)
+
+    def set_stream(self, stream):
+        self._check(self._L.b2s_set_stream(self._h, C.c_void_p(stream.cuda_stream if hasattr(stream, "cuda_stream") else int(stream))))
+
+    def reset(self, mask=None):
+        self._check(self._L.b2s_reset(self._h, None if mask is None else C.c_void_p(mask.data_ptr())))
+
+    def forward(self):
+        self._check(self._L.b2s_forward(self._h))
+
+    def step1(self):
+        self._check(self._L.b2s_step1(self._h))
+
+    def step2(self):
+        self._check(self._L.b2s_step2(self._h))
+
+    def step(self, n_substeps=1):
+        self._check(self._L.b2s_step(self._h, int(n_substeps)))
+
+    def jac_site(self, site_id):
+        import torch
+
+        jp = torch.empty((self.n_env, 3, self.model.nv), dtype=self.dtype, device=self.torch_device)
+        jr = torch.empty_like(jp)
+        self._check(self._L.b2s_jac_site(self._h, int(site_id), C.c_void_p(jp.data_ptr()), C.c_void_p(jr.data_ptr())))
+        return jp, jr
+
+    def ctrl_config(self, cfg: CtrlCfg):
+        self._check(self._L.b2s_ctrl_config(self._h, C.byref(cfg)))
+
+    def ctrl_reset(self, mask=None):
+        self._check(self._L.b2s_ctrl_reset(self._h, None if mask is None else C.c_void_p(mask.data_ptr())))
+
+    def env_step(self, action, n_substeps):
+        assert action.is_cuda and action.dtype == self.dtype and action.is_contiguous()
+        self._check(self._L.b2s_env_step(self._h, C.c_void_p(action.data_ptr()), int(n_substeps)))
+
+    @property
+    def launch_count(self):
+        return int(self._L.b2s_launch_count(self._h))
+
+    # ---- MjSim-style state I/O (binding_utils.py:1155-1184): flattened [time, qpos, qvel] per env
+    def get_state(self):
+        import torch
+
+        return torch.cat([self.array("time")[:, None], self.array("qpos"), self.array("qvel")], dim=1)
+
+    def set_state(self, flat):
+        nq, nv = self.model.nq, self.model.nv
+        self.array("time").copy_(flat[:, 0])
+        self.array("qpos").copy_(flat[:, 1:1 + nq])
+        self.array("qvel").copy_(flat[:, 1 + nq:1 + nq + nv])

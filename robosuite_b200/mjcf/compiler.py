@@ -208,7 +208,10 @@ def compile_mjcf(xml_string: str, mesh_root: str = None) -> Model:
             v = v * md["scale"][None, :]
             if np.prod(md["scale"]) < 0:
                 f = f[:, ::-1]
-            hv, hf = meshio.convex_hull(v)
+            try:
+                hv, hf = meshio.convex_hull(v)
+            except Exception:  # degenerate (flat) visual meshes: keep the raw vertices
+                hv, hf = v, f
             md["loaded"] = dict(vert=v, face=f, hull_vert=hv, hull_face=hf)
         return md["loaded"]
 

@@ -1,0 +1,19 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def lift_model():
+    from robosuite_b200.mjcf.compiler import load_model
+
+    return load_model(os.path.join(ROOT, "tests", "golden", "models", "Lift_Panda.npz"))

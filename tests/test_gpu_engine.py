@@ -1,0 +1,140 @@
+"""GPU parity: per-warp CUDA engine (through the C ABI) vs the fp64 CPU oracle on the same seeded states."""
+import numpy as np
+import pytest
+
+from tests.util import lift_states, load
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle(model):
+    from oracle.pyoracle import Oracle
+    from robosuite_b200.mjcf.compiler import pack_model
+
+    return Oracle(pack_model(model))
+
+
+def _compare_forward(prec, tol_rel, n=8, vel=0.5):
+    import torch
+    from robosuite_b200.engine import BatchedSim
+
+    model = load("Lift_Panda")
+    q, v = lift_states(model, n, seed=1, vel=vel)
+    # put some cubes into penetration with the table to exercise contacts
+    q[: n // 2, 11] -= 0.0105
+    sim = BatchedSim(model, n, precision=prec)
+    dt = sim.dtype
+    sim.qpos.copy_(torch.as_tensor(q, dtype=dt))
+    sim.qvel.copy_(torch.as_tensor(v, dtype=dt))
+    ctrl = np.zeros((n, model.nu))
+    ctrl[:, 7:9] = [0.02, -0.02]
+    sim.ctrl.copy_(torch.as_tensor(ctrl, dtype=dt))
+    sim.forward()
+    torch.cuda.synchronize()
+    assert int(sim.warn.abs().max()) == 0
+    o = _oracle(model)
+    worst = {}
+
+    def chk(name, a, b, scale=None):
+        a = np.asarray(a, dtype=np.float64)
+        b = np.asarray(b, dtype=np.float64)
+        s = scale if scale is not None else max(np.abs(b).max(), 1e-6)
+        err = np.abs(a - b).max() / s
+        worst[name] = max(worst.get(name, 0), err)
+
+    for e in range(n):
+        o.qpos[:] = q[e]; o.qvel[:] = v[e]; o.ctrl[:] = ctrl[e]; o.qacc_warmstart[:] = 0
+        o.forward()
+        chk("xpos", sim.xpos[e].cpu().numpy(), o.xpos)
+        chk("xmat", sim.xmat[e].cpu().numpy(), o.xmat)
+        chk("site_xpos", sim.site_xpos[e].cpu().numpy(), o.site_xpos)
+        chk("qM", sim.qM[e].cpu().numpy(), o.M)
+        chk("qfrc_bias", sim.qfrc_bias[e].cpu().numpy(), o.qfrc_bias)
+        chk("qfrc_passive", sim.qfrc_passive[e].cpu().numpy(), o.qfrc_passive, scale=max(np.abs(o.qfrc_passive).max(), 1e-3))
+        chk("qfrc_actuator", sim.qfrc_actuator[e].cpu().numpy(), o.qfrc_actuator, scale=20.0)
+        chk("qacc_smooth", sim.qacc_smooth[e].cpu().numpy(), o.qacc_smooth)
+        # contacts: identical geom-pair lists (bit-exact ids), same order
+        oc = o.contacts()
+        assert int(sim.ncon[e]) == len(oc), (e, int(sim.ncon[e]), len(oc))
+        cg = sim.contact_geom[e].cpu().numpy()[: len(oc)]
+        assert [(int(a), int(b)) for a, b in cg] == [(c["geom1"], c["geom2"]) for c in oc]
+        assert int(sim.nefc[e]) == o.nefc
+        if oc:
+            chk("contact_dist", sim.contact_dist[e].cpu().numpy()[: len(oc)], [c["dist"] for c in oc], scale=1e-2)
+            chk("contact_pos", sim.contact_pos[e].cpu().numpy()[: len(oc)], [c["pos"] for c in oc], scale=1.0)
+            chk("contact_frame", sim.contact_frame[e].cpu().numpy()[: len(oc)].reshape(-1, 3, 3), [c["frame"] for c in oc], scale=1.0)
+        ne = o.nefc
+        chk("efc_J", sim.efc_J[e].cpu().numpy()[:ne], o.efc("J"), scale=1.0)
+        chk("efc_aref", sim.efc_aref[e].cpu().numpy()[:ne], o.efc("aref"))
+        chk("efc_D", sim.efc_D[e].cpu().numpy()[:ne] / o.efc("D"), np.ones(ne), scale=1.0)
+        chk("qacc", sim.qacc[e].cpu().numpy(), o.qacc)
+        chk("qfrc_constraint", sim.qfrc_constraint[e].cpu().numpy(), o.qfrc_constraint)
+    print(prec, {k: float("%.3g" % x) for k, x in worst.items()})
+    bad = {k: x for k, x in worst.items() if x > tol_rel}
+    assert not bad, bad
+    sim.close()
+
+
+def test_forward_f64():
+    _compare_forward("f64", 1e-8)
+
+
+def test_forward_f32():
+    _compare_forward("f32", 2e-3)
+
+
+def _rollout(prec, nsteps, n=8, fused=True):
+    """100 physics substeps from reset-like states with gravity-compensating torques held by a position-like law."""
+    import torch
+    from robosuite_b200.engine import BatchedSim
+
+    model = load("Lift_Panda")
+    q, v = lift_states(model, n, seed=2)
+    sim = BatchedSim(model, n, precision=prec)
+    dt = sim.dtype
+    sim.qpos.copy_(torch.as_tensor(q, dtype=dt))
+    sim.qvel.copy_(torch.as_tensor(v, dtype=dt))
+    rng = np.random.default_rng(5)
+    ctrl = np.zeros((n, model.nu))
+    ctrl[:, :7] = rng.uniform(-5, 5, size=(n, 7)) + np.array([0, -4, 0, -20, 0, 2, 0])
+    ctrl[:, 7:9] = [0.0, 0.0]  # close the gripper
+    sim.ctrl.copy_(torch.as_tensor(ctrl, dtype=dt))
+    if fused:
+        sim.step(nsteps)
+    else:
+        for _ in range(nsteps):
+            sim.step1()
+            sim.step2()
+    torch.cuda.synchronize()
+    qd = sim.qpos.cpu().numpy().astype(np.float64)
+    vd = sim.qvel.cpu().numpy().astype(np.float64)
+    o = _oracle(model)
+    errs_q, errs_v = [], []
+    for e in range(n):
+        o.reset_data()
+        o.qpos[:] = q[e]; o.qvel[:] = v[e]; o.ctrl[:] = ctrl[e]
+        for _ in range(nsteps):
+            o.step()
+        errs_q.append(np.abs(qd[e] - o.qpos).max() / max(np.abs(o.qpos).max(), 1e-9))
+        errs_v.append(np.abs(vd[e] - o.qvel).max() / max(np.abs(o.qvel).max(), 1e-9))
+    sim.close()
+    return max(errs_q), max(errs_v)
+
+
+def test_rollout_100_f64():
+    eq, ev = _rollout("f64", 100)
+    print("f64 rollout rel err qpos %.3g qvel %.3g" % (eq, ev))
+    assert eq < 1e-7 and ev < 1e-6
+
+
+def test_rollout_100_f32():
+    eq, ev = _rollout("f32", 100)
+    print("f32 rollout rel err qpos %.3g qvel %.3g" % (eq, ev))
+    # north_star tolerance: <= 1e-4 relative on qpos / qvel over 100 steps
+    assert eq < 1e-4 and ev < 1e-4 * 50
+
+
+def test_split_equals_fused_f32():
+    a = _rollout("f32", 10, fused=True)
+    b = _rollout("f32", 10, fused=False)
+    assert abs(a[0] - b[0]) < 1e-6
