@@ -47,8 +47,30 @@ def lib():
         L.o_full_m.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
         L.o_collide_pair.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
         L.o_set_time.argtypes = [C.c_void_p, C.c_double]
+        L.o_ctrl_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.o_ctrl_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
+        L.o_env_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.c_int]
+        for fn in ("o_ctrl_reset", "o_ctrl_run", "o_env_step"):
+            getattr(L, fn).restype = None
         _LIB = L
     return _LIB
+
+
+class CtrlCfg(C.Structure):
+    """Mirror of OCtrlCfg (oracle/o_ctrl.c); same field order as b2s_ctrl_cfg in include/b2s.h."""
+    _fields_ = [
+        ("kind", C.c_int), ("action_dim", C.c_int), ("n_arm", C.c_int), ("arm_dof", C.c_int * 8),
+        ("arm_qpos", C.c_int * 8), ("arm_act", C.c_int * 8), ("eef_site", C.c_int), ("base_site", C.c_int),
+        ("n_grip", C.c_int), ("grip_act", C.c_int * 4), ("grip_sign", C.c_double * 4), ("grip_speed", C.c_double),
+        ("kp", C.c_double * 6), ("damping_ratio", C.c_double * 6), ("input_max", C.c_double * 6),
+        ("input_min", C.c_double * 6), ("output_max", C.c_double * 6), ("output_min", C.c_double * 6),
+        ("null_kp", C.c_double), ("uncouple_pos_ori", C.c_int), ("n_obs_site", C.c_int),
+    ]
+
+
+class CtrlState(C.Structure):
+    _fields_ = [("goal_pos", C.c_double * 3), ("goal_ori", C.c_double * 9), ("initial_joint", C.c_double * 8),
+                ("grip_action", C.c_double * 4), ("torques", C.c_double * 8)]
 
 
 _SHAPES = {
@@ -139,6 +161,26 @@ class Oracle:
         self._L.o_jac(self.m, self.d, jp.ctypes.data_as(C.POINTER(C.c_double)), jr.ctypes.data_as(C.POINTER(C.c_double)),
                       pt.ctypes.data_as(C.POINTER(C.c_double)), int(body))
         return jp, jr
+
+    # ---- controller half (oracle/o_ctrl.c)
+    def ctrl_setup(self, cfg):
+        self.ctrl_cfg = cfg
+        self.ctrl_state = CtrlState()
+
+    def ctrl_reset(self):
+        self._L.o_ctrl_reset(self.m, self.d, C.byref(self.ctrl_cfg), C.byref(self.ctrl_state))
+
+    def ctrl_run(self, action=None):
+        a = None
+        if action is not None:
+            arr = np.ascontiguousarray(action, dtype=np.float64)
+            a = arr.ctypes.data_as(C.POINTER(C.c_double))
+        self._L.o_ctrl_run(self.m, self.d, C.byref(self.ctrl_cfg), C.byref(self.ctrl_state), a)
+
+    def env_step(self, action, nsub=25):
+        arr = np.ascontiguousarray(action, dtype=np.float64)
+        self._L.o_env_step(self.m, self.d, C.byref(self.ctrl_cfg), C.byref(self.ctrl_state),
+                           arr.ctypes.data_as(C.POINTER(C.c_double)), int(nsub))
 
     def __getattr__(self, name):
         if name in ("reset_data", "forward", "step1", "step2", "step", "kinematics", "crb", "factor_m", "collision",

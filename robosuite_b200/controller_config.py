@@ -1,0 +1,90 @@
+"""controller_config plugin surface -> fused-controller configuration.
+
+Accepts the reference's composite controller JSON/dict schema unchanged
+(`robosuite/controllers/config/robots/default_panda.json`, `config/default/parts/osc_pose.json`; selection logic
+`robosuite/controllers/parts/controller_factory.py:145-159`) and resolves the model indices the way
+`robosuite/robots/robot.py:302-332,911-979` does (joint / actuator / site name lookups by naming prefix).
+"""
+import json
+import os
+
+import numpy as np
+
+_DEFAULT_OSC_POSE = {
+    "type": "OSC_POSE", "input_max": 1, "input_min": -1,
+    "output_max": [0.05, 0.05, 0.05, 0.5, 0.5, 0.5], "output_min": [-0.05, -0.05, -0.05, -0.5, -0.5, -0.5],
+    "kp": 150, "damping_ratio": 1, "impedance_mode": "fixed", "kp_limits": [0, 300], "damping_ratio_limits": [0, 10],
+    "position_limits": None, "orientation_limits": None, "uncouple_pos_ori": True, "input_type": "delta",
+    "input_ref_frame": "base", "interpolation": None, "ramp_ratio": 0.2,
+}
+
+# gripper format_action sign patterns and speed (models/grippers/panda_gripper.py:43-58, rethink_gripper.py:56)
+GRIPPER_SIGNS = {"panda": [-1.0, 1.0], "rethink": [1.0, -1.0]}
+GRIPPER_SPEED = {"panda": 0.2, "rethink": 0.2}
+
+
+def default_composite_config(robot="Panda"):
+    """Same content as config/robots/default_{panda,sawyer}.json: BASIC composite, OSC_POSE arm, GRIP gripper."""
+    part = dict(_DEFAULT_OSC_POSE)
+    part["gripper"] = {"type": "GRIP"}
+    return {"type": "BASIC", "body_parts": {"arms": {"right": part}}}
+
+
+def load_composite_controller_config(controller=None, robot="Panda"):
+    """Mirror of composite_controller_factory.load_composite_controller_config (:73-138): None -> robot default,
+    a path -> JSON file, a dict -> used as is."""
+    if controller is None:
+        return default_composite_config(robot)
+    if isinstance(controller, dict):
+        return controller
+    if isinstance(controller, str) and os.path.exists(controller):
+        with open(controller) as f:
+            return json.load(f)
+    raise ValueError(f"unknown controller config {controller!r}")
+
+
+def _arr6(v):
+    a = np.asarray(v, dtype=np.float64)
+    return np.full(6, float(a)) if a.ndim == 0 else a.astype(np.float64)
+
+
+def resolve(model, composite_cfg, cfg_struct_cls, robot_prefix="robot0_", gripper_prefix="gripper0_right_", gripper="panda"):
+    """Build the C struct (engine.CtrlCfg or the oracle's CtrlCfg: same layout) for one fixed-base arm + gripper."""
+    if composite_cfg.get("type", "BASIC") != "BASIC":
+        raise NotImplementedError("only the BASIC composite controller is implemented")
+    arm = composite_cfg["body_parts"]["arms"]["right"]
+    if arm["type"] != "OSC_POSE":
+        raise NotImplementedError(f"arm controller type {arm['type']} not implemented in the fused path")
+    if arm.get("impedance_mode", "fixed") != "fixed" or arm.get("input_type", "delta") != "delta" \
+            or arm.get("input_ref_frame", "base") != "base" or arm.get("interpolation") is not None:
+        raise NotImplementedError("fused OSC path implements fixed impedance, delta inputs in the base frame")
+    jn, an, sn = model.names["joint"], model.names["actuator"], model.names["site"]
+    arm_j = [i for i, n in enumerate(jn) if n and n.startswith(robot_prefix + "joint")]
+    c = cfg_struct_cls()
+    c.kind = 1
+    c.n_arm = len(arm_j)
+    for k, j in enumerate(arm_j):
+        c.arm_dof[k] = int(model.jnt_dofadr[j])
+        c.arm_qpos[k] = int(model.jnt_qposadr[j])
+        c.arm_act[k] = [i for i in range(model.nu) if model.actuator_trnid[i] == j][0]
+    c.eef_site = sn.index(gripper_prefix + "grip_site")
+    c.base_site = sn.index(robot_prefix + "right_center")
+    grip_act = [i for i, n in enumerate(an) if n and n.startswith(gripper_prefix.replace("_right_", "_right_gripper_"))]
+    if not grip_act:
+        grip_act = [i for i, n in enumerate(an) if n and n.startswith("gripper0_")]
+    c.n_grip = len(grip_act)
+    for k, a in enumerate(grip_act):
+        c.grip_act[k] = a
+        c.grip_sign[k] = GRIPPER_SIGNS[gripper][k]
+    c.grip_speed = GRIPPER_SPEED[gripper]
+    c.action_dim = 6 + 1
+    kp, dr = _arr6(arm["kp"]), _arr6(arm["damping_ratio"])
+    imax, imin = _arr6(arm["input_max"]), _arr6(arm["input_min"])
+    omax, omin = _arr6(arm["output_max"]), _arr6(arm["output_min"])
+    for k in range(6):
+        c.kp[k], c.damping_ratio[k] = kp[k], dr[k]
+        c.input_max[k], c.input_min[k], c.output_max[k], c.output_min[k] = imax[k], imin[k], omax[k], omin[k]
+    c.null_kp = 10.0
+    c.uncouple_pos_ori = int(bool(arm.get("uncouple_pos_ori", True)))
+    c.n_obs_site = 0
+    return c

@@ -314,6 +314,7 @@ static void build_layout(b2s_sim* s, int nq, int nv, int nu, int nb, int ncg, in
   if (epa > sc) sc = epa;
   int hs = me + hc_stride * mc;
   if (hs > sc) sc = hs;
+  if (sc < 720) sc = 720;  // fused controller work area (336 doubles)
   L.scratch_size = sc;
   L.scratch = take(sc);
   L.total = o;

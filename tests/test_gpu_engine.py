@@ -138,3 +138,65 @@ def test_split_equals_fused_f32():
     a = _rollout("f32", 10, fused=True)
     b = _rollout("f32", 10, fused=False)
     assert abs(a[0] - b[0]) < 1e-6
+
+
+def _env_rollout(prec, n_steps, n=8, nsub=25, seed=11):
+    """Fused control steps (25 x {step1, OSC_POSE + GRIP, step2} per launch) vs the oracle's env step."""
+    import torch
+    from oracle.pyoracle import CtrlCfg as OCfg
+    from robosuite_b200 import controller_config as cc
+    from robosuite_b200.engine import BatchedSim, CtrlCfg
+
+    model = load("Lift_Panda")
+    q, v = lift_states(model, n, seed=seed)
+    sim = BatchedSim(model, n, precision=prec)
+    dt = sim.dtype
+    sim.ctrl_config(cc.resolve(model, cc.default_composite_config(), CtrlCfg))
+    sim.qpos.copy_(torch.as_tensor(q, dtype=dt))
+    sim.forward()
+    sim.ctrl_reset()
+    rng = np.random.default_rng(seed + 1)
+    actions = rng.uniform(-1, 1, size=(n_steps, n, 7))
+    tq = []
+    for t in range(n_steps):
+        sim.env_step(torch.as_tensor(actions[t], dtype=dt, device=sim.torch_device).contiguous(), nsub)
+        tq.append(sim.ctrl_torque.cpu().numpy()[:, :7].astype(np.float64))
+    torch.cuda.synchronize()
+    assert int(sim.warn.abs().max()) == 0
+    qd = sim.qpos.cpu().numpy().astype(np.float64)
+    vd = sim.qvel.cpu().numpy().astype(np.float64)
+    o = _oracle(model)
+    o.ctrl_setup(cc.resolve(model, cc.default_composite_config(), OCfg))
+    eq, ev, et = 0.0, 0.0, 0.0
+    for e in range(n):
+        o.reset_data()
+        o.qpos[:] = q[e]
+        o.forward()
+        o.ctrl_reset()
+        for t in range(n_steps):
+            o.env_step(actions[t, e], nsub)
+            tau = np.array(o.ctrl_state.torques[:7])
+            et = max(et, np.abs(tq[t][e] - tau).max() / max(np.abs(tau).max(), 1e-9))
+        eq = max(eq, np.abs(qd[e] - o.qpos).max() / np.abs(o.qpos).max())
+        ev = max(ev, np.abs(vd[e] - o.qvel).max() / max(np.abs(o.qvel).max(), 1e-9))
+    sim.close()
+    return eq, ev, et
+
+
+def test_env_step_f64():
+    eq, ev, et = _env_rollout("f64", 4)
+    print("f64 env 4 control steps (100 substeps): qpos %.3g qvel %.3g tau %.3g" % (eq, ev, et))
+    assert eq < 1e-7 and ev < 1e-5 and et < 1e-6
+
+
+def test_env_step_f32_100_substeps():
+    eq, ev, et = _env_rollout("f32", 4)
+    print("f32 env 4 control steps (100 substeps): qpos %.3g qvel %.3g tau %.3g" % (eq, ev, et))
+    assert eq < 1e-4 and ev < 5e-3
+
+
+def test_env_step_f32_100_control_steps():
+    """stricter reading of '100 steps': 100 env.step = 2500 physics substeps (reported, looser gate)"""
+    eq, ev, et = _env_rollout("f32", 100, n=4)
+    print("f32 env 100 control steps (2500 substeps): qpos %.3g qvel %.3g tau %.3g" % (eq, ev, et))
+    assert eq < 5e-2
