@@ -80,6 +80,20 @@ int b2s_ctrl_config(b2s_sim* sim, const b2s_ctrl_cfg* cfg);
 int b2s_ctrl_reset(b2s_sim* sim, const uint8_t* env_mask);
 int b2s_env_step(b2s_sim* sim, const void* action, int n_substeps);
 
+/* Observation program = MujocoEnv._get_observations flattened (environments/base.py:429-465): one (op, a, b) entry
+ * per output scalar (ops: enum OB_* in csrc/b2s_types.cuh).  Creates the device array "obs" [n_env, obs_dim], written by
+ * b2s_env_step after the FIRST substep (Observable sampling rule, utils/observables.py:230-240) and by b2s_forward. */
+int b2s_obs_config(b2s_sim* sim, int obs_dim, const int* op_host, const int* a_host, const int* b_host);
+/* Task outputs "task_out" [n_env,4] = (target body height, |site - body|, grasp flag, 0) from the poses/contacts of the
+ * last step1 (what the reference's reward()/_check_grasp read: manipulation/lift.py:224-273, manipulation_env.py:331-376).
+ * Geom id lists: left / right finger(pad) groups and object geoms. */
+int b2s_task_config(b2s_sim* sim, int body, int site, const int* left, int nleft, const int* right, int nright,
+                    const int* obj, int nobj);
+
+/* b2s_env_step also exports the derived arrays of its last substep (xpos, contacts, efc ...) when flag != 0 (default 1);
+ * the throughput path switches it off so that per-step HBM traffic is state + action + obs only */
+int b2s_set_export(b2s_sim* sim, int flag);
+
 /* number of kernels this handle has launched since creation (bench.py "gpu_launches") */
 int64_t b2s_launch_count(const b2s_sim* sim);
 

@@ -61,7 +61,8 @@ struct b2s_sim {
   int64_t launches = 0;
   int nq = 0, nv = 0, nu = 0, nbody = 0, ngeom = 0, nsite = 0, maxcon = 0, maxefc = 0;
   std::vector<double> qpos0;
-  std::vector<int> site_bodyid;
+  std::vector<int> site_bodyid, cgid;
+  int has_obs = 0, export_env_step = 1;
 };
 
 template <typename T> static T* dev_upload(b2s_sim* s, const std::vector<T>& h) {
@@ -190,6 +191,8 @@ template <typename R> static void build_model(b2s_sim* s, const Blob& b, DModel<
     for (int k = 0; k < 2; k++) { int g = pair[2 * p + k]; if (cgid[g] < 0) cgid[g] = 1; }
   for (int g = 0; g < ng; g++) if (cgid[g] > 0) { cgid[g] = (int)cg.size(); cg.push_back(g); }
   m.ncg = (int)cg.size();
+  s->cgid = cgid;
+  if (m.ncg > 64) throw std::string("more than 64 colliding geoms not supported");
   const int* condim = b.i32("geom_condim");
   int maxdim = 1;
   for (int g : cg) if (condim[g] > maxdim) maxdim = condim[g];
@@ -386,6 +389,8 @@ int b2s_set_stream(b2s_sim* s, void* stream) {
   return B2S_OK;
 }
 
+int b2s_set_export(b2s_sim* s, int flag) { if (!s) return fail(B2S_ERR_ARG, "null handle"); s->export_env_step = flag != 0; return B2S_OK; }
+
 int64_t b2s_launch_count(const b2s_sim* s) { return s ? s->launches : 0; }
 
 int b2s_array(b2s_sim* s, const char* name, void** dev_ptr, int* dtype, int* ndim, int64_t shape[4]) {
@@ -422,7 +427,7 @@ int b2s_reset(b2s_sim* s, const uint8_t* mask) {
   return B2S_OK;
 }
 
-int b2s_forward(b2s_sim* s) { return s ? launch(s, PH_STEP1 | PH_STEP2 | PH_NOINTEGRATE | PH_EXPORT, 1) : fail(B2S_ERR_ARG, "null handle"); }
+int b2s_forward(b2s_sim* s) { return s ? launch(s, PH_STEP1 | PH_STEP2 | PH_NOINTEGRATE | PH_EXPORT | (s->has_obs ? PH_OBS : 0), 1) : fail(B2S_ERR_ARG, "null handle"); }
 int b2s_step1(b2s_sim* s) { return s ? launch(s, PH_STEP1 | PH_EXPORT, 1) : fail(B2S_ERR_ARG, "null handle"); }
 int b2s_step2(b2s_sim* s) { return s ? launch(s, PH_STEP1 | PH_STEP2 | PH_EXPORT, 1) : fail(B2S_ERR_ARG, "null handle"); }
 int b2s_step(b2s_sim* s, int n) {
@@ -475,7 +480,38 @@ int b2s_ctrl_reset(b2s_sim* s, const uint8_t* mask) {
 int b2s_env_step(b2s_sim* s, const void* action, int nsub) {
   if (!s || !s->has_ctrl || !action || nsub < 1) return fail(B2S_ERR_ARG, "b2s_env_step: bad argument / controller not configured");
   if (s->precision == B2S_F32) s->sf.action = (const float*)action; else s->sd.action = (const double*)action;
-  return launch(s, PH_STEP1 | PH_STEP2 | PH_CTRL | PH_EXPORT, nsub);
+  return launch(s, PH_STEP1 | PH_STEP2 | PH_CTRL | (s->has_obs ? PH_OBS : 0) | (s->export_env_step ? PH_EXPORT : 0), nsub);
+}
+
+int b2s_obs_config(b2s_sim* s, int obs_dim, const int* op, const int* a, const int* b) {
+  if (!s || obs_dim <= 0 || !op || !a || !b) return fail(B2S_ERR_ARG, "b2s_obs_config: bad argument");
+  CUDA_TRY(cudaSetDevice(s->device));
+  try {
+    std::vector<int> vo(op, op + obs_dim), va(a, a + obs_dim), vb(b, b + obs_dim);
+    s->ctrl.obs_dim = obs_dim;
+    s->ctrl.obs_op = dev_upload(s, vo); s->ctrl.obs_a = dev_upload(s, va); s->ctrl.obs_b = dev_upload(s, vb);
+    if (s->precision == B2S_F32) { s->sf.obs = state_arr<float>(s, "obs", obs_dim); s->sf.task_out = state_arr<float>(s, "task_out", 4); }
+    else { s->sd.obs = state_arr<double>(s, "obs", obs_dim); s->sd.task_out = state_arr<double>(s, "task_out", 4); }
+  } catch (const std::string& e) { return fail(B2S_ERR_CUDA, e); }
+  s->has_obs = 1;
+  return B2S_OK;
+}
+
+int b2s_task_config(b2s_sim* s, int body, int site, const int* left, int nl, const int* right, int nr, const int* obj, int no) {
+  if (!s || body < 0 || body >= s->nbody || site < 0 || site >= s->nsite) return fail(B2S_ERR_ARG, "b2s_task_config: bad argument");
+  auto mk = [&](const int* g, int n, unsigned long long& out) {
+    out = 0;
+    for (int i = 0; i < n; i++) {
+      if (g[i] < 0 || g[i] >= s->ngeom) return false;
+      int k = s->cgid[g[i]];
+      if (k >= 0) out |= 1ull << k;
+    }
+    return true;
+  };
+  if (!mk(left, nl, s->ctrl.mask_left) || !mk(right, nr, s->ctrl.mask_right) || !mk(obj, no, s->ctrl.mask_obj))
+    return fail(B2S_ERR_ARG, "b2s_task_config: geom id out of range");
+  s->ctrl.task_body = body; s->ctrl.task_site = site;
+  return B2S_OK;
 }
 
 }  // extern "C"

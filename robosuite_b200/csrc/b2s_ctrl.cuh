@@ -277,6 +277,76 @@ DEV void ctrl_run(Eng<R>& e, const DState<R>& s, const CtrlCfgDev& cc, CtrlState
   __syncwarp();
 }
 
+// rotation matrix -> quaternion (w >= 0), same canonical sign as the reference's mat2quat (transform_utils.py:316-356)
+template <typename R> DEV void mat2quat_wpos(const R* M, R* q) {
+  R tr = M[0] + M[4] + M[8];
+  if (tr > 0) {
+    R s = r_sqrt(tr + R(1)) * 2;
+    q[0] = R(0.25) * s; q[1] = (M[7] - M[5]) / s; q[2] = (M[2] - M[6]) / s; q[3] = (M[3] - M[1]) / s;
+  } else if (M[0] > M[4] && M[0] > M[8]) {
+    R s = r_sqrt(R(1) + M[0] - M[4] - M[8]) * 2;
+    q[0] = (M[7] - M[5]) / s; q[1] = R(0.25) * s; q[2] = (M[1] + M[3]) / s; q[3] = (M[2] + M[6]) / s;
+  } else if (M[4] > M[8]) {
+    R s = r_sqrt(R(1) + M[4] - M[0] - M[8]) * 2;
+    q[0] = (M[2] - M[6]) / s; q[1] = (M[1] + M[3]) / s; q[2] = R(0.25) * s; q[3] = (M[5] + M[7]) / s;
+  } else {
+    R s = r_sqrt(R(1) + M[8] - M[0] - M[4]) * 2;
+    q[0] = (M[3] - M[1]) / s; q[1] = (M[2] + M[6]) / s; q[2] = (M[5] + M[7]) / s; q[3] = R(0.25) * s;
+  }
+  if (q[0] < 0) { q[0] = -q[0]; q[1] = -q[1]; q[2] = -q[2]; q[3] = -q[3]; }
+  qnormalize(q);
+}
+
+// Observation row: one table entry per scalar (MujocoEnv._get_observations, environments/base.py:429-465; sensors
+// robots/robot.py:347-392,412-484 and the task's object observables e.g. manipulation/lift.py:371-397).
+// qpos/qvel/qacc are the freshly integrated values, poses are those of the last step1 (reference staleness).
+template <typename R> DEV void write_obs(const Eng<R>& e, const DState<R>& s, const CtrlCfgDev& cc, int env) {
+  const WSLayout& L = e.L;
+  R* out = s.obs + (size_t)env * cc.obs_dim;
+  for (int k = e.lane; k < cc.obs_dim; k += 32) {
+    int op = cc.obs_op[k], a = cc.obs_a[k], b = cc.obs_b[k];
+    R v = 0;
+    switch (op) {
+      case OB_QPOS: v = e.p(L.qpos)[a]; break;
+      case OB_COS_QPOS: { R sn, cs; r_sincos(e.p(L.qpos)[a], &sn, &cs); v = cs; break; }
+      case OB_SIN_QPOS: { R sn, cs; r_sincos(e.p(L.qpos)[a], &sn, &cs); v = sn; break; }
+      case OB_QVEL: v = e.p(L.qvel)[a]; break;
+      case OB_QACC: v = e.p(L.qacc)[a]; break;
+      case OB_SITE_POS: v = e.p(L.spos)[3 * a + b]; break;
+      case OB_BODY_POS: v = e.p(L.xpos)[3 * a + b]; break;
+      case OB_BODY_QUAT_XYZW: v = e.p(L.xquat)[4 * a + ((b + 1) & 3)]; break;
+      case OB_SITE_QUAT_XYZW: { R q[4]; mat2quat_wpos(e.p(L.smat) + 9 * a, q); v = q[(b + 1) & 3]; break; }
+      case OB_BODY_MINUS_SITE: v = e.p(L.xpos)[3 * (a >> 8) + b] - e.p(L.spos)[3 * (a & 255) + b]; break;
+      case OB_SITE_MINUS_SITE: v = e.p(L.spos)[3 * (a >> 8) + b] - e.p(L.spos)[3 * (a & 255) + b]; break;
+      default: v = 0;
+    }
+    out[k] = v;
+  }
+}
+
+// Task outputs after the last substep (poses / contacts of the last step1, as the reference's reward() sees them:
+// manipulation/lift.py:224-273,433-444; manipulation_env.py:331-376 _check_grasp; utils/sim_utils.py:8-40)
+template <typename R> DEV void write_task(const Eng<R>& e, const DState<R>& s, const CtrlCfgDev& cc, int env, int ncon) {
+  const DModel<R>& m = e.m;
+  const WSLayout& L = e.L;
+  const int* cint = e.pi(L.c_int);
+  int hitl = 0, hitr = 0;
+  for (int c = e.lane; c < ncon; c += 32) {
+    unsigned long long b1 = 1ull << m.geom_cgid[cint[5 * c]], b2 = 1ull << m.geom_cgid[cint[5 * c + 1]];
+    bool o1 = b1 & cc.mask_obj, o2 = b2 & cc.mask_obj;
+    if ((o1 && (b2 & cc.mask_left)) || (o2 && (b1 & cc.mask_left))) hitl = 1;
+    if ((o1 && (b2 & cc.mask_right)) || (o2 && (b1 & cc.mask_right))) hitr = 1;
+  }
+  hitl = warp_or_i(hitl); hitr = warp_or_i(hitr);
+  if (e.lane == 0) {
+    R* out = s.task_out + (size_t)env * 4;
+    const R* bp = e.p(L.xpos) + 3 * cc.task_body; const R* sp = e.p(L.spos) + 3 * cc.task_site;
+    R d[3];
+    v3sub(d, bp, sp);
+    out[0] = bp[2]; out[1] = v3norm(d); out[2] = (hitl && hitr) ? R(1) : R(0); out[3] = 0;
+  }
+}
+
 // controller.reset_goal + initial joints (osc.py:520-544, controller.py:126-132): goal <- current eef pose (world),
 // initial_joint <- current arm qpos, gripper integrator <- 0.  Uses the exported site arrays of a prior forward.
 template <typename R>

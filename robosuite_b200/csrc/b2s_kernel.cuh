@@ -104,6 +104,10 @@ __global__ void step_kernel(const __grid_constant__ DModel<R> m, const __grid_co
         if (e.euler(&time)) warn |= 2;
       }
     }
+    if ((phases & PH_OBS) && cc.obs_dim > 0) {
+      if (sub == 0) write_obs(e, s, cc, env);
+      if (sub == nsub - 1) write_task(e, s, cc, env, ncon);
+    }
     __syncwarp();
   }
   // write back

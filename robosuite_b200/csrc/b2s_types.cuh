@@ -20,7 +20,8 @@ enum {
   PH_NOINTEGRATE = 4,  // forward(): everything of step2 except the Euler update
   PH_EXPORT = 8,     // write derived arrays (xpos, qM, contacts, efc ...) to HBM
   PH_CTRL = 16,      // run the fused controller between step1 and step2
-  PH_POLICY = 32     // first substep of a control step: consume `action` (set_goal)
+  PH_POLICY = 32,    // first substep of a control step: consume `action` (set_goal)
+  PH_OBS = 64        // write the observation row (after substep 0) and the task outputs (after the last substep)
 };
 
 template <typename R>
@@ -72,6 +73,8 @@ struct DState {
   R *goal_pos, *goal_ori, *init_qpos_arm, *grip_state;
   const R* action;
   R* ctrl_torque;  // exported arm torques before clipping (tests)
+  R* obs;          // [n_env, obs_dim] sampled after the first substep of a control step (observables.py:230-240)
+  R* task_out;     // [n_env, 4]: target body height, |grip site - target body|, grasp flag, reserved
 };
 
 // offsets (in units of R) of the per-warp shared-memory workspace
@@ -89,8 +92,14 @@ struct WSLayout {
   int total;
 };
 
+// observation scalar ops (one table entry per output scalar)
+enum { OB_QPOS = 0, OB_COS_QPOS, OB_SIN_QPOS, OB_QVEL, OB_QACC, OB_SITE_POS, OB_BODY_POS, OB_BODY_QUAT_XYZW, OB_SITE_QUAT_XYZW,
+       OB_BODY_MINUS_SITE, OB_SITE_MINUS_SITE, OB_BODY_QUAT_REL_SITE_XYZW, OB_ZERO };
+
 struct CtrlCfgDev {
   int kind, action_dim, n_arm, eef_site, base_site, n_grip, uncouple;
+  int obs_dim; const int* obs_op; const int* obs_a; const int* obs_b;  // device arrays
+  int task_body, task_site; unsigned long long mask_left, mask_right, mask_obj;  // grasp check geom sets (colliding-geom index bits)
   int arm_dof[8], arm_qpos[8], arm_act[8], grip_act[4];
   double grip_sign[4], grip_speed, kp[6], kd[6], input_max[6], input_min[6], output_max[6], output_min[6], null_kp;
 };

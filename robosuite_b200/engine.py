@@ -54,6 +54,9 @@ def lib():
         L.b2s_ctrl_config.argtypes = [C.c_void_p, C.POINTER(CtrlCfg)]
         L.b2s_ctrl_reset.argtypes = [C.c_void_p, C.c_void_p]
         L.b2s_env_step.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.b2s_obs_config.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.b2s_task_config.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        L.b2s_set_export.argtypes = [C.c_void_p, C.c_int]
         L.b2s_launch_count.argtypes = [C.c_void_p]
         L.b2s_launch_count.restype = C.c_int64
         _LIB = L
@@ -173,6 +176,19 @@ class BatchedSim:
     def env_step(self, action, n_substeps):
         assert action.is_cuda and action.dtype == self.dtype and action.is_contiguous()
         self._check(self._L.b2s_env_step(self._h, C.c_void_p(action.data_ptr()), int(n_substeps)))
+
+    def obs_config(self, ops, a, b):
+        ops, a, b = (np.ascontiguousarray(x, dtype=np.int32) for x in (ops, a, b))
+        self._check(self._L.b2s_obs_config(self._h, len(ops), ops.ctypes.data, a.ctypes.data, b.ctypes.data))
+
+    def task_config(self, body, site, left, right, obj):
+        left, right, obj = (np.ascontiguousarray(x, dtype=np.int32) for x in (left, right, obj))
+        self._check(self._L.b2s_task_config(self._h, int(body), int(site), left.ctypes.data, len(left), right.ctypes.data,
+                                            len(right), obj.ctypes.data, len(obj)))
+
+    def set_export(self, flag):
+        """whether b2s_env_step also writes the derived arrays (xpos, contacts, ...) of its last substep to HBM"""
+        self._check(self._L.b2s_set_export(self._h, int(bool(flag))))
 
     @property
     def launch_count(self):

@@ -1,0 +1,2 @@
+from .base import REGISTERED_ENVS, BatchedMujocoEnv, make  # noqa: F401
+from .lift import BatchedLift  # noqa: F401

@@ -1,0 +1,249 @@
+"""Batched environment API: the reference's MujocoEnv surface (`make`, `reset`, `step`, `_get_observations`,
+`action_spec`, `reward`, `_check_success`) over N environments living on one GPU.
+
+Behavioural spec, file:line in the reference:
+  make / registry            robosuite/environments/base.py:23-56
+  reset                      robosuite/environments/base.py:277-347 (+ robots/robot.py:234-300)
+  step (25-substep loop)     robosuite/environments/base.py:467-521
+  _get_observations          robosuite/environments/base.py:429-465
+  action_spec                robosuite/environments/robot_env.py:271-285
+The substep loop, controller, observation sampling and task outputs run inside ONE CUDA kernel per control step
+(csrc/b2s_kernel.cuh); this module only assembles tensors.
+"""
+import os
+from collections import OrderedDict
+
+import numpy as np
+
+from .. import controller_config as cc
+from ..engine import BatchedSim, CtrlCfg
+from ..mjcf.compiler import Model, compile_mjcf, load_model
+
+REGISTERED_ENVS = {}
+_ASSETS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "assets", "models")
+
+# observation scalar ops (must match enum OB_* in csrc/b2s_types.cuh)
+OB_QPOS, OB_COS_QPOS, OB_SIN_QPOS, OB_QVEL, OB_QACC, OB_SITE_POS, OB_BODY_POS, OB_BODY_QUAT_XYZW, OB_SITE_QUAT_XYZW, \
+    OB_BODY_MINUS_SITE, OB_SITE_MINUS_SITE, OB_BODY_QUAT_REL_SITE_XYZW, OB_ZERO = range(13)
+
+
+def register_env(cls):
+    REGISTERED_ENVS[cls.__name__.replace("Batched", "")] = cls
+    return cls
+
+
+def make(env_name, *args, **kwargs):
+    """suite.make(env_name, robots=..., num_envs=N, **kw) (environments/base.py:23-42)"""
+    if env_name not in REGISTERED_ENVS:
+        raise Exception("Environment {} not found. Make sure it is a registered environment among: {}".format(
+            env_name, ", ".join(REGISTERED_ENVS)))
+    return REGISTERED_ENVS[env_name](*args, **kwargs)
+
+
+def load_task_model(task, robot, xml=None):
+    """Compiled model for task/robot: from a composed MJCF string (reference composer output) when given, else the
+    packaged compiled fixture (mesh files do not travel to GPU boxes)."""
+    if xml is not None:
+        return compile_mjcf(xml)
+    path = os.path.join(_ASSETS, f"{task}_{robot}.npz")
+    if not os.path.exists(path):
+        raise FileNotFoundError(f"no packaged model for {task}/{robot}; pass the composed MJCF via xml=")
+    return load_model(path)
+
+
+class ObsBuilder:
+    """Collects (name, modality, op table rows) in the reference's observable order."""
+
+    def __init__(self):
+        self.items = []  # (name, modality, [(op,a,b),...])
+
+    def add(self, name, modality, rows):
+        self.items.append((name, modality, rows))
+
+    def tables(self):
+        """rows ordered modality by modality (first-seen order), as _get_observations concatenates them"""
+        mods = []
+        for _, mod, _ in self.items:
+            if mod not in mods:
+                mods.append(mod)
+        ops, slices, mod_slices = [], OrderedDict(), OrderedDict()
+        for mod in mods:
+            start = len(ops)
+            for name, m2, rows in self.items:
+                if m2 != mod:
+                    continue
+                slices[name] = (len(ops), len(ops) + len(rows))
+                ops += rows
+            mod_slices[mod + "-state"] = (start, len(ops))
+        arr = np.array(ops, dtype=np.int32).reshape(-1, 3)
+        return arr[:, 0], arr[:, 1], arr[:, 2], slices, mod_slices
+
+
+class BatchedMujocoEnv:
+    """N copies of one task on one GPU.  All returned arrays are torch.cuda tensors with leading dim N."""
+
+    def __init__(self, robots="Panda", num_envs=1, device=0, controller_configs=None, control_freq=20, horizon=500,
+                 ignore_done=False, reward_scale=1.0, reward_shaping=False, use_object_obs=True, seed=None,
+                 initialization_noise="default", precision="f32", xml=None, has_renderer=False,
+                 has_offscreen_renderer=False, use_camera_obs=False, hard_reset=False, lite_physics=True, **kwargs):
+        import torch
+
+        if has_renderer or has_offscreen_renderer or use_camera_obs:
+            raise NotImplementedError("rendering / camera observations are out of scope of the batched engine")
+        if not lite_physics:
+            raise NotImplementedError("only lite_physics=True semantics (environments/base.py:494-503) are implemented")
+        self.robot_name = robots if isinstance(robots, str) else robots[0]
+        self.num_envs = int(num_envs)
+        self.control_freq = control_freq
+        self.horizon = horizon
+        self.ignore_done = ignore_done
+        self.reward_scale = reward_scale
+        self.reward_shaping = reward_shaping
+        self.use_object_obs = use_object_obs
+        self.initialization_noise = {"magnitude": 0.02, "type": "gaussian"} if initialization_noise == "default" \
+            else (initialization_noise or {"magnitude": 0.0, "type": "gaussian"})
+        self.model = self._load_model(xml)
+        self.model_timestep = self.model.opt_timestep
+        self.control_timestep = 1.0 / control_freq
+        if control_freq <= 0:
+            raise ValueError("Control frequency {} is invalid".format(control_freq))
+        self.n_substeps = int(self.control_timestep / self.model_timestep)
+        self.sim = BatchedSim(self.model, self.num_envs, device=device, precision=precision)
+        self.device = self.sim.torch_device
+        self.dtype = self.sim.dtype
+        self.composite_controller_config = cc.load_composite_controller_config(controller_configs, self.robot_name)
+        self._ctrl_cfg = cc.resolve(self.model, self.composite_controller_config, CtrlCfg,
+                                    gripper="panda" if self.robot_name == "Panda" else "rethink")
+        self.sim.ctrl_config(self._ctrl_cfg)
+        self._setup_references()
+        ob = ObsBuilder()
+        self._setup_observables(ob)
+        op, a, b, self._obs_slices, self._modality_slices = ob.tables()
+        self.obs_dim = len(op)
+        self.sim.obs_config(op, a, b)
+        self._setup_task()
+        self.sim.set_export(False)
+        self.rng = torch.Generator(device=self.device)
+        self.seed = seed
+        if seed is not None:
+            self.rng.manual_seed(int(seed))
+        self.timestep = torch.zeros(self.num_envs, dtype=torch.long, device=self.device)
+        self.done = torch.zeros(self.num_envs, dtype=torch.bool, device=self.device)
+        self.cur_time = 0.0
+        self.reset()
+
+    # ---- to be provided by tasks
+    def _load_model(self, xml):
+        raise NotImplementedError
+
+    def _setup_references(self):
+        m = self.model
+        jn = m.names["joint"]
+        pf = "robot0_"
+        self.robot_joints = [i for i, n in enumerate(jn) if n and n.startswith(pf + "joint")]
+        self._ref_joint_pos_indexes = [int(m.jnt_qposadr[j]) for j in self.robot_joints]
+        self._ref_joint_vel_indexes = [int(m.jnt_dofadr[j]) for j in self.robot_joints]
+        self.gripper_joints = [i for i, n in enumerate(jn) if n and n.startswith("gripper0_")]
+        self._ref_gripper_joint_pos_indexes = [int(m.jnt_qposadr[j]) for j in self.gripper_joints]
+        self._ref_gripper_joint_vel_indexes = [int(m.jnt_dofadr[j]) for j in self.gripper_joints]
+        self.eef_site_id = m.names["site"].index("gripper0_right_grip_site")
+        self.eef_body_id = m.names["body"].index("robot0_right_hand")
+
+    def _setup_observables(self, ob):
+        """robot proprio observables in the reference's order (robots/robot.py:347-392, 412-484)"""
+        mod = "robot0_proprio"
+        qp, qv = self._ref_joint_pos_indexes, self._ref_joint_vel_indexes
+        ob.add("robot0_joint_pos", mod, [(OB_QPOS, i, 0) for i in qp])
+        ob.add("robot0_joint_pos_cos", mod, [(OB_COS_QPOS, i, 0) for i in qp])
+        ob.add("robot0_joint_pos_sin", mod, [(OB_SIN_QPOS, i, 0) for i in qp])
+        ob.add("robot0_joint_vel", mod, [(OB_QVEL, i, 0) for i in qv])
+        ob.add("robot0_joint_acc", mod, [(OB_QACC, i, 0) for i in qv])
+        ob.add("robot0_eef_pos", mod, [(OB_SITE_POS, self.eef_site_id, k) for k in range(3)])
+        ob.add("robot0_eef_quat", mod, [(OB_BODY_QUAT_XYZW, self.eef_body_id, k) for k in range(4)])
+        ob.add("robot0_eef_quat_site", mod, [(OB_SITE_QUAT_XYZW, self.eef_site_id, k) for k in range(4)])
+        ob.add("robot0_gripper_qpos", mod, [(OB_QPOS, i, 0) for i in self._ref_gripper_joint_pos_indexes])
+        ob.add("robot0_gripper_qvel", mod, [(OB_QVEL, i, 0) for i in self._ref_gripper_joint_vel_indexes])
+
+    def _setup_task(self):
+        pass
+
+    def _sample_reset_state(self, n):
+        raise NotImplementedError
+
+    def reward(self, action=None):
+        raise NotImplementedError
+
+    def _check_success(self):
+        raise NotImplementedError
+
+    # ---- API
+    @property
+    def action_dim(self):
+        return int(self._ctrl_cfg.action_dim)
+
+    @property
+    def action_spec(self):
+        """(low, high) bounds (robot_env.py:271-285): OSC input limits + gripper [-1, 1]"""
+        c = self._ctrl_cfg
+        low = np.array(list(c.input_min)[:6] + [-1.0] * (c.action_dim - 6))
+        high = np.array(list(c.input_max)[:6] + [1.0] * (c.action_dim - 6))
+        return low, high
+
+    def reset(self, mask=None):
+        """Re-initialise all (or masked) environments: robot init pose + noise, gripper open, task objects sampled,
+        controllers rebuilt (goal <- current eef pose), observations force-updated (environments/base.py:277-347)."""
+        import torch
+
+        idx = torch.arange(self.num_envs, device=self.device) if mask is None else torch.nonzero(mask).flatten()
+        n = int(idx.numel())
+        if n:
+            q = self._sample_reset_state(n)
+            self.sim.qpos[idx] = q.to(self.dtype)
+            self.sim.qvel[idx] = 0
+            self.sim.qacc[idx] = 0
+            self.sim.qacc_warmstart[idx] = 0
+            self.sim.ctrl[idx] = 0
+            self.sim.time[idx] = 0
+            self.timestep[idx] = 0
+            self.done[idx] = False
+        self.sim.forward()
+        m8 = None if mask is None else mask.to(torch.uint8).contiguous()
+        self.sim.ctrl_reset(m8)
+        self.cur_time = 0.0
+        return self._get_observations()
+
+    def step(self, action):
+        """One control step = n_substeps x {step1, controller, step2} in one kernel launch (base.py:467-521)."""
+        import torch
+
+        if bool(self.done.any()):
+            raise ValueError("executing action in terminated episode")
+        action = torch.as_tensor(action, dtype=self.dtype, device=self.device).contiguous()
+        assert action.shape == (self.num_envs, self.action_dim), "environment got invalid action dimension -- expected {}, got {}".format(
+            (self.num_envs, self.action_dim), tuple(action.shape))
+        self.timestep += 1
+        self.sim.env_step(action, self.n_substeps)
+        self.cur_time += self.control_timestep
+        reward = self.reward(action)
+        self.done = (self.timestep >= self.horizon) & (not self.ignore_done)
+        return self._get_observations(), reward, self.done, {}
+
+    def _get_observations(self):
+        """OrderedDict of per-observable tensors plus the per-modality concatenations (base.py:429-465)."""
+        obs = self.sim.obs
+        out = OrderedDict()
+        for name, (a, b) in self._obs_slices.items():
+            out[name] = obs[:, a:b]
+        for name, (a, b) in self._modality_slices.items():
+            out[name] = obs[:, a:b]
+        return out
+
+    def flat_obs(self):
+        """[N, obs_dim] tensor aliasing the kernel's observation buffer (GymWrapper-style flattening)"""
+        return self.sim.obs
+
+    def get_state(self):
+        return self.sim.get_state()
+
+    def close(self):
+        self.sim.close()

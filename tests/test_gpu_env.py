@@ -1,0 +1,89 @@
+"""GPU: batched env API (make / reset / step / _get_observations) against the oracle's env step."""
+import numpy as np
+import pytest
+
+from tests.util import load
+
+pytestmark = pytest.mark.gpu
+
+
+def _expected_obs(model, o, env):
+    """observation row recomputed from oracle arrays with the reference's formulas (robots/robot.py:347-484,
+    manipulation/lift.py:371-397)"""
+    qp, qv = env._ref_joint_pos_indexes, env._ref_joint_vel_indexes
+    jp = o.qpos[qp]
+    site = env.eef_site_id
+    M = o.site_xmat[site].reshape(3, 3)
+    # mat2quat with w >= 0, xyzw
+    tr = np.trace(M)
+    w = np.sqrt(max(0.0, 1 + tr)) / 2
+    x = (M[2, 1] - M[1, 2]) / (4 * w); y = (M[0, 2] - M[2, 0]) / (4 * w); z = (M[1, 0] - M[0, 1]) / (4 * w)
+    bq = o.xquat[env.eef_body_id]
+    cq = o.xquat[env.cube_body_id]
+    return np.concatenate([
+        jp, np.cos(jp), np.sin(jp), o.qvel[qv], o.qacc[qv], o.site_xpos[site], bq[[1, 2, 3, 0]], [x, y, z, w],
+        o.qpos[env._ref_gripper_joint_pos_indexes], o.qvel[env._ref_gripper_joint_vel_indexes],
+        o.xpos[env.cube_body_id], cq[[1, 2, 3, 0]], o.xpos[env.cube_body_id] - o.site_xpos[site]])
+
+
+def test_env_api_and_obs_parity():
+    import torch
+
+    import robosuite_b200 as suite
+    from oracle.pyoracle import CtrlCfg as OCfg
+    from oracle.pyoracle import Oracle
+    from robosuite_b200 import controller_config as cc
+    from robosuite_b200.mjcf.compiler import pack_model
+
+    n = 6
+    env = suite.make("Lift", robots="Panda", num_envs=n, seed=3, has_renderer=False, has_offscreen_renderer=False,
+                     use_camera_obs=False, horizon=5, reward_shaping=True)
+    assert env.action_dim == 7 and env.obs_dim == 60
+    low, high = env.action_spec
+    assert np.all(low == -1) and np.all(high == 1)
+    obs = env._get_observations()
+    assert obs["robot0_proprio-state"].shape == (n, 50) and obs["object-state"].shape == (n, 10)
+    assert list(obs.keys())[:3] == ["robot0_joint_pos", "robot0_joint_pos_cos", "robot0_joint_pos_sin"]
+    model = env.model
+    q0 = env.sim.qpos.cpu().numpy().astype(np.float64)
+    # reset distribution sanity (lift.py:311-336): cube on the table within +-3 cm
+    a = env.cube_qadr
+    assert np.all(np.abs(q0[:, a:a + 2]) <= 0.03 + 1e-6) and np.allclose(q0[:, a + 2], 0.81 + env.cube_half_height, atol=1e-6)
+    oracles = []
+    for e in range(n):
+        o = Oracle(pack_model(model))
+        o.ctrl_setup(cc.resolve(model, cc.default_composite_config(), OCfg))
+        o.qpos[:] = q0[e]
+        o.forward()
+        o.ctrl_reset()
+        oracles.append(o)
+    # reset observation = forced update at the reset state
+    flat = env.flat_obs().cpu().numpy().astype(np.float64)
+    for e in range(n):
+        assert np.abs(flat[e] - _expected_obs(model, oracles[e], env)).max() < 2e-5
+    rng = np.random.default_rng(0)
+    for t in range(5):
+        act = rng.uniform(-1, 1, size=(n, 7))
+        obs, rew, done, info = env.step(torch.as_tensor(act))
+        flat = env.flat_obs().cpu().numpy().astype(np.float64)
+        for e in range(n):
+            o = oracles[e]
+            # first substep, then sample (observables.py:230-240), then the remaining 24
+            o.step1(); o.ctrl_run(act[e]); o.step2()
+            exp = _expected_obs(model, o, env)
+            for _ in range(24):
+                o.step1(); o.ctrl_run(None); o.step2()
+            err = np.abs(flat[e] - exp)
+            err[28:35] /= max(1.0, np.abs(exp[28:35]).max())  # joint_acc: relative
+            assert err.max() < 5e-4, (t, e, err.argmax(), err.max())
+            # shaped reward from the last step1 poses
+            dist = np.linalg.norm(o.xpos[env.cube_body_id] - o.site_xpos[env.eef_site_id])
+            lifted = o.xpos[env.cube_body_id][2] > 0.84
+            expect = 2.25 if lifted else (1 - np.tanh(10 * dist))
+            assert abs(float(rew[e]) - expect / 2.25) < 1e-3
+    assert bool(done.all())
+    with pytest.raises(ValueError):
+        env.step(torch.zeros((n, 7)))
+    env.reset()
+    assert not bool(env.done.any())
+    env.close()
