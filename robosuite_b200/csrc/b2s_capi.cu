@@ -62,7 +62,7 @@ struct b2s_sim {
   int nq = 0, nv = 0, nu = 0, nbody = 0, ngeom = 0, nsite = 0, maxcon = 0, maxefc = 0;
   std::vector<double> qpos0;
   std::vector<int> site_bodyid, cgid;
-  int has_obs = 0, export_env_step = 1;
+  int has_obs = 0, export_env_step = 1, dirty = 1;
 };
 
 template <typename T> static T* dev_upload(b2s_sim* s, const std::vector<T>& h) {
@@ -292,7 +292,6 @@ template <typename R> static void build_state(b2s_sim* s, const DModel<R>& m, DS
   st.goal_pos = state_arr<R>(s, "ctrl_goal_pos", 3); st.goal_ori = state_arr<R>(s, "ctrl_goal_ori", 9);
   st.init_qpos_arm = state_arr<R>(s, "ctrl_initial_joint", 8); st.grip_state = state_arr<R>(s, "ctrl_grip_state", 4);
   st.ctrl_torque = state_arr<R>(s, "ctrl_torque", 8);
-  st.action = nullptr;
 }
 
 static void build_layout(b2s_sim* s, int nq, int nv, int nu, int nb, int ncg, int ns, int mc, int me, int hc_stride) {
@@ -322,6 +321,8 @@ static void build_layout(b2s_sim* s, int nq, int nv, int nu, int nb, int ncg, in
   L.scratch = take(sc);
   L.total = o;
 }
+
+static b2s_sim* g_owner[64] = {nullptr};
 
 // ------------------------------------------------------------------------------------------------ API
 extern "C" {
@@ -378,6 +379,7 @@ int b2s_create(const void* blob_host, size_t nbytes, int n_env, int device, int 
 
 void b2s_destroy(b2s_sim* s) {
   if (!s) return;
+  if (g_owner[s->device & 63] == s) g_owner[s->device & 63] = nullptr;
   cudaSetDevice(s->device);
   for (void* p : s->allocs) cudaFree(p);
   delete s;
@@ -404,14 +406,32 @@ int b2s_array(b2s_sim* s, const char* name, void** dev_ptr, int* dtype, int* ndi
   return B2S_OK;
 }
 
-static int launch(b2s_sim* s, int phases, int nsub) {
+// constant-memory descriptors belong to one handle at a time (per device); re-upload when the owner changes or is dirty
+static int bind_constants(b2s_sim* s) {
   CUDA_TRY(cudaSetDevice(s->device));
+  if (g_owner[s->device & 63] == s && !s->dirty) return B2S_OK;
+  if (s->precision == B2S_F32) {
+    CUDA_TRY(cudaMemcpyToSymbolAsync(c_model_f, &s->mf, sizeof(s->mf), 0, cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaMemcpyToSymbolAsync(c_state_f, &s->sf, sizeof(s->sf), 0, cudaMemcpyHostToDevice, s->stream));
+  } else {
+    CUDA_TRY(cudaMemcpyToSymbolAsync(c_model_d, &s->md, sizeof(s->md), 0, cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaMemcpyToSymbolAsync(c_state_d, &s->sd, sizeof(s->sd), 0, cudaMemcpyHostToDevice, s->stream));
+  }
+  CUDA_TRY(cudaMemcpyToSymbolAsync(c_L, &s->L, sizeof(s->L), 0, cudaMemcpyHostToDevice, s->stream));
+  CUDA_TRY(cudaMemcpyToSymbolAsync(c_cc, &s->ctrl, sizeof(s->ctrl), 0, cudaMemcpyHostToDevice, s->stream));
+  g_owner[s->device & 63] = s;
+  s->dirty = 0;
+  return B2S_OK;
+}
+
+static int launch(b2s_sim* s, int phases, int nsub, const void* action = nullptr) {
+  int rc = bind_constants(s);
+  if (rc != B2S_OK) return rc;
   int blocks = (s->n_env + s->wpb - 1) / s->wpb;
-  CtrlCfgDev cc = s->ctrl;
   if (s->precision == B2S_F32)
-    step_kernel<float><<<blocks, s->wpb * 32, s->smem_bytes, s->stream>>>(s->mf, s->sf, s->L, cc, phases, nsub);
+    step_kernel<float><<<blocks, s->wpb * 32, s->smem_bytes, s->stream>>>(phases, nsub, (const float*)action);
   else
-    step_kernel<double><<<blocks, s->wpb * 32, s->smem_bytes, s->stream>>>(s->md, s->sd, s->L, cc, phases, nsub);
+    step_kernel<double><<<blocks, s->wpb * 32, s->smem_bytes, s->stream>>>(phases, nsub, (const double*)action);
   s->launches++;
   CUDA_TRY(cudaGetLastError());
   return B2S_OK;
@@ -419,9 +439,9 @@ static int launch(b2s_sim* s, int phases, int nsub) {
 
 int b2s_reset(b2s_sim* s, const uint8_t* mask) {
   if (!s) return fail(B2S_ERR_ARG, "null handle");
-  CUDA_TRY(cudaSetDevice(s->device));
-  if (s->precision == B2S_F32) reset_kernel<float><<<(s->n_env + 127) / 128, 128, 0, s->stream>>>(s->mf, s->sf, mask);
-  else reset_kernel<double><<<(s->n_env + 127) / 128, 128, 0, s->stream>>>(s->md, s->sd, mask);
+  { int rc = bind_constants(s); if (rc != B2S_OK) return rc; }
+  if (s->precision == B2S_F32) reset_kernel<float><<<(s->n_env + 127) / 128, 128, 0, s->stream>>>(mask);
+  else reset_kernel<double><<<(s->n_env + 127) / 128, 128, 0, s->stream>>>(mask);
   s->launches++;
   CUDA_TRY(cudaGetLastError());
   return B2S_OK;
@@ -437,10 +457,10 @@ int b2s_step(b2s_sim* s, int n) {
 
 int b2s_jac_site(b2s_sim* s, int site_id, void* jacp, void* jacr) {
   if (!s || site_id < 0 || site_id >= s->nsite) return fail(B2S_ERR_ARG, "b2s_jac_site: bad argument");
-  CUDA_TRY(cudaSetDevice(s->device));
+  { int rc = bind_constants(s); if (rc != B2S_OK) return rc; }
   int threads = 128, blocks = (s->n_env * s->nv + threads - 1) / threads;
-  if (s->precision == B2S_F32) jac_site_kernel<float><<<blocks, threads, 0, s->stream>>>(s->mf, s->sf, site_id, (float*)jacp, (float*)jacr);
-  else jac_site_kernel<double><<<blocks, threads, 0, s->stream>>>(s->md, s->sd, site_id, (double*)jacp, (double*)jacr);
+  if (s->precision == B2S_F32) jac_site_kernel<float><<<blocks, threads, 0, s->stream>>>(site_id, (float*)jacp, (float*)jacr);
+  else jac_site_kernel<double><<<blocks, threads, 0, s->stream>>>(site_id, (double*)jacp, (double*)jacr);
   s->launches++;
   CUDA_TRY(cudaGetLastError());
   return B2S_OK;
@@ -462,16 +482,16 @@ int b2s_ctrl_config(b2s_sim* s, const b2s_ctrl_cfg* c) {
     d.output_max[i] = c->output_max[i]; d.output_min[i] = c->output_min[i];
   }
   s->has_ctrl = c->kind != B2S_CTRL_NONE;
+  s->dirty = 1;
   return B2S_OK;
 }
 
 int b2s_ctrl_reset(b2s_sim* s, const uint8_t* mask) {
   if (!s || !s->has_ctrl) return fail(B2S_ERR_ARG, "b2s_ctrl_reset: controller not configured");
-  CUDA_TRY(cudaSetDevice(s->device));
+  { int rc = bind_constants(s); if (rc != B2S_OK) return rc; }
   int threads = 128, blocks = (s->n_env + threads - 1) / threads;
-  CtrlCfgDev cc = s->ctrl;
-  if (s->precision == B2S_F32) ctrl_reset_kernel<float><<<blocks, threads, 0, s->stream>>>(s->mf, s->sf, cc, mask);
-  else ctrl_reset_kernel<double><<<blocks, threads, 0, s->stream>>>(s->md, s->sd, cc, mask);
+  if (s->precision == B2S_F32) ctrl_reset_kernel<float><<<blocks, threads, 0, s->stream>>>(mask);
+  else ctrl_reset_kernel<double><<<blocks, threads, 0, s->stream>>>(mask);
   s->launches++;
   CUDA_TRY(cudaGetLastError());
   return B2S_OK;
@@ -479,8 +499,7 @@ int b2s_ctrl_reset(b2s_sim* s, const uint8_t* mask) {
 
 int b2s_env_step(b2s_sim* s, const void* action, int nsub) {
   if (!s || !s->has_ctrl || !action || nsub < 1) return fail(B2S_ERR_ARG, "b2s_env_step: bad argument / controller not configured");
-  if (s->precision == B2S_F32) s->sf.action = (const float*)action; else s->sd.action = (const double*)action;
-  return launch(s, PH_STEP1 | PH_STEP2 | PH_CTRL | (s->has_obs ? PH_OBS : 0) | (s->export_env_step ? PH_EXPORT : 0), nsub);
+  return launch(s, PH_STEP1 | PH_STEP2 | PH_CTRL | (s->has_obs ? PH_OBS : 0) | (s->export_env_step ? PH_EXPORT : 0), nsub, action);
 }
 
 int b2s_obs_config(b2s_sim* s, int obs_dim, const int* op, const int* a, const int* b) {
@@ -494,6 +513,7 @@ int b2s_obs_config(b2s_sim* s, int obs_dim, const int* op, const int* a, const i
     else { s->sd.obs = state_arr<double>(s, "obs", obs_dim); s->sd.task_out = state_arr<double>(s, "task_out", 4); }
   } catch (const std::string& e) { return fail(B2S_ERR_CUDA, e); }
   s->has_obs = 1;
+  s->dirty = 1;
   return B2S_OK;
 }
 
@@ -511,6 +531,7 @@ int b2s_task_config(b2s_sim* s, int body, int site, const int* left, int nl, con
   if (!mk(left, nl, s->ctrl.mask_left) || !mk(right, nr, s->ctrl.mask_right) || !mk(obj, no, s->ctrl.mask_obj))
     return fail(B2S_ERR_ARG, "b2s_task_config: geom id out of range");
   s->ctrl.task_body = body; s->ctrl.task_site = site;
+  s->dirty = 1;
   return B2S_OK;
 }
 

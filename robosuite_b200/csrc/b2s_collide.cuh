@@ -17,16 +17,17 @@ struct Shape {
 
 template <typename R>
 DEV void shape_get(const Eng<R>& e, int g, Shape<R>& s) {
-  int k = e.m.geom_cgid[g];
-  s.type = e.m.geom_type[g];
-  s.pos = e.p(e.L.gpos) + 3 * k;
-  s.mat = e.p(e.L.gmat) + 9 * k;
-  s.size[0] = e.m.geom_size[3 * g]; s.size[1] = e.m.geom_size[3 * g + 1]; s.size[2] = e.m.geom_size[3 * g + 2];
+  const DModel<R>& m = cmodel<R>();
+  int k = m.geom_cgid[g];
+  s.type = m.geom_type[g];
+  s.pos = e.p(c_L.gpos) + 3 * k;
+  s.mat = e.p(c_L.gmat) + 9 * k;
+  s.size[0] = m.geom_size[3 * g]; s.size[1] = m.geom_size[3 * g + 1]; s.size[2] = m.geom_size[3 * g + 2];
   s.vert = nullptr; s.nvert = 0;
   if (s.type == G_MESH) {
-    int id = e.m.geom_dataid[g];
-    s.vert = e.m.mesh_vert + 3 * e.m.mesh_vertadr[id];
-    s.nvert = e.m.mesh_vertnum[id];
+    int id = m.geom_dataid[g];
+    s.vert = m.mesh_vert + 3 * m.mesh_vertadr[id];
+    s.nvert = m.mesh_vertnum[id];
   }
 }
 
@@ -52,7 +53,7 @@ template <typename R> DEV int put(R* out, int n, int maxn, const R* pos, const R
 #define COLV(M, k) {(M)[k], (M)[3 + (k)], (M)[6 + (k)]}
 
 // ---------------------------------------------------------------------------------------------- analytic pairs
-template <typename R> DEV int plane_sphere(const Shape<R>& p, const Shape<R>& s, R* out, int maxn) {
+template <typename R> DEVN int plane_sphere(const Shape<R>& p, const Shape<R>& s, R* out, int maxn) {
   R n[3] = COLV(p.mat, 2), df[3], pos[3];
   v3sub(df, s.pos, p.pos);
   R dist = v3dot(df, n) - s.size[0];
@@ -60,7 +61,7 @@ template <typename R> DEV int plane_sphere(const Shape<R>& p, const Shape<R>& s,
   v3addscl(pos, s.pos, n, -(s.size[0] + R(0.5) * dist));
   return put(out, 0, maxn, pos, n, dist);
 }
-template <typename R> DEV int plane_box(const Shape<R>& p, const Shape<R>& b, R* out, int maxn) {
+template <typename R> DEVN int plane_box(const Shape<R>& p, const Shape<R>& b, R* out, int maxn) {
   R n[3] = COLV(p.mat, 2), df[3];
   v3sub(df, b.pos, p.pos);
   R dist = v3dot(df, n);
@@ -78,7 +79,7 @@ template <typename R> DEV int plane_box(const Shape<R>& p, const Shape<R>& b, R*
   }
   return cnt;
 }
-template <typename R> DEV int plane_cylinder(const Shape<R>& p, const Shape<R>& c, R* out, int maxn) {
+template <typename R> DEVN int plane_cylinder(const Shape<R>& p, const Shape<R>& c, R* out, int maxn) {
   R n[3] = COLV(p.mat, 2), axis[3] = COLV(c.mat, 2), df[3], vec[3], pos[3];
   R r = c.size[0], h = c.size[1];
   v3sub(df, c.pos, p.pos);
@@ -122,7 +123,7 @@ template <typename R> DEV int plane_cylinder(const Shape<R>& p, const Shape<R>& 
   }
   return cnt;
 }
-template <typename R> DEV int plane_mesh(const Shape<R>& p, const Shape<R>& s, R* out, int maxn) {
+template <typename R> DEVN int plane_mesh(const Shape<R>& p, const Shape<R>& s, R* out, int maxn) {
   R n[3] = COLV(p.mat, 2), nl[3], df[3];
   m3mulTv(nl, s.mat, n);
   v3sub(df, s.pos, p.pos);
@@ -162,7 +163,7 @@ template <typename R> DEV int plane_mesh(const Shape<R>& p, const Shape<R>& s, R
   }
   return cnt;
 }
-template <typename R> DEV int sphere_sphere(const Shape<R>& a, const Shape<R>& b, R* out, int maxn) {
+template <typename R> DEVN int sphere_sphere(const Shape<R>& a, const Shape<R>& b, R* out, int maxn) {
   R n[3], pos[3];
   v3sub(n, b.pos, a.pos);
   R len = v3norm(n), dist = len - a.size[0] - b.size[0];
@@ -171,7 +172,7 @@ template <typename R> DEV int sphere_sphere(const Shape<R>& a, const Shape<R>& b
   v3addscl(pos, a.pos, n, a.size[0] + R(0.5) * dist);
   return put(out, 0, maxn, pos, n, dist);
 }
-template <typename R> DEV int sphere_box(const Shape<R>& s, const Shape<R>& b, R* out, int maxn) {
+template <typename R> DEVN int sphere_box(const Shape<R>& s, const Shape<R>& b, R* out, int maxn) {
   R df[3], c[3], cl[3], n[3], pos[3];
   v3sub(df, s.pos, b.pos);
   m3mulTv(c, b.mat, df);
@@ -204,7 +205,7 @@ template <typename R> DEV int sphere_box(const Shape<R>& s, const Shape<R>& b, R
   v3addscl(pos, s.pos, n, r + R(0.5) * dist);
   return put(out, 0, maxn, pos, n, dist);
 }
-template <typename R> DEV int sphere_cylinder(const Shape<R>& s, const Shape<R>& c, R* out, int maxn) {
+template <typename R> DEVN int sphere_cylinder(const Shape<R>& s, const Shape<R>& c, R* out, int maxn) {
   R df[3], p[3], q[3], n[3], pos[3];
   R Rc = c.size[0], h = c.size[1], r = s.size[0];
   v3sub(df, s.pos, c.pos);
@@ -253,7 +254,7 @@ template <typename R> DEV int clip_poly(R (*poly)[2], int n, int axis, R lim, R 
   return no;
 }
 
-template <typename R> DEV int box_box(const Shape<R>& A, const Shape<R>& B, R* out, int maxn) {
+template <typename R> DEVN int box_box(const Shape<R>& A, const Shape<R>& B, R* out, int maxn) {
   R Aax[3][3], Bax[3][3], T[3];
   for (int k = 0; k < 3; k++) {
     Aax[k][0] = A.mat[k]; Aax[k][1] = A.mat[3 + k]; Aax[k][2] = A.mat[6 + k];
@@ -373,7 +374,7 @@ template <typename R> DEV int box_box(const Shape<R>& A, const Shape<R>& B, R* o
 
 // ---------------------------------------------------------------------------------------------- GJK / EPA (warp)
 // support point of the core shape in world direction dir; mesh scans are split across lanes, result warp-uniform
-template <typename R> DEV void support_w(const Shape<R>& s, const R* dir, R* out, int lane) {
+template <typename R> DEVN void support_w(const Shape<R>& s, const R* dir, R* out, int lane) {
   R l[3], pnt[3] = {0, 0, 0};
   m3mulTv(l, s.mat, dir);
   switch (s.type) {
@@ -431,7 +432,7 @@ template <typename R> DEV void closest_seg(SV<R>* s, int& n, R* lam) {
   else if (t >= 1) { s[0] = s[1]; n = 1; lam[0] = 1; }
   else { lam[0] = 1 - t; lam[1] = t; }
 }
-template <typename R> DEV void closest_tri(SV<R>* s, int& n, R* lam) {
+template <typename R> DEVN void closest_tri(SV<R>* s, int& n, R* lam) {
   const R *a = s[0].w, *b = s[1].w, *c = s[2].w;
   R ab[3], ac[3];
   v3sub(ab, b, a); v3sub(ac, c, a);
@@ -459,7 +460,7 @@ template <typename R> DEV R orient3(const R* a, const R* b, const R* c, const R*
   v3cross(cr, ab, ac);
   return v3dot(cr, ad);
 }
-template <typename R> DEV int closest_tet(SV<R>* s, int& n, R* lam) {
+template <typename R> DEVN int closest_tet(SV<R>* s, int& n, R* lam) {
   const int F[4][3] = {{0, 1, 2}, {0, 1, 3}, {0, 2, 3}, {1, 2, 3}};
   const int O[4] = {3, 2, 1, 0};
   R zero[3] = {0, 0, 0};
@@ -491,7 +492,7 @@ template <typename R> DEV int closest_tet(SV<R>* s, int& n, R* lam) {
 
 // returns 1 if the cores overlap (simplex valid), else 0 with dist / witnesses
 template <typename R>
-DEV int gjk(const Shape<R>& A, const Shape<R>& B, SV<R>* simplex, int& ns, R& dist, R* wa, R* wb, R cutoff, int lane) {
+DEVN int gjk(const Shape<R>& A, const Shape<R>& B, SV<R>* simplex, int& ns, R& dist, R* wa, R* wb, R cutoff, int lane) {
   const R tol_vv = sizeof(R) == 4 ? R(1e-16) : R(1e-24);
   const R tol_rel = sizeof(R) == 4 ? R(1e-6) : R(1e-12);
   R v[3], nv[3];
@@ -538,7 +539,7 @@ DEV int gjk(const Shape<R>& A, const Shape<R>& B, SV<R>* simplex, int& ns, R& di
 #define EPA_MAXF 96
 // EPA polytope lives in this warp's scratch: V[EPA_MAXV][9], Fn[EPA_MAXF][4] (normal, dist), Fi[EPA_MAXF] packed ids
 template <typename R>
-DEV int epa(const Shape<R>& A, const Shape<R>& B, SV<R>* simplex, int ns, R& depth, R* normal, R* wa, R* wb, R* scratch, int lane) {
+DEVN int epa(const Shape<R>& A, const Shape<R>& B, SV<R>* simplex, int ns, R& depth, R* normal, R* wa, R* wb, R* scratch, int lane) {
   R* V = scratch;
   R* Fn = V + 9 * EPA_MAXV;
   int* Fi = reinterpret_cast<int*>(Fn + 4 * EPA_MAXF);
@@ -679,7 +680,7 @@ DEV int epa(const Shape<R>& A, const Shape<R>& B, SV<R>* simplex, int ns, R& dep
 }
 
 template <typename R>
-DEV int convex_convex(const Shape<R>& A, const Shape<R>& B, R* out, int maxn, R* scratch, int lane) {
+DEVN int convex_convex(const Shape<R>& A, const Shape<R>& B, R* out, int maxn, R* scratch, int lane) {
   SV<R> simplex[4];
   int ns = 0;
   R dist = 0, wa[3], wb[3], n[3], pos[3], pa[3], pb[3];
@@ -706,20 +707,20 @@ DEV int convex_convex(const Shape<R>& A, const Shape<R>& B, R* out, int maxn, R*
 
 // ---------------------------------------------------------------------------------------------- driver
 // oriented-box overlap of the two geoms' local AABBs (15-axis separating test); planes use the box/plane distance
-template <typename R> DEV bool obb_overlap(const Eng<R>& e, int g1, int g2) {
-  const DModel<R>& m = e.m;
+template <typename R> DEVN bool obb_overlap(const Eng<R> e, int g1, int g2) {
+  const DModel<R>& m = cmodel<R>();
   int k1 = m.geom_cgid[g1], k2 = m.geom_cgid[g2];
-  const R* M1 = e.p(e.L.gmat) + 9 * k1; const R* M2 = e.p(e.L.gmat) + 9 * k2;
+  const R* M1 = e.p(c_L.gmat) + 9 * k1; const R* M2 = e.p(c_L.gmat) + 9 * k2;
   const R* a1 = m.geom_aabb + 6 * g1; const R* a2 = m.geom_aabb + 6 * g2;
   R c1[3], c2[3], t[3];
   R o1[3] = {a1[0], a1[1], a1[2]}, o2[3] = {a2[0], a2[1], a2[2]};
-  m3mulv(t, M1, o1); v3add(c1, t, e.p(e.L.gpos) + 3 * k1);
-  m3mulv(t, M2, o2); v3add(c2, t, e.p(e.L.gpos) + 3 * k2);
+  m3mulv(t, M1, o1); v3add(c1, t, e.p(c_L.gpos) + 3 * k1);
+  m3mulv(t, M2, o2); v3add(c2, t, e.p(c_L.gpos) + 3 * k2);
   R ha[3] = {a1[3], a1[4], a1[5]}, hb[3] = {a2[3], a2[4], a2[5]};
   int t1 = m.geom_type[g1], t2 = m.geom_type[g2];
   if (t1 == G_PLANE || t2 == G_PLANE) {
     const R* Mp = t1 == G_PLANE ? M1 : M2; const R* Mo = t1 == G_PLANE ? M2 : M1;
-    const R* pp = e.p(e.L.gpos) + 3 * (t1 == G_PLANE ? k1 : k2);
+    const R* pp = e.p(c_L.gpos) + 3 * (t1 == G_PLANE ? k1 : k2);
     const R* co = t1 == G_PLANE ? c2 : c1; const R* ho = t1 == G_PLANE ? hb : ha;
     R n[3] = COLV(Mp, 2), df[3];
     v3sub(df, co, pp);
@@ -775,9 +776,9 @@ template <typename R> DEV void mix_contact(const DModel<R>& m, int g1, int g2, R
 }
 
 // Fills the contact arrays in the workspace; returns ncon (warp-uniform).  warn bit 4 on overflow.
-template <typename R> DEV int collide(Eng<R>& e, int& warn) {
-  const DModel<R>& m = e.m;
-  const WSLayout& L = e.L;
+template <typename R> DEVN int collide(Eng<R> e, int& warn) {
+  const DModel<R>& m = cmodel<R>();
+  const WSLayout& L = c_L;
   int lane = e.lane;
   int* cand = reinterpret_cast<int*>(e.p(L.scratch));  // candidate pair indices, analytic first then gjk
   int* cand_g = cand + 64;

@@ -17,13 +17,15 @@ template <typename R> struct CtrlState {
   R goal_pos[3], goal_ori[9], grip[4];
 };
 
-template <typename R> DEV void ctrl_load(Eng<R>& e, const DState<R>& s, const CtrlCfgDev& cc, CtrlState<R>& cs, int env) {
+template <typename R> DEV void ctrl_load(Eng<R> e, CtrlState<R>& cs, int env) {
+  const DState<R>& s = cstate<R>();
   size_t E = env;
   for (int k = 0; k < 3; k++) cs.goal_pos[k] = s.goal_pos[E * 3 + k];
   for (int k = 0; k < 9; k++) cs.goal_ori[k] = s.goal_ori[E * 9 + k];
   for (int k = 0; k < 4; k++) cs.grip[k] = s.grip_state[E * 4 + k];
 }
-template <typename R> DEV void ctrl_store(Eng<R>& e, const DState<R>& s, const CtrlCfgDev& cc, CtrlState<R>& cs, int env) {
+template <typename R> DEV void ctrl_store(Eng<R> e, CtrlState<R>& cs, int env) {
+  const DState<R>& s = cstate<R>();
   size_t E = env;
   if (e.lane == 0) {
     for (int k = 0; k < 3; k++) s.goal_pos[E * 3 + k] = cs.goal_pos[k];
@@ -55,14 +57,17 @@ template <typename R> DEV void delta_rotmat(R* Rm, const R* aa) {
 }
 
 template <typename R>
-DEV void ctrl_run(Eng<R>& e, const DState<R>& s, const CtrlCfgDev& cc, CtrlState<R>& cs, int env, bool policy_step) {
-  const DModel<R>& m = e.m;
-  const WSLayout& L = e.L;
+DEVN void ctrl_run(Eng<R> e, CtrlState<R>& cs, int env, const R* action) {
+  const DModel<R>& m = cmodel<R>();
+  const WSLayout& L = c_L;
+  const DState<R>& s = cstate<R>();
+  const CtrlCfgDev& cc = c_cc;
+  bool policy_step = action != nullptr;
   int lane = e.lane, nv = m.nv, na = cc.n_arm;
   const R* ref_pos = e.p(L.spos) + 3 * cc.eef_site; const R* ref_ori = e.p(L.smat) + 9 * cc.eef_site;
   const R* org_pos = e.p(L.spos) + 3 * cc.base_site; const R* org_ori = e.p(L.smat) + 9 * cc.base_site;
   if (policy_step) {
-    const R* act = s.action + (size_t)env * cc.action_dim;
+    const R* act = action + (size_t)env * cc.action_dim;
     R sd[6];
     for (int k = 0; k < 6; k++) {
       R a = r_clamp(act[k], (R)cc.input_min[k], (R)cc.input_max[k]);
@@ -300,8 +305,10 @@ template <typename R> DEV void mat2quat_wpos(const R* M, R* q) {
 // Observation row: one table entry per scalar (MujocoEnv._get_observations, environments/base.py:429-465; sensors
 // robots/robot.py:347-392,412-484 and the task's object observables e.g. manipulation/lift.py:371-397).
 // qpos/qvel/qacc are the freshly integrated values, poses are those of the last step1 (reference staleness).
-template <typename R> DEV void write_obs(const Eng<R>& e, const DState<R>& s, const CtrlCfgDev& cc, int env) {
-  const WSLayout& L = e.L;
+template <typename R> DEVN void write_obs(const Eng<R> e, int env) {
+  const WSLayout& L = c_L;
+  const DState<R>& s = cstate<R>();
+  const CtrlCfgDev& cc = c_cc;
   R* out = s.obs + (size_t)env * cc.obs_dim;
   for (int k = e.lane; k < cc.obs_dim; k += 32) {
     int op = cc.obs_op[k], a = cc.obs_a[k], b = cc.obs_b[k];
@@ -326,9 +333,11 @@ template <typename R> DEV void write_obs(const Eng<R>& e, const DState<R>& s, co
 
 // Task outputs after the last substep (poses / contacts of the last step1, as the reference's reward() sees them:
 // manipulation/lift.py:224-273,433-444; manipulation_env.py:331-376 _check_grasp; utils/sim_utils.py:8-40)
-template <typename R> DEV void write_task(const Eng<R>& e, const DState<R>& s, const CtrlCfgDev& cc, int env, int ncon) {
-  const DModel<R>& m = e.m;
-  const WSLayout& L = e.L;
+template <typename R> DEVN void write_task(const Eng<R> e, int env, int ncon) {
+  const DModel<R>& m = cmodel<R>();
+  const WSLayout& L = c_L;
+  const DState<R>& s = cstate<R>();
+  const CtrlCfgDev& cc = c_cc;
   const int* cint = e.pi(L.c_int);
   int hitl = 0, hitr = 0;
   for (int c = e.lane; c < ncon; c += 32) {
@@ -350,8 +359,10 @@ template <typename R> DEV void write_task(const Eng<R>& e, const DState<R>& s, c
 // controller.reset_goal + initial joints (osc.py:520-544, controller.py:126-132): goal <- current eef pose (world),
 // initial_joint <- current arm qpos, gripper integrator <- 0.  Uses the exported site arrays of a prior forward.
 template <typename R>
-__global__ void ctrl_reset_kernel(const __grid_constant__ DModel<R> m, const __grid_constant__ DState<R> s,
-                                  const __grid_constant__ CtrlCfgDev cc, const uint8_t* mask) {
+__global__ void ctrl_reset_kernel(const uint8_t* mask) {
+  const DModel<R>& m = cmodel<R>();
+  const DState<R>& s = cstate<R>();
+  const CtrlCfgDev& cc = c_cc;
   int env = blockIdx.x * blockDim.x + threadIdx.x;
   if (env >= s.n_env) return;
   if (mask && !mask[env]) return;

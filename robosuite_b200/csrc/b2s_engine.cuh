@@ -9,17 +9,16 @@
 
 template <typename R>
 struct Eng {
-  const DModel<R>& m;
-  const WSLayout& L;
   R* ws;  // this warp's workspace
   int lane;
 
-  DEV Eng(const DModel<R>& m_, const WSLayout& L_, R* ws_, int lane_) : m(m_), L(L_), ws(ws_), lane(lane_) {}
+  DEV Eng(R* ws_, int lane_) : ws(ws_), lane(lane_) {}
   DEV R* p(int off) const { return ws + off; }
   DEV int* pi(int off) const { return reinterpret_cast<int*>(ws + off); }
 
   // ------------------------------------------------------------------------------------------- kinematics
-  DEV void kinematics() {
+  DEVN void kinematics() {
+    const DModel<R>& m = cmodel<R>(); const WSLayout& L = c_L;
     R* xpos = p(L.xpos); R* xquat = p(L.xquat); R* xmat = p(L.xmat);
     const R* qpos = p(L.qpos);
     // bodies welded to the world: constant pose
@@ -153,13 +152,15 @@ struct Eng {
 
   // last dof on the kinematic chain ending at body b (-1 if none)
   DEV int chain_end(int b) const {
+    const DModel<R>& m = cmodel<R>();
     while (b > 0 && m.body_dofnum[b] == 0) b = m.body_parentid[b];
     return b > 0 ? m.body_dofadr[b] + m.body_dofnum[b] - 1 : -1;
   }
 
   // ------------------------------------------------------------------------------------------- velocity stage
   // cvel, cdof_dot, RNE bias forces, passive (damping + fluid) forces
-  DEV void velocity() {
+  DEVN void velocity() {
+    const DModel<R>& m = cmodel<R>(); const WSLayout& L = c_L;
     const R* cdof = p(L.cdof); const R* qvel = p(L.qvel);
     R* cvel = p(L.cvel); R* cdd = p(L.cdofdot);
     for (int b = lane; b < m.nbody; b += 32) {
@@ -268,7 +269,8 @@ struct Eng {
   }
 
   // ------------------------------------------------------------------------------------------- CRB -> dense M
-  DEV void crb() {
+  DEVN void crb() {
+    const DModel<R>& m = cmodel<R>(); const WSLayout& L = c_L;
     R* cinert = p(L.cinert);
     // composite inertia = sum over the (contiguous, DFS-ordered) subtree, written to scratch
     int nb = m.nbody;
@@ -306,7 +308,7 @@ struct Eng {
 
   // ------------------------------------------------------------------------------------------- dense Cholesky
   // A (n x n, row-major, lower part used) -> L in place (lower).  Returns 0 on success (warp-uniform).
-  DEV int chol(R* A, int n) {
+  DEVN int chol(R* A, int n) {
     int bad = 0;
     for (int j = 0; j < n; j++) {
       // s_i = A[i][j] - sum_k<j L[i][k] L[j][k] for i >= j
@@ -327,7 +329,7 @@ struct Eng {
     return bad;
   }
   // x <- (L L^T)^-1 x, x in shared memory (n <= 64)
-  DEV void chol_solve(const R* Lm, R* x, int n) {
+  DEVN void chol_solve(const R* Lm, R* x, int n) {
     for (int k = 0; k < n; k++) {
       R xk = x[k] / Lm[k * n + k];
       __syncwarp();
@@ -345,7 +347,8 @@ struct Eng {
   }
 
   // ------------------------------------------------------------------------------------------- actuation
-  DEV void actuation(R* act_force_out) {
+  DEVN void actuation(R* act_force_out) {
+    const DModel<R>& m = cmodel<R>(); const WSLayout& L = c_L;
     R* qact = p(L.qact);
     const R* ctrl = p(L.ctrl); const R* qpos = p(L.qpos); const R* qvel = p(L.qvel);
     for (int i = lane; i < m.nv; i += 32) qact[i] = 0;
@@ -366,7 +369,8 @@ struct Eng {
   }
 
   // qfrc_smooth, qacc_smooth = M^-1 qfrc_smooth (factor of M left in H)
-  DEV int acceleration() {
+  DEVN int acceleration() {
+    const DModel<R>& m = cmodel<R>(); const WSLayout& L = c_L;
     int nv = m.nv;
     R* H = p(L.H); const R* M = p(L.M);
     R* qs = p(L.qsmooth); R* qa = p(L.qaccs);
@@ -384,7 +388,8 @@ struct Eng {
 
   // ------------------------------------------------------------------------------------------- Euler
   // semi-implicit Euler with implicit joint damping: (M + h D) a = qfrc_smooth + qfrc_constraint
-  DEV int euler(R* time) {
+  DEVN int euler(R* time) {
+    const DModel<R>& m = cmodel<R>(); const WSLayout& L = c_L;
     int nv = m.nv;
     R h = m.timestep;
     R* H = p(L.H); const R* M = p(L.M);

@@ -8,9 +8,10 @@ template <typename R> DEV void load_row(R* dst, const R* src, int n, int lane) {
 }
 
 template <typename R>
-DEV void export_step1(const Eng<R>& e, const DState<R>& s, int env, int ncon, int nefc) {
-  const DModel<R>& m = e.m;
-  const WSLayout& L = e.L;
+DEVN void export_step1(const Eng<R> e, int env, int ncon, int nefc) {
+  const DModel<R>& m = cmodel<R>();
+  const WSLayout& L = c_L;
+  const DState<R>& s = cstate<R>();
   int lane = e.lane;
   size_t E = env;
   load_row(s.xpos + E * 3 * m.nbody, e.p(L.xpos), 3 * m.nbody, lane);
@@ -50,9 +51,10 @@ DEV void export_step1(const Eng<R>& e, const DState<R>& s, int env, int ncon, in
 }
 
 template <typename R>
-DEV void export_step2(const Eng<R>& e, const DState<R>& s, int env, int nefc, int niter) {
-  const DModel<R>& m = e.m;
-  const WSLayout& L = e.L;
+DEVN void export_step2(const Eng<R> e, int env, int nefc, int niter) {
+  const DModel<R>& m = cmodel<R>();
+  const WSLayout& L = c_L;
+  const DState<R>& s = cstate<R>();
   int lane = e.lane;
   size_t E = env;
   load_row(s.qfrc_actuator + E * m.nv, e.p(L.qact), m.nv, lane);
@@ -64,14 +66,19 @@ DEV void export_step2(const Eng<R>& e, const DState<R>& s, int env, int nefc, in
 }
 
 template <typename R>
-__global__ void step_kernel(const __grid_constant__ DModel<R> m, const __grid_constant__ DState<R> s,
-                            const __grid_constant__ WSLayout L, const __grid_constant__ CtrlCfgDev cc, int phases, int nsub) {
+__global__ void step_kernel(int phases, int nsub, const R* action) {
+  const DModel<R>& m = cmodel<R>();
+  const DState<R>& s = cstate<R>();
+  const WSLayout& L = c_L;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   R* smem = reinterpret_cast<R*>(smem_raw);
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   int env = blockIdx.x * wpb + warp;
-  if (env >= s.n_env) return;
-  Eng<R> e(m, L, smem + (size_t)warp * L.total, lane);
+  // every warp of the block runs the phase sequence (block barriers keep the warps of an SM in the same code
+  // region, which is what bounds the instruction-cache working set); warps beyond n_env shadow the last env
+  bool live = env < s.n_env;
+  if (!live) env = s.n_env - 1;
+  Eng<R> e(smem + (size_t)warp * L.total, lane);
   size_t E = env;
   load_row(e.p(L.qpos), s.qpos + E * m.nq, m.nq, lane);
   load_row(e.p(L.qvel), s.qvel + E * m.nv, m.nv, lane);
@@ -80,36 +87,42 @@ __global__ void step_kernel(const __grid_constant__ DModel<R> m, const __grid_co
   load_row(e.p(L.ctrl), s.ctrl + E * m.nu, m.nu, lane);
   R time = s.time[env];
   CtrlState<R> cs;
-  if (phases & PH_CTRL) ctrl_load(e, s, cc, cs, env);
+  if (phases & PH_CTRL) ctrl_load(e, cs, env);
   __syncwarp();
   int warn = 0;
   for (int sub = 0; sub < nsub; sub++) {
     int ncon = 0, nefc = 0, niter = 0;
+    bool ex = live && (phases & PH_EXPORT) && sub == nsub - 1;
+    __syncthreads();
     if (phases & PH_STEP1) {
       e.kinematics();
       e.velocity();
       e.crb();
+      __syncthreads();
       ncon = collide(e, warn);
+      __syncthreads();
       nefc = make_constraint(e, ncon, warn);
-      if ((phases & PH_EXPORT) && sub == nsub - 1) export_step1(e, s, env, ncon, nefc);
+      if (ex) export_step1(e, env, ncon, nefc);
     }
-    if (phases & PH_CTRL) ctrl_run(e, s, cc, cs, env, sub == 0);
+    if (phases & PH_CTRL) ctrl_run(e, cs, env, sub == 0 ? action : (const R*)nullptr);
     if (phases & PH_STEP2) {
-      bool ex = (phases & PH_EXPORT) && sub == nsub - 1;
       e.actuation(ex ? s.actuator_force + E * m.nu : nullptr);
       if (e.acceleration()) warn |= 1;
+      __syncthreads();
       niter = solve(e, nefc, ncon, warn);
-      if (ex) export_step2(e, s, env, nefc, niter);
+      if (ex) export_step2(e, env, nefc, niter);
+      __syncthreads();
       if (!(phases & PH_NOINTEGRATE)) {
         if (e.euler(&time)) warn |= 2;
       }
     }
-    if ((phases & PH_OBS) && cc.obs_dim > 0) {
-      if (sub == 0) write_obs(e, s, cc, env);
-      if (sub == nsub - 1) write_task(e, s, cc, env, ncon);
+    if (live && (phases & PH_OBS) && c_cc.obs_dim > 0) {
+      if (sub == 0) write_obs(e, env);
+      if (sub == nsub - 1) write_task(e, env, ncon);
     }
     __syncwarp();
   }
+  if (!live) return;
   // write back
   for (int i = lane; i < m.nq; i += 32) s.qpos[E * m.nq + i] = e.p(L.qpos)[i];
   for (int i = lane; i < m.nv; i += 32) {
@@ -119,13 +132,15 @@ __global__ void step_kernel(const __grid_constant__ DModel<R> m, const __grid_co
   }
   if (phases & PH_CTRL) {
     for (int i = lane; i < m.nu; i += 32) s.ctrl[E * m.nu + i] = e.p(L.ctrl)[i];
-    ctrl_store(e, s, cc, cs, env);
+    ctrl_store(e, cs, env);
   }
   if (lane == 0) { s.time[env] = time; s.warn[env] |= warn; }
 }
 
 template <typename R>
-__global__ void reset_kernel(const __grid_constant__ DModel<R> m, const __grid_constant__ DState<R> s, const uint8_t* mask) {
+__global__ void reset_kernel(const uint8_t* mask) {
+  const DModel<R>& m = cmodel<R>();
+  const DState<R>& s = cstate<R>();
   int env = blockIdx.x * blockDim.x + threadIdx.x;
   if (env >= s.n_env) return;
   if (mask && !mask[env]) return;
@@ -139,7 +154,9 @@ __global__ void reset_kernel(const __grid_constant__ DModel<R> m, const __grid_c
 
 // translational / rotational Jacobian of a site from the exported cdof and site_xpos (valid after forward/step1)
 template <typename R>
-__global__ void jac_site_kernel(const __grid_constant__ DModel<R> m, const __grid_constant__ DState<R> s, int site, R* jacp, R* jacr) {
+__global__ void jac_site_kernel(int site, R* jacp, R* jacr) {
+  const DModel<R>& m = cmodel<R>();
+  const DState<R>& s = cstate<R>();
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= s.n_env * m.nv) return;
   int env = idx / m.nv, i = idx % m.nv;

@@ -3,6 +3,7 @@
 #include "b2s_types.cuh"
 
 #define DEV __device__ __forceinline__
+#define DEVN __device__ __noinline__
 
 template <typename R> DEV R r_sqrt(R x);
 template <> DEV float r_sqrt<float>(float x) { return sqrtf(x); }

@@ -38,9 +38,9 @@ template <typename R> DEV void kb_from_solref(const R* solref, R dmax, R timeste
 template <typename R> DEV R row_friction(const R* f3, int k) { return k <= 2 ? f3[0] : (k == 3 ? f3[1] : f3[2]); }
 
 // Builds all constraint rows in the workspace.  Returns nefc (warp-uniform).
-template <typename R> DEV int make_constraint(Eng<R>& e, int ncon, int& warn) {
-  const DModel<R>& m = e.m;
-  const WSLayout& L = e.L;
+template <typename R> DEVN int make_constraint(Eng<R> e, int ncon, int& warn) {
+  const DModel<R>& m = cmodel<R>();
+  const WSLayout& L = c_L;
   int lane = e.lane, nv = m.nv;
   R* J = e.p(L.J);
   R* eD = e.p(L.e_D); R* eR = e.p(L.e_R); R* earef = e.p(L.e_aref); R* efl = e.p(L.e_floss);
@@ -216,9 +216,9 @@ template <typename R> DEV int make_constraint(Eng<R>& e, int ncon, int& warn) {
 // Evaluate all constraints at jar (in workspace): forces, per-row active curvature (e_jv borrowed as `act`), cone
 // Hessian blocks (scratch), returns total constraint cost (warp-uniform).  If hess==0 only cost/forces.
 template <typename R>
-DEV R constraint_update(Eng<R>& e, int nefc, int ncon, bool hess) {
-  const DModel<R>& m = e.m;
-  const WSLayout& L = e.L;
+DEVN R constraint_update(Eng<R> e, int nefc, int ncon, bool hess) {
+  const DModel<R>& m = cmodel<R>();
+  const WSLayout& L = c_L;
   int lane = e.lane;
   const R* jar = e.p(L.e_jar); const R* eD = e.p(L.e_D); const R* eR = e.p(L.e_R); const R* efl = e.p(L.e_floss);
   R* force = e.p(L.e_force);
@@ -304,9 +304,9 @@ DEV R constraint_update(Eng<R>& e, int nefc, int ncon, bool hess) {
 
 // first / second derivative of the cost along the search direction at step alpha (warp-uniform result)
 template <typename R>
-DEV void ls_eval(Eng<R>& e, int nefc, int ncon, int first_contact_row, R alpha, R quad1, R quad2, R& d1, R& d2) {
-  const DModel<R>& m = e.m;
-  const WSLayout& L = e.L;
+DEVN void ls_eval(Eng<R> e, int nefc, int ncon, int first_contact_row, R alpha, R quad1, R quad2, R& d1, R& d2) {
+  const DModel<R>& m = cmodel<R>();
+  const WSLayout& L = c_L;
   int lane = e.lane;
   const R* jar = e.p(L.e_jar); const R* jv = e.p(L.e_jv); const R* eD = e.p(L.e_D); const R* eR = e.p(L.e_R);
   const R* efl = e.p(L.e_floss);
@@ -356,9 +356,9 @@ DEV void ls_eval(Eng<R>& e, int nefc, int ncon, int first_contact_row, R alpha, 
 }
 
 // Newton solve: qacc (workspace) <- argmin; efc_force, qfrc_constraint filled.  Returns iterations used.
-template <typename R> DEV int solve(Eng<R>& e, int nefc, int ncon, int& warn) {
-  const DModel<R>& m = e.m;
-  const WSLayout& L = e.L;
+template <typename R> DEVN int solve(Eng<R> e, int nefc, int ncon, int& warn) {
+  const DModel<R>& m = cmodel<R>();
+  const WSLayout& L = c_L;
   int lane = e.lane, nv = m.nv;
   R* qacc = e.p(L.qacc); R* qcon = e.p(L.qcon);
   const R* qs = e.p(L.qsmooth); const R* qas = e.p(L.qaccs);

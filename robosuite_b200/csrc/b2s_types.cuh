@@ -71,7 +71,6 @@ struct DState {
       *efc_aref, *efc_D, *efc_R;
   // fused controller state / io
   R *goal_pos, *goal_ori, *init_qpos_arm, *grip_state;
-  const R* action;
   R* ctrl_torque;  // exported arm torques before clipping (tests)
   R* obs;          // [n_env, obs_dim] sampled after the first substep of a control step (observables.py:230-240)
   R* task_out;     // [n_env, 4]: target body height, |grip site - target body|, grasp flag, reserved
@@ -103,3 +102,19 @@ struct CtrlCfgDev {
   int arm_dof[8], arm_qpos[8], arm_act[8], grip_act[4];
   double grip_sign[4], grip_speed, kp[6], kd[6], input_max[6], input_min[6], output_max[6], output_min[6], null_kp;
 };
+
+// ---- per-process constant-memory copies of the descriptors (uploaded by the host before a launch whenever the
+// owning handle changes).  Device code reads them through the constant bank, so non-inlined phase functions need no
+// descriptor arguments and the kernel's instruction footprint stays small.
+__constant__ DModel<float> c_model_f;
+__constant__ DModel<double> c_model_d;
+__constant__ DState<float> c_state_f;
+__constant__ DState<double> c_state_d;
+__constant__ WSLayout c_L;
+__constant__ CtrlCfgDev c_cc;
+template <typename R> __device__ __forceinline__ const DModel<R>& cmodel();
+template <> __device__ __forceinline__ const DModel<float>& cmodel<float>() { return c_model_f; }
+template <> __device__ __forceinline__ const DModel<double>& cmodel<double>() { return c_model_d; }
+template <typename R> __device__ __forceinline__ const DState<R>& cstate();
+template <> __device__ __forceinline__ const DState<float>& cstate<float>() { return c_state_f; }
+template <> __device__ __forceinline__ const DState<double>& cstate<double>() { return c_state_d; }
