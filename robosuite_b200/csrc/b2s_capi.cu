@@ -298,19 +298,28 @@ static void build_layout(b2s_sim* s, int nq, int nv, int nu, int nb, int ncg, in
   WSLayout& L = s->L;
   int o = 0;
   auto take = [&](int n) { int r = o; o += (n + 1) & ~1; return r; };  // keep 8-byte alignment for fp32 builds
+  // persistent across substeps
   L.qpos = take(nq); L.qvel = take(nv); L.qacc = take(nv); L.qacc_ws = take(nv); L.ctrl = take(nu);
-  L.xpos = take(3 * nb); L.xquat = take(4 * nb); L.xmat = take(9 * nb); L.xipos = take(3 * nb);
-  L.cdof = take(6 * nv); L.cdofdot = take(6 * nv); L.cinert = take(10 * nb); L.cvel = take(6 * nb);
-  L.frne = take(6 * nb); L.ffl = take(6 * nb);
+  // live from step1 to the end of the substep (controller, solver, observations read them)
+  L.xpos = take(3 * nb); L.xquat = take(4 * nb); L.xmat = take(9 * nb);
+  L.cdof = take(6 * nv); L.cvel = take(6 * nb);
   L.M = take(nv * nv); L.H = take(nv * nv);
   L.bias = take(nv); L.passive = take(nv); L.qact = take(nv); L.qsmooth = take(nv); L.qaccs = take(nv); L.qcon = take(nv);
-  L.gpos = take(3 * ncg); L.gmat = take(9 * ncg); L.spos = take(3 * ns); L.smat = take(9 * ns);
+  L.spos = take(3 * ns); L.smat = take(9 * ns);
   L.c_pos = take(3 * mc); L.c_frame = take(9 * mc); L.c_dist = take(mc); L.c_fric = take(3 * mc);
   L.c_solref = 0; L.c_solimp = 0;
   L.c_mu = take(mc); L.c_int = take(5 * mc);
-  L.J = take(me * nv); L.e_D = take(me); L.e_R = take(me); L.e_aref = take(me); L.e_jar = take(me); L.e_jv = take(me);
+  L.e_D = take(me); L.e_R = take(me); L.e_aref = take(me); L.e_jar = take(me); L.e_jv = take(me);
   L.e_force = take(me); L.e_floss = take(me); L.e_int = take(2 * me);
   L.Ma = take(nv); L.grad = take(nv); L.search = take(nv); L.Mv = take(nv);
+  // union: kinematics intermediates that are dead once collision is done  |  the constraint Jacobian
+  int ubase = o;
+  L.xipos = take(3 * nb); L.cdofdot = take(6 * nv); L.cinert = take(10 * nb); L.frne = take(6 * nb); L.ffl = take(6 * nb);
+  L.gpos = take(3 * ncg); L.gmat = take(9 * ncg);
+  int uend = o;
+  L.J = ubase;
+  if (ubase + me * nv > uend) uend = ubase + ((me * nv + 1) & ~1);
+  o = uend;
   int sc = 10 * nb;
   int epa = 128 + 9 * EPA_MAXV + 4 * EPA_MAXF + EPA_MAXF + 8;
   if (epa > sc) sc = epa;
@@ -344,7 +353,7 @@ int b2s_create(const void* blob_host, size_t nbytes, int n_env, int device, int 
     s->nq = b.scalar_i("nq"); s->nv = b.scalar_i("nv"); s->nu = b.scalar_i("nu"); s->nbody = b.scalar_i("nbody");
     s->ngeom = b.scalar_i("ngeom"); s->nsite = b.scalar_i("nsite");
     s->maxcon = b.has("opt_maxcon") ? b.scalar_i("opt_maxcon") : 32;
-    s->maxefc = b.has("opt_maxefc") ? b.scalar_i("opt_maxefc") : 96;
+    s->maxefc = b.has("opt_maxefc") ? b.scalar_i("opt_maxefc") : 64;
     if (s->maxcon > 64) throw std::string("opt_maxcon > 64 not supported");
     const double* q0 = b.f64("qpos0");
     s->qpos0.assign(q0, q0 + s->nq);
@@ -360,11 +369,11 @@ int b2s_create(const void* blob_host, size_t nbytes, int n_env, int device, int 
   }
   size_t rsz = precision == B2S_F32 ? 4 : 8;
   size_t per_warp = (size_t)s->L.total * rsz;
-  int wpb = 4;
+  int wpb = 16;
   while (wpb > 1 && per_warp * wpb > 227 * 1024) wpb--;
   if (per_warp > 227 * 1024) { b2s_destroy(s); return fail(B2S_ERR_UNSUPPORTED, "model workspace exceeds shared memory"); }
   const char* env_wpb = getenv("B2S_WARPS_PER_BLOCK");
-  if (env_wpb) { int v = atoi(env_wpb); if (v >= 1 && per_warp * v <= 227 * 1024) wpb = v; }
+  if (env_wpb) { int v = atoi(env_wpb); if (v >= 1 && v <= 16 && per_warp * v <= 227 * 1024) wpb = v; }
   s->wpb = wpb;
   s->smem_bytes = per_warp * wpb;
   cudaError_t e1 = precision == B2S_F32

@@ -535,8 +535,8 @@ DEVN int gjk(const Shape<R>& A, const Shape<R>& B, SV<R>* simplex, int& ns, R& d
   return 0;
 }
 
-#define EPA_MAXV 48
-#define EPA_MAXF 96
+#define EPA_MAXV 32
+#define EPA_MAXF 64
 // EPA polytope lives in this warp's scratch: V[EPA_MAXV][9], Fn[EPA_MAXF][4] (normal, dist), Fi[EPA_MAXF] packed ids
 template <typename R>
 DEVN int epa(const Shape<R>& A, const Shape<R>& B, SV<R>* simplex, int ns, R& depth, R* normal, R* wa, R* wb, R* scratch, int lane) {
@@ -625,9 +625,9 @@ DEVN int epa(const Shape<R>& A, const Shape<R>& B, SV<R>* simplex, int ns, R& de
     SV<R> w;
     sv_support(A, B, fn, w, lane);
     R dw = v3dot(w.w, fn);
-    if (dw - bd < epa_tol || nV >= EPA_MAXV - 1 || nF >= EPA_MAXF - 24) break;
+    if (dw - bd < epa_tol || nV >= EPA_MAXV - 1 || nF >= EPA_MAXF - 16) break;
     // remove visible faces, build the horizon (sequential, warp-uniform; lane 0 writes)
-    int edges[48];
+    int edges[32];
     int ne = 0;
     for (int f = 0; f < nF; f++) {
       int fi = Fi[f];
@@ -644,7 +644,7 @@ DEVN int epa(const Shape<R>& A, const Shape<R>& B, SV<R>* simplex, int ns, R& de
           int a = vs[k], b = vs[(k + 1) % 3], found = 0;
           for (int q = 0; q < ne; q++)
             if (edges[q] == (b | (a << 8))) { edges[q] = edges[ne - 1]; ne--; found = 1; break; }
-          if (!found && ne < 48) edges[ne++] = a | (b << 8);
+          if (!found && ne < 32) edges[ne++] = a | (b << 8);
         }
       }
     }

@@ -7,6 +7,59 @@
 #pragma once
 #include "b2s_math.cuh"
 
+
+// ------------------------------------------------------------------------------------------- small SPD solve
+// x <- (A + diag(hd))^-1 x for an n x n symmetric positive definite A (n <= NVP <= 32), A and x in shared memory.
+// Lane i keeps the FULL row i of the symmetric working matrix in registers: at elimination step j lane j's row is
+// column j of L (by symmetry), so the rank-1 update needs one shuffle + one FMA per entry and both triangular solves
+// read only the lane's own registers.  Returns non-zero (warp-uniform) if a pivot was not positive.
+template <typename R, int NVP>
+DEVN int spd_solve_reg(const R* A, int n, const R* dadd, R dscale, R* x, int lane) {
+  R a[NVP];
+  int row = lane < n ? lane : 0;
+#pragma unroll
+  for (int k = 0; k < NVP; k++) a[k] = (lane < n && k < n) ? A[row * n + k] : (k == lane ? R(1) : R(0));
+  if (dadd && lane < n) {
+#pragma unroll
+    for (int k = 0; k < NVP; k++) if (k == lane) a[k] += dscale * dadd[lane];
+  }
+  R b = lane < n ? x[lane] : R(0);
+  R invd = 1;  // 1 / L[lane][lane]
+  int bad = 0;
+#pragma unroll
+  for (int j = 0; j < NVP; j++) {
+    R d = __shfl_sync(B2S_FULL, a[j], j);
+    if (!(d > Lim<R>::minval())) { bad = 1; d = Lim<R>::minval(); }
+    R inv = R(1) / r_sqrt(d);
+    if (lane == j) invd = inv;
+    if (lane >= j) a[j] *= inv;  // lane i > j: l_ij ; lane j: sqrt(d) ; lanes < j keep their finished u_ij
+#pragma unroll
+    for (int k = j + 1; k < NVP; k++) {
+      R ajk = lane == j ? a[k] * inv : R(0);  // lane j scales its row: u_jk = l_kj
+      R u = __shfl_sync(B2S_FULL, ajk, j);
+      if (lane == j) a[k] = u;
+      else if (lane > j) a[k] -= a[j] * u;
+    }
+  }
+  // forward: L y = b
+#pragma unroll
+  for (int k = 0; k < NVP; k++) {
+    R yk = __shfl_sync(B2S_FULL, b * invd, k);
+    if (lane == k) b = yk;
+    else if (lane > k) b -= a[k] * yk;
+  }
+  // backward: L^T x = y   (a[k], k > lane, holds u_lane,k = l_k,lane)
+#pragma unroll
+  for (int k = NVP - 1; k >= 0; k--) {
+    R xk = __shfl_sync(B2S_FULL, b * invd, k);
+    if (lane == k) b = xk;
+    else if (lane < k) b -= a[k] * xk;
+  }
+  if (lane < n) x[lane] = b;
+  __syncwarp();
+  return bad;
+}
+
 template <typename R>
 struct Eng {
   R* ws;  // this warp's workspace
@@ -346,6 +399,21 @@ struct Eng {
     }
   }
 
+
+  // x <- (A + dscale*diag(dadd))^-1 x ; A symmetric n x n in shared memory (not modified unless n > 32)
+  DEV int spd_solve(R* A, int n, const R* dadd, R dscale, R* x, R* work) {
+    if (n <= 16) return spd_solve_reg<R, 16>(A, n, dadd, dscale, x, lane);
+    if (n <= 24) return spd_solve_reg<R, 24>(A, n, dadd, dscale, x, lane);
+    if (n <= 32) return spd_solve_reg<R, 32>(A, n, dadd, dscale, x, lane);
+    for (int k = lane; k < n * n; k += 32) work[k] = A[k];
+    __syncwarp();
+    if (dadd) for (int i = lane; i < n; i += 32) work[i * n + i] += dscale * dadd[i];
+    __syncwarp();
+    int bad = chol(work, n);
+    chol_solve(work, x, n);
+    return bad;
+  }
+
   // ------------------------------------------------------------------------------------------- actuation
   DEVN void actuation(R* act_force_out) {
     const DModel<R>& m = cmodel<R>(); const WSLayout& L = c_L;
@@ -372,18 +440,14 @@ struct Eng {
   DEVN int acceleration() {
     const DModel<R>& m = cmodel<R>(); const WSLayout& L = c_L;
     int nv = m.nv;
-    R* H = p(L.H); const R* M = p(L.M);
     R* qs = p(L.qsmooth); R* qa = p(L.qaccs);
-    for (int k = lane; k < nv * nv; k += 32) H[k] = M[k];
     for (int i = lane; i < nv; i += 32) {
       R v = p(L.passive)[i] - p(L.bias)[i] + p(L.qact)[i];
       qs[i] = v;
       qa[i] = v;
     }
     __syncwarp();
-    int bad = chol(H, nv);
-    chol_solve(H, qa, nv);
-    return bad;
+    return spd_solve(p(L.M), nv, (const R*)nullptr, R(0), qa, p(L.H));
   }
 
   // ------------------------------------------------------------------------------------------- Euler
@@ -392,17 +456,10 @@ struct Eng {
     const DModel<R>& m = cmodel<R>(); const WSLayout& L = c_L;
     int nv = m.nv;
     R h = m.timestep;
-    R* H = p(L.H); const R* M = p(L.M);
     R* a = p(L.grad);  // reuse solver vector as the integration acceleration
-    for (int k = lane; k < nv * nv; k += 32) H[k] = M[k];
+    for (int i = lane; i < nv; i += 32) a[i] = p(L.qsmooth)[i] + p(L.qcon)[i];
     __syncwarp();
-    for (int i = lane; i < nv; i += 32) {
-      H[i * nv + i] += h * m.dof_damping[i];
-      a[i] = p(L.qsmooth)[i] + p(L.qcon)[i];
-    }
-    __syncwarp();
-    int bad = chol(H, nv);
-    chol_solve(H, a, nv);
+    int bad = spd_solve(p(L.M), nv, m.dof_damping, h, a, p(L.H));
     R* qvel = p(L.qvel); R* qpos = p(L.qpos);
     for (int i = lane; i < nv; i += 32) qvel[i] += h * a[i];
     __syncwarp();

@@ -8,7 +8,7 @@ template <typename R> DEV void load_row(R* dst, const R* src, int n, int lane) {
 }
 
 template <typename R>
-DEVN void export_step1(const Eng<R> e, int env, int ncon, int nefc) {
+DEVN void export_step1(const Eng<R> e, int env, int ncon) {
   const DModel<R>& m = cmodel<R>();
   const WSLayout& L = c_L;
   const DState<R>& s = cstate<R>();
@@ -39,6 +39,17 @@ DEVN void export_step1(const Eng<R> e, int env, int ncon, int nefc) {
     for (int q = 0; q < 9; q++) s.contact_frame[(E * m.maxcon + c) * 9 + q] = v ? e.p(L.c_frame)[9 * c + q] : R(0);
     for (int q = 0; q < 3; q++) s.contact_friction[(E * m.maxcon + c) * 3 + q] = v ? e.p(L.c_fric)[3 * c + q] : R(0);
   }
+  if (lane == 0) s.ncon[env] = ncon;
+}
+
+// constraint rows (the Jacobian overlays kinematics scratch, so this runs after make_constraint)
+template <typename R>
+DEVN void export_efc(const Eng<R> e, int env, int nefc) {
+  const DModel<R>& m = cmodel<R>();
+  const WSLayout& L = c_L;
+  const DState<R>& s = cstate<R>();
+  int lane = e.lane;
+  size_t E = env;
   for (int r = lane; r < m.maxefc; r += 32) {
     bool v = r < nefc;
     s.efc_type[E * m.maxefc + r] = v ? e.pi(L.e_int)[2 * r] : 0;
@@ -47,7 +58,7 @@ DEVN void export_step1(const Eng<R> e, int env, int ncon, int nefc) {
     s.efc_R[E * m.maxefc + r] = v ? e.p(L.e_R)[r] : R(0);
   }
   for (int k = lane; k < nefc * m.nv; k += 32) s.efc_J[E * m.maxefc * m.nv + k] = e.p(L.J)[k];
-  if (lane == 0) { s.ncon[env] = ncon; s.nefc[env] = nefc; }
+  if (lane == 0) s.nefc[env] = nefc;
 }
 
 template <typename R>
@@ -66,7 +77,7 @@ DEVN void export_step2(const Eng<R> e, int env, int nefc, int niter) {
 }
 
 template <typename R>
-__global__ void step_kernel(int phases, int nsub, const R* action) {
+__global__ void __launch_bounds__(512, 1) step_kernel(int phases, int nsub, const R* action) {
   const DModel<R>& m = cmodel<R>();
   const DState<R>& s = cstate<R>();
   const WSLayout& L = c_L;
@@ -98,11 +109,10 @@ __global__ void step_kernel(int phases, int nsub, const R* action) {
       e.kinematics();
       e.velocity();
       e.crb();
-      __syncthreads();
       ncon = collide(e, warn);
-      __syncthreads();
+      if (ex) export_step1(e, env, ncon);
       nefc = make_constraint(e, ncon, warn);
-      if (ex) export_step1(e, env, ncon, nefc);
+      if (ex) export_efc(e, env, nefc);
     }
     if (phases & PH_CTRL) ctrl_run(e, cs, env, sub == 0 ? action : (const R*)nullptr);
     if (phases & PH_STEP2) {
@@ -111,7 +121,6 @@ __global__ void step_kernel(int phases, int nsub, const R* action) {
       __syncthreads();
       niter = solve(e, nefc, ncon, warn);
       if (ex) export_step2(e, env, nefc, niter);
-      __syncthreads();
       if (!(phases & PH_NOINTEGRATE)) {
         if (e.euler(&time)) warn |= 2;
       }

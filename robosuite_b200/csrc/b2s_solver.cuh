@@ -462,11 +462,11 @@ template <typename R> DEVN int solve(Eng<R> e, int nefc, int ncon, int& warn) {
         }
       }
       H[a * nv + b] = s;
+      H[b * nv + a] = s;
     }
     for (int i = lane; i < nv; i += 32) search[i] = -grad[i];
     __syncwarp();
-    if (e.chol(H, nv)) { warn |= 16; break; }
-    e.chol_solve(H, search, nv);
+    if (e.spd_solve(H, nv, (const R*)nullptr, R(0), search, H)) { warn |= 16; break; }
     // --- exact line search
     R q1 = 0, q2 = 0;
     for (int i = lane; i < nv; i += 32) {
