@@ -13,47 +13,48 @@
 // Lane i keeps the FULL row i of the symmetric working matrix in registers: at elimination step j lane j's row is
 // column j of L (by symmetry), so the rank-1 update needs one shuffle + one FMA per entry and both triangular solves
 // read only the lane's own registers.  Returns non-zero (warp-uniform) if a pivot was not positive.
+template <typename R> DEV R r_rsqrt(R x);
+template <> DEV float r_rsqrt<float>(float x) { float y = rsqrtf(x); return y * (1.5f - 0.5f * x * y * y); }
+template <> DEV double r_rsqrt<double>(double x) { return 1.0 / sqrt(x); }
+
 template <typename R, int NVP>
 DEVN int spd_solve_reg(const R* A, int n, const R* dadd, R dscale, R* x, int lane) {
-  R a[NVP];
+  R a[NVP];  // must stay in registers: every index below is a compile-time constant after unrolling
   int row = lane < n ? lane : 0;
+  R dl = (dadd != nullptr && lane < n) ? dscale * dadd[row] : R(0);
 #pragma unroll
-  for (int k = 0; k < NVP; k++) a[k] = (lane < n && k < n) ? A[row * n + k] : (k == lane ? R(1) : R(0));
-  if (dadd && lane < n) {
-#pragma unroll
-    for (int k = 0; k < NVP; k++) if (k == lane) a[k] += dscale * dadd[lane];
+  for (int k = 0; k < NVP; k++) {
+    R v = (k < n) ? A[row * n + (k < n ? k : 0)] : R(0);
+    v = lane < n ? v : R(0);
+    a[k] = v + ((k == lane) ? (lane < n ? dl : R(1)) : R(0));
   }
-  R b = lane < n ? x[lane] : R(0);
+  R b = lane < n ? x[row] : R(0);
   R invd = 1;  // 1 / L[lane][lane]
   int bad = 0;
 #pragma unroll
   for (int j = 0; j < NVP; j++) {
     R d = __shfl_sync(B2S_FULL, a[j], j);
     if (!(d > Lim<R>::minval())) { bad = 1; d = Lim<R>::minval(); }
-    R inv = R(1) / r_sqrt(d);
-    if (lane == j) invd = inv;
-    if (lane >= j) a[j] *= inv;  // lane i > j: l_ij ; lane j: sqrt(d) ; lanes < j keep their finished u_ij
+    R inv = r_rsqrt(d);
+    invd = (lane == j) ? inv : invd;
+    a[j] = (lane >= j) ? a[j] * inv : a[j];  // lane i > j: l_ij ; lane j: sqrt(d) ; lanes < j keep their finished u_ij
 #pragma unroll
     for (int k = j + 1; k < NVP; k++) {
-      R ajk = lane == j ? a[k] * inv : R(0);  // lane j scales its row: u_jk = l_kj
-      R u = __shfl_sync(B2S_FULL, ajk, j);
-      if (lane == j) a[k] = u;
-      else if (lane > j) a[k] -= a[j] * u;
+      R u = __shfl_sync(B2S_FULL, a[k] * inv, j);  // lane j's scaled row entry: u_jk = l_kj
+      a[k] = (lane == j) ? u : ((lane > j) ? a[k] - a[j] * u : a[k]);
     }
   }
   // forward: L y = b
 #pragma unroll
   for (int k = 0; k < NVP; k++) {
     R yk = __shfl_sync(B2S_FULL, b * invd, k);
-    if (lane == k) b = yk;
-    else if (lane > k) b -= a[k] * yk;
+    b = (lane == k) ? yk : ((lane > k) ? b - a[k] * yk : b);
   }
   // backward: L^T x = y   (a[k], k > lane, holds u_lane,k = l_k,lane)
 #pragma unroll
   for (int k = NVP - 1; k >= 0; k--) {
     R xk = __shfl_sync(B2S_FULL, b * invd, k);
-    if (lane == k) b = xk;
-    else if (lane < k) b -= a[k] * xk;
+    b = (lane == k) ? xk : ((lane < k) ? b - a[k] * xk : b);
   }
   if (lane < n) x[lane] = b;
   __syncwarp();

@@ -19,7 +19,7 @@ def main():
     for l in syms:
         f = l.split()
         if len(f) >= 8 and f[3] == "FUNC" and kname in f[7]:
-            funcs.append((int(f[1], 16), int(f[2]), f[7].split("$")[-1] if "$" in f[7] else "<kernel body>"))
+            funcs.append((int(f[1], 16), int(f[2], 0), f[7].split("$")[-1] if "$" in f[7] else "<kernel body>"))
     funcs.sort()
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
