@@ -19,7 +19,9 @@ def build(force=False, verbose=False):
     if not force and os.path.exists(SO) and all(os.path.getmtime(p) <= os.path.getmtime(SO) for p in _deps()):
         return SO
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO, SRC]
+    extra = os.environ.get("B2S_NVCC_EXTRA", "").split()
+    out = os.environ.get("B2S_SO_OUT", SO)
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", out, SRC]
     subprocess.check_call(cmd)
     return SO
 

@@ -306,11 +306,11 @@ static void build_layout(b2s_sim* s, int nq, int nv, int nu, int nb, int ncg, in
   L.M = take(nv * nv); L.H = take(nv * nv);
   L.bias = take(nv); L.passive = take(nv); L.qact = take(nv); L.qsmooth = take(nv); L.qaccs = take(nv); L.qcon = take(nv);
   L.spos = take(3 * ns); L.smat = take(9 * ns);
-  L.c_pos = take(3 * mc); L.c_frame = take(9 * mc); L.c_dist = take(mc); L.c_fric = take(3 * mc);
+  L.c_pos = take(3 * mc); L.c_frame = take(3 * mc); L.c_dist = take(mc); L.c_fric = take(3 * mc);
   L.c_solref = 0; L.c_solimp = 0;
-  L.c_mu = take(mc); L.c_int = take(5 * mc);
+  L.c_mu = 0; L.c_int = take(5 * mc);
   L.e_D = take(me); L.e_R = take(me); L.e_aref = take(me); L.e_jar = take(me); L.e_jv = take(me);
-  L.e_force = take(me); L.e_floss = take(me); L.e_int = take(2 * me);
+  L.e_force = take(me); L.e_floss = take(me); L.e_int = take(me);
   L.Ma = take(nv); L.grad = take(nv); L.search = take(nv); L.Mv = take(nv);
   // union: kinematics intermediates that are dead once collision is done  |  the constraint Jacobian
   int ubase = o;
@@ -321,10 +321,11 @@ static void build_layout(b2s_sim* s, int nq, int nv, int nu, int nb, int ncg, in
   if (ubase + me * nv > uend) uend = ubase + ((me * nv + 1) & ~1);
   o = uend;
   int sc = 10 * nb;
-  int epa = 128 + 9 * EPA_MAXV + 4 * EPA_MAXF + EPA_MAXF + 8;
+  int epa = 96 + 9 * EPA_MAXV + 4 * EPA_MAXF + EPA_MAXF + 8;
   if (epa > sc) sc = epa;
   int hs = me + hc_stride * mc;
   if (hs > sc) sc = hs;
+  if (9 * mc > sc) sc = 9 * mc;
   if (sc < 720) sc = 720;  // fused controller work area (336 doubles)
   L.scratch_size = sc;
   L.scratch = take(sc);

@@ -781,8 +781,8 @@ template <typename R> DEVN int collide(Eng<R> e, int& warn) {
   const WSLayout& L = c_L;
   int lane = e.lane;
   int* cand = reinterpret_cast<int*>(e.p(L.scratch));  // candidate pair indices, analytic first then gjk
-  int* cand_g = cand + 64;
-  const int MAXC = 64;
+  int* cand_g = cand + 48;
+  const int MAXC = 48;
   int na = 0, ng = 0;
   const R* gpos = e.p(L.gpos); const R* gmat = e.p(L.gmat);
   for (int base = 0; base < m.npair; base += 32) {
@@ -853,10 +853,7 @@ template <typename R> DEVN int collide(Eng<R> e, int& warn) {
       if (c >= m.maxcon) break;
       const R* b = buf + CREC * k;
       cpos[3 * c] = b[0]; cpos[3 * c + 1] = b[1]; cpos[3 * c + 2] = b[2];
-      R fr[9] = {b[3], b[4], b[5], 0, 0, 0, 0, 0, 0};
-      make_frame(fr);
-#pragma unroll
-      for (int q = 0; q < 9; q++) cfr[9 * c + q] = fr[q];
+      cfr[3 * c] = b[3]; cfr[3 * c + 1] = b[4]; cfr[3 * c + 2] = b[5];
       cdist[c] = b[6];
       cint[5 * c] = g1; cint[5 * c + 1] = g2; cint[5 * c + 4] = pidx;
     }
@@ -865,7 +862,7 @@ template <typename R> DEVN int collide(Eng<R> e, int& warn) {
   if (ncon > m.maxcon) { ncon = m.maxcon; warn |= 4; }
   __syncwarp();
   // --- convex candidates: the whole warp per pair (scratch beyond the candidate lists holds the EPA polytope)
-  R* epa_scratch = e.p(L.scratch) + 128;
+  R* epa_scratch = e.p(L.scratch) + 96;
   for (int ci = 0; ci < ng; ci++) {
     int pidx = cand_g[ci];
     int g1 = m.pair_geom[2 * pidx], g2 = m.pair_geom[2 * pidx + 1];
@@ -880,9 +877,7 @@ template <typename R> DEVN int collide(Eng<R> e, int& warn) {
         int c = ncon;
         if (lane == 0) {
           cpos[3 * c] = buf[0]; cpos[3 * c + 1] = buf[1]; cpos[3 * c + 2] = buf[2];
-          R fr[9] = {buf[3], buf[4], buf[5], 0, 0, 0, 0, 0, 0};
-          make_frame(fr);
-          for (int q = 0; q < 9; q++) cfr[9 * c + q] = fr[q];
+          cfr[3 * c] = buf[3]; cfr[3 * c + 1] = buf[4]; cfr[3 * c + 2] = buf[5];
           cdist[c] = buf[6];
           cint[5 * c] = g1; cint[5 * c + 1] = g2; cint[5 * c + 4] = pidx;
         }
@@ -900,14 +895,14 @@ template <typename R> DEVN int collide(Eng<R> e, int& warn) {
     }
     if (ncon <= 32) {
       int c = lane;
-      R rec[13];
+      R rec[7];
       int gi1 = 0, gi2 = 0, key = 0x7fffffff, rank = 0;
       if (c < ncon) {
         key = cint[5 * c + 4] * 64 + c;
         gi1 = cint[5 * c]; gi2 = cint[5 * c + 1];
         rec[0] = cpos[3 * c]; rec[1] = cpos[3 * c + 1]; rec[2] = cpos[3 * c + 2];
-        for (int q = 0; q < 9; q++) rec[3 + q] = cfr[9 * c + q];
-        rec[12] = cdist[c];
+        rec[3] = cfr[3 * c]; rec[4] = cfr[3 * c + 1]; rec[5] = cfr[3 * c + 2];
+        rec[6] = cdist[c];
       }
       for (int o = 0; o < 32; o++) {
         int ok = __shfl_sync(B2S_FULL, key, o);
@@ -916,15 +911,15 @@ template <typename R> DEVN int collide(Eng<R> e, int& warn) {
       __syncwarp();
       if (c < ncon) {
         cpos[3 * rank] = rec[0]; cpos[3 * rank + 1] = rec[1]; cpos[3 * rank + 2] = rec[2];
-        for (int q = 0; q < 9; q++) cfr[9 * rank + q] = rec[3 + q];
-        cdist[rank] = rec[12];
+        cfr[3 * rank] = rec[3]; cfr[3 * rank + 1] = rec[4]; cfr[3 * rank + 2] = rec[5];
+        cdist[rank] = rec[6];
         cint[5 * rank] = gi1; cint[5 * rank + 1] = gi2; cint[5 * rank + 4] = key / 64;
       }
     } else if (lane == 0) {
       for (int i = 1; i < ncon; i++)
         for (int j = i; j > 0 && cint[5 * j + 4] < cint[5 * (j - 1) + 4]; j--) {
           for (int q = 0; q < 3; q++) { R t = cpos[3 * j + q]; cpos[3 * j + q] = cpos[3 * (j - 1) + q]; cpos[3 * (j - 1) + q] = t; }
-          for (int q = 0; q < 9; q++) { R t = cfr[9 * j + q]; cfr[9 * j + q] = cfr[9 * (j - 1) + q]; cfr[9 * (j - 1) + q] = t; }
+          for (int q = 0; q < 3; q++) { R t = cfr[3 * j + q]; cfr[3 * j + q] = cfr[3 * (j - 1) + q]; cfr[3 * (j - 1) + q] = t; }
           { R t = cdist[j]; cdist[j] = cdist[j - 1]; cdist[j - 1] = t; }
           for (int q = 0; q < 5; q++) { int t = cint[5 * j + q]; cint[5 * j + q] = cint[5 * (j - 1) + q]; cint[5 * (j - 1) + q] = t; }
         }

@@ -3,6 +3,10 @@
 #pragma once
 #include "b2s_ctrl.cuh"
 
+#ifndef B2S_BARRIERS
+#define B2S_BARRIERS 4  // block barriers per substep that keep the warps of an SM in the same code region
+#endif
+
 template <typename R> DEV void load_row(R* dst, const R* src, int n, int lane) {
   for (int i = lane; i < n; i += 32) dst[i] = src[i];
 }
@@ -36,7 +40,11 @@ DEVN void export_step1(const Eng<R> e, int env, int ncon) {
     s.contact_dim[E * m.maxcon + c] = v ? cint[5 * c + 2] : 0;
     s.contact_dist[E * m.maxcon + c] = v ? e.p(L.c_dist)[c] : R(0);
     for (int q = 0; q < 3; q++) s.contact_pos[(E * m.maxcon + c) * 3 + q] = v ? e.p(L.c_pos)[3 * c + q] : R(0);
-    for (int q = 0; q < 9; q++) s.contact_frame[(E * m.maxcon + c) * 9 + q] = v ? e.p(L.c_frame)[9 * c + q] : R(0);
+    {
+      R f9[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+      if (v) { f9[0] = e.p(L.c_frame)[3 * c]; f9[1] = e.p(L.c_frame)[3 * c + 1]; f9[2] = e.p(L.c_frame)[3 * c + 2]; make_frame(f9); }
+      for (int q = 0; q < 9; q++) s.contact_frame[(E * m.maxcon + c) * 9 + q] = f9[q];
+    }
     for (int q = 0; q < 3; q++) s.contact_friction[(E * m.maxcon + c) * 3 + q] = v ? e.p(L.c_fric)[3 * c + q] : R(0);
   }
   if (lane == 0) s.ncon[env] = ncon;
@@ -52,7 +60,7 @@ DEVN void export_efc(const Eng<R> e, int env, int nefc) {
   size_t E = env;
   for (int r = lane; r < m.maxefc; r += 32) {
     bool v = r < nefc;
-    s.efc_type[E * m.maxefc + r] = v ? e.pi(L.e_int)[2 * r] : 0;
+    s.efc_type[E * m.maxefc + r] = v ? (e.pi(L.e_int)[r] & 255) : 0;
     s.efc_aref[E * m.maxefc + r] = v ? e.p(L.e_aref)[r] : R(0);
     s.efc_D[E * m.maxefc + r] = v ? e.p(L.e_D)[r] : R(0);
     s.efc_R[E * m.maxefc + r] = v ? e.p(L.e_R)[r] : R(0);
@@ -104,23 +112,39 @@ __global__ void __launch_bounds__(512, 1) step_kernel(int phases, int nsub, cons
   for (int sub = 0; sub < nsub; sub++) {
     int ncon = 0, nefc = 0, niter = 0;
     bool ex = live && (phases & PH_EXPORT) && sub == nsub - 1;
+#if B2S_BARRIERS >= 1
     __syncthreads();
+#endif
     if (phases & PH_STEP1) {
       e.kinematics();
       e.velocity();
       e.crb();
+#if B2S_BARRIERS >= 3
+      __syncthreads();
+#endif
       ncon = collide(e, warn);
       if (ex) export_step1(e, env, ncon);
+#if B2S_BARRIERS >= 4
+      __syncthreads();
+#endif
       nefc = make_constraint(e, ncon, warn);
       if (ex) export_efc(e, env, nefc);
     }
+#if B2S_BARRIERS >= 5
+    __syncthreads();
+#endif
     if (phases & PH_CTRL) ctrl_run(e, cs, env, sub == 0 ? action : (const R*)nullptr);
     if (phases & PH_STEP2) {
       e.actuation(ex ? s.actuator_force + E * m.nu : nullptr);
       if (e.acceleration()) warn |= 1;
+#if B2S_BARRIERS >= 2
       __syncthreads();
+#endif
       niter = solve(e, nefc, ncon, warn);
       if (ex) export_step2(e, env, nefc, niter);
+#if B2S_BARRIERS >= 6
+      __syncthreads();
+#endif
       if (!(phases & PH_NOINTEGRATE)) {
         if (e.euler(&time)) warn |= 2;
       }

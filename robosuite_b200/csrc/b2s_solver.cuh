@@ -52,7 +52,7 @@ template <typename R> DEVN int make_constraint(Eng<R> e, int ncon, int& warn) {
   for (int r = lane; r < m.nfl; r += 32) {
     int dof = m.fl_dof[r];
     for (int i = 0; i < nv; i++) J[r * nv + i] = i == dof ? R(1) : R(0);
-    eint[2 * r] = C_FRICTION; eint[2 * r + 1] = dof;
+    eint[r] = C_FRICTION | (dof << 8);
     epos[r] = 0;
     efl[r] = m.dof_frictionloss[dof];
   }
@@ -74,7 +74,7 @@ template <typename R> DEVN int make_constraint(Eng<R> e, int ncon, int& warn) {
       if (r < m.maxefc) {
         int dof = m.jnt_dofadr[j];
         for (int i = 0; i < nv; i++) J[r * nv + i] = i == dof ? R(-side) : R(0);
-        eint[2 * r] = C_LIMIT; eint[2 * r + 1] = j;
+        eint[r] = C_LIMIT | (j << 8);
         epos[r] = dist;
         efl[r] = 0;
       }
@@ -116,20 +116,31 @@ template <typename R> DEVN int make_constraint(Eng<R> e, int ncon, int& warn) {
     if (adr < 0) continue;
     int dim = cint[5 * c + 2];
     for (int k = 0; k < dim; k++) {
-      eint[2 * (adr + k)] = dim == 1 ? C_FRICTIONLESS : C_ELLIPTIC;
-      eint[2 * (adr + k) + 1] = c;
+      eint[adr + k] = (dim == 1 ? C_FRICTIONLESS : C_ELLIPTIC) | (c << 8);
       epos[adr + k] = k == 0 ? cdist[c] : R(0);
       efl[adr + k] = 0;
     }
   }
   __syncwarp();
+  // full contact frames (normal, two tangents) into scratch
+  {
+    R* fr = e.p(L.scratch);
+    const R* cn = e.p(L.c_frame);
+    for (int c = lane; c < ncon; c += 32) {
+      R f9[9] = {cn[3 * c], cn[3 * c + 1], cn[3 * c + 2], 0, 0, 0, 0, 0, 0};
+      make_frame(f9);
+#pragma unroll
+      for (int q = 0; q < 9; q++) fr[9 * c + q] = f9[q];
+    }
+  }
+  __syncwarp();
   // contact Jacobian: work items = (row, dof)
   {
-    const R* cdof = e.p(L.cdof); const R* cpos = e.p(L.c_pos); const R* cfr = e.p(L.c_frame);
+    const R* cdof = e.p(L.cdof); const R* cpos = e.p(L.c_pos); const R* cfr = e.p(L.scratch);
     int nrows = nefc - first_contact_row;
     for (int w = lane; w < nrows * nv; w += 32) {
       int r = first_contact_row + w / nv, i = w % nv;
-      int c = eint[2 * r + 1], k = r - cint[5 * c + 3];
+      int c = eint[r] >> 8, k = r - cint[5 * c + 3];
       int b1 = m.geom_bodyid[cint[5 * c]], b2 = m.geom_bodyid[cint[5 * c + 1]];
       int s = (int)((m.body_dofmask[b2] >> i) & 1ull) - (int)((m.body_dofmask[b1] >> i) & 1ull);
       R v = 0;
@@ -152,7 +163,7 @@ template <typename R> DEVN int make_constraint(Eng<R> e, int ncon, int& warn) {
   for (int r = lane; r < nefc; r += 32) {
     R vel = 0;
     for (int i = 0; i < nv; i++) vel += J[r * nv + i] * qvel[i];
-    int type = eint[2 * r], id = eint[2 * r + 1];
+    int type = eint[r] & 255, id = eint[r] >> 8;
     R solref[2], solimp[5], diag;
     int first = 1;
     if (type == C_FRICTION) {
@@ -194,17 +205,16 @@ template <typename R> DEVN int make_constraint(Eng<R> e, int ncon, int& warn) {
   }
   __syncwarp();
   // elliptic cones: friction-row regularisation and cone coefficient mu
-  R* cmu = e.p(L.c_mu); const R* cfric = e.p(L.c_fric);
+  const R* cfric = e.p(L.c_fric);
   for (int c = lane; c < ncon; c += 32) {
     int adr = cint[5 * c + 3], dim = cint[5 * c + 2];
-    cmu[c] = 0;
     if (adr < 0 || dim < 3) continue;
     R f0 = cfric[3 * c];
     R R0 = eR[adr];
     R R1 = R0 / r_max(Lim<R>::minval(), m.impratio);
     eR[adr + 1] = R1;
     for (int k = 2; k < dim; k++) { R fk = row_friction(cfric + 3 * c, k); eR[adr + k] = R1 * f0 * f0 / (fk * fk); }
-    cmu[c] = f0 * r_sqrt(R1 / R0);
+    efl[adr] = f0 * r_sqrt(R1 / R0);  // cone coefficient mu, kept in the (otherwise unused) frictionloss slot
   }
   __syncwarp();
   for (int r = lane; r < nefc; r += 32) eD[r] = R(1) / eR[r];
@@ -233,7 +243,7 @@ DEVN R constraint_update(Eng<R> e, int nefc, int ncon, bool hess) {
   for (int c = 0; c < ncon; c++) { int a = cint[5 * c + 3]; if (a >= 0) { first_contact_row = a; break; } }
   (void)nsimple;
   for (int r = lane; r < first_contact_row; r += 32) {
-    int type = eint[2 * r];
+    int type = eint[r] & 255;
     R x = jar[r], D = eD[r], a = 0, f;
     if (type == C_FRICTION) {
       R fl = efl[r], Rr = eR[r];
@@ -247,7 +257,7 @@ DEVN R constraint_update(Eng<R> e, int nefc, int ncon, bool hess) {
     force[r] = f;
     if (hess) act[r] = a;
   }
-  const R* cmu = e.p(L.c_mu); const R* cfric = e.p(L.c_fric);
+  const R* cfric = e.p(L.c_fric);
   for (int c = lane; c < ncon; c += 32) {
     int adr = cint[5 * c + 3];
     if (adr < 0) continue;
@@ -259,7 +269,7 @@ DEVN R constraint_update(Eng<R> e, int nefc, int ncon, bool hess) {
       if (hess) Hc[m.hc_stride * c] = -1;
       continue;
     }
-    R mu = cmu[c], U[6], fr[6];
+    R mu = efl[adr], U[6], fr[6];
     fr[0] = mu;
     U[0] = jar[adr] * mu;
     R TT = 0;
@@ -311,11 +321,11 @@ DEVN void ls_eval(Eng<R> e, int nefc, int ncon, int first_contact_row, R alpha, 
   const R* jar = e.p(L.e_jar); const R* jv = e.p(L.e_jv); const R* eD = e.p(L.e_D); const R* eR = e.p(L.e_R);
   const R* efl = e.p(L.e_floss);
   const int* eint = e.pi(L.e_int); const int* cint = e.pi(L.c_int);
-  const R* cmu = e.p(L.c_mu); const R* cfric = e.p(L.c_fric);
+  const R* cfric = e.p(L.c_fric);
   R g = 0, h = 0;
   for (int r = lane; r < first_contact_row; r += 32) {
     R x = jar[r] + alpha * jv[r], v = jv[r], D = eD[r];
-    if (eint[2 * r] == C_FRICTION) {
+    if ((eint[r] & 255) == C_FRICTION) {
       R fl = efl[r], Rr = eR[r];
       if (x <= -Rr * fl) g += -fl * v;
       else if (x >= Rr * fl) g += fl * v;
@@ -328,7 +338,7 @@ DEVN void ls_eval(Eng<R> e, int nefc, int ncon, int first_contact_row, R alpha, 
     int dim = cint[5 * c + 2];
     R x0 = jar[adr] + alpha * jv[adr], v0 = jv[adr];
     if (dim == 1) { if (x0 < 0) { g += eD[adr] * x0 * v0; h += eD[adr] * v0 * v0; } continue; }
-    R mu = cmu[c];
+    R mu = efl[adr];
     R N = x0 * mu, Nd = v0 * mu, TT = 0, UV = 0, VV = 0;
     for (int k = 1; k < dim; k++) {
       R fk = row_friction(cfric + 3 * c, k);

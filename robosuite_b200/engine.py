@@ -35,7 +35,7 @@ class CtrlCfg(C.Structure):
 def lib():
     global _LIB
     if _LIB is None:
-        so = os.path.join(_HERE, "libb2s.so")
+        so = os.environ.get("B2S_LIB", os.path.join(_HERE, "libb2s.so"))
         if not os.path.exists(so):
             raise B2SError(f"{so} is missing: run `python -m robosuite_b200.build` (no CPU fallback exists)")
         L = C.CDLL(so)
