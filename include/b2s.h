@@ -94,6 +94,11 @@ int b2s_task_config(b2s_sim* sim, int body, int site, const int* left, int nleft
  * the throughput path switches it off so that per-step HBM traffic is state + action + obs only */
 int b2s_set_export(b2s_sim* sim, int flag);
 
+/* debugging aid: b2s_env_step accumulates per-phase clock cycles per environment into the array "prof" [n_env,12]
+ * (0 kinematics, 1 velocity+crb, 2 collision, 3 constraint rows, 4 controller, 5 actuation+smooth acc, 6 solver,
+ * 7 integrate, 11 time spent waiting at block barriers) and collision candidate counts into "dbg" [n_env,4] */
+int b2s_set_profile(b2s_sim* sim, int flag);
+
 /* number of kernels this handle has launched since creation (bench.py "gpu_launches") */
 int64_t b2s_launch_count(const b2s_sim* sim);
 

@@ -62,7 +62,7 @@ struct b2s_sim {
   int nq = 0, nv = 0, nu = 0, nbody = 0, ngeom = 0, nsite = 0, maxcon = 0, maxefc = 0;
   std::vector<double> qpos0;
   std::vector<int> site_bodyid, cgid;
-  int has_obs = 0, export_env_step = 1, dirty = 1;
+  int has_obs = 0, export_env_step = 1, dirty = 1, profile = 0;
 };
 
 template <typename T> static T* dev_upload(b2s_sim* s, const std::vector<T>& h) {
@@ -292,6 +292,12 @@ template <typename R> static void build_state(b2s_sim* s, const DModel<R>& m, DS
   st.goal_pos = state_arr<R>(s, "ctrl_goal_pos", 3); st.goal_ori = state_arr<R>(s, "ctrl_goal_ori", 9);
   st.init_qpos_arm = state_arr<R>(s, "ctrl_initial_joint", 8); st.grip_state = state_arr<R>(s, "ctrl_grip_state", 4);
   st.ctrl_torque = state_arr<R>(s, "ctrl_torque", 8);
+  {
+    float* p = dev_zeros<float>(s, (size_t)s->n_env * 12);
+    s->arrays["prof"] = ArrayInfo{p, B2S_F32, 2, {s->n_env, 12, 0, 0}};
+    st.prof = p;
+    st.dbg = state_arr_i(s, "dbg", 4);
+  }
 }
 
 static void build_layout(b2s_sim* s, int nq, int nv, int nu, int nb, int ncg, int ns, int mc, int me, int hc_stride) {
@@ -401,6 +407,8 @@ int b2s_set_stream(b2s_sim* s, void* stream) {
   return B2S_OK;
 }
 
+int b2s_set_profile(b2s_sim* s, int flag) { if (!s) return fail(B2S_ERR_ARG, "null handle"); s->profile = flag != 0; return B2S_OK; }
+
 int b2s_set_export(b2s_sim* s, int flag) { if (!s) return fail(B2S_ERR_ARG, "null handle"); s->export_env_step = flag != 0; return B2S_OK; }
 
 int64_t b2s_launch_count(const b2s_sim* s) { return s ? s->launches : 0; }
@@ -509,7 +517,7 @@ int b2s_ctrl_reset(b2s_sim* s, const uint8_t* mask) {
 
 int b2s_env_step(b2s_sim* s, const void* action, int nsub) {
   if (!s || !s->has_ctrl || !action || nsub < 1) return fail(B2S_ERR_ARG, "b2s_env_step: bad argument / controller not configured");
-  return launch(s, PH_STEP1 | PH_STEP2 | PH_CTRL | (s->has_obs ? PH_OBS : 0) | (s->export_env_step ? PH_EXPORT : 0), nsub, action);
+  return launch(s, PH_STEP1 | PH_STEP2 | PH_CTRL | (s->has_obs ? PH_OBS : 0) | (s->export_env_step ? PH_EXPORT : 0) | (s->profile ? PH_PROFILE : 0), nsub, action);
 }
 
 int b2s_obs_config(b2s_sim* s, int obs_dim, const int* op, const int* a, const int* b) {

@@ -776,7 +776,9 @@ template <typename R> DEV void mix_contact(const DModel<R>& m, int g1, int g2, R
 }
 
 // Fills the contact arrays in the workspace; returns ncon (warp-uniform).  warn bit 4 on overflow.
-template <typename R> DEVN int collide(Eng<R> e, int& warn) {
+template <typename R> DEVN int collide(Eng<R> e, int& warn, int* dbg3, float* pc = nullptr) {
+  long long tp0 = pc ? clock64() : 0;
+#define CTICK(slot) if (pc) { __syncwarp(); long long tp1 = clock64(); pc[slot] += (float)(tp1 - tp0); tp0 = tp1; }
   const DModel<R>& m = cmodel<R>();
   const WSLayout& L = c_L;
   int lane = e.lane;
@@ -813,6 +815,8 @@ template <typename R> DEVN int collide(Eng<R> e, int& warn) {
     na += __popc(ma);
     ng += __popc(mg);
   }
+  dbg3[0] += na; dbg3[1] += ng;
+  CTICK(8)
   if (na > MAXC) { na = MAXC; warn |= 4; }
   if (ng > MAXC) { ng = MAXC; warn |= 4; }
   __syncwarp();
@@ -861,6 +865,7 @@ template <typename R> DEVN int collide(Eng<R> e, int& warn) {
   }
   if (ncon > m.maxcon) { ncon = m.maxcon; warn |= 4; }
   __syncwarp();
+  CTICK(9)
   // --- convex candidates: the whole warp per pair (scratch beyond the candidate lists holds the EPA polytope)
   R* epa_scratch = e.p(L.scratch) + 96;
   for (int ci = 0; ci < ng; ci++) {
@@ -873,6 +878,7 @@ template <typename R> DEVN int collide(Eng<R> e, int& warn) {
     R buf[CREC];
     int n = convex_convex(A, B, buf, 1, epa_scratch, lane);
     if (n > 0) {
+      dbg3[2]++;
       if (ncon < m.maxcon) {
         int c = ncon;
         if (lane == 0) {
@@ -887,6 +893,7 @@ template <typename R> DEVN int collide(Eng<R> e, int& warn) {
     __syncwarp();
   }
   __syncwarp();
+  CTICK(10)
   // --- order contacts by pair index (stable): rank = #contacts with smaller key
   if (ng > 0 && ncon > 1) {
     for (int base = 0; base < ncon; base += 32) {

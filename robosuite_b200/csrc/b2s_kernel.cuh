@@ -109,51 +109,61 @@ __global__ void __launch_bounds__(512, 1) step_kernel(int phases, int nsub, cons
   if (phases & PH_CTRL) ctrl_load(e, cs, env);
   __syncwarp();
   int warn = 0;
+  float pc[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) pc[i] = 0;
+  const bool prof = phases & PH_PROFILE;
+  int dbgc[3] = {0, 0, 0};
+  long long t0 = 0;
+#define TICK(slot) if (prof) { long long t1 = clock64(); pc[slot] += (float)(t1 - t0); t0 = t1; }
+#define BAR(level, slot) if (B2S_BARRIERS >= level) { __syncthreads(); TICK(slot) }
   for (int sub = 0; sub < nsub; sub++) {
     int ncon = 0, nefc = 0, niter = 0;
     bool ex = live && (phases & PH_EXPORT) && sub == nsub - 1;
-#if B2S_BARRIERS >= 1
-    __syncthreads();
-#endif
+    if (prof) t0 = clock64();
+    BAR(1, 11)
     if (phases & PH_STEP1) {
       e.kinematics();
+      TICK(0)
       e.velocity();
       e.crb();
-#if B2S_BARRIERS >= 3
-      __syncthreads();
-#endif
-      ncon = collide(e, warn);
+      TICK(1)
+      BAR(3, 11)
+      ncon = collide(e, warn, dbgc, prof ? pc : (float*)nullptr);
+      TICK(2)
       if (ex) export_step1(e, env, ncon);
-#if B2S_BARRIERS >= 4
-      __syncthreads();
-#endif
+      BAR(4, 11)
       nefc = make_constraint(e, ncon, warn);
+      TICK(3)
       if (ex) export_efc(e, env, nefc);
     }
-#if B2S_BARRIERS >= 5
-    __syncthreads();
-#endif
+    BAR(5, 11)
     if (phases & PH_CTRL) ctrl_run(e, cs, env, sub == 0 ? action : (const R*)nullptr);
+    TICK(4)
     if (phases & PH_STEP2) {
       e.actuation(ex ? s.actuator_force + E * m.nu : nullptr);
       if (e.acceleration()) warn |= 1;
-#if B2S_BARRIERS >= 2
-      __syncthreads();
-#endif
+      TICK(5)
+      BAR(2, 11)
       niter = solve(e, nefc, ncon, warn);
+      TICK(6)
       if (ex) export_step2(e, env, nefc, niter);
-#if B2S_BARRIERS >= 6
-      __syncthreads();
-#endif
+      BAR(6, 11)
       if (!(phases & PH_NOINTEGRATE)) {
         if (e.euler(&time)) warn |= 2;
       }
+      TICK(7)
     }
     if (live && (phases & PH_OBS) && c_cc.obs_dim > 0) {
       if (sub == 0) write_obs(e, env);
       if (sub == nsub - 1) write_task(e, env, ncon);
     }
     __syncwarp();
+  }
+  if (prof && live && lane == 0)
+  {
+    for (int i = 0; i < 12; i++) s.prof[E * 12 + i] = pc[i];
+    s.dbg[E * 4] = dbgc[0]; s.dbg[E * 4 + 1] = dbgc[1]; s.dbg[E * 4 + 2] = dbgc[2];
   }
   if (!live) return;
   // write back

@@ -38,7 +38,8 @@ template <typename R> DEV void kb_from_solref(const R* solref, R dmax, R timeste
 template <typename R> DEV R row_friction(const R* f3, int k) { return k <= 2 ? f3[0] : (k == 3 ? f3[1] : f3[2]); }
 
 // Builds all constraint rows in the workspace.  Returns nefc (warp-uniform).
-template <typename R> DEVN int make_constraint(Eng<R> e, int ncon, int& warn) {
+template <typename R> DEVN int make_constraint(Eng<R> e, int ncon, int& warn, float* pc = nullptr) {
+#define MTICK(slot)
   const DModel<R>& m = cmodel<R>();
   const WSLayout& L = c_L;
   int lane = e.lane, nv = m.nv;
@@ -122,6 +123,7 @@ template <typename R> DEVN int make_constraint(Eng<R> e, int ncon, int& warn) {
     }
   }
   __syncwarp();
+  MTICK(7)
   // full contact frames (normal, two tangents) into scratch
   {
     R* fr = e.p(L.scratch);
@@ -158,6 +160,7 @@ template <typename R> DEVN int make_constraint(Eng<R> e, int ncon, int& warn) {
     }
   }
   __syncwarp();
+  MTICK(7)
   // per row: velocity, impedance, regularisation, reference acceleration
   R* ejv = e.p(L.e_jv);  // borrow: holds imp of each row until the cone pass
   for (int r = lane; r < nefc; r += 32) {
@@ -204,6 +207,7 @@ template <typename R> DEVN int make_constraint(Eng<R> e, int ncon, int& warn) {
     ejv[r] = imp;
   }
   __syncwarp();
+  MTICK(8)
   // elliptic cones: friction-row regularisation and cone coefficient mu
   const R* cfric = e.p(L.c_fric);
   for (int c = lane; c < ncon; c += 32) {
@@ -217,8 +221,10 @@ template <typename R> DEVN int make_constraint(Eng<R> e, int ncon, int& warn) {
     efl[adr] = f0 * r_sqrt(R1 / R0);  // cone coefficient mu, kept in the (otherwise unused) frictionloss slot
   }
   __syncwarp();
+  MTICK(9)
   for (int r = lane; r < nefc; r += 32) eD[r] = R(1) / eR[r];
   __syncwarp();
+  MTICK(10)
   return nefc;
 }
 

@@ -21,6 +21,7 @@ enum {
   PH_EXPORT = 8,     // write derived arrays (xpos, qM, contacts, efc ...) to HBM
   PH_CTRL = 16,      // run the fused controller between step1 and step2
   PH_POLICY = 32,    // first substep of a control step: consume `action` (set_goal)
+  PH_PROFILE = 128,  // accumulate per-phase clock() cycles per environment into `prof`
   PH_OBS = 64        // write the observation row (after substep 0) and the task outputs (after the last substep)
 };
 
@@ -73,6 +74,8 @@ struct DState {
   R *goal_pos, *goal_ori, *init_qpos_arm, *grip_state;
   R* ctrl_torque;  // exported arm torques before clipping (tests)
   R* obs;          // [n_env, obs_dim] sampled after the first substep of a control step (observables.py:230-240)
+  float* prof;     // [n_env, 12] cycles per phase (PH_PROFILE)
+  int* dbg;        // [n_env, 4] analytic candidates, convex candidates, EPA calls, reserved
   R* task_out;     // [n_env, 4]: target body height, |grip site - target body|, grasp flag, reserved
 };
 

@@ -57,6 +57,7 @@ def lib():
         L.b2s_obs_config.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.b2s_task_config.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.b2s_set_export.argtypes = [C.c_void_p, C.c_int]
+        L.b2s_set_profile.argtypes = [C.c_void_p, C.c_int]
         L.b2s_launch_count.argtypes = [C.c_void_p]
         L.b2s_launch_count.restype = C.c_int64
         _LIB = L
@@ -189,6 +190,9 @@ class BatchedSim:
     def set_export(self, flag):
         """whether b2s_env_step also writes the derived arrays (xpos, contacts, ...) of its last substep to HBM"""
         self._check(self._L.b2s_set_export(self._h, int(bool(flag))))
+
+    def set_profile(self, flag):
+        self._check(self._L.b2s_set_profile(self._h, int(bool(flag))))
 
     @property
     def launch_count(self):
