@@ -94,6 +94,11 @@ int b2s_task_config(b2s_sim* sim, int body, int site, const int* left, int nleft
  * the throughput path switches it off so that per-step HBM traffic is state + action + obs only */
 int b2s_set_export(b2s_sim* sim, int flag);
 
+/* Scheduling of b2s_env_step / b2s_step: 0 = fused (one kernel per call, state resident in shared memory for all
+ * substeps), 1 = pipeline (five phase kernels per substep exchanging a workspace row through L2).  Results are
+ * identical; see DESIGN.md section 5 for when each wins. */
+int b2s_set_mode(b2s_sim* sim, int mode);
+
 /* debugging aid: b2s_env_step accumulates per-phase clock cycles per environment into the array "prof" [n_env,12]
  * (0 kinematics, 1 velocity+crb, 2 collision, 3 constraint rows, 4 controller, 5 actuation+smooth acc, 6 solver,
  * 7 integrate, 11 time spent waiting at block barriers) and collision candidate counts into "dbg" [n_env,4] */

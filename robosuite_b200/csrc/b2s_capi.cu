@@ -1,7 +1,7 @@
 // libb2s: C ABI + host side of the batched engine (model upload, workspace layout, kernel launches).
 // Entry points are declared in include/b2s.h; each cites the reference call it replaces.
 #include "../../include/b2s.h"
-#include "b2s_kernel.cuh"
+#include "b2s_pipeline.cuh"
 
 #include <cstdio>
 #include <cstdlib>
@@ -62,7 +62,9 @@ struct b2s_sim {
   int nq = 0, nv = 0, nu = 0, nbody = 0, ngeom = 0, nsite = 0, maxcon = 0, maxefc = 0;
   std::vector<double> qpos0;
   std::vector<int> site_bodyid, cgid;
-  int has_obs = 0, export_env_step = 1, dirty = 1, profile = 0;
+  int has_obs = 0, export_env_step = 1, dirty = 1, profile = 0, mode = 0;
+  PhaseIO pio[B2S_NPHASE];
+  std::map<std::string, Region> reg;
 };
 
 template <typename T> static T* dev_upload(b2s_sim* s, const std::vector<T>& h) {
@@ -292,6 +294,7 @@ template <typename R> static void build_state(b2s_sim* s, const DModel<R>& m, DS
   st.goal_pos = state_arr<R>(s, "ctrl_goal_pos", 3); st.goal_ori = state_arr<R>(s, "ctrl_goal_ori", 9);
   st.init_qpos_arm = state_arr<R>(s, "ctrl_initial_joint", 8); st.grip_state = state_arr<R>(s, "ctrl_grip_state", 4);
   st.ctrl_torque = state_arr<R>(s, "ctrl_torque", 8);
+  st.wsg = nullptr;
   {
     float* p = dev_zeros<float>(s, (size_t)s->n_env * 12);
     s->arrays["prof"] = ArrayInfo{p, B2S_F32, 2, {s->n_env, 12, 0, 0}};
@@ -304,6 +307,7 @@ static void build_layout(b2s_sim* s, int nq, int nv, int nu, int nb, int ncg, in
   WSLayout& L = s->L;
   int o = 0;
   auto take = [&](int n) { int r = o; o += (n + 1) & ~1; return r; };  // keep 8-byte alignment for fp32 builds
+  auto rec = [&](const char* name, int off, int n) { s->reg[name] = Region{off, (n + 1) & ~1, 0}; };
   // persistent across substeps
   L.qpos = take(nq); L.qvel = take(nv); L.qacc = take(nv); L.qacc_ws = take(nv); L.ctrl = take(nu);
   // live from step1 to the end of the substep (controller, solver, observations read them)
@@ -335,7 +339,25 @@ static void build_layout(b2s_sim* s, int nq, int nv, int nu, int nb, int ncg, in
   if (sc < 720) sc = 720;  // fused controller work area (336 doubles)
   L.scratch_size = sc;
   L.scratch = take(sc);
+  L.hdr = take(8);
   L.total = o;
+  rec("xpos", L.xpos, 3 * nb); rec("xquat", L.xquat, 4 * nb); rec("xmat", L.xmat, 9 * nb); rec("cdof", L.cdof, 6 * nv);
+  rec("cvel", L.cvel, 6 * nb); rec("M", L.M, nv * nv); rec("bias", L.bias, nv); rec("passive", L.passive, nv);
+  rec("spos", L.spos, 3 * ns); rec("smat", L.smat, 9 * ns); rec("gpos", L.gpos, 3 * ncg); rec("gmat", L.gmat, 9 * ncg);
+  rec("c_pos", L.c_pos, 3 * mc); rec("c_frame", L.c_frame, 3 * mc); rec("c_dist", L.c_dist, mc); rec("c_fric", L.c_fric, 3 * mc);
+  rec("c_int", L.c_int, 5 * mc); rec("e_D", L.e_D, me); rec("e_R", L.e_R, me); rec("e_aref", L.e_aref, me);
+  rec("e_floss", L.e_floss, me); rec("e_int", L.e_int, me);
+  s->reg["J"] = Region{L.J, (me * nv + 1) & ~1, 1};
+  auto mk = [&](PhaseIO& io, std::initializer_list<const char*> ld, std::initializer_list<const char*> st) {
+    io.nload = io.nstore = 0;
+    for (const char* n : ld) io.load[io.nload++] = s->reg[n];
+    for (const char* n : st) io.store[io.nstore++] = s->reg[n];
+  };
+  mk(s->pio[0], {}, {"xpos", "xquat", "xmat", "cdof", "cvel", "M", "bias", "passive", "spos", "smat", "gpos", "gmat"});
+  mk(s->pio[1], {"gpos", "gmat"}, {"c_pos", "c_frame", "c_dist", "c_fric", "c_int"});
+  mk(s->pio[2], {"c_pos", "c_frame", "c_dist", "c_fric", "c_int", "cdof"}, {"J", "e_D", "e_R", "e_aref", "e_floss", "e_int", "c_int"});
+  mk(s->pio[3], {"cdof", "cvel", "M", "bias", "spos", "smat"}, {});
+  mk(s->pio[4], {"M", "bias", "passive", "J", "e_D", "e_R", "e_aref", "e_floss", "e_int", "c_fric", "c_int", "c_dist", "xpos", "xquat", "spos", "smat"}, {});
 }
 
 static b2s_sim* g_owner[64] = {nullptr};
@@ -386,6 +408,22 @@ int b2s_create(const void* blob_host, size_t nbytes, int n_env, int device, int 
   cudaError_t e1 = precision == B2S_F32
                        ? cudaFuncSetAttribute(step_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes)
                        : cudaFuncSetAttribute(step_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes);
+  if (e1 == cudaSuccess) {
+    int sb = (int)s->smem_bytes;
+    if (precision == B2S_F32) {
+      cudaFuncSetAttribute(phase_kernel<float, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
+      cudaFuncSetAttribute(phase_kernel<float, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
+      cudaFuncSetAttribute(phase_kernel<float, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
+      cudaFuncSetAttribute(phase_kernel<float, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
+      e1 = cudaFuncSetAttribute(phase_kernel<float, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
+    } else {
+      cudaFuncSetAttribute(phase_kernel<double, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
+      cudaFuncSetAttribute(phase_kernel<double, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
+      cudaFuncSetAttribute(phase_kernel<double, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
+      cudaFuncSetAttribute(phase_kernel<double, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
+      e1 = cudaFuncSetAttribute(phase_kernel<double, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
+    }
+  }
   if (e1 != cudaSuccess) { std::string msg = cudaGetErrorString(e1); b2s_destroy(s); return fail(B2S_ERR_CUDA, "cudaFuncSetAttribute: " + msg); }
   *out = s;
   int rc = b2s_reset(s, nullptr);
@@ -437,6 +475,7 @@ static int bind_constants(b2s_sim* s) {
   }
   CUDA_TRY(cudaMemcpyToSymbolAsync(c_L, &s->L, sizeof(s->L), 0, cudaMemcpyHostToDevice, s->stream));
   CUDA_TRY(cudaMemcpyToSymbolAsync(c_cc, &s->ctrl, sizeof(s->ctrl), 0, cudaMemcpyHostToDevice, s->stream));
+  CUDA_TRY(cudaMemcpyToSymbolAsync(c_pio, s->pio, sizeof(s->pio), 0, cudaMemcpyHostToDevice, s->stream));
   g_owner[s->device & 63] = s;
   s->dirty = 0;
   return B2S_OK;
@@ -455,6 +494,46 @@ static int launch(b2s_sim* s, int phases, int nsub, const void* action = nullptr
   return B2S_OK;
 }
 
+}  // extern "C"
+
+template <typename R> static int launch_pipeline_t(b2s_sim* s, DState<R>& st, int phases, int nsub, const R* action) {
+  if (!st.wsg) {
+    R* p = nullptr;
+    if (cudaMalloc(&p, (size_t)s->n_env * s->L.total * sizeof(R)) != cudaSuccess) return fail(B2S_ERR_CUDA, "cudaMalloc(pipeline workspace) failed");
+    cudaMemsetAsync(p, 0, (size_t)s->n_env * s->L.total * sizeof(R), s->stream);
+    s->allocs.push_back(p);
+    st.wsg = p;
+    s->dirty = 1;
+    static bool attr_done[2] = {false, false};
+    (void)attr_done;
+  }
+  int rc = bind_constants(s);
+  if (rc != B2S_OK) return rc;
+  int blocks = (s->n_env + s->wpb - 1) / s->wpb, threads = s->wpb * 32;
+  for (int sub = 0; sub < nsub; sub++) {
+    phase_kernel<R, 0><<<blocks, threads, s->smem_bytes, s->stream>>>(phases, sub, nsub, action);
+    phase_kernel<R, 1><<<blocks, threads, s->smem_bytes, s->stream>>>(phases, sub, nsub, action);
+    phase_kernel<R, 2><<<blocks, threads, s->smem_bytes, s->stream>>>(phases, sub, nsub, action);
+    if (phases & PH_CTRL) phase_kernel<R, 3><<<blocks, threads, s->smem_bytes, s->stream>>>(phases, sub, nsub, action);
+    phase_kernel<R, 4><<<blocks, threads, s->smem_bytes, s->stream>>>(phases, sub, nsub, action);
+    s->launches += (phases & PH_CTRL) ? 5 : 4;
+  }
+  CUDA_TRY(cudaGetLastError());
+  return B2S_OK;
+}
+static int launch_pipeline(b2s_sim* s, int phases, int nsub, const void* action) {
+  return s->precision == B2S_F32 ? launch_pipeline_t<float>(s, s->sf, phases, nsub, (const float*)action)
+                                 : launch_pipeline_t<double>(s, s->sd, phases, nsub, (const double*)action);
+}
+
+extern "C" {
+
+int b2s_set_mode(b2s_sim* s, int mode) {
+  if (!s || (mode != 0 && mode != 1)) return fail(B2S_ERR_ARG, "b2s_set_mode: mode must be 0 (fused) or 1 (pipeline)");
+  s->mode = mode;
+  return B2S_OK;
+}
+
 int b2s_reset(b2s_sim* s, const uint8_t* mask) {
   if (!s) return fail(B2S_ERR_ARG, "null handle");
   { int rc = bind_constants(s); if (rc != B2S_OK) return rc; }
@@ -470,6 +549,7 @@ int b2s_step1(b2s_sim* s) { return s ? launch(s, PH_STEP1 | PH_EXPORT, 1) : fail
 int b2s_step2(b2s_sim* s) { return s ? launch(s, PH_STEP1 | PH_STEP2 | PH_EXPORT, 1) : fail(B2S_ERR_ARG, "null handle"); }
 int b2s_step(b2s_sim* s, int n) {
   if (!s || n < 1) return fail(B2S_ERR_ARG, "b2s_step: bad argument");
+  if (s->mode == 1) return launch_pipeline(s, PH_STEP1 | PH_STEP2, n, nullptr);
   return launch(s, PH_STEP1 | PH_STEP2, n);
 }
 
@@ -517,6 +597,8 @@ int b2s_ctrl_reset(b2s_sim* s, const uint8_t* mask) {
 
 int b2s_env_step(b2s_sim* s, const void* action, int nsub) {
   if (!s || !s->has_ctrl || !action || nsub < 1) return fail(B2S_ERR_ARG, "b2s_env_step: bad argument / controller not configured");
+  if (s->mode == 1 && !s->export_env_step && !s->profile)
+    return launch_pipeline(s, PH_STEP1 | PH_STEP2 | PH_CTRL | (s->has_obs ? PH_OBS : 0), nsub, action);
   return launch(s, PH_STEP1 | PH_STEP2 | PH_CTRL | (s->has_obs ? PH_OBS : 0) | (s->export_env_step ? PH_EXPORT : 0) | (s->profile ? PH_PROFILE : 0), nsub, action);
 }
 

@@ -76,6 +76,7 @@ struct DState {
   R* obs;          // [n_env, obs_dim] sampled after the first substep of a control step (observables.py:230-240)
   float* prof;     // [n_env, 12] cycles per phase (PH_PROFILE)
   int* dbg;        // [n_env, 4] analytic candidates, convex candidates, EPA calls, reserved
+  R* wsg;          // [n_env, L.total] global workspace rows (pipeline mode)
   R* task_out;     // [n_env, 4]: target body height, |grip site - target body|, grasp flag, reserved
 };
 
@@ -91,8 +92,16 @@ struct WSLayout {
   int J, e_D, e_R, e_aref, e_jar, e_jv, e_force, e_floss, e_int;        // e_int: 2 ints per row (type,id)
   int Ma, grad, search, Mv;
   int scratch, scratch_size;
+  int hdr;  // 8 words of per-env integers passed between pipeline phases: ncon, nefc, warn, niter
   int total;
 };
+
+// Pipeline mode: the substep is split into phase kernels; each phase loads / stores these workspace regions
+// from / to the per-environment global workspace row (L2 resident).
+struct Region { int off, len, dyn; };  // dyn: 0 fixed, 1 = nefc*nv words (constraint Jacobian)
+#define B2S_NPHASE 5
+#define B2S_MAXREG 20
+struct PhaseIO { int nload, nstore; Region load[B2S_MAXREG], store[B2S_MAXREG]; };
 
 // observation scalar ops (one table entry per output scalar)
 enum { OB_QPOS = 0, OB_COS_QPOS, OB_SIN_QPOS, OB_QVEL, OB_QACC, OB_SITE_POS, OB_BODY_POS, OB_BODY_QUAT_XYZW, OB_SITE_QUAT_XYZW,
@@ -115,6 +124,7 @@ __constant__ DState<float> c_state_f;
 __constant__ DState<double> c_state_d;
 __constant__ WSLayout c_L;
 __constant__ CtrlCfgDev c_cc;
+__constant__ PhaseIO c_pio[B2S_NPHASE];
 template <typename R> __device__ __forceinline__ const DModel<R>& cmodel();
 template <> __device__ __forceinline__ const DModel<float>& cmodel<float>() { return c_model_f; }
 template <> __device__ __forceinline__ const DModel<double>& cmodel<double>() { return c_model_d; }

@@ -58,6 +58,7 @@ def lib():
         L.b2s_task_config.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.b2s_set_export.argtypes = [C.c_void_p, C.c_int]
         L.b2s_set_profile.argtypes = [C.c_void_p, C.c_int]
+        L.b2s_set_mode.argtypes = [C.c_void_p, C.c_int]
         L.b2s_launch_count.argtypes = [C.c_void_p]
         L.b2s_launch_count.restype = C.c_int64
         _LIB = L
@@ -190,6 +191,10 @@ class BatchedSim:
     def set_export(self, flag):
         """whether b2s_env_step also writes the derived arrays (xpos, contacts, ...) of its last substep to HBM"""
         self._check(self._L.b2s_set_export(self._h, int(bool(flag))))
+
+    def set_mode(self, mode):
+        """0 = fused single kernel, 1 = pipelined phase kernels (identical results)"""
+        self._check(self._L.b2s_set_mode(self._h, int(mode)))
 
     def set_profile(self, flag):
         self._check(self._L.b2s_set_profile(self._h, int(bool(flag))))

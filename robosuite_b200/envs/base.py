@@ -85,7 +85,8 @@ class BatchedMujocoEnv:
     def __init__(self, robots="Panda", num_envs=1, device=0, controller_configs=None, control_freq=20, horizon=500,
                  ignore_done=False, reward_scale=1.0, reward_shaping=False, use_object_obs=True, seed=None,
                  initialization_noise="default", precision="f32", xml=None, has_renderer=False,
-                 has_offscreen_renderer=False, use_camera_obs=False, hard_reset=False, lite_physics=True, **kwargs):
+                 has_offscreen_renderer=False, use_camera_obs=False, hard_reset=False, lite_physics=True, model=None,
+                 **kwargs):
         import torch
 
         if has_renderer or has_offscreen_renderer or use_camera_obs:
@@ -102,7 +103,7 @@ class BatchedMujocoEnv:
         self.use_object_obs = use_object_obs
         self.initialization_noise = {"magnitude": 0.02, "type": "gaussian"} if initialization_noise == "default" \
             else (initialization_noise or {"magnitude": 0.0, "type": "gaussian"})
-        self.model = self._load_model(xml)
+        self.model = model if model is not None else self._load_model(xml)
         self.model_timestep = self.model.opt_timestep
         self.control_timestep = 1.0 / control_freq
         if control_freq <= 0:
