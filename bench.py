@@ -273,7 +273,7 @@ def run_gpu(args):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        n_env, n_steps = max(cores, 8) * 2, 6
+        n_env, n_steps = max(cores, 8) * 2, 150
         r, dtc = cpu_oracle_rate(n_env, n_steps, cores)
         cpu = {"value": r, "unit": "env-steps/s", "cores": cores, "kind": "port",
                "sample": f"{n_env} Lift envs x {n_steps} control steps ({dtc:.1f}s), oracle port (fp64 C) incl. OSC, {cores} threads"}

@@ -62,7 +62,7 @@ struct b2s_sim {
   int nq = 0, nv = 0, nu = 0, nbody = 0, ngeom = 0, nsite = 0, maxcon = 0, maxefc = 0;
   std::vector<double> qpos0;
   std::vector<int> site_bodyid, cgid;
-  int has_obs = 0, export_env_step = 1, dirty = 1, profile = 0, mode = 0;
+  int has_obs = 0, export_env_step = 1, dirty = 1, profile = 0, mode = 0, worklist = 1;
   PhaseIO pio[B2S_NPHASE];
   std::map<std::string, Region> reg;
 };
@@ -503,6 +503,11 @@ template <typename R> static int launch_pipeline_t(b2s_sim* s, DState<R>& st, in
     cudaMemsetAsync(p, 0, (size_t)s->n_env * s->L.total * sizeof(R), s->stream);
     s->allocs.push_back(p);
     st.wsg = p;
+    size_t ne = (size_t)s->n_env;
+    st.cl_cnt = dev_zeros<int>(s, 2);
+    st.cl_listA = dev_zeros<int>(s, ne * CL_MAXA); st.cl_listG = dev_zeros<int>(s, ne * CL_MAXG);
+    st.cl_outA = dev_zeros<R>(s, ne * CL_MAXA * CL_RECA); st.cl_outG = dev_zeros<R>(s, ne * CL_MAXG * 8);
+    st.cl_env = dev_zeros<int>(s, ne * CL_ENVW);
     s->dirty = 1;
     static bool attr_done[2] = {false, false};
     (void)attr_done;
@@ -510,13 +515,26 @@ template <typename R> static int launch_pipeline_t(b2s_sim* s, DState<R>& st, in
   int rc = bind_constants(s);
   if (rc != B2S_OK) return rc;
   int blocks = (s->n_env + s->wpb - 1) / s->wpb, threads = s->wpb * 32;
+  const int epaw = (9 * EPA_MAXV + 4 * EPA_MAXF + EPA_MAXF + 8) * (int)sizeof(R);
+  const bool worklist = s->worklist != 0;
+  if (worklist) phases |= PH_WORKLIST;
   for (int sub = 0; sub < nsub; sub++) {
+    if (worklist) cudaMemsetAsync(st.cl_cnt, 0, 2 * sizeof(int), s->stream);
     phase_kernel<R, 0><<<blocks, threads, s->smem_bytes, s->stream>>>(phases, sub, nsub, action);
-    phase_kernel<R, 1><<<blocks, threads, s->smem_bytes, s->stream>>>(phases, sub, nsub, action);
+    if (worklist) {
+      // upper bounds of the candidate counts size the grids; threads / warps beyond the device-side count exit at once
+      int nA = s->n_env * CL_MAXA, nG = s->n_env * CL_MAXG;
+      narrow_analytic_kernel<R><<<(nA + 127) / 128, 128, 0, s->stream>>>();
+      narrow_convex_kernel<R><<<(nG + 7) / 8, 256, 8 * epaw, s->stream>>>();
+      s->launches += 2;
+    } else {
+      phase_kernel<R, 1><<<blocks, threads, s->smem_bytes, s->stream>>>(phases, sub, nsub, action);
+      s->launches += 1;
+    }
     phase_kernel<R, 2><<<blocks, threads, s->smem_bytes, s->stream>>>(phases, sub, nsub, action);
     if (phases & PH_CTRL) phase_kernel<R, 3><<<blocks, threads, s->smem_bytes, s->stream>>>(phases, sub, nsub, action);
     phase_kernel<R, 4><<<blocks, threads, s->smem_bytes, s->stream>>>(phases, sub, nsub, action);
-    s->launches += (phases & PH_CTRL) ? 5 : 4;
+    s->launches += (phases & PH_CTRL) ? 4 : 3;
   }
   CUDA_TRY(cudaGetLastError());
   return B2S_OK;

@@ -31,6 +31,22 @@ DEV void shape_get(const Eng<R>& e, int g, Shape<R>& s) {
   }
 }
 
+template <typename R>
+DEV void shape_from(int g, const R* gpos, const R* gmat, Shape<R>& s) {
+  const DModel<R>& m = cmodel<R>();
+  int k = m.geom_cgid[g];
+  s.type = m.geom_type[g];
+  s.pos = gpos + 3 * k;
+  s.mat = gmat + 9 * k;
+  s.size[0] = m.geom_size[3 * g]; s.size[1] = m.geom_size[3 * g + 1]; s.size[2] = m.geom_size[3 * g + 2];
+  s.vert = nullptr; s.nvert = 0;
+  if (s.type == G_MESH) {
+    int id = m.geom_dataid[g];
+    s.vert = m.mesh_vert + 3 * m.mesh_vertadr[id];
+    s.nvert = m.mesh_vertnum[id];
+  }
+}
+
 template <typename R> DEV void make_frame(R* f) {
   R* x = f; R* y = f + 3; R* z = f + 6;
   v3normalize(x);
@@ -773,6 +789,75 @@ template <typename R> DEV void mix_contact(const DModel<R>& m, int g1, int g2, R
   }
   dim = max(m.geom_condim[g1], m.geom_condim[g2]);
   for (int k = 0; k < 3; k++) fric3[k] = r_max(m.geom_friction[3 * g1 + k], m.geom_friction[3 * g2 + k]);
+}
+
+template <typename R> DEV int narrow_analytic(const Shape<R>& A, const Shape<R>& B, R* buf) {
+  int t1 = A.type, t2 = B.type, n = 0;
+  if (t1 == G_PLANE) {
+    if (t2 == G_SPHERE) n = plane_sphere(A, B, buf, 8);
+    else if (t2 == G_BOX) n = plane_box(A, B, buf, 8);
+    else if (t2 == G_CYLINDER) n = plane_cylinder(A, B, buf, 8);
+    else if (t2 == G_MESH) n = plane_mesh(A, B, buf, 8);
+  } else if (t1 == G_SPHERE && t2 == G_SPHERE) n = sphere_sphere(A, B, buf, 8);
+  else if (t1 == G_SPHERE && t2 == G_BOX) n = sphere_box(A, B, buf, 8);
+  else if (t1 == G_SPHERE && t2 == G_CYLINDER) n = sphere_cylinder(A, B, buf, 8);
+  else if (t1 == G_BOX && t2 == G_BOX) n = box_box(A, B, buf, 8);
+  return n;
+}
+
+// Cull the static pair list (bounding spheres, then oriented boxes); candidate pair indices in pair order.
+template <typename R> DEVN void cull_pairs(Eng<R> e, int* cand, int* cand_g, int maxa, int maxg, int& na_out, int& ng_out) {
+  const DModel<R>& m = cmodel<R>();
+  const WSLayout& L = c_L;
+  int lane = e.lane, na = 0, ng = 0;
+  const R* gpos = e.p(L.gpos); const R* gmat = e.p(L.gmat);
+  for (int base = 0; base < m.npair; base += 32) {
+    int pidx = base + lane;
+    int pass = 0, isg = 0;
+    if (pidx < m.npair) {
+      int g1 = m.pair_geom[2 * pidx], g2 = m.pair_geom[2 * pidx + 1];
+      int t1 = m.geom_type[g1], t2 = m.geom_type[g2];
+      int k1 = m.geom_cgid[g1], k2 = m.geom_cgid[g2];
+      if (t1 != G_PLANE && t2 != G_PLANE) {
+        R df[3];
+        v3sub(df, gpos + 3 * k1, gpos + 3 * k2);
+        R bound = m.geom_rbound[g1] + m.geom_rbound[g2];
+        pass = v3dot(df, df) <= bound * bound;
+      } else {
+        int kp = t1 == G_PLANE ? k1 : k2, ko = t1 == G_PLANE ? k2 : k1, go = t1 == G_PLANE ? g2 : g1;
+        R nrm[3] = COLV(gmat + 9 * kp, 2), df[3];
+        v3sub(df, gpos + 3 * ko, gpos + 3 * kp);
+        pass = v3dot(df, nrm) <= m.geom_rbound[go];
+      }
+      if (pass) pass = obb_overlap(e, g1, g2);
+      isg = is_gjk_pair<R>(t1, t2);
+    }
+    unsigned ma = __ballot_sync(B2S_FULL, pass && !isg), mg = __ballot_sync(B2S_FULL, pass && isg);
+    unsigned lt = (1u << lane) - 1;
+    if (pass && !isg) { int r = na + __popc(ma & lt); if (r < maxa) cand[r] = pidx; }
+    if (pass && isg) { int r = ng + __popc(mg & lt); if (r < maxg) cand_g[r] = pidx; }
+    na += __popc(ma);
+    ng += __popc(mg);
+  }
+  na_out = na; ng_out = ng;
+  __syncwarp();
+}
+
+// per contact: condim + friction mixing (shared by the fused and the pipelined collision paths)
+template <typename R> DEV void finish_contacts(const Eng<R>& e, int ncon) {
+  const DModel<R>& m = cmodel<R>();
+  const WSLayout& L = c_L;
+  R* cfric = e.p(L.c_fric);
+  int* cint = e.pi(L.c_int);
+  for (int c = e.lane; c < ncon; c += 32) {
+    R f3[3];
+    int dim;
+    mix_contact(m, cint[5 * c], cint[5 * c + 1], f3, dim);
+    cfric[3 * c] = f3[0]; cfric[3 * c + 1] = f3[1]; cfric[3 * c + 2] = f3[2];
+    cint[5 * c + 2] = dim;
+    cint[5 * c + 3] = -1;
+  }
+  __syncwarp();
 }
 
 // Fills the contact arrays in the workspace; returns ncon (warp-uniform).  warn bit 4 on overflow.

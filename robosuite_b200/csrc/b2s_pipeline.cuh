@@ -31,6 +31,99 @@ template <typename R> DEV void ws_store(const Eng<R>& e, R* row, const PhaseIO& 
   }
 }
 
+// ---- work-list narrow phase --------------------------------------------------------------------------------------
+// analytic pairs: ONE THREAD per candidate pair of any environment (32 different pairs per warp)
+template <typename R>
+__global__ void __launch_bounds__(128) narrow_analytic_kernel() {
+  const DModel<R>& m = cmodel<R>();
+  const DState<R>& s = cstate<R>();
+  const WSLayout& L = c_L;
+  int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= s.cl_cnt[0]) return;
+  int code = s.cl_listA[tid];
+  int env = code >> 12, pidx = code & 4095;
+  const R* row = s.wsg + (size_t)env * L.total;
+  int g1 = m.pair_geom[2 * pidx], g2 = m.pair_geom[2 * pidx + 1];
+  if (m.geom_type[g1] > m.geom_type[g2]) { int t = g1; g1 = g2; g2 = t; }
+  Shape<R> A, B;
+  shape_from(g1, row + L.gpos, row + L.gmat, A);
+  shape_from(g2, row + L.gpos, row + L.gmat, B);
+  R buf[8 * CREC];
+  int n = narrow_analytic(A, B, buf);
+  R* out = s.cl_outA + (size_t)tid * CL_RECA;
+  out[0] = R(n);
+  for (int k = 0; k < n * CREC; k++) out[1 + k] = buf[k];
+}
+
+// convex pairs: ONE WARP per candidate pair (mesh support scans split over the lanes); EPA polytope in shared memory
+template <typename R>
+__global__ void __launch_bounds__(256) narrow_convex_kernel() {
+  const DModel<R>& m = cmodel<R>();
+  const DState<R>& s = cstate<R>();
+  const WSLayout& L = c_L;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  int wid = blockIdx.x * wpb + warp;
+  if (wid >= s.cl_cnt[1]) return;
+  const int EPAW = 9 * EPA_MAXV + 4 * EPA_MAXF + EPA_MAXF + 8;
+  R* scratch = reinterpret_cast<R*>(smem_raw) + (size_t)warp * EPAW;
+  int code = s.cl_listG[wid];
+  int env = code >> 12, pidx = code & 4095;
+  const R* row = s.wsg + (size_t)env * L.total;
+  int g1 = m.pair_geom[2 * pidx], g2 = m.pair_geom[2 * pidx + 1];
+  if (m.geom_type[g1] > m.geom_type[g2]) { int t = g1; g1 = g2; g2 = t; }
+  Shape<R> A, B;
+  shape_from(g1, row + L.gpos, row + L.gmat, A);
+  shape_from(g2, row + L.gpos, row + L.gmat, B);
+  R buf[CREC];
+  int n = convex_convex(A, B, buf, 1, scratch, lane);
+  R* out = s.cl_outG + (size_t)wid * 8;
+  if (lane == 0) {
+    out[0] = R(n);
+    for (int k = 0; k < CREC; k++) out[1 + k] = n ? buf[k] : R(0);
+  }
+}
+
+// collect this environment's contacts from the work-list outputs, in static-pair order (what the fused collide produces)
+template <typename R> DEVN int gather_contacts(Eng<R> e, int env, int& warn) {
+  const DModel<R>& m = cmodel<R>();
+  const DState<R>& s = cstate<R>();
+  const WSLayout& L = c_L;
+  int lane = e.lane;
+  const int* tab = s.cl_env + (size_t)env * CL_ENVW;
+  int na = tab[0], ng = tab[1], nc = na + ng;  // nc <= 24 <= 32 lanes
+  int pair = 0x7fffffff, slot = 0, isg = 0, n = 0;
+  if (lane < na) { pair = tab[2 + 2 * lane]; slot = tab[3 + 2 * lane]; n = (int)s.cl_outA[(size_t)slot * CL_RECA]; }
+  else if (lane < nc) { int k = lane - na; isg = 1; pair = tab[2 + 2 * (CL_MAXA + k)]; slot = tab[3 + 2 * (CL_MAXA + k)]; n = (int)s.cl_outG[(size_t)slot * 8]; }
+  // contact offset = contacts of candidates with a smaller pair index
+  int off = 0;
+  for (int o = 0; o < nc; o++) {
+    int op = __shfl_sync(B2S_FULL, pair, o), on = __shfl_sync(B2S_FULL, n, o);
+    if (op < pair) off += on;
+  }
+  int total = warp_sum_i(lane < nc ? n : 0);
+  R* cpos = e.p(L.c_pos); R* cfr = e.p(L.c_frame); R* cdist = e.p(L.c_dist);
+  int* cint = e.pi(L.c_int);
+  if (lane < nc) {
+    const R* rec = isg ? s.cl_outG + (size_t)slot * 8 + 1 : s.cl_outA + (size_t)slot * CL_RECA + 1;
+    int g1 = m.pair_geom[2 * pair], g2 = m.pair_geom[2 * pair + 1];
+    if (m.geom_type[g1] > m.geom_type[g2]) { int t = g1; g1 = g2; g2 = t; }
+    for (int k = 0; k < n; k++) {
+      int c = off + k;
+      if (c >= m.maxcon) break;
+      const R* b = rec + CREC * k;
+      cpos[3 * c] = b[0]; cpos[3 * c + 1] = b[1]; cpos[3 * c + 2] = b[2];
+      cfr[3 * c] = b[3]; cfr[3 * c + 1] = b[4]; cfr[3 * c + 2] = b[5];
+      cdist[c] = b[6];
+      cint[5 * c] = g1; cint[5 * c + 1] = g2; cint[5 * c + 4] = pair;
+    }
+  }
+  if (total > m.maxcon) { total = m.maxcon; warn |= 4; }
+  __syncwarp();
+  finish_contacts(e, total);
+  return total;
+}
+
 // PH: 0 kinematics+velocity+crb, 1 collision, 2 constraint rows, 3 controller, 4 actuation+solve+integrate(+obs)
 template <typename R, int PH>
 __global__ void __launch_bounds__(512, 1) phase_kernel(int phases, int sub, int nsub, const R* action) {
@@ -64,14 +157,35 @@ __global__ void __launch_bounds__(512, 1) phase_kernel(int phases, int sub, int 
     e.kinematics();
     e.velocity();
     e.crb();
+    // collision candidates of this environment -> global work lists (slots by warp-aggregated atomics)
+    int* cand = reinterpret_cast<int*>(e.p(L.scratch));
+    int* cand_g = cand + 48;
+    int na, ng;
+    cull_pairs(e, cand, cand_g, CL_MAXA, CL_MAXG, na, ng);
+    if (na > CL_MAXA) { na = CL_MAXA; warn |= 4; }
+    if (ng > CL_MAXG) { ng = CL_MAXG; warn |= 4; }
+    int baseA = 0, baseG = 0;
+    if (lane == 0) {
+      if (na) baseA = atomicAdd(s.cl_cnt, na);
+      if (ng) baseG = atomicAdd(s.cl_cnt + 1, ng);
+    }
+    baseA = __shfl_sync(B2S_FULL, baseA, 0);
+    baseG = __shfl_sync(B2S_FULL, baseG, 0);
+    int* tab = s.cl_env + E * CL_ENVW;
+    if (lane == 0) { tab[0] = na; tab[1] = ng; }
+    if (lane < na) { s.cl_listA[baseA + lane] = (env << 12) | cand[lane]; tab[2 + 2 * lane] = cand[lane]; tab[3 + 2 * lane] = baseA + lane; }
+    if (lane < ng) { s.cl_listG[baseG + lane] = (env << 12) | cand_g[lane]; tab[2 + 2 * (CL_MAXA + lane)] = cand_g[lane]; tab[3 + 2 * (CL_MAXA + lane)] = baseG + lane; }
+    hdr[0] = 0; hdr[1] = 0;
+    if (lane == 0) { hdr[2] = warn; reinterpret_cast<int*>(row + L.hdr)[2] = warn; }
   } else if (PH == 1) {
     int dbgc[3] = {0, 0, 0};
     ncon = collide(e, warn, dbgc);
     if (lane == 0) { hdr[0] = ncon; hdr[1] = 0; hdr[2] = warn; hdr[3] = 0; }
     __syncwarp();
   } else if (PH == 2) {
+    if (phases & PH_WORKLIST) ncon = gather_contacts(e, env, warn);
     nefc = make_constraint(e, ncon, warn);
-    if (lane == 0) { hdr[1] = nefc; hdr[2] = warn; }
+    if (lane == 0) { hdr[0] = ncon; hdr[1] = nefc; hdr[2] = warn; }
     __syncwarp();
   } else if (PH == 3) {
     CtrlState<R> cs;

@@ -22,6 +22,7 @@ enum {
   PH_CTRL = 16,      // run the fused controller between step1 and step2
   PH_POLICY = 32,    // first substep of a control step: consume `action` (set_goal)
   PH_PROFILE = 128,  // accumulate per-phase clock() cycles per environment into `prof`
+  PH_WORKLIST = 256, // pipeline mode: collision narrow phase runs as global work-list kernels
   PH_OBS = 64        // write the observation row (after substep 0) and the task outputs (after the last substep)
 };
 
@@ -77,6 +78,13 @@ struct DState {
   float* prof;     // [n_env, 12] cycles per phase (PH_PROFILE)
   int* dbg;        // [n_env, 4] analytic candidates, convex candidates, EPA calls, reserved
   R* wsg;          // [n_env, L.total] global workspace rows (pipeline mode)
+  // pipeline-mode collision work lists (candidate pairs of ALL environments, compacted with atomics)
+  int* cl_cnt;     // [2] number of analytic / convex candidates this substep
+  int* cl_listA;   // [n_env * CL_MAXA] env << 12 | pair
+  int* cl_listG;   // [n_env * CL_MAXG]
+  R* cl_outA;      // [n_env * CL_MAXA][CL_RECA] count + 8 x (pos3 normal3 dist)
+  R* cl_outG;      // [n_env * CL_MAXG][8]       count + (pos3 normal3 dist)
+  int* cl_env;     // [n_env][2 + 2 * (CL_MAXA + CL_MAXG)] na, ng, then (pair, slot) of each candidate
   R* task_out;     // [n_env, 4]: target body height, |grip site - target body|, grasp flag, reserved
 };
 
@@ -100,6 +108,10 @@ struct WSLayout {
 // from / to the per-environment global workspace row (L2 resident).
 struct Region { int off, len, dyn; };  // dyn: 0 fixed, 1 = nefc*nv words (constraint Jacobian)
 #define B2S_NPHASE 5
+#define CL_MAXA 8
+#define CL_MAXG 16
+#define CL_RECA 58
+#define CL_ENVW (2 + 2 * (CL_MAXA + CL_MAXG))
 #define B2S_MAXREG 20
 struct PhaseIO { int nload, nstore; Region load[B2S_MAXREG], store[B2S_MAXREG]; };
 
