@@ -333,7 +333,7 @@ static void build_layout(b2s_sim* s, int nq, int nv, int nu, int nb, int ncg, in
   int sc = 10 * nb;
   int epa = 96 + 9 * EPA_MAXV + 4 * EPA_MAXF + EPA_MAXF + 8;
   if (epa > sc) sc = epa;
-  int hs = me + hc_stride * mc;
+  int hs = me + hc_stride * mc + 64;  // + support dof list of the Hessian assembly
   if (hs > sc) sc = hs;
   if (9 * mc > sc) sc = 9 * mc;
   if (sc < 720) sc = 720;  // fused controller work area (336 doubles)
@@ -508,6 +508,7 @@ template <typename R> static int launch_pipeline_t(b2s_sim* s, DState<R>& st, in
     st.cl_listA = dev_zeros<int>(s, ne * CL_MAXA); st.cl_listG = dev_zeros<int>(s, ne * CL_MAXG);
     st.cl_outA = dev_zeros<R>(s, ne * CL_MAXA * CL_RECA); st.cl_outG = dev_zeros<R>(s, ne * CL_MAXG * 8);
     st.cl_env = dev_zeros<int>(s, ne * CL_ENVW);
+    st.gjk_cache = dev_zeros<R>(s, ne * (size_t)(s->precision == B2S_F32 ? s->mf.npair : s->md.npair) * 3);
     s->dirty = 1;
     static bool attr_done[2] = {false, false};
     (void)attr_done;

@@ -508,26 +508,38 @@ template <typename R> DEVN int closest_tet(SV<R>* s, int& n, R* lam) {
 
 // returns 1 if the cores overlap (simplex valid), else 0 with dist / witnesses
 template <typename R>
-DEVN int gjk(const Shape<R>& A, const Shape<R>& B, SV<R>* simplex, int& ns, R& dist, R* wa, R* wb, R cutoff, int lane) {
+DEVN int gjk(const Shape<R>& A, const Shape<R>& B, SV<R>* simplex, int& ns, R& dist, R* wa, R* wb, R cutoff, int lane, R* cache = nullptr) {
   const R tol_vv = sizeof(R) == 4 ? R(1e-16) : R(1e-24);
   const R tol_rel = sizeof(R) == 4 ? R(1e-6) : R(1e-12);
   R v[3], nv[3];
   v3sub(v, A.pos, B.pos);
   if (v3dot(v, v) < R(1e-20)) v3set(v, R(1), R(0), R(0));
+  if (cache) {  // separating direction found for this pair on the previous substep (temporal coherence)
+    R cv[3] = {cache[0], cache[1], cache[2]};
+    if (v3dot(cv, cv) > R(1e-12)) v3copy(v, cv);
+  }
   int n = 0;
   R lam[4] = {1, 0, 0, 0};
   v3scl(nv, v, R(-1));
   sv_support(A, B, nv, simplex[0], lane);
   n = 1;
+  if (cache && cutoff >= 0) {  // does the remembered direction still separate the pair?  (one support pair, no iteration)
+    R vv0 = v3dot(v, v), vw0 = v3dot(v, simplex[0].w);
+    if (vw0 > 0 && vw0 * vw0 > cutoff * cutoff * vv0) { dist = cutoff + 1; ns = 1; return 0; }
+  }
   v3copy(v, simplex[0].w);
   for (int it = 0; it < 64; it++) {
     R vv = v3dot(v, v);
-    if (vv < tol_vv) { ns = n; return 1; }
+    if (vv < tol_vv) { ns = n; if (cache && lane == 0) { cache[0] = 0; cache[1] = 0; cache[2] = 0; } return 1; }
     SV<R> w;
     v3scl(nv, v, R(-1));
     sv_support(A, B, nv, w, lane);
     R vw = v3dot(v, w.w);
-    if (cutoff >= 0 && vw > 0 && vw * vw > cutoff * cutoff * vv) { dist = cutoff + 1; ns = n; return 0; }
+    if (cutoff >= 0 && vw > 0 && vw * vw > cutoff * cutoff * vv) {
+      dist = cutoff + 1; ns = n;
+      if (cache && lane == 0) { cache[0] = v[0]; cache[1] = v[1]; cache[2] = v[2]; }
+      return 0;
+    }
     if (vv - vw <= tol_rel * vv) break;
     int dup = 0;
     for (int k = 0; k < n; k++) {
@@ -539,12 +551,13 @@ DEVN int gjk(const Shape<R>& A, const Shape<R>& B, SV<R>* simplex, int& ns, R& d
     simplex[n++] = w;
     if (n == 2) closest_seg(simplex, n, lam);
     else if (n == 3) closest_tri(simplex, n, lam);
-    else if (closest_tet(simplex, n, lam)) { ns = 4; return 1; }
+    else if (closest_tet(simplex, n, lam)) { ns = 4; if (cache && lane == 0) { cache[0] = 0; cache[1] = 0; cache[2] = 0; } return 1; }
     v3set(v, R(0), R(0), R(0));
     for (int k = 0; k < n; k++) v3addscl(v, v, simplex[k].w, lam[k]);
   }
   ns = n;
   dist = v3norm(v);
+  if (cache && lane == 0) { cache[0] = v[0]; cache[1] = v[1]; cache[2] = v[2]; }
   v3set(wa, R(0), R(0), R(0));
   v3set(wb, R(0), R(0), R(0));
   for (int k = 0; k < n; k++) { v3addscl(wa, wa, simplex[k].a, lam[k]); v3addscl(wb, wb, simplex[k].b, lam[k]); }
@@ -696,12 +709,12 @@ DEVN int epa(const Shape<R>& A, const Shape<R>& B, SV<R>* simplex, int ns, R& de
 }
 
 template <typename R>
-DEVN int convex_convex(const Shape<R>& A, const Shape<R>& B, R* out, int maxn, R* scratch, int lane) {
+DEVN int convex_convex(const Shape<R>& A, const Shape<R>& B, R* out, int maxn, R* scratch, int lane, R* cache = nullptr) {
   SV<R> simplex[4];
   int ns = 0;
   R dist = 0, wa[3], wb[3], n[3], pos[3], pa[3], pb[3];
   R ra = shape_radius(A), rb = shape_radius(B);
-  int hit = gjk(A, B, simplex, ns, dist, wa, wb, ra + rb, lane);
+  int hit = gjk(A, B, simplex, ns, dist, wa, wb, ra + rb, lane, cache);
   if (!hit) {
     if (ra + rb <= 0 || dist > ra + rb) return 0;
     v3sub(n, wb, wa);

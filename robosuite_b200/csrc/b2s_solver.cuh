@@ -387,6 +387,7 @@ template <typename R> DEVN int solve(Eng<R> e, int nefc, int ncon, int& warn) {
   R* jar = e.p(L.e_jar); R* jv = e.p(L.e_jv); R* force = e.p(L.e_force); const R* aref = e.p(L.e_aref);
   R* Ma = e.p(L.Ma); R* grad = e.p(L.grad); R* search = e.p(L.search); R* Mv = e.p(L.Mv);
   const int* cint = e.pi(L.c_int);
+  const int* eint = e.pi(L.e_int);
   R* act = e.p(L.scratch); R* Hcb = e.p(L.scratch) + m.maxefc;
   R scale = R(1) / (m.meaninertia * R(nv > 1 ? nv : 1));
   int first_contact_row = nefc;
@@ -444,41 +445,67 @@ template <typename R> DEVN int solve(Eng<R> e, int nefc, int ncon, int& warn) {
     }
     R gnorm = r_sqrt(warp_sum(gn));
     __syncwarp();
+    // fp32: cost differences below the rounding noise of the cost itself carry no information
+    const R noise = sizeof(R) == 4 ? R(16) * Lim<R>::eps() * r_abs(cost) : R(0);
     if (iter > 0) {
       R improvement = scale * (prev_cost - cost);
-      if (improvement < m.tolerance || scale * gnorm < m.tolerance) break;
+      if (improvement < m.tolerance || prev_cost - cost < noise || scale * gnorm < m.tolerance) break;
     } else if (scale * gnorm < m.tolerance) break;
     if (iter == m.iterations) break;
     prev_cost = cost;
     niter = iter + 1;
-    // --- Hessian (lower triangle, one entry per lane round): H = M + J^T act J + cone blocks
-    for (int w = lane; w < nv * (nv + 1) / 2; w += 32) {
-      // unrank w -> (a, b), b <= a
-      int a = (int)((r_sqrt(R(8 * w + 1)) - R(1)) * R(0.5));
-      while ((a + 1) * (a + 2) / 2 <= w) a++;
-      while (a * (a + 1) / 2 > w) a--;
-      int b = w - a * (a + 1) / 2;
-      R s = M[a * nv + b];
-      for (int r = 0; r < nefc; r++) {
-        R d = act[r];
-        if (d != 0) s += d * J[r * nv + a] * J[r * nv + b];
+    // --- Hessian H = M + J^T act J + cone blocks, exploiting row structure:
+    //   friction-loss / limit rows are +-unit vectors -> diagonal terms only;
+    //   a contact's rows touch only the dofs that move exactly one of its two bodies -> entries on that support only
+    for (int k = lane; k < nv * nv; k += 32) H[k] = M[k];
+    __syncwarp();
+    for (int r = lane; r < first_contact_row; r += 32) {
+      R d = act[r];
+      if (d != 0) {
+        int ty = eint[r] & 255, id = eint[r] >> 8;
+        int dof = ty == C_FRICTION ? id : m.jnt_dofadr[id];
+        atomicAdd(&H[dof * nv + dof], d);
       }
+    }
+    __syncwarp();
+    {
+      int* dofs = reinterpret_cast<int*>(Hcb + m.hc_stride * m.maxcon);
       for (int c = 0; c < ncon; c++) {
         int adr = cint[5 * c + 3];
         if (adr < 0) continue;
-        const R* h = Hcb + m.hc_stride * c;
-        if (h[0] < 0) continue;
         int dim = cint[5 * c + 2];
-        for (int x = 0; x < dim; x++) {
-          R ja = J[(adr + x) * nv + a];
-          if (ja == 0) continue;
-          R t = 0;
-          for (int y = 0; y < dim; y++) t += h[x * dim + y] * J[(adr + y) * nv + b];
-          s += ja * t;
+        const R* h = Hcb + m.hc_stride * c;
+        bool cone = h[0] >= 0;
+        bool any = cone;
+        for (int k = 0; k < dim && !any; k++) any = act[adr + k] != 0;
+        if (!any) continue;
+        unsigned long long mask = m.body_dofmask[m.geom_bodyid[cint[5 * c]]] ^ m.body_dofmask[m.geom_bodyid[cint[5 * c + 1]]];
+        int ns = __popcll(mask);
+        for (int i = lane; i < nv; i += 32)
+          if ((mask >> i) & 1ull) dofs[__popcll(mask & ((1ull << i) - 1ull))] = i;
+        __syncwarp();
+        int ne = ns * (ns + 1) / 2;
+        for (int w = lane; w < ne; w += 32) {
+          int ia = (int)((r_sqrt(R(8 * w + 1)) - R(1)) * R(0.5));
+          while ((ia + 1) * (ia + 2) / 2 <= w) ia++;
+          while (ia * (ia + 1) / 2 > w) ia--;
+          int ib = w - ia * (ia + 1) / 2;
+          int a = dofs[ia], b = dofs[ib];
+          R sacc = 0;
+          if (cone) {
+            for (int x = 0; x < dim; x++) {
+              R t = 0;
+              for (int y = 0; y < dim; y++) t += h[x * dim + y] * J[(adr + y) * nv + b];
+              sacc += J[(adr + x) * nv + a] * t;
+            }
+          } else {
+            for (int k = 0; k < dim; k++) sacc += act[adr + k] * J[(adr + k) * nv + a] * J[(adr + k) * nv + b];
+          }
+          H[a * nv + b] += sacc;
+          if (a != b) H[b * nv + a] += sacc;
         }
+        __syncwarp();
       }
-      H[a * nv + b] = s;
-      H[b * nv + a] = s;
     }
     for (int i = lane; i < nv; i += 32) search[i] = -grad[i];
     __syncwarp();
@@ -502,7 +529,10 @@ template <typename R> DEVN int solve(Eng<R> e, int nefc, int ncon, int& warn) {
     R d1, d2, alpha = 0, lo = 0, hi = -1;
     ls_eval(e, nefc, ncon, first_contact_row, R(0), quad1, quad2, d1, d2);
     if (d1 >= 0) break;
-    R gtol = (sizeof(R) == 4 ? R(1e-5) : R(1e-12)) * r_abs(d1);
+    // Newton decrement: -d1(0) = grad^T H^-1 grad.  When half of it is below the stopping tolerance this step is the
+    // last one: take it and skip the iteration that would only confirm convergence.
+    bool last = R(0.5) * scale * (-d1) < m.tolerance || R(0.5) * (-d1) < noise;
+    R gtol = (sizeof(R) == 4 ? R(1e-3) : R(1e-12)) * r_abs(d1);
     alpha = -d1 / d2;
     for (int ls = 0; ls < (sizeof(R) == 4 ? 20 : 100); ls++) {
       ls_eval(e, nefc, ncon, first_contact_row, alpha, quad1, quad2, d1, d2);
@@ -516,6 +546,7 @@ template <typename R> DEVN int solve(Eng<R> e, int nefc, int ncon, int& warn) {
     }
     for (int i = lane; i < nv; i += 32) qacc[i] += alpha * search[i];
     __syncwarp();
+    if (last) break;
   }
   // --- final forces at the solution
   for (int r = lane; r < nefc; r += 32) {

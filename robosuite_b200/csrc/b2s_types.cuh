@@ -84,6 +84,7 @@ struct DState {
   int* cl_listG;   // [n_env * CL_MAXG]
   R* cl_outA;      // [n_env * CL_MAXA][CL_RECA] count + 8 x (pos3 normal3 dist)
   R* cl_outG;      // [n_env * CL_MAXG][8]       count + (pos3 normal3 dist)
+  R* gjk_cache;    // [n_env][npair][3] last separating direction of each convex pair (GJK warm start)
   int* cl_env;     // [n_env][2 + 2 * (CL_MAXA + CL_MAXG)] na, ng, then (pair, slot) of each candidate
   R* task_out;     // [n_env, 4]: target body height, |grip site - target body|, grasp flag, reserved
 };

@@ -10,6 +10,7 @@ for t in range(100):
 torch.cuda.synchronize()
 sim.set_mode(1)
 a = torch.rand((4096, 7), generator=g, device="cuda") * 2 - 1
-sim.env_step(a, 25)
+for _ in range(3):
+    sim.env_step(a, 25)
 torch.cuda.synchronize()
 print("done")
