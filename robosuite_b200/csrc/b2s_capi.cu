@@ -62,7 +62,10 @@ struct b2s_sim {
   int nq = 0, nv = 0, nu = 0, nbody = 0, ngeom = 0, nsite = 0, maxcon = 0, maxefc = 0;
   std::vector<double> qpos0;
   std::vector<int> site_bodyid, cgid;
-  int has_obs = 0, export_env_step = 1, dirty = 1, profile = 0, mode = 0, worklist = 1;
+  int has_obs = 0, export_env_step = 1, dirty = 1, profile = 0, mode = 0, worklist = 1, ngroups = 4;
+  std::vector<cudaStream_t> gstreams;
+  std::vector<cudaEvent_t> gevents;
+  cudaEvent_t fork_event = nullptr;
   PhaseIO pio[B2S_NPHASE];
   std::map<std::string, Region> reg;
 };
@@ -436,6 +439,9 @@ void b2s_destroy(b2s_sim* s) {
   if (g_owner[s->device & 63] == s) g_owner[s->device & 63] = nullptr;
   cudaSetDevice(s->device);
   for (void* p : s->allocs) cudaFree(p);
+  for (auto q : s->gstreams) cudaStreamDestroy(q);
+  for (auto ev : s->gevents) cudaEventDestroy(ev);
+  if (s->fork_event) cudaEventDestroy(s->fork_event);
   delete s;
 }
 
@@ -504,7 +510,7 @@ template <typename R> static int launch_pipeline_t(b2s_sim* s, DState<R>& st, in
     s->allocs.push_back(p);
     st.wsg = p;
     size_t ne = (size_t)s->n_env;
-    st.cl_cnt = dev_zeros<int>(s, 2);
+    st.cl_cnt = dev_zeros<int>(s, 2 * 64);
     st.cl_listA = dev_zeros<int>(s, ne * CL_MAXA); st.cl_listG = dev_zeros<int>(s, ne * CL_MAXG);
     st.cl_outA = dev_zeros<R>(s, ne * CL_MAXA * CL_RECA); st.cl_outG = dev_zeros<R>(s, ne * CL_MAXG * 8);
     st.cl_env = dev_zeros<int>(s, ne * CL_ENVW);
@@ -515,27 +521,44 @@ template <typename R> static int launch_pipeline_t(b2s_sim* s, DState<R>& st, in
   }
   int rc = bind_constants(s);
   if (rc != B2S_OK) return rc;
-  int blocks = (s->n_env + s->wpb - 1) / s->wpb, threads = s->wpb * 32;
+  const int threads = s->wpb * 32;
   const int epaw = (9 * EPA_MAXV + 4 * EPA_MAXF + EPA_MAXF + 8) * (int)sizeof(R);
-  const bool worklist = s->worklist != 0;
-  if (worklist) phases |= PH_WORKLIST;
-  for (int sub = 0; sub < nsub; sub++) {
-    if (worklist) cudaMemsetAsync(st.cl_cnt, 0, 2 * sizeof(int), s->stream);
-    phase_kernel<R, 0><<<blocks, threads, s->smem_bytes, s->stream>>>(phases, sub, nsub, action);
-    if (worklist) {
-      // upper bounds of the candidate counts size the grids; threads / warps beyond the device-side count exit at once
-      int nA = s->n_env * CL_MAXA, nG = s->n_env * CL_MAXG;
-      narrow_analytic_kernel<R><<<(nA + 127) / 128, 128, 0, s->stream>>>();
-      narrow_convex_kernel<R><<<(nG + 7) / 8, 256, 8 * epaw, s->stream>>>();
-      s->launches += 2;
-    } else {
-      phase_kernel<R, 1><<<blocks, threads, s->smem_bytes, s->stream>>>(phases, sub, nsub, action);
-      s->launches += 1;
+  phases |= PH_WORKLIST;
+  // environment groups on their own streams (created lazily); fork from / join to the handle's stream with events
+  int G = s->ngroups;
+  if (G > s->n_env) G = s->n_env;
+  if ((int)s->gstreams.size() < G) {
+    while ((int)s->gstreams.size() < G) {
+      cudaStream_t st2; cudaEvent_t ev;
+      CUDA_TRY(cudaStreamCreateWithFlags(&st2, cudaStreamNonBlocking));
+      CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      s->gstreams.push_back(st2); s->gevents.push_back(ev);
     }
-    phase_kernel<R, 2><<<blocks, threads, s->smem_bytes, s->stream>>>(phases, sub, nsub, action);
-    if (phases & PH_CTRL) phase_kernel<R, 3><<<blocks, threads, s->smem_bytes, s->stream>>>(phases, sub, nsub, action);
-    phase_kernel<R, 4><<<blocks, threads, s->smem_bytes, s->stream>>>(phases, sub, nsub, action);
-    s->launches += (phases & PH_CTRL) ? 4 : 3;
+    if (!s->fork_event) CUDA_TRY(cudaEventCreateWithFlags(&s->fork_event, cudaEventDisableTiming));
+  }
+  CUDA_TRY(cudaEventRecord(s->fork_event, s->stream));
+  for (int gi = 0; gi < G; gi++) {
+    cudaStream_t q = G == 1 ? s->stream : s->gstreams[gi];
+    if (G > 1) CUDA_TRY(cudaStreamWaitEvent(q, s->fork_event, 0));
+    int e0 = (int)((long long)s->n_env * gi / G), e1 = (int)((long long)s->n_env * (gi + 1) / G);
+    Grp g{e0, e1 - e0, gi};
+    int blocks = (g.nenv + s->wpb - 1) / s->wpb;
+    int nA = g.nenv * CL_MAXA, nG = g.nenv * CL_MAXG;
+    for (int sub = 0; sub < nsub; sub++) {
+      cudaMemsetAsync(st.cl_cnt + 2 * gi, 0, 2 * sizeof(int), q);
+      phase_kernel<R, 0><<<blocks, threads, s->smem_bytes, q>>>(phases, sub, nsub, action, g);
+      // upper bounds of the candidate counts size the grids; threads / warps beyond the device-side count exit at once
+      narrow_analytic_kernel<R><<<(nA + 127) / 128, 128, 0, q>>>(g);
+      narrow_convex_kernel<R><<<(nG + 7) / 8, 256, 8 * epaw, q>>>(g);
+      phase_kernel<R, 2><<<blocks, threads, s->smem_bytes, q>>>(phases, sub, nsub, action, g);
+      if (phases & PH_CTRL) phase_kernel<R, 3><<<blocks, threads, s->smem_bytes, q>>>(phases, sub, nsub, action, g);
+      phase_kernel<R, 4><<<blocks, threads, s->smem_bytes, q>>>(phases, sub, nsub, action, g);
+      s->launches += (phases & PH_CTRL) ? 6 : 5;
+    }
+    if (G > 1) {
+      CUDA_TRY(cudaEventRecord(s->gevents[gi], q));
+      CUDA_TRY(cudaStreamWaitEvent(s->stream, s->gevents[gi], 0));
+    }
   }
   CUDA_TRY(cudaGetLastError());
   return B2S_OK;
@@ -550,6 +573,8 @@ extern "C" {
 int b2s_set_mode(b2s_sim* s, int mode) {
   if (!s || (mode != 0 && mode != 1)) return fail(B2S_ERR_ARG, "b2s_set_mode: mode must be 0 (fused) or 1 (pipeline)");
   s->mode = mode;
+  const char* eg = getenv("B2S_GROUPS");
+  if (eg) { int v = atoi(eg); if (v >= 1 && v <= 64) s->ngroups = v; }
   return B2S_OK;
 }
 

@@ -31,15 +31,20 @@ template <typename R> DEV void ws_store(const Eng<R>& e, R* row, const PhaseIO& 
   }
 }
 
+// A launch covers one group of environments [env0, env0 + nenv); groups run on separate streams so that the tail of one
+// group's kernel (its slowest environment) overlaps with other groups' work.
+struct Grp { int env0, nenv, gid; };
+
 // ---- work-list narrow phase --------------------------------------------------------------------------------------
 // analytic pairs: ONE THREAD per candidate pair of any environment (32 different pairs per warp)
 template <typename R>
-__global__ void __launch_bounds__(128) narrow_analytic_kernel() {
+__global__ void __launch_bounds__(128) narrow_analytic_kernel(Grp g) {
   const DModel<R>& m = cmodel<R>();
   const DState<R>& s = cstate<R>();
   const WSLayout& L = c_L;
   int tid = blockIdx.x * blockDim.x + threadIdx.x;
-  if (tid >= s.cl_cnt[0]) return;
+  if (tid >= s.cl_cnt[2 * g.gid]) return;
+  tid += g.env0 * CL_MAXA;  // this group's slice of the candidate list / output slots
   int code = s.cl_listA[tid];
   int env = code >> 12, pidx = code & 4095;
   const R* row = s.wsg + (size_t)env * L.total;
@@ -57,14 +62,15 @@ __global__ void __launch_bounds__(128) narrow_analytic_kernel() {
 
 // convex pairs: ONE WARP per candidate pair (mesh support scans split over the lanes); EPA polytope in shared memory
 template <typename R>
-__global__ void __launch_bounds__(256) narrow_convex_kernel() {
+__global__ void __launch_bounds__(256) narrow_convex_kernel(Grp g) {
   const DModel<R>& m = cmodel<R>();
   const DState<R>& s = cstate<R>();
   const WSLayout& L = c_L;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   int wid = blockIdx.x * wpb + warp;
-  if (wid >= s.cl_cnt[1]) return;
+  if (wid >= s.cl_cnt[2 * g.gid + 1]) return;
+  wid += g.env0 * CL_MAXG;
   const int EPAW = 9 * EPA_MAXV + 4 * EPA_MAXF + EPA_MAXF + 8;
   R* scratch = reinterpret_cast<R*>(smem_raw) + (size_t)warp * EPAW;
   int code = s.cl_listG[wid];
@@ -126,7 +132,7 @@ template <typename R> DEVN int gather_contacts(Eng<R> e, int env, int& warn) {
 
 // PH: 0 kinematics+velocity+crb, 1 collision, 2 constraint rows, 3 controller, 4 actuation+solve+integrate(+obs)
 template <typename R, int PH>
-__global__ void __launch_bounds__(512, 1) phase_kernel(int phases, int sub, int nsub, const R* action) {
+__global__ void __launch_bounds__(512, 1) phase_kernel(int phases, int sub, int nsub, const R* action, Grp g) {
   const DModel<R>& m = cmodel<R>();
   const DState<R>& s = cstate<R>();
   const WSLayout& L = c_L;
@@ -135,7 +141,8 @@ __global__ void __launch_bounds__(512, 1) phase_kernel(int phases, int sub, int 
   R* smem = reinterpret_cast<R*>(smem_raw);
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   int env = blockIdx.x * wpb + warp;
-  if (env >= s.n_env) return;
+  if (env >= g.nenv) return;
+  env += g.env0;
   Eng<R> e(smem + (size_t)warp * L.total, lane);
   size_t E = env;
   R* row = s.wsg + E * L.total;
@@ -166,8 +173,8 @@ __global__ void __launch_bounds__(512, 1) phase_kernel(int phases, int sub, int 
     if (ng > CL_MAXG) { ng = CL_MAXG; warn |= 4; }
     int baseA = 0, baseG = 0;
     if (lane == 0) {
-      if (na) baseA = atomicAdd(s.cl_cnt, na);
-      if (ng) baseG = atomicAdd(s.cl_cnt + 1, ng);
+      if (na) baseA = g.env0 * CL_MAXA + atomicAdd(s.cl_cnt + 2 * g.gid, na);
+      if (ng) baseG = g.env0 * CL_MAXG + atomicAdd(s.cl_cnt + 2 * g.gid + 1, ng);
     }
     baseA = __shfl_sync(B2S_FULL, baseA, 0);
     baseG = __shfl_sync(B2S_FULL, baseG, 0);
