@@ -307,7 +307,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--preroll", type=int, default=100, help="untimed control steps before the timed region")
-    ap.add_argument("--mode", type=int, default=0, help="0 fused kernel, 1 phase-kernel pipeline")
+    ap.add_argument("--mode", type=int, default=1, help="0 fused kernel, 1 phase-kernel pipeline (default)")
     ap.add_argument("--allgather-obs", type=int, default=1, help="N>1: all-gather observations over NCCL every e2e step")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl != "reference":

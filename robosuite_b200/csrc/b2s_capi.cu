@@ -185,6 +185,27 @@ template <typename R> static void build_model(b2s_sim* s, const Blob& b, DModel<
     dofmask[i] = dofmask[parent[i]];
     for (int d = 0; d < dofnum[i]; d++) dofmask[i] |= 1ull << (dofadr[i] + d);
   }
+  // kinematic trees: dofs of one tree are contiguous (DFS numbering); world-welded bodies have tree id -1
+  const int* rootid = b.i32("body_rootid");
+  std::vector<int> treebase(nv, 0), treesize(nv, 0), body_tree(nb, -1);
+  {
+    std::vector<int> root_first(nb, -1), root_last(nb, -1);
+    for (int i = 0; i < nv; i++) {
+      int r = rootid[dofbody[i]];
+      if (root_first[r] < 0) root_first[r] = i;
+      root_last[r] = i;
+    }
+    int mx = 0;
+    for (int i = 0; i < nv; i++) {
+      int r = rootid[dofbody[i]];
+      treebase[i] = root_first[r];
+      treesize[i] = root_last[r] - root_first[r] + 1;
+      if (treesize[i] > mx) mx = treesize[i];
+    }
+    m.max_treesize = mx;
+    for (int i = 1; i < nb; i++) body_tree[i] = weld[i] == 0 ? -1 : rootid[i];
+  }
+  m.dof_treebase = dev_upload(s, treebase); m.dof_treesize = dev_upload(s, treesize); m.body_treeid = dev_upload(s, body_tree);
   std::vector<int> ment_i, ment_j;
   for (int i = 0; i < nv; i++)
     for (int j = i; j >= 0; j = dofpar[j]) { ment_i.push_back(i); ment_j.push_back(j); }
@@ -358,7 +379,7 @@ static void build_layout(b2s_sim* s, int nq, int nv, int nu, int nb, int ncg, in
   };
   mk(s->pio[0], {}, {"xpos", "xquat", "xmat", "cdof", "cvel", "M", "bias", "passive", "spos", "smat", "gpos", "gmat"});
   mk(s->pio[1], {"gpos", "gmat"}, {"c_pos", "c_frame", "c_dist", "c_fric", "c_int"});
-  mk(s->pio[2], {"c_pos", "c_frame", "c_dist", "c_fric", "c_int", "cdof"}, {"J", "e_D", "e_R", "e_aref", "e_floss", "e_int", "c_int"});
+  mk(s->pio[2], {"cdof"}, {"J", "e_D", "e_R", "e_aref", "e_floss", "e_int", "c_int", "c_fric", "c_dist"});
   mk(s->pio[3], {"cdof", "cvel", "M", "bias", "spos", "smat"}, {});
   mk(s->pio[4], {"M", "bias", "passive", "J", "e_D", "e_R", "e_aref", "e_floss", "e_int", "c_fric", "c_int", "c_dist", "xpos", "xquat", "spos", "smat"}, {});
 }
@@ -514,7 +535,7 @@ template <typename R> static int launch_pipeline_t(b2s_sim* s, DState<R>& st, in
     st.cl_listA = dev_zeros<int>(s, ne * CL_MAXA); st.cl_listG = dev_zeros<int>(s, ne * CL_MAXG);
     st.cl_outA = dev_zeros<R>(s, ne * CL_MAXA * CL_RECA); st.cl_outG = dev_zeros<R>(s, ne * CL_MAXG * 8);
     st.cl_env = dev_zeros<int>(s, ne * CL_ENVW);
-    st.gjk_cache = dev_zeros<R>(s, ne * (size_t)(s->precision == B2S_F32 ? s->mf.npair : s->md.npair) * 3);
+    st.gjk_cache = getenv("B2S_NO_GJK_CACHE") ? nullptr : dev_zeros<R>(s, ne * (size_t)(s->precision == B2S_F32 ? s->mf.npair : s->md.npair) * 3);
     s->dirty = 1;
     static bool attr_done[2] = {false, false};
     (void)attr_done;

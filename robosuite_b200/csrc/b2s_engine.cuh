@@ -61,6 +61,59 @@ DEVN int spd_solve_reg(const R* A, int n, const R* dadd, R dscale, R* x, int lan
   return bad;
 }
 
+// Block-diagonal variant: the matrix couples dofs only within kinematic trees (always true for M and M + h D, true for
+// the Newton Hessian when no active contact joins two different moving trees).  Every tree is eliminated at the same
+// time by its own lanes: lane i keeps row i restricted to its tree's columns (NVB = padded size of the largest tree).
+template <typename R, int NVB>
+DEVN int spd_solve_blk(const R* A, int n, const R* dadd, R dscale, R* x, int lane) {
+  const DModel<R>& m = cmodel<R>();
+  R a[NVB];
+  int row = lane < n ? lane : 0;
+  int base = m.dof_treebase[row], size = m.dof_treesize[row];
+  int li = row - base;  // local index of this lane's row inside its tree
+  if (lane >= n) size = 0;
+  R dl = (dadd != nullptr && lane < n) ? dscale * dadd[row] : R(0);
+#pragma unroll
+  for (int k = 0; k < NVB; k++) {
+    R v = (k < size) ? A[row * n + base + (k < size ? k : 0)] : R(0);
+    a[k] = v + ((k == li && lane < n) ? dl : R(0));
+  }
+  R b = lane < n ? x[row] : R(0);
+  R invd = 1;
+  int bad = 0;
+#pragma unroll
+  for (int j = 0; j < NVB; j++) {
+    bool on = j < size;
+    int src = on ? base + j : lane;
+    R d = __shfl_sync(B2S_FULL, a[j], src);
+    if (on && !(d > Lim<R>::minval())) { bad = 1; d = Lim<R>::minval(); }
+    if (!on) d = 1;
+    R inv = r_rsqrt(d);
+    invd = (on && li == j) ? inv : invd;
+    a[j] = (on && li >= j) ? a[j] * inv : a[j];
+#pragma unroll
+    for (int k = j + 1; k < NVB; k++) {
+      R u = __shfl_sync(B2S_FULL, a[k] * inv, src);
+      a[k] = !on ? a[k] : ((li == j) ? u : ((li > j) ? a[k] - a[j] * u : a[k]));
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NVB; k++) {
+    bool on = k < size;
+    R yk = __shfl_sync(B2S_FULL, b * invd, on ? base + k : lane);
+    b = !on ? b : ((li == k) ? yk : ((li > k) ? b - a[k] * yk : b));
+  }
+#pragma unroll
+  for (int k = NVB - 1; k >= 0; k--) {
+    bool on = k < size;
+    R xk = __shfl_sync(B2S_FULL, b * invd, on ? base + k : lane);
+    b = !on ? b : ((li == k) ? xk : ((li < k) ? b - a[k] * xk : b));
+  }
+  if (lane < n) x[lane] = b;
+  __syncwarp();
+  return __any_sync(B2S_FULL, bad);
+}
+
 template <typename R>
 struct Eng {
   R* ws;  // this warp's workspace
@@ -402,7 +455,13 @@ struct Eng {
 
 
   // x <- (A + dscale*diag(dadd))^-1 x ; A symmetric n x n in shared memory (not modified unless n > 32)
-  DEV int spd_solve(R* A, int n, const R* dadd, R dscale, R* x, R* work) {
+  // blockdiag: the caller guarantees that A has no entries between different kinematic trees
+  DEV int spd_solve(R* A, int n, const R* dadd, R dscale, R* x, R* work, bool blockdiag = false) {
+    if (blockdiag && n <= 32) {
+      int ts = cmodel<R>().max_treesize;
+      if (ts <= 8) return spd_solve_blk<R, 8>(A, n, dadd, dscale, x, lane);
+      if (ts <= 12) return spd_solve_blk<R, 12>(A, n, dadd, dscale, x, lane);
+    }
     if (n <= 16) return spd_solve_reg<R, 16>(A, n, dadd, dscale, x, lane);
     if (n <= 24) return spd_solve_reg<R, 24>(A, n, dadd, dscale, x, lane);
     if (n <= 32) return spd_solve_reg<R, 32>(A, n, dadd, dscale, x, lane);
@@ -448,7 +507,7 @@ struct Eng {
       qa[i] = v;
     }
     __syncwarp();
-    return spd_solve(p(L.M), nv, (const R*)nullptr, R(0), qa, p(L.H));
+    return spd_solve(p(L.M), nv, (const R*)nullptr, R(0), qa, p(L.H), true);
   }
 
   // ------------------------------------------------------------------------------------------- Euler
@@ -460,7 +519,7 @@ struct Eng {
     R* a = p(L.grad);  // reuse solver vector as the integration acceleration
     for (int i = lane; i < nv; i += 32) a[i] = p(L.qsmooth)[i] + p(L.qcon)[i];
     __syncwarp();
-    int bad = spd_solve(p(L.M), nv, m.dof_damping, h, a, p(L.H));
+    int bad = spd_solve(p(L.M), nv, m.dof_damping, h, a, p(L.H), true);
     R* qvel = p(L.qvel); R* qpos = p(L.qpos);
     for (int i = lane; i < nv; i += 32) qvel[i] += h * a[i];
     __syncwarp();

@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(256) narrow_convex_kernel(Grp g) {
   shape_from(g1, row + L.gpos, row + L.gmat, A);
   shape_from(g2, row + L.gpos, row + L.gmat, B);
   R buf[CREC];
-  int n = convex_convex(A, B, buf, 1, scratch, lane, s.gjk_cache + ((size_t)env * m.npair + pidx) * 3);
+  int n = convex_convex(A, B, buf, 1, scratch, lane, s.gjk_cache ? s.gjk_cache + ((size_t)env * m.npair + pidx) * 3 : (R*)nullptr);
   R* out = s.cl_outG + (size_t)wid * 8;
   if (lane == 0) {
     out[0] = R(n);

@@ -392,6 +392,13 @@ template <typename R> DEVN int solve(Eng<R> e, int nefc, int ncon, int& warn) {
   R scale = R(1) / (m.meaninertia * R(nv > 1 ? nv : 1));
   int first_contact_row = nefc;
   for (int c = 0; c < ncon; c++) { int a = cint[5 * c + 3]; if (a >= 0) { first_contact_row = a; break; } }
+  // does any constraint couple two different moving trees?  (then the Hessian is not block diagonal)
+  bool cross_tree = false;
+  for (int c = 0; c < ncon; c++) {
+    if (cint[5 * c + 3] < 0) continue;
+    int t1 = m.body_treeid[m.geom_bodyid[cint[5 * c]]], t2 = m.body_treeid[m.geom_bodyid[cint[5 * c + 1]]];
+    if (t1 >= 0 && t2 >= 0 && t1 != t2) cross_tree = true;
+  }
 
   // --- warm start: previous qacc unless the unconstrained acceleration is cheaper
   R cost_ws = 0, cost_sm = 0;
@@ -509,7 +516,7 @@ template <typename R> DEVN int solve(Eng<R> e, int nefc, int ncon, int& warn) {
     }
     for (int i = lane; i < nv; i += 32) search[i] = -grad[i];
     __syncwarp();
-    if (e.spd_solve(H, nv, (const R*)nullptr, R(0), search, H)) { warn |= 16; break; }
+    if (e.spd_solve(H, nv, (const R*)nullptr, R(0), search, H, !cross_tree)) { warn |= 16; break; }
     // --- exact line search
     R q1 = 0, q2 = 0;
     for (int i = lane; i < nv; i += 32) {

@@ -28,7 +28,7 @@ enum {
 
 template <typename R>
 struct DModel {
-  int nq, nv, nu, nbody, njnt, ngeom, nsite, npair, ncg, nment, maxdepth, maxcon, maxefc, nmocap, nfl, nlim, hc_stride;
+  int nq, nv, nu, nbody, njnt, ngeom, nsite, npair, ncg, nment, maxdepth, maxcon, maxefc, nmocap, nfl, nlim, hc_stride, max_treesize;
   R timestep, impratio, density, viscosity, tolerance, meaninertia;
   int iterations, ls_iterations;
   R gravity[3];
@@ -40,7 +40,7 @@ struct DModel {
   const int *jnt_type, *jnt_qposadr, *jnt_dofadr, *jnt_bodyid, *jnt_limited;
   const R *jnt_pos, *jnt_axis, *jnt_range, *jnt_solref, *jnt_solimp, *qpos0;
   // dofs
-  const int *dof_bodyid, *dof_jntid, *dof_parentid, *dof_kind, *dof_cddstart, *fl_dof, *lim_jnt;
+  const int *dof_bodyid, *dof_jntid, *dof_parentid, *dof_kind, *dof_cddstart, *fl_dof, *lim_jnt, *dof_treebase, *dof_treesize, *body_treeid;
   const unsigned long long* body_dofmask;  // bit i set: dof i is on the chain of this body
   const R *dof_armature, *dof_damping, *dof_frictionloss, *dof_solref, *dof_solimp, *dof_invweight0;
   // nonzero lower-triangular mass-matrix entries (i >= j, j on the chain of i)

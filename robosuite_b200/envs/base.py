@@ -86,7 +86,7 @@ class BatchedMujocoEnv:
                  ignore_done=False, reward_scale=1.0, reward_shaping=False, use_object_obs=True, seed=None,
                  initialization_noise="default", precision="f32", xml=None, has_renderer=False,
                  has_offscreen_renderer=False, use_camera_obs=False, hard_reset=False, lite_physics=True, model=None,
-                 **kwargs):
+                 kernel_mode="pipeline", **kwargs):
         import torch
 
         if has_renderer or has_offscreen_renderer or use_camera_obs:
@@ -124,6 +124,8 @@ class BatchedMujocoEnv:
         self.sim.obs_config(op, a, b)
         self._setup_task()
         self.sim.set_export(False)
+        # "pipeline": phase kernels + global collision work lists (fastest in steady state); "fused": one kernel per step
+        self.sim.set_mode(1 if kernel_mode == "pipeline" else 0)
         self.rng = torch.Generator(device=self.device)
         self.seed = seed
         if seed is not None:

@@ -202,8 +202,8 @@ def test_env_step_f32_100_control_steps():
     assert eq < 5e-2
 
 
-def test_pipeline_mode_matches_fused():
-    """the phase-kernel pipeline and the fused kernel run the same device functions: results must agree"""
+def _scripted_rollout(mode, steps, no_cache):
+    import os
     import torch
     from robosuite_b200 import controller_config as cc
     from robosuite_b200.engine import BatchedSim, CtrlCfg
@@ -212,23 +212,44 @@ def test_pipeline_mode_matches_fused():
     n = 16
     q, v = lift_states(model, n, seed=21)
     rng = np.random.default_rng(3)
-    actions = rng.uniform(-1, 1, size=(6, n, 7))
-    out = []
-    for mode in (0, 1):
-        sim = BatchedSim(model, n, precision="f32")
-        sim.ctrl_config(cc.resolve(model, cc.default_composite_config(), CtrlCfg))
-        sim.set_export(False)
-        sim.set_mode(mode)
-        sim.qpos.copy_(torch.as_tensor(q, dtype=torch.float32))
-        sim.forward()
-        sim.ctrl_reset()
-        for t in range(6):
-            sim.env_step(torch.as_tensor(actions[t], dtype=torch.float32, device=sim.torch_device).contiguous(), 25)
-        torch.cuda.synchronize()
-        assert int(sim.warn.abs().max()) == 0
-        out.append((sim.qpos.cpu().numpy().copy(), sim.qvel.cpu().numpy().copy(), sim.ctrl.cpu().numpy().copy()))
-        sim.close()
-    dq = np.abs(out[0][0] - out[1][0]).max()
-    dv = np.abs(out[0][1] - out[1][1]).max()
-    print("pipeline vs fused: max |dqpos| %.3g max |dqvel| %.3g" % (dq, dv))
-    assert dq < 1e-5 and dv < 1e-3
+    actions = rng.uniform(-1, 1, size=(steps, n, 7))
+    actions[:, :, 6] = 1.0  # keep closing the gripper: sliding / sticking finger contacts exercise the friction cones
+    actions[8:, : n // 2, :3] = [0.0, 0.0, -1.0]  # half of the arms push down onto the table / cube
+    if no_cache:
+        os.environ["B2S_NO_GJK_CACHE"] = "1"
+    else:
+        os.environ.pop("B2S_NO_GJK_CACHE", None)
+    sim = BatchedSim(model, n, precision="f32")
+    sim.ctrl_config(cc.resolve(model, cc.default_composite_config(), CtrlCfg))
+    sim.set_export(False)
+    sim.set_mode(mode)
+    sim.qpos.copy_(torch.as_tensor(q, dtype=torch.float32))
+    sim.forward()
+    sim.ctrl_reset()
+    for t in range(steps):
+        sim.env_step(torch.as_tensor(actions[t], dtype=torch.float32, device=sim.torch_device).contiguous(), 25)
+    torch.cuda.synchronize()
+    assert int(sim.warn.abs().max()) == 0
+    out = (sim.qpos.cpu().numpy().copy(), sim.qvel.cpu().numpy().copy())
+    sim.close()
+    os.environ.pop("B2S_NO_GJK_CACHE", None)
+    return out
+
+
+def test_pipeline_mode_matches_fused_bit_exact():
+    """phase kernels + collision work lists run the same device functions as the fused kernel: without the GJK warm
+    start the two schedules are bit-identical over a contact-rich 1000-substep rollout"""
+    a = _scripted_rollout(0, 40, True)
+    b = _scripted_rollout(1, 40, True)
+    assert np.isfinite(b[0]).all()
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_pipeline_gjk_warm_start_changes_paths_not_results():
+    """the remembered separating direction only shortens GJK: over 300 substeps results stay within fp32 noise of the
+    fused kernel (beyond that, arms pressing on the table are chaotic and any rounding difference is amplified)"""
+    a = _scripted_rollout(0, 12, False)
+    b = _scripted_rollout(1, 12, False)
+    dq = np.abs(a[0] - b[0]).max()
+    print("pipeline(warm start) vs fused after 300 substeps: max |dqpos| %.3g" % dq)
+    assert dq < 1e-4
