@@ -364,7 +364,7 @@ static void build_layout(b2s_sim* s, int nq, int nv, int nu, int nb, int ncg, in
   L.scratch_size = sc;
   L.scratch = take(sc);
   L.hdr = take(8);
-  L.total = o;
+  L.total = (o + 3) & ~3;  // rows stay 16-byte aligned (TMA bulk copies of workspace regions)
   rec("xpos", L.xpos, 3 * nb); rec("xquat", L.xquat, 4 * nb); rec("xmat", L.xmat, 9 * nb); rec("cdof", L.cdof, 6 * nv);
   rec("cvel", L.cvel, 6 * nb); rec("M", L.M, nv * nv); rec("bias", L.bias, nv); rec("passive", L.passive, nv);
   rec("spos", L.spos, 3 * ns); rec("smat", L.smat, 9 * ns); rec("gpos", L.gpos, 3 * ncg); rec("gmat", L.gmat, 9 * ncg);

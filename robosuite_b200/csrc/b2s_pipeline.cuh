@@ -18,17 +18,106 @@ template <> DEV void row_copy<float>(float* dst, const float* src, int n, int la
   if ((n & 1) && lane == 0) dst[n - 1] = src[n - 1];
 }
 
-template <typename R> DEV void ws_load(const Eng<R>& e, const R* row, const PhaseIO& io, int nefc_nv) {
+#ifndef B2S_TMA
+#define B2S_TMA 1  // move workspace regions with the TMA bulk-copy engine (cp.async.bulk + mbarrier)
+#endif
+
+// ---- TMA 1-D bulk copies (SASS: UBLKCP).  One elected lane per warp issues the copies; completion of loads is signalled on
+// the warp's mbarrier (transaction bytes), stores are tracked with a bulk async-group.
+DEV unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+DEV void mbar_init(unsigned long long* bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+DEV void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+DEV void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+DEV void tma_load_1d(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+DEV void tma_store_1d(void* gdst, const void* smem_src, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+
+// 16-byte aligned interior of a region goes through TMA, the (<= 3 word) head and tail through ordinary lane copies
+template <typename R> DEV void span16(int off, int len, int& a0, int& a1) {
+  const int W = 16 / (int)sizeof(R);
+  a0 = (off + W - 1) / W * W;
+  a1 = (off + len) / W * W;
+  if (a1 < a0) a1 = a0;
+}
+
+template <typename R> DEV void ws_load(const Eng<R>& e, const R* row, const PhaseIO& io, int nefc_nv, unsigned long long* bar) {
+#if B2S_TMA
+  unsigned total = 0;
+  for (int k = 0; k < io.nload; k++) {
+    int len = io.load[k].dyn == 1 ? ((nefc_nv + 1) & ~1) : io.load[k].len, a0, a1;
+    span16<R>(io.load[k].off, len, a0, a1);
+    total += (unsigned)(a1 - a0) * sizeof(R);
+  }
+  if (e.lane == 0) {
+    mbar_expect_tx(bar, total);
+    for (int k = 0; k < io.nload; k++) {
+      int len = io.load[k].dyn == 1 ? ((nefc_nv + 1) & ~1) : io.load[k].len, a0, a1;
+      span16<R>(io.load[k].off, len, a0, a1);
+      if (a1 > a0) tma_load_1d(e.ws + a0, row + a0, (unsigned)(a1 - a0) * sizeof(R), bar);
+    }
+  }
+  for (int k = 0; k < io.nload; k++) {
+    int off = io.load[k].off, len = io.load[k].dyn == 1 ? ((nefc_nv + 1) & ~1) : io.load[k].len, a0, a1;
+    span16<R>(off, len, a0, a1);
+    int nh = (a0 < off + len ? a0 : off + len) - off, nt = off + len - a1;
+    if (e.lane < nh) e.ws[off + e.lane] = row[off + e.lane];
+    if (a1 > a0 && e.lane < nt) e.ws[a1 + e.lane] = row[a1 + e.lane];
+  }
+  mbar_wait(bar, 0);
+#else
   for (int k = 0; k < io.nload; k++) {
     int len = io.load[k].dyn == 1 ? ((nefc_nv + 1) & ~1) : io.load[k].len;
     row_copy(e.ws + io.load[k].off, row + io.load[k].off, len, e.lane);
   }
+#endif
 }
 template <typename R> DEV void ws_store(const Eng<R>& e, R* row, const PhaseIO& io, int nefc_nv) {
+#if B2S_TMA
+  __syncwarp();
+  if (e.lane == 0) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the async proxy
+    for (int k = 0; k < io.nstore; k++) {
+      int len = io.store[k].dyn == 1 ? ((nefc_nv + 1) & ~1) : io.store[k].len, a0, a1;
+      span16<R>(io.store[k].off, len, a0, a1);
+      if (a1 > a0) tma_store_1d(row + a0, e.ws + a0, (unsigned)(a1 - a0) * sizeof(R));
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  }
+  for (int k = 0; k < io.nstore; k++) {
+    int off = io.store[k].off, len = io.store[k].dyn == 1 ? ((nefc_nv + 1) & ~1) : io.store[k].len, a0, a1;
+    span16<R>(off, len, a0, a1);
+    int nh = (a0 < off + len ? a0 : off + len) - off, nt = off + len - a1;
+    if (e.lane < nh) row[off + e.lane] = e.ws[off + e.lane];
+    if (a1 > a0 && e.lane < nt) row[a1 + e.lane] = e.ws[a1 + e.lane];
+  }
+  if (e.lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  __syncwarp();
+#else
   for (int k = 0; k < io.nstore; k++) {
     int len = io.store[k].dyn == 1 ? ((nefc_nv + 1) & ~1) : io.store[k].len;
     row_copy(row + io.store[k].off, e.ws + io.store[k].off, len, e.lane);
   }
+#endif
 }
 
 // A launch covers one group of environments [env0, env0 + nenv); groups run on separate streams so that the tail of one
@@ -143,6 +232,9 @@ __global__ void __launch_bounds__(512, 1) phase_kernel(int phases, int sub, int 
   int env = blockIdx.x * wpb + warp;
   if (env >= g.nenv) return;
   env += g.env0;
+  __shared__ unsigned long long mbar[16];  // one transaction barrier per warp (TMA loads of its workspace regions)
+  if (lane == 0) mbar_init(&mbar[warp]);
+  __syncwarp();
   Eng<R> e(smem + (size_t)warp * L.total, lane);
   size_t E = env;
   R* row = s.wsg + E * L.total;
@@ -152,7 +244,7 @@ __global__ void __launch_bounds__(512, 1) phase_kernel(int phases, int sub, int 
     __syncwarp();
   }
   int ncon = PH >= 2 ? hdr[0] : 0, nefc = PH >= 3 ? hdr[1] : 0, warn = PH >= 2 ? hdr[2] : 0;
-  ws_load(e, row, io, nefc * m.nv);
+  ws_load(e, row, io, nefc * m.nv, &mbar[warp]);
   if (PH == 0 || PH == 2 || PH == 3 || PH == 4) {
     load_row(e.p(L.qpos), s.qpos + E * m.nq, m.nq, lane);
     load_row(e.p(L.qvel), s.qvel + E * m.nv, m.nv, lane);
