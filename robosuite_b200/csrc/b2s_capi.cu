@@ -65,7 +65,11 @@ struct b2s_sim {
   int has_obs = 0, export_env_step = 1, dirty = 1, profile = 0, mode = 0, worklist = 1, ngroups = 4;
   std::vector<cudaStream_t> gstreams;
   std::vector<cudaEvent_t> gevents;
-  cudaEvent_t fork_event = nullptr;
+  cudaEvent_t fork_event = nullptr, in_event = nullptr, out_event = nullptr;
+  cudaStream_t pstream = nullptr;
+  void* action_buf = nullptr;
+  int use_graph = 1;
+  std::map<long long, cudaGraphExec_t> graphs;
   PhaseIO pio[B2S_NPHASE];
   std::map<std::string, Region> reg;
 };
@@ -463,6 +467,10 @@ void b2s_destroy(b2s_sim* s) {
   for (auto q : s->gstreams) cudaStreamDestroy(q);
   for (auto ev : s->gevents) cudaEventDestroy(ev);
   if (s->fork_event) cudaEventDestroy(s->fork_event);
+  if (s->in_event) cudaEventDestroy(s->in_event);
+  if (s->out_event) cudaEventDestroy(s->out_event);
+  for (auto& kv : s->graphs) cudaGraphExecDestroy(kv.second);
+  if (s->pstream) cudaStreamDestroy(s->pstream);
   delete s;
 }
 
@@ -523,6 +531,39 @@ static int launch(b2s_sim* s, int phases, int nsub, const void* action = nullptr
 
 }  // extern "C"
 
+// enqueue the launches of `nsub` substeps for every environment group; `q0` is the stream the caller forks from / joins to
+template <typename R> static int enqueue_pipeline(b2s_sim* s, DState<R>& st, int phases, int nsub, const R* action, cudaStream_t q0) {
+  const int threads = s->wpb * 32;
+  const int epaw = (9 * EPA_MAXV + 4 * EPA_MAXF + EPA_MAXF + 8) * (int)sizeof(R);
+  int G = s->ngroups;
+  if (G > s->n_env) G = s->n_env;
+  CUDA_TRY(cudaEventRecord(s->fork_event, q0));
+  for (int gi = 0; gi < G; gi++) {
+    cudaStream_t q = G == 1 ? q0 : s->gstreams[gi];
+    if (G > 1) CUDA_TRY(cudaStreamWaitEvent(q, s->fork_event, 0));
+    int e0 = (int)((long long)s->n_env * gi / G), e1 = (int)((long long)s->n_env * (gi + 1) / G);
+    Grp g{e0, e1 - e0, gi};
+    int blocks = (g.nenv + s->wpb - 1) / s->wpb;
+    int nA = g.nenv * CL_MAXA, nG = g.nenv * CL_MAXG;
+    for (int sub = 0; sub < nsub; sub++) {
+      CUDA_TRY(cudaMemsetAsync(st.cl_cnt + 2 * gi, 0, 2 * sizeof(int), q));
+      phase_kernel<R, 0><<<blocks, threads, s->smem_bytes, q>>>(phases, sub, nsub, action, g);
+      // upper bounds of the candidate counts size the grids; threads / warps beyond the device-side count exit at once
+      narrow_analytic_kernel<R><<<(nA + 127) / 128, 128, 0, q>>>(g);
+      narrow_convex_kernel<R><<<(nG + 7) / 8, 256, 8 * epaw, q>>>(g);
+      phase_kernel<R, 2><<<blocks, threads, s->smem_bytes, q>>>(phases, sub, nsub, action, g);
+      if (phases & PH_CTRL) phase_kernel<R, 3><<<blocks, threads, s->smem_bytes, q>>>(phases, sub, nsub, action, g);
+      phase_kernel<R, 4><<<blocks, threads, s->smem_bytes, q>>>(phases, sub, nsub, action, g);
+    }
+    if (G > 1) {
+      CUDA_TRY(cudaEventRecord(s->gevents[gi], q));
+      CUDA_TRY(cudaStreamWaitEvent(q0, s->gevents[gi], 0));
+    }
+  }
+  CUDA_TRY(cudaGetLastError());
+  return B2S_OK;
+}
+
 template <typename R> static int launch_pipeline_t(b2s_sim* s, DState<R>& st, int phases, int nsub, const R* action) {
   if (!st.wsg) {
     R* p = nullptr;
@@ -536,52 +577,61 @@ template <typename R> static int launch_pipeline_t(b2s_sim* s, DState<R>& st, in
     st.cl_outA = dev_zeros<R>(s, ne * CL_MAXA * CL_RECA); st.cl_outG = dev_zeros<R>(s, ne * CL_MAXG * 8);
     st.cl_env = dev_zeros<int>(s, ne * CL_ENVW);
     st.gjk_cache = getenv("B2S_NO_GJK_CACHE") ? nullptr : dev_zeros<R>(s, ne * (size_t)(s->precision == B2S_F32 ? s->mf.npair : s->md.npair) * 3);
+    s->action_buf = dev_zeros<R>(s, ne * 16);
     s->dirty = 1;
-    static bool attr_done[2] = {false, false};
-    (void)attr_done;
   }
   int rc = bind_constants(s);
   if (rc != B2S_OK) return rc;
-  const int threads = s->wpb * 32;
-  const int epaw = (9 * EPA_MAXV + 4 * EPA_MAXF + EPA_MAXF + 8) * (int)sizeof(R);
   phases |= PH_WORKLIST;
-  // environment groups on their own streams (created lazily); fork from / join to the handle's stream with events
   int G = s->ngroups;
   if (G > s->n_env) G = s->n_env;
-  if ((int)s->gstreams.size() < G) {
-    while ((int)s->gstreams.size() < G) {
-      cudaStream_t st2; cudaEvent_t ev;
-      CUDA_TRY(cudaStreamCreateWithFlags(&st2, cudaStreamNonBlocking));
-      CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-      s->gstreams.push_back(st2); s->gevents.push_back(ev);
-    }
-    if (!s->fork_event) CUDA_TRY(cudaEventCreateWithFlags(&s->fork_event, cudaEventDisableTiming));
+  while ((int)s->gstreams.size() < G) {
+    cudaStream_t st2; cudaEvent_t ev;
+    CUDA_TRY(cudaStreamCreateWithFlags(&st2, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    s->gstreams.push_back(st2); s->gevents.push_back(ev);
   }
-  CUDA_TRY(cudaEventRecord(s->fork_event, s->stream));
-  for (int gi = 0; gi < G; gi++) {
-    cudaStream_t q = G == 1 ? s->stream : s->gstreams[gi];
-    if (G > 1) CUDA_TRY(cudaStreamWaitEvent(q, s->fork_event, 0));
-    int e0 = (int)((long long)s->n_env * gi / G), e1 = (int)((long long)s->n_env * (gi + 1) / G);
-    Grp g{e0, e1 - e0, gi};
-    int blocks = (g.nenv + s->wpb - 1) / s->wpb;
-    int nA = g.nenv * CL_MAXA, nG = g.nenv * CL_MAXG;
-    for (int sub = 0; sub < nsub; sub++) {
-      cudaMemsetAsync(st.cl_cnt + 2 * gi, 0, 2 * sizeof(int), q);
-      phase_kernel<R, 0><<<blocks, threads, s->smem_bytes, q>>>(phases, sub, nsub, action, g);
-      // upper bounds of the candidate counts size the grids; threads / warps beyond the device-side count exit at once
-      narrow_analytic_kernel<R><<<(nA + 127) / 128, 128, 0, q>>>(g);
-      narrow_convex_kernel<R><<<(nG + 7) / 8, 256, 8 * epaw, q>>>(g);
-      phase_kernel<R, 2><<<blocks, threads, s->smem_bytes, q>>>(phases, sub, nsub, action, g);
-      if (phases & PH_CTRL) phase_kernel<R, 3><<<blocks, threads, s->smem_bytes, q>>>(phases, sub, nsub, action, g);
-      phase_kernel<R, 4><<<blocks, threads, s->smem_bytes, q>>>(phases, sub, nsub, action, g);
-      s->launches += (phases & PH_CTRL) ? 6 : 5;
-    }
-    if (G > 1) {
-      CUDA_TRY(cudaEventRecord(s->gevents[gi], q));
-      CUDA_TRY(cudaStreamWaitEvent(s->stream, s->gevents[gi], 0));
-    }
+  if (!s->fork_event) {
+    CUDA_TRY(cudaEventCreateWithFlags(&s->fork_event, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&s->in_event, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&s->out_event, cudaEventDisableTiming));
+    CUDA_TRY(cudaStreamCreateWithFlags(&s->pstream, cudaStreamNonBlocking));
   }
-  CUDA_TRY(cudaGetLastError());
+  int launches_per_call = G * nsub * ((phases & PH_CTRL) ? 6 : 5);
+  if (!s->use_graph) {
+    rc = enqueue_pipeline<R>(s, st, phases, nsub, action, s->stream);
+    s->launches += launches_per_call;
+    return rc;
+  }
+  // CUDA-graph replay: the launch sequence of one call (G groups x nsub substeps x 6 kernels) is captured once per
+  // (phases, nsub) on an internal stream; the action rows are staged into a fixed buffer so kernel arguments never change
+  const R* act_in = action;
+  if (action) {
+    int ad = s->ctrl.action_dim > 0 ? s->ctrl.action_dim : 1;
+    if (ad > 16) return fail(B2S_ERR_UNSUPPORTED, "action_dim > 16");
+    CUDA_TRY(cudaMemcpyAsync(s->action_buf, action, (size_t)s->n_env * ad * sizeof(R), cudaMemcpyDeviceToDevice, s->stream));
+    act_in = (const R*)s->action_buf;
+  }
+  CUDA_TRY(cudaEventRecord(s->in_event, s->stream));
+  CUDA_TRY(cudaStreamWaitEvent(s->pstream, s->in_event, 0));
+  long long key = ((long long)phases << 20) | (long long)nsub << 4 | (action ? 1 : 0);
+  auto it = s->graphs.find(key);
+  if (it == s->graphs.end()) {
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    CUDA_TRY(cudaStreamBeginCapture(s->pstream, cudaStreamCaptureModeRelaxed));
+    rc = enqueue_pipeline<R>(s, st, phases, nsub, act_in, s->pstream);
+    cudaError_t ce = cudaStreamEndCapture(s->pstream, &graph);
+    if (rc != B2S_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (ce != cudaSuccess) return fail(B2S_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
+    CUDA_TRY(cudaGraphInstantiate(&exec, graph, 0));
+    cudaGraphDestroy(graph);
+    it = s->graphs.emplace(key, exec).first;
+  }
+  CUDA_TRY(cudaGraphLaunch(it->second, s->pstream));
+  CUDA_TRY(cudaEventRecord(s->out_event, s->pstream));
+  CUDA_TRY(cudaStreamWaitEvent(s->stream, s->out_event, 0));
+  s->launches += launches_per_call;
   return B2S_OK;
 }
 static int launch_pipeline(b2s_sim* s, int phases, int nsub, const void* action) {
@@ -596,6 +646,7 @@ int b2s_set_mode(b2s_sim* s, int mode) {
   s->mode = mode;
   const char* eg = getenv("B2S_GROUPS");
   if (eg) { int v = atoi(eg); if (v >= 1 && v <= 64) s->ngroups = v; }
+  if (getenv("B2S_NO_GRAPH")) s->use_graph = 0;
   return B2S_OK;
 }
 

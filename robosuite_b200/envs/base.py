@@ -133,6 +133,7 @@ class BatchedMujocoEnv:
         self.timestep = torch.zeros(self.num_envs, dtype=torch.long, device=self.device)
         self.done = torch.zeros(self.num_envs, dtype=torch.bool, device=self.device)
         self.cur_time = 0.0
+        self._max_steps_since_reset = 0  # host-side upper bound of `timestep` (avoids a device sync per step)
         self.reset()
 
     # ---- to be provided by tasks
@@ -209,6 +210,8 @@ class BatchedMujocoEnv:
             self.sim.time[idx] = 0
             self.timestep[idx] = 0
             self.done[idx] = False
+        if mask is None:
+            self._max_steps_since_reset = 0
         self.sim.forward()
         m8 = None if mask is None else mask.to(torch.uint8).contiguous()
         self.sim.ctrl_reset(m8)
@@ -219,8 +222,10 @@ class BatchedMujocoEnv:
         """One control step = n_substeps x {step1, controller, step2} in one kernel launch (base.py:467-521)."""
         import torch
 
-        if bool(self.done.any()):
+        # an env can only be done once the longest-running one has reached the horizon: no device sync before that
+        if not self.ignore_done and self._max_steps_since_reset >= self.horizon and bool(self.done.any()):
             raise ValueError("executing action in terminated episode")
+        self._max_steps_since_reset += 1
         action = torch.as_tensor(action, dtype=self.dtype, device=self.device).contiguous()
         assert action.shape == (self.num_envs, self.action_dim), "environment got invalid action dimension -- expected {}, got {}".format(
             (self.num_envs, self.action_dim), tuple(action.shape))
