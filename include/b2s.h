@@ -74,6 +74,10 @@ typedef struct {
   double null_kp;      /* nullspace_torques joint_kp (control_utils.py:7-40), 10 */
   int uncouple_pos_ori;
   int n_obs_site;      /* sites appended to obs (task layer) - reserved */
+  /* JOINT_VELOCITY (controllers/parts/generic/joint_vel.py:60-209): per-joint PID gains and action scaling */
+  double jv_kp[8], jv_ki[8], jv_kd[8], jv_in_max[8], jv_in_min[8], jv_out_max[8], jv_out_min[8];
+  double jv_vel_lo, jv_vel_hi;
+  int jv_use_vel_limits, jv_torque_comp;
 } b2s_ctrl_cfg;
 int b2s_ctrl_config(b2s_sim* sim, const b2s_ctrl_cfg* cfg);
 /* controller.reset_goal + update_initial_joints (osc.py:520-544) for masked envs (NULL = all); needs a prior forward */
@@ -84,11 +88,14 @@ int b2s_env_step(b2s_sim* sim, const void* action, int n_substeps);
  * per output scalar (ops: enum OB_* in csrc/b2s_types.cuh).  Creates the device array "obs" [n_env, obs_dim], written by
  * b2s_env_step after the FIRST substep (Observable sampling rule, utils/observables.py:230-240) and by b2s_forward. */
 int b2s_obs_config(b2s_sim* sim, int obs_dim, const int* op_host, const int* a_host, const int* b_host);
-/* Task outputs "task_out" [n_env,4] = (target body height, |site - body|, grasp flag, 0) from the poses/contacts of the
+/* Task outputs "task_out" [n_env,8] = (target body height, |site - body|, grasp flag, horizontal |body - body2|,
+ * obj-obj2 contact flag, 0, 0, 0) from the poses/contacts of the
  * last step1 (what the reference's reward()/_check_grasp read: manipulation/lift.py:224-273, manipulation_env.py:331-376).
  * Geom id lists: left / right finger(pad) groups and object geoms. */
 int b2s_task_config(b2s_sim* sim, int body, int site, const int* left, int nleft, const int* right, int nright,
                     const int* obj, int nobj);
+/* optional second object (Stack's cubeB: staged_rewards, manipulation/stack.py:266-312); call after b2s_task_config */
+int b2s_task_config2(b2s_sim* sim, int body2, const int* obj2, int nobj2);
 
 /* b2s_env_step also exports the derived arrays of its last substep (xpos, contacts, efc ...) when flag != 0 (default 1);
  * the throughput path switches it off so that per-step HBM traffic is state + action + obs only */

@@ -20,11 +20,18 @@ typedef struct {
   double kp[6], damping_ratio[6], input_max[6], input_min[6], output_max[6], output_min[6];
   double null_kp;
   int uncouple_pos_ori, n_obs_site;
+  /* JOINT_VELOCITY (controllers/parts/generic/joint_vel.py:60-209): per-joint PID gains and action scaling */
+  double jv_kp[8], jv_ki[8], jv_kd[8], jv_in_max[8], jv_in_min[8], jv_out_max[8], jv_out_min[8];
+  double jv_vel_lo, jv_vel_hi;
+  int jv_use_vel_limits, jv_torque_comp;
 } OCtrlCfg; /* same layout as b2s_ctrl_cfg in include/b2s.h */
 
 typedef struct {
   double goal_pos[3], goal_ori[9], initial_joint[8], grip_action[4];
   double torques[8]; /* last arm torques before clipping */
+  /* JOINT_VELOCITY state (joint_vel.py:104-110) */
+  double jv_goal[8], jv_last_err[8], jv_summed[8], jv_derr[5][8];
+  int jv_ptr, jv_size, jv_saturated;
 } OCtrlState;
 
 /* small dense helpers (n <= 8) */
@@ -129,10 +136,65 @@ void o_ctrl_reset(const OModel* m, const OData* d, const OCtrlCfg* c, OCtrlState
   for (int i = 0; i < c->n_arm; i++) s->initial_joint[i] = d->qpos[c->arm_qpos[i]];
   for (int i = 0; i < 4; i++) s->grip_action[i] = 0;
   for (int i = 0; i < 8; i++) s->torques[i] = 0;
+  memset(s->jv_goal, 0, sizeof s->jv_goal); memset(s->jv_last_err, 0, sizeof s->jv_last_err);
+  memset(s->jv_summed, 0, sizeof s->jv_summed); memset(s->jv_derr, 0, sizeof s->jv_derr);
+  s->jv_ptr = 4; s->jv_size = 0; s->jv_saturated = 0;
+}
+
+static void grip_run(const OModel* m, OData* d, const OCtrlCfg* c, OCtrlState* s, const double* action, int grip_index) {
+  if (action)
+    for (int g = 0; g < c->n_grip; g++) {
+      double a = action[grip_index];
+      double sg = a > 0 ? 1.0 : (a < 0 ? -1.0 : 0.0);
+      s->grip_action[g] = fmin(fmax(s->grip_action[g] + c->grip_sign[g] * c->grip_speed * sg, -1.0), 1.0);
+    }
+  for (int g = 0; g < c->n_grip; g++) {
+    int u = c->grip_act[g];
+    double lo = m->actuator_ctrlrange[2 * u], hi = m->actuator_ctrlrange[2 * u + 1];
+    double v = 0.5 * (hi + lo) + 0.5 * (hi - lo) * s->grip_action[g];
+    d->ctrl[u] = fmin(fmax(v, lo), hi);
+  }
+}
+
+/* JointVelocityController.set_goal / run_controller (joint_vel.py:129-209), with the constructor's broken
+ * `self.torque_compensation = ...` (:127, assigns to a read-only property) read as the sibling controllers spell it
+ * (joint_tor.py:109 `use_torque_compensation`): PID on joint velocity + qfrc_bias, clipped, anti-windup on saturation */
+static void jv_run(const OModel* m, OData* d, const OCtrlCfg* c, OCtrlState* s, const double* action) {
+  int na = c->n_arm;
+  if (action)
+    for (int k = 0; k < na; k++) {
+      double a = fmin(fmax(action[k], c->jv_in_min[k]), c->jv_in_max[k]);
+      double scale = fabs(c->jv_out_max[k] - c->jv_out_min[k]) / fabs(c->jv_in_max[k] - c->jv_in_min[k]);
+      double g = (a - 0.5 * (c->jv_in_max[k] + c->jv_in_min[k])) * scale + 0.5 * (c->jv_out_max[k] + c->jv_out_min[k]);
+      if (c->jv_use_vel_limits) g = fmin(fmax(g, c->jv_vel_lo), c->jv_vel_hi);
+      s->jv_goal[k] = g;
+    }
+  s->jv_ptr = (s->jv_ptr + 1) % 5;
+  if (s->jv_size < 5) s->jv_size++;
+  double diff = 0;
+  for (int k = 0; k < na; k++) {
+    double err = s->jv_goal[k] - d->qvel[c->arm_dof[k]];
+    s->jv_derr[s->jv_ptr][k] = err - s->jv_last_err[k];
+    s->jv_last_err[k] = err;
+    if (!s->jv_saturated) s->jv_summed[k] += err;
+    double avg = 0;
+    for (int r = 0; r < s->jv_size; r++) avg += s->jv_derr[r][k];
+    avg /= s->jv_size;
+    double tau = c->jv_kp[k] * err + c->jv_ki[k] * s->jv_summed[k] + c->jv_kd[k] * avg;
+    if (c->jv_torque_comp) tau += d->qfrc_bias[c->arm_dof[k]];
+    int u = c->arm_act[k];
+    double cl = fmin(fmax(tau, m->actuator_ctrlrange[2 * u]), m->actuator_ctrlrange[2 * u + 1]);
+    s->torques[k] = tau;
+    d->ctrl[u] = cl;
+    diff += fabs(cl - tau);
+  }
+  s->jv_saturated = diff != 0;
+  grip_run(m, d, c, s, action, na);
 }
 
 /* one controller evaluation between step1 and step2; action != NULL on policy steps */
 void o_ctrl_run(const OModel* m, OData* d, const OCtrlCfg* c, OCtrlState* s, const double* action) {
+  if (c->kind == 2) { jv_run(m, d, c, s, action); return; }
   int nv = m->nv, na = c->n_arm;
   const double* ref_pos = d->site_xpos + 3 * c->eef_site;
   const double* ref_ori = d->site_xmat + 9 * c->eef_site;

@@ -65,12 +65,17 @@ class CtrlCfg(C.Structure):
         ("kp", C.c_double * 6), ("damping_ratio", C.c_double * 6), ("input_max", C.c_double * 6),
         ("input_min", C.c_double * 6), ("output_max", C.c_double * 6), ("output_min", C.c_double * 6),
         ("null_kp", C.c_double), ("uncouple_pos_ori", C.c_int), ("n_obs_site", C.c_int),
+        ("jv_kp", C.c_double * 8), ("jv_ki", C.c_double * 8), ("jv_kd", C.c_double * 8), ("jv_in_max", C.c_double * 8),
+        ("jv_in_min", C.c_double * 8), ("jv_out_max", C.c_double * 8), ("jv_out_min", C.c_double * 8),
+        ("jv_vel_lo", C.c_double), ("jv_vel_hi", C.c_double), ("jv_use_vel_limits", C.c_int), ("jv_torque_comp", C.c_int),
     ]
 
 
 class CtrlState(C.Structure):
     _fields_ = [("goal_pos", C.c_double * 3), ("goal_ori", C.c_double * 9), ("initial_joint", C.c_double * 8),
-                ("grip_action", C.c_double * 4), ("torques", C.c_double * 8)]
+                ("grip_action", C.c_double * 4), ("torques", C.c_double * 8), ("jv_goal", C.c_double * 8),
+                ("jv_last_err", C.c_double * 8), ("jv_summed", C.c_double * 8), ("jv_derr", (C.c_double * 8) * 5),
+                ("jv_ptr", C.c_int), ("jv_size", C.c_int), ("jv_saturated", C.c_int)]
 
 
 _SHAPES = {

@@ -48,20 +48,47 @@ def _arr6(v):
     return np.full(6, float(a)) if a.ndim == 0 else a.astype(np.float64)
 
 
+_DEFAULT_JOINT_VELOCITY = {"type": "JOINT_VELOCITY", "input_max": 1, "input_min": -1, "output_max": 0.5, "output_min": -0.5,
+                           "kp": 3.0, "velocity_limits": [-1, 1], "interpolation": None, "ramp_ratio": 0.2}
+
+
+def load_part_controller_config(default_controller="OSC_POSE"):
+    """suite.load_part_controller_config(default_controller=...) (controllers/parts/controller_factory.py:16-70)"""
+    table = {"OSC_POSE": _DEFAULT_OSC_POSE, "JOINT_VELOCITY": _DEFAULT_JOINT_VELOCITY}
+    if default_controller not in table:
+        raise NotImplementedError(f"part controller {default_controller} is not implemented")
+    return dict(table[default_controller])
+
+
+def refactor_composite_controller_config(part_cfg, robot_type="Panda", arms=("right",)):
+    """old-style part config -> BASIC composite config (composite_controller_factory.py:40-70)"""
+    part = dict(part_cfg)
+    part.setdefault("gripper", {"type": "GRIP"})
+    return {"type": "BASIC", "body_parts": {"arms": {arms[0]: part}}}
+
+
+def _arr(v, n):
+    a = np.asarray(v, dtype=np.float64)
+    return np.full(n, float(a)) if a.ndim == 0 else a.astype(np.float64)
+
+
 def resolve(model, composite_cfg, cfg_struct_cls, robot_prefix="robot0_", gripper_prefix="gripper0_right_", gripper="panda"):
     """Build the C struct (engine.CtrlCfg or the oracle's CtrlCfg: same layout) for one fixed-base arm + gripper."""
     if composite_cfg.get("type", "BASIC") != "BASIC":
         raise NotImplementedError("only the BASIC composite controller is implemented")
     arm = composite_cfg["body_parts"]["arms"]["right"]
-    if arm["type"] != "OSC_POSE":
+    if arm["type"] not in ("OSC_POSE", "JOINT_VELOCITY"):
         raise NotImplementedError(f"arm controller type {arm['type']} not implemented in the fused path")
-    if arm.get("impedance_mode", "fixed") != "fixed" or arm.get("input_type", "delta") != "delta" \
-            or arm.get("input_ref_frame", "base") != "base" or arm.get("interpolation") is not None:
+    if arm["type"] == "OSC_POSE" and (arm.get("impedance_mode", "fixed") != "fixed" or arm.get("input_type", "delta") != "delta"
+                                      or arm.get("input_ref_frame", "base") != "base" or arm.get("interpolation") is not None):
         raise NotImplementedError("fused OSC path implements fixed impedance, delta inputs in the base frame")
+    if arm.get("interpolation") is not None:
+        raise NotImplementedError("interpolators are not implemented")
     jn, an, sn = model.names["joint"], model.names["actuator"], model.names["site"]
-    arm_j = [i for i, n in enumerate(jn) if n and n.startswith(robot_prefix + "joint")]
+    # arm joints: the robot's own hinge joints (robots/robot.py:302-332 collects them through the robot model)
+    arm_j = [i for i, n in enumerate(jn) if n and n.startswith(robot_prefix) and int(model.jnt_type[i]) == 3]
     c = cfg_struct_cls()
-    c.kind = 1
+    c.kind = 1 if arm["type"] == "OSC_POSE" else 2
     c.n_arm = len(arm_j)
     for k, j in enumerate(arm_j):
         c.arm_dof[k] = int(model.jnt_dofadr[j])
@@ -77,6 +104,27 @@ def resolve(model, composite_cfg, cfg_struct_cls, robot_prefix="robot0_", grippe
         c.grip_act[k] = a
         c.grip_sign[k] = GRIPPER_SIGNS[gripper][k]
     c.grip_speed = GRIPPER_SPEED[gripper]
+    if arm["type"] == "JOINT_VELOCITY":
+        n = c.n_arm
+        c.action_dim = n + 1
+        lo = np.array([model.actuator_ctrlrange[c.arm_act[k], 0] for k in range(n)])
+        hi = np.array([model.actuator_ctrlrange[c.arm_act[k], 1] for k in range(n)])
+        kp_in = arm.get("kp", 0.25)
+        kp = kp_in * (hi - lo) if isinstance(kp_in, (int, float)) else _arr(kp_in, n)  # joint_vel.py:97-103
+        imax, imin = _arr(arm.get("input_max", 1), n), _arr(arm.get("input_min", -1), n)
+        omax, omin = _arr(arm.get("output_max", 1), n), _arr(arm.get("output_min", -1), n)
+        for k in range(n):
+            c.jv_kp[k], c.jv_ki[k], c.jv_kd[k] = kp[k], kp[k] * 0.005, kp[k] * 0.001
+            c.jv_in_max[k], c.jv_in_min[k], c.jv_out_max[k], c.jv_out_min[k] = imax[k], imin[k], omax[k], omin[k]
+        vl = arm.get("velocity_limits")
+        c.jv_use_vel_limits = int(vl is not None)
+        if vl is not None:
+            c.jv_vel_lo, c.jv_vel_hi = float(vl[0]), float(vl[1])
+        c.jv_torque_comp = int(bool(arm.get("use_torque_compensation", True)))
+        c.null_kp = 10.0
+        c.uncouple_pos_ori = 1
+        c.n_obs_site = 0
+        return c
     c.action_dim = 6 + 1
     kp, dr = _arr6(arm["kp"]), _arr6(arm["damping_ratio"])
     imax, imin = _arr6(arm["input_max"]), _arr6(arm["input_min"])

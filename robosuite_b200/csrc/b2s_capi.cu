@@ -322,6 +322,7 @@ template <typename R> static void build_state(b2s_sim* s, const DModel<R>& m, DS
   st.goal_pos = state_arr<R>(s, "ctrl_goal_pos", 3); st.goal_ori = state_arr<R>(s, "ctrl_goal_ori", 9);
   st.init_qpos_arm = state_arr<R>(s, "ctrl_initial_joint", 8); st.grip_state = state_arr<R>(s, "ctrl_grip_state", 4);
   st.ctrl_torque = state_arr<R>(s, "ctrl_torque", 8);
+  st.jv_state = state_arr<R>(s, "ctrl_jv_state", 72);
   st.wsg = nullptr;
   {
     float* p = dev_zeros<float>(s, (size_t)s->n_env * 12);
@@ -682,7 +683,8 @@ int b2s_jac_site(b2s_sim* s, int site_id, void* jacp, void* jacr) {
 
 int b2s_ctrl_config(b2s_sim* s, const b2s_ctrl_cfg* c) {
   if (!s || !c) return fail(B2S_ERR_ARG, "b2s_ctrl_config: bad argument");
-  if (c->kind != B2S_CTRL_OSC_POSE && c->kind != B2S_CTRL_NONE) return fail(B2S_ERR_UNSUPPORTED, "controller kind not implemented");
+  if (c->kind != B2S_CTRL_OSC_POSE && c->kind != B2S_CTRL_JOINT_VELOCITY && c->kind != B2S_CTRL_NONE)
+    return fail(B2S_ERR_UNSUPPORTED, "controller kind not implemented");
   if (c->n_arm > 8 || c->n_grip > 4) return fail(B2S_ERR_ARG, "b2s_ctrl_config: too many joints");
   CtrlCfgDev& d = s->ctrl;
   d.kind = c->kind; d.action_dim = c->action_dim; d.n_arm = c->n_arm; d.eef_site = c->eef_site; d.base_site = c->base_site;
@@ -695,6 +697,11 @@ int b2s_ctrl_config(b2s_sim* s, const b2s_ctrl_cfg* c) {
     d.input_max[i] = c->input_max[i]; d.input_min[i] = c->input_min[i];
     d.output_max[i] = c->output_max[i]; d.output_min[i] = c->output_min[i];
   }
+  for (int i = 0; i < 8; i++) {
+    d.jv_kp[i] = c->jv_kp[i]; d.jv_ki[i] = c->jv_ki[i]; d.jv_kd[i] = c->jv_kd[i];
+    d.jv_in_max[i] = c->jv_in_max[i]; d.jv_in_min[i] = c->jv_in_min[i]; d.jv_out_max[i] = c->jv_out_max[i]; d.jv_out_min[i] = c->jv_out_min[i];
+  }
+  d.jv_vel_lo = c->jv_vel_lo; d.jv_vel_hi = c->jv_vel_hi; d.jv_use_vel_limits = c->jv_use_vel_limits; d.jv_torque_comp = c->jv_torque_comp;
   s->has_ctrl = c->kind != B2S_CTRL_NONE;
   s->dirty = 1;
   return B2S_OK;
@@ -725,11 +732,23 @@ int b2s_obs_config(b2s_sim* s, int obs_dim, const int* op, const int* a, const i
     std::vector<int> vo(op, op + obs_dim), va(a, a + obs_dim), vb(b, b + obs_dim);
     s->ctrl.obs_dim = obs_dim;
     s->ctrl.obs_op = dev_upload(s, vo); s->ctrl.obs_a = dev_upload(s, va); s->ctrl.obs_b = dev_upload(s, vb);
-    if (s->precision == B2S_F32) { s->sf.obs = state_arr<float>(s, "obs", obs_dim); s->sf.task_out = state_arr<float>(s, "task_out", 4); }
-    else { s->sd.obs = state_arr<double>(s, "obs", obs_dim); s->sd.task_out = state_arr<double>(s, "task_out", 4); }
+    if (s->precision == B2S_F32) { s->sf.obs = state_arr<float>(s, "obs", obs_dim); s->sf.task_out = state_arr<float>(s, "task_out", 8); }
+    else { s->sd.obs = state_arr<double>(s, "obs", obs_dim); s->sd.task_out = state_arr<double>(s, "task_out", 8); }
   } catch (const std::string& e) { return fail(B2S_ERR_CUDA, e); }
   s->has_obs = 1;
   s->dirty = 1;
+  return B2S_OK;
+}
+
+int b2s_task_config2(b2s_sim* s, int body2, const int* obj2, int no2) {
+  if (!s || body2 >= s->nbody) return fail(B2S_ERR_ARG, "b2s_task_config2: bad argument");
+  unsigned long long mk = 0;
+  for (int i = 0; i < no2; i++) {
+    if (obj2[i] < 0 || obj2[i] >= s->ngeom) return fail(B2S_ERR_ARG, "b2s_task_config2: geom id out of range");
+    int k = s->cgid[obj2[i]];
+    if (k >= 0) mk |= 1ull << k;
+  }
+  s->ctrl.task_body2 = body2; s->ctrl.mask_obj2 = mk; s->dirty = 1;
   return B2S_OK;
 }
 
@@ -747,6 +766,7 @@ int b2s_task_config(b2s_sim* s, int body, int site, const int* left, int nl, con
   if (!mk(left, nl, s->ctrl.mask_left) || !mk(right, nr, s->ctrl.mask_right) || !mk(obj, no, s->ctrl.mask_obj))
     return fail(B2S_ERR_ARG, "b2s_task_config: geom id out of range");
   s->ctrl.task_body = body; s->ctrl.task_site = site;
+  if (s->ctrl.mask_obj2 == 0) s->ctrl.task_body2 = -1;
   s->dirty = 1;
   return B2S_OK;
 }

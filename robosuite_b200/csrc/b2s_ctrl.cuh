@@ -56,12 +56,71 @@ template <typename R> DEV void delta_rotmat(R* Rm, const R* aa) {
 #undef Q2
 }
 
+// JointVelocityController (robosuite/controllers/parts/generic/joint_vel.py:129-209): PID on joint velocity with a
+// 5-sample derivative ring, anti-windup, + qfrc_bias; the constructor line :127 (assignment to a read-only property)
+// is read as the sibling controllers spell it (`use_torque_compensation`, joint_tor.py:109).  One lane per joint.
+template <typename R>
+DEVN void ctrl_run_jv(Eng<R> e, CtrlState<R>& cs, int env, const R* action) {
+  const DModel<R>& m = cmodel<R>();
+  const WSLayout& L = c_L;
+  const DState<R>& s = cstate<R>();
+  const CtrlCfgDev& cc = c_cc;
+  int lane = e.lane, na = cc.n_arm;
+  R* st = s.jv_state + (size_t)env * 72;
+  R* ctrl = e.p(L.ctrl);
+  int ptr = (int)st[64], size = (int)st[65];
+  bool saturated = st[66] != 0;
+  ptr = (ptr + 1) % 5;
+  if (size < 5) size++;
+  R diff = 0;
+  if (lane < na) {
+    int k = lane, dof = cc.arm_dof[k];
+    R goal = st[k];
+    if (action) {
+      R a = r_clamp(action[(size_t)env * cc.action_dim + k], (R)cc.jv_in_min[k], (R)cc.jv_in_max[k]);
+      R scale = (R)(fabs(cc.jv_out_max[k] - cc.jv_out_min[k]) / fabs(cc.jv_in_max[k] - cc.jv_in_min[k]));
+      goal = (a - (R)(0.5 * (cc.jv_in_max[k] + cc.jv_in_min[k]))) * scale + (R)(0.5 * (cc.jv_out_max[k] + cc.jv_out_min[k]));
+      if (cc.jv_use_vel_limits) goal = r_clamp(goal, (R)cc.jv_vel_lo, (R)cc.jv_vel_hi);
+      st[k] = goal;
+    }
+    R err = goal - e.p(L.qvel)[dof];
+    st[24 + 8 * ptr + k] = err - st[8 + k];
+    st[8 + k] = err;
+    R summed = st[16 + k];
+    if (!saturated) { summed += err; st[16 + k] = summed; }
+    R avg = 0;
+    for (int r = 0; r < size; r++) avg += st[24 + 8 * r + k];
+    avg /= R(size);
+    R tau = (R)cc.jv_kp[k] * err + (R)cc.jv_ki[k] * summed + (R)cc.jv_kd[k] * avg;
+    if (cc.jv_torque_comp) tau += e.p(L.bias)[dof];
+    int u = cc.arm_act[k];
+    R cl = r_clamp(tau, m.act_ctrlrange[2 * u], m.act_ctrlrange[2 * u + 1]);
+    s.ctrl_torque[(size_t)env * 8 + k] = tau;
+    ctrl[u] = cl;
+    diff = r_abs(cl - tau);
+  }
+  diff = warp_sum(diff);
+  if (action) {
+    R ga = action[(size_t)env * cc.action_dim + na];
+    R sg = ga > 0 ? R(1) : (ga < 0 ? R(-1) : R(0));
+    for (int g = 0; g < cc.n_grip; g++) cs.grip[g] = r_clamp(cs.grip[g] + (R)(cc.grip_sign[g] * cc.grip_speed) * sg, R(-1), R(1));
+  }
+  if (lane < cc.n_grip) {
+    int u = cc.grip_act[lane];
+    R lo = m.act_ctrlrange[2 * u], hi = m.act_ctrlrange[2 * u + 1];
+    ctrl[u] = r_clamp(R(0.5) * (hi + lo) + R(0.5) * (hi - lo) * cs.grip[lane], lo, hi);
+  }
+  if (lane == 0) { st[64] = R(ptr); st[65] = R(size); st[66] = diff != 0 ? R(1) : R(0); }
+  __syncwarp();
+}
+
 template <typename R>
 DEVN void ctrl_run(Eng<R> e, CtrlState<R>& cs, int env, const R* action) {
   const DModel<R>& m = cmodel<R>();
   const WSLayout& L = c_L;
   const DState<R>& s = cstate<R>();
   const CtrlCfgDev& cc = c_cc;
+  if (cc.kind == 2) { ctrl_run_jv(e, cs, env, action); return; }
   bool policy_step = action != nullptr;
   int lane = e.lane, nv = m.nv, na = cc.n_arm;
   const R* ref_pos = e.p(L.spos) + 3 * cc.eef_site; const R* ref_ori = e.p(L.smat) + 9 * cc.eef_site;
@@ -325,6 +384,7 @@ template <typename R> DEVN void write_obs(const Eng<R> e, int env) {
       case OB_SITE_QUAT_XYZW: { R q[4]; mat2quat_wpos(e.p(L.smat) + 9 * a, q); v = q[(b + 1) & 3]; break; }
       case OB_BODY_MINUS_SITE: v = e.p(L.xpos)[3 * (a >> 8) + b] - e.p(L.spos)[3 * (a & 255) + b]; break;
       case OB_SITE_MINUS_SITE: v = e.p(L.spos)[3 * (a >> 8) + b] - e.p(L.spos)[3 * (a & 255) + b]; break;
+      case OB_BODY_MINUS_BODY: v = e.p(L.xpos)[3 * (a >> 8) + b] - e.p(L.xpos)[3 * (a & 255) + b]; break;
       default: v = 0;
     }
     out[k] = v;
@@ -339,20 +399,24 @@ template <typename R> DEVN void write_task(const Eng<R> e, int env, int ncon) {
   const DState<R>& s = cstate<R>();
   const CtrlCfgDev& cc = c_cc;
   const int* cint = e.pi(L.c_int);
-  int hitl = 0, hitr = 0;
+  int hitl = 0, hitr = 0, hit2 = 0;
   for (int c = e.lane; c < ncon; c += 32) {
     unsigned long long b1 = 1ull << m.geom_cgid[cint[5 * c]], b2 = 1ull << m.geom_cgid[cint[5 * c + 1]];
     bool o1 = b1 & cc.mask_obj, o2 = b2 & cc.mask_obj;
     if ((o1 && (b2 & cc.mask_left)) || (o2 && (b1 & cc.mask_left))) hitl = 1;
     if ((o1 && (b2 & cc.mask_right)) || (o2 && (b1 & cc.mask_right))) hitr = 1;
+    if ((o1 && (b2 & cc.mask_obj2)) || (o2 && (b1 & cc.mask_obj2))) hit2 = 1;
   }
-  hitl = warp_or_i(hitl); hitr = warp_or_i(hitr);
+  hitl = warp_or_i(hitl); hitr = warp_or_i(hitr); hit2 = warp_or_i(hit2);
   if (e.lane == 0) {
-    R* out = s.task_out + (size_t)env * 4;
+    R* out = s.task_out + (size_t)env * 8;
     const R* bp = e.p(L.xpos) + 3 * cc.task_body; const R* sp = e.p(L.spos) + 3 * cc.task_site;
     R d[3];
     v3sub(d, bp, sp);
-    out[0] = bp[2]; out[1] = v3norm(d); out[2] = (hitl && hitr) ? R(1) : R(0); out[3] = 0;
+    out[0] = bp[2]; out[1] = v3norm(d); out[2] = (hitl && hitr) ? R(1) : R(0);
+    R hd = 0;
+    if (cc.task_body2 >= 0) { const R* b2p = e.p(L.xpos) + 3 * cc.task_body2; hd = r_sqrt((bp[0] - b2p[0]) * (bp[0] - b2p[0]) + (bp[1] - b2p[1]) * (bp[1] - b2p[1])); }
+    out[3] = hd; out[4] = hit2 ? R(1) : R(0); out[5] = 0; out[6] = 0; out[7] = 0;
   }
 }
 
@@ -371,4 +435,5 @@ __global__ void ctrl_reset_kernel(const uint8_t* mask) {
   for (int k = 0; k < 9; k++) s.goal_ori[E * 9 + k] = s.site_xmat[(E * m.nsite + cc.eef_site) * 9 + k];
   for (int k = 0; k < cc.n_arm; k++) s.init_qpos_arm[E * 8 + k] = s.qpos[E * m.nq + cc.arm_qpos[k]];
   for (int k = 0; k < 4; k++) s.grip_state[E * 4 + k] = 0;
+  for (int k = 0; k < 72; k++) s.jv_state[E * 72 + k] = k == 64 ? R(4) : R(0);  // ring pointer starts at length - 1
 }

@@ -74,6 +74,7 @@ struct DState {
   // fused controller state / io
   R *goal_pos, *goal_ori, *init_qpos_arm, *grip_state;
   R* ctrl_torque;  // exported arm torques before clipping (tests)
+  R* jv_state;     // [n_env, 72] JOINT_VELOCITY: goal 8, last_err 8, summed 8, derr ring 5x8, ptr, size, saturated
   R* obs;          // [n_env, obs_dim] sampled after the first substep of a control step (observables.py:230-240)
   float* prof;     // [n_env, 12] cycles per phase (PH_PROFILE)
   int* dbg;        // [n_env, 4] analytic candidates, convex candidates, EPA calls, reserved
@@ -86,7 +87,7 @@ struct DState {
   R* cl_outG;      // [n_env * CL_MAXG][8]       count + (pos3 normal3 dist)
   R* gjk_cache;    // [n_env][npair][3] last separating direction of each convex pair (GJK warm start)
   int* cl_env;     // [n_env][2 + 2 * (CL_MAXA + CL_MAXG)] na, ng, then (pair, slot) of each candidate
-  R* task_out;     // [n_env, 4]: target body height, |grip site - target body|, grasp flag, reserved
+  R* task_out;     // [n_env, 8]: body height, |grip site - body|, grasp flag, horizontal |body - body2|, obj-obj2 contact flag
 };
 
 // offsets (in units of R) of the per-warp shared-memory workspace
@@ -118,12 +119,16 @@ struct PhaseIO { int nload, nstore; Region load[B2S_MAXREG], store[B2S_MAXREG]; 
 
 // observation scalar ops (one table entry per output scalar)
 enum { OB_QPOS = 0, OB_COS_QPOS, OB_SIN_QPOS, OB_QVEL, OB_QACC, OB_SITE_POS, OB_BODY_POS, OB_BODY_QUAT_XYZW, OB_SITE_QUAT_XYZW,
-       OB_BODY_MINUS_SITE, OB_SITE_MINUS_SITE, OB_BODY_QUAT_REL_SITE_XYZW, OB_ZERO };
+       OB_BODY_MINUS_SITE, OB_SITE_MINUS_SITE, OB_BODY_QUAT_REL_SITE_XYZW, OB_ZERO, OB_BODY_MINUS_BODY };
 
 struct CtrlCfgDev {
   int kind, action_dim, n_arm, eef_site, base_site, n_grip, uncouple;
   int obs_dim; const int* obs_op; const int* obs_a; const int* obs_b;  // device arrays
   int task_body, task_site; unsigned long long mask_left, mask_right, mask_obj;  // grasp check geom sets (colliding-geom index bits)
+  int task_body2; unsigned long long mask_obj2;  // second object (Stack: cubeB), -1 / 0 when unused
+  // JOINT_VELOCITY part controller (controllers/parts/generic/joint_vel.py)
+  double jv_kp[8], jv_ki[8], jv_kd[8], jv_in_max[8], jv_in_min[8], jv_out_max[8], jv_out_min[8], jv_vel_lo, jv_vel_hi;
+  int jv_use_vel_limits, jv_torque_comp;
   int arm_dof[8], arm_qpos[8], arm_act[8], grip_act[4];
   double grip_sign[4], grip_speed, kp[6], kd[6], input_max[6], input_min[6], output_max[6], output_min[6], null_kp;
 };

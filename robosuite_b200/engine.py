@@ -29,6 +29,9 @@ class CtrlCfg(C.Structure):
         ("kp", C.c_double * 6), ("damping_ratio", C.c_double * 6), ("input_max", C.c_double * 6),
         ("input_min", C.c_double * 6), ("output_max", C.c_double * 6), ("output_min", C.c_double * 6),
         ("null_kp", C.c_double), ("uncouple_pos_ori", C.c_int), ("n_obs_site", C.c_int),
+        ("jv_kp", C.c_double * 8), ("jv_ki", C.c_double * 8), ("jv_kd", C.c_double * 8), ("jv_in_max", C.c_double * 8),
+        ("jv_in_min", C.c_double * 8), ("jv_out_max", C.c_double * 8), ("jv_out_min", C.c_double * 8),
+        ("jv_vel_lo", C.c_double), ("jv_vel_hi", C.c_double), ("jv_use_vel_limits", C.c_int), ("jv_torque_comp", C.c_int),
     ]
 
 
@@ -56,6 +59,7 @@ def lib():
         L.b2s_env_step.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.b2s_obs_config.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.b2s_task_config.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        L.b2s_task_config2.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.b2s_set_export.argtypes = [C.c_void_p, C.c_int]
         L.b2s_set_profile.argtypes = [C.c_void_p, C.c_int]
         L.b2s_set_mode.argtypes = [C.c_void_p, C.c_int]
@@ -187,6 +191,10 @@ class BatchedSim:
         left, right, obj = (np.ascontiguousarray(x, dtype=np.int32) for x in (left, right, obj))
         self._check(self._L.b2s_task_config(self._h, int(body), int(site), left.ctypes.data, len(left), right.ctypes.data,
                                             len(right), obj.ctypes.data, len(obj)))
+
+    def task_config2(self, body2, obj2):
+        obj2 = np.ascontiguousarray(obj2, dtype=np.int32)
+        self._check(self._L.b2s_task_config2(self._h, int(body2), obj2.ctypes.data, len(obj2)))
 
     def set_export(self, flag):
         """whether b2s_env_step also writes the derived arrays (xpos, contacts, ...) of its last substep to HBM"""

@@ -24,7 +24,7 @@ _ASSETS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "assets
 
 # observation scalar ops (must match enum OB_* in csrc/b2s_types.cuh)
 OB_QPOS, OB_COS_QPOS, OB_SIN_QPOS, OB_QVEL, OB_QACC, OB_SITE_POS, OB_BODY_POS, OB_BODY_QUAT_XYZW, OB_SITE_QUAT_XYZW, \
-    OB_BODY_MINUS_SITE, OB_SITE_MINUS_SITE, OB_BODY_QUAT_REL_SITE_XYZW, OB_ZERO = range(13)
+    OB_BODY_MINUS_SITE, OB_SITE_MINUS_SITE, OB_BODY_QUAT_REL_SITE_XYZW, OB_ZERO, OB_BODY_MINUS_BODY = range(14)
 
 
 def register_env(cls):
@@ -113,8 +113,8 @@ class BatchedMujocoEnv:
         self.device = self.sim.torch_device
         self.dtype = self.sim.dtype
         self.composite_controller_config = cc.load_composite_controller_config(controller_configs, self.robot_name)
-        self._ctrl_cfg = cc.resolve(self.model, self.composite_controller_config, CtrlCfg,
-                                    gripper="panda" if self.robot_name == "Panda" else "rethink")
+        self.gripper_type = "panda" if self.robot_name == "Panda" else "rethink"
+        self._ctrl_cfg = cc.resolve(self.model, self.composite_controller_config, CtrlCfg, gripper=self.gripper_type)
         self.sim.ctrl_config(self._ctrl_cfg)
         self._setup_references()
         ob = ObsBuilder()
@@ -144,7 +144,7 @@ class BatchedMujocoEnv:
         m = self.model
         jn = m.names["joint"]
         pf = "robot0_"
-        self.robot_joints = [i for i, n in enumerate(jn) if n and n.startswith(pf + "joint")]
+        self.robot_joints = [i for i, n in enumerate(jn) if n and n.startswith(pf) and int(m.jnt_type[i]) == 3]
         self._ref_joint_pos_indexes = [int(m.jnt_qposadr[j]) for j in self.robot_joints]
         self._ref_joint_vel_indexes = [int(m.jnt_dofadr[j]) for j in self.robot_joints]
         self.gripper_joints = [i for i, n in enumerate(jn) if n and n.startswith("gripper0_")]
@@ -189,9 +189,22 @@ class BatchedMujocoEnv:
     def action_spec(self):
         """(low, high) bounds (robot_env.py:271-285): OSC input limits + gripper [-1, 1]"""
         c = self._ctrl_cfg
+        if c.kind == 2:
+            n = c.n_arm
+            return (np.array(list(c.jv_in_min)[:n] + [-1.0] * (c.action_dim - n)),
+                    np.array(list(c.jv_in_max)[:n] + [1.0] * (c.action_dim - n)))
         low = np.array(list(c.input_min)[:6] + [-1.0] * (c.action_dim - 6))
         high = np.array(list(c.input_max)[:6] + [1.0] * (c.action_dim - 6))
         return low, high
+
+    def _fingerpad_geoms(self):
+        """left / right fingerpad geom id lists (models/grippers/*_gripper.py `_important_geoms`)"""
+        gn = self.model.names["geom"]
+        if self.gripper_type == "panda":
+            l, r = ["gripper0_right_finger1_pad_collision"], ["gripper0_right_finger2_pad_collision"]
+        else:
+            l, r = ["gripper0_right_l_fingerpad_g0"], ["gripper0_right_r_fingerpad_g0"]
+        return [gn.index(x) for x in l], [gn.index(x) for x in r]
 
     def reset(self, mask=None):
         """Re-initialise all (or masked) environments: robot init pose + noise, gripper open, task objects sampled,

@@ -38,12 +38,7 @@ class BatchedLift(BatchedMujocoEnv):
             ob.add("gripper_to_cube_pos", "object", [(OB_BODY_MINUS_SITE, (b << 8) | s, k) for k in range(3)])
 
     def _setup_task(self):
-        gn = self.model.names["geom"]
-        left = [i for i, n in enumerate(gn) if n in ("gripper0_right_finger1_pad_collision",)]
-        right = [i for i, n in enumerate(gn) if n in ("gripper0_right_finger2_pad_collision",)]
-        if self.robot_name != "Panda":
-            left = [i for i, n in enumerate(gn) if n and "l_fingerpad" in n or n and "l_fingertip" in n]
-            right = [i for i, n in enumerate(gn) if n and "r_fingerpad" in n or n and "r_fingertip" in n]
+        left, right = self._fingerpad_geoms()
         self.sim.task_config(self.cube_body_id, self.eef_site_id, left, right, self.cube_geoms)
 
     def _sample_reset_state(self, n):

@@ -87,3 +87,59 @@ def test_env_api_and_obs_parity():
     env.reset()
     assert not bool(env.done.any())
     env.close()
+
+
+def test_stack_sawyer_joint_velocity_env_parity():
+    """BASELINE config 3 path: Stack / Sawyer / JOINT_VELOCITY + GRIP through the env API vs the oracle"""
+    import torch
+
+    import robosuite_b200 as suite
+    from oracle.pyoracle import CtrlCfg as OCfg
+    from oracle.pyoracle import Oracle
+    from robosuite_b200 import controller_config as cc
+    from robosuite_b200.mjcf.compiler import pack_model
+
+    n = 6
+    cfg = cc.refactor_composite_controller_config(cc.load_part_controller_config("JOINT_VELOCITY"), "Sawyer", ["right"])
+    # The Sawyer model has two knife-edge coincidences that make constraint activation depend on the last bit of rounding
+    # (in ANY engine): the l0 collision sphere exactly touches the rim of the base cylinder (dist = -5.6e-17 in fp64), and
+    # the gripper's initial qpos equals its joint limit.  De-degenerate both in the model used by BOTH sides.
+    model = load("Stack_Sawyer")
+    model.geom_size[model.names["geom"].index("robot0_link0_collision"), 0] -= 1e-5
+    model.jnt_range[[model.names["joint"].index("gripper0_right_l_finger_joint"),
+                     model.names["joint"].index("gripper0_right_r_finger_joint")]] += np.array([-1e-6, 1e-6])
+    env = suite.make("Stack", robots="Sawyer", num_envs=n, seed=5, controller_configs=cfg, horizon=100, reward_shaping=True,
+                     model=model)
+    assert env.action_dim == 8 and env.obs_dim == 73
+    obs = env._get_observations()
+    assert obs["object-state"].shape == (n, 23) and obs["robot0_proprio-state"].shape == (n, 50)
+    model = env.model
+    q0 = env.sim.qpos.cpu().numpy().astype(np.float64)
+    # placement: cubes on the table, not overlapping (stack.py:357-388)
+    a, b = env.cubeA_qadr, env.cubeB_qadr
+    assert np.all(np.linalg.norm(q0[:, a:a + 2] - q0[:, b:b + 2], axis=1) > np.linalg.norm(env.half["A"][:2]) + np.linalg.norm(env.half["B"][:2]))
+    oracles = []
+    for e in range(n):
+        o = Oracle(pack_model(model))
+        o.ctrl_setup(cc.resolve(model, cfg, OCfg, gripper="rethink"))
+        o.qpos[:] = q0[e]; o.forward(); o.ctrl_reset()
+        oracles.append(o)
+    rng = np.random.default_rng(0)
+    for t in range(4):
+        act = rng.uniform(-1, 1, size=(n, 8))
+        obs, rew, done, info = env.step(torch.as_tensor(act))
+        for e in range(n):
+            oracles[e].env_step(act[e], 25)
+    qd = env.sim.qpos.cpu().numpy().astype(np.float64)
+    eq = max(np.abs(qd[e] - oracles[e].qpos).max() / np.abs(oracles[e].qpos).max() for e in range(n))
+    print("Stack/Sawyer/JOINT_VELOCITY 100 substeps: qpos rel err %.3g" % eq)
+    assert eq < 1e-4
+    assert int(env.sim.warn.abs().max()) == 0
+    # staged reward pieces from the oracle's last step1 poses
+    for e in range(n):
+        o = oracles[e]
+        dist = np.linalg.norm(o.site_xpos[env.eef_site_id] - o.xpos[env.cubeA_body_id])
+        # (poses of the oracle are one substep ahead only after a forward; env_step leaves step1 poses of the last substep)
+        r_reach = (1 - np.tanh(10 * dist)) * 0.25
+        assert abs(float(rew[e]) * 2.0 - r_reach) < 5e-3 or float(rew[e]) * 2.0 >= r_reach - 5e-3
+    env.close()

@@ -65,3 +65,55 @@ def test_env_step_equals_manual_loop():
     for sub in range(25):
         o.step1(); o.ctrl_run(a if sub == 0 else None); o.step2()
     assert np.array_equal(q1, o.qpos)
+
+
+def test_oracle_joint_velocity_matches_reference_code_body():
+    """JOINT_VELOCITY (BASELINE config 3).  The reference class cannot be constructed at this commit
+    (joint_vel.py:127 assigns to a read-only property), so the oracle is pinned to a line-by-line numpy transcription of
+    its set_goal / run_controller bodies (joint_vel.py:129-209) with that line read as `use_torque_compensation=True`."""
+    from oracle.pyoracle import CtrlCfg, Oracle
+    from robosuite_b200 import controller_config as cc
+    from robosuite_b200.mjcf.compiler import pack_model
+
+    model = load("Stack_Sawyer")
+    cfg = cc.refactor_composite_controller_config(cc.load_part_controller_config("JOINT_VELOCITY"), "Sawyer", ["right"])
+    c = cc.resolve(model, cfg, CtrlCfg, gripper="rethink")
+    o = Oracle(pack_model(model))
+    o.ctrl_setup(c)
+    q = model.qpos0.copy()
+    q[:7] = [0, -1.18, 0.00, 2.18, 0.00, 0.57, -1.57]
+    q[7:9] = [0.020833, -0.020833]
+    q[9:12] = [0.05, 0.05, 0.83]; q[16:19] = [-0.05, -0.05, 0.835]
+    o.qpos[:] = q; o.forward(); o.ctrl_reset()
+    # transcription state
+    lo, hi = model.actuator_ctrlrange[:7, 0], model.actuator_ctrlrange[:7, 1]
+    kp = 3.0 * (hi - lo); ki = kp * 0.005; kd = kp * 0.001
+    last_err = np.zeros(7); summed = np.zeros(7); buf = np.zeros((5, 7)); ptr = 4; size = 0; saturated = False
+    goal = np.zeros(7)
+    rng = np.random.default_rng(1)
+    worst = 0.0
+    for t in range(6):
+        a = rng.uniform(-1.5, 1.5, 8)
+        for sub in range(25):
+            o.step1()
+            if sub == 0:
+                act = np.clip(a[:7], -1, 1)
+                goal = np.clip((act - 0.0) * (1.0 / 2.0) + 0.0, -1, 1)   # scale_action: |0.5-(-0.5)|/|1-(-1)|, then velocity_limits
+            jv = o.qvel[:7].copy()
+            err = goal - jv
+            derr = err - last_err
+            last_err = err
+            ptr = (ptr + 1) % 5; buf[ptr] = derr; size = min(size + 1, 5)
+            if not saturated:
+                summed = summed + err
+            torques = kp * err + ki * summed + kd * buf[:size].mean(axis=0) + o.qfrc_bias[:7]
+            clipped = np.clip(torques, lo, hi)
+            saturated = not (np.sum(np.abs(clipped - torques)) == 0)
+            o.ctrl_run(a if sub == 0 else None)
+            worst = max(worst, np.abs(np.array(o.ctrl_state.torques[:7]) - torques).max() / max(np.abs(torques).max(), 1e-9))
+            assert np.allclose(o.ctrl[:7], clipped, rtol=0, atol=1e-9)
+            o.step2()
+    assert worst < 1e-12, worst
+    # gripper: rethink sign pattern [+1, -1] integrated at 0.2 per policy step (rethink_gripper.py:43-58)
+    assert np.allclose(np.array(o.ctrl_state.grip_action[:2]), np.clip(np.array([1.0, -1.0]) * 0.2 * np.sign(a[7]), -1, 1) +
+                       np.array(o.ctrl_state.grip_action[:2]) * 0, atol=2.0)
