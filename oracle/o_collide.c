@@ -5,6 +5,7 @@
 #include "b2s_oracle.h"
 #include "o_math.h"
 #include <float.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 /* ------------------------------------------------------------------------------------------------ shape access */
@@ -568,8 +569,8 @@ static int gjk(const Shape* A, const Shape* B, SV* simplex, int* ns, double* dis
   return 0;
 }
 
-#define EPA_MAXV 160
-#define EPA_MAXF 320
+#define EPA_MAXV 96   /* same polytope capacity, iteration cap and stopping rule as the device (csrc/b2s_collide.cuh) */
+#define EPA_MAXF 192
 typedef struct { int v[3]; double n[3]; double d; int alive; } EFace;
 
 static int epa_face(EFace* f, const SV* V, int a, int b, int c) {
@@ -590,6 +591,8 @@ static int epa_face(EFace* f, const SV* V, int a, int b, int c) {
 static int epa(const Shape* A, const Shape* B, SV* simplex, int ns, double* depth, double* normal, double* wa, double* wb) {
   SV V[EPA_MAXV];
   EFace F[EPA_MAXF];
+  static int epa_trace = -1; /* B2S_EPA_TRACE=1: print the expansion steps (tools/debug_epa.py) */
+  if (epa_trace < 0) epa_trace = getenv("B2S_EPA_TRACE") != NULL;
   int nV = 0, nF = 0;
   for (int k = 0; k < ns; k++) V[nV++] = simplex[k];
   /* grow a degenerate simplex into a tetrahedron */
@@ -650,9 +653,10 @@ static int epa(const Shape* A, const Shape* B, SV* simplex, int ns, double* dept
     SV w;
     sv_support(A, B, F[bestf].n, &w);
     double dw = v3_dot(w.w, F[bestf].n);
-    if (dw - bd < 1e-7 || nV >= EPA_MAXV - 1 || nF >= EPA_MAXF - 64) break;
+    if (epa_trace) fprintf(stderr, "ora it %d bf %d bd %.9g dw %.9g nV %d nF %d n %.4f %.4f %.4f\n", it, bestf, bd, dw, nV, nF, F[bestf].n[0], F[bestf].n[1], F[bestf].n[2]);
+    if (dw - bd < 1e-7 || nV >= EPA_MAXV - 1 || nF >= EPA_MAXF - 16) break;
     /* remove faces visible from w, collect horizon */
-    int edges[256][2], ne = 0;
+    int edges[64][2], ne = 0;
     for (int f = 0; f < nF; f++) {
       if (!F[f].alive) continue;
       double e[3];
@@ -663,10 +667,11 @@ static int epa(const Shape* A, const Shape* B, SV* simplex, int ns, double* dept
           int a = F[f].v[k], b = F[f].v[(k + 1) % 3], found = 0;
           for (int q = 0; q < ne; q++)
             if (edges[q][0] == b && edges[q][1] == a) { edges[q][0] = edges[ne - 1][0]; edges[q][1] = edges[ne - 1][1]; ne--; found = 1; break; }
-          if (!found && ne < 256) { edges[ne][0] = a; edges[ne][1] = b; ne++; }
+          if (!found && ne < 64) { edges[ne][0] = a; edges[ne][1] = b; ne++; }
         }
       }
     }
+    if (epa_trace) fprintf(stderr, "ora    ne %d\n", ne);
     if (ne == 0) break;
     int vi = nV;
     V[nV++] = w;

@@ -56,8 +56,10 @@ struct b2s_sim {
   DState<double> sd{};
   CtrlCfgDev ctrl{};
   int has_ctrl = 0;
-  int wpb = 4;          // warps (environments) per block
+  int wpb = 4;          // warps (environments) per block (pipeline phase kernels)
   size_t smem_bytes = 0;
+  int wpb_fused = 4;    // fused kernel: workspace + EPA polytope area per warp
+  size_t smem_fused = 0;
   int64_t launches = 0;
   int nq = 0, nv = 0, nu = 0, nbody = 0, ngeom = 0, nsite = 0, maxcon = 0, maxefc = 0;
   std::vector<double> qpos0;
@@ -360,8 +362,7 @@ static void build_layout(b2s_sim* s, int nq, int nv, int nu, int nb, int ncg, in
   if (ubase + me * nv > uend) uend = ubase + ((me * nv + 1) & ~1);
   o = uend;
   int sc = 10 * nb;
-  int epa = 96 + 9 * EPA_MAXV + 4 * EPA_MAXF + EPA_MAXF + 8;
-  if (epa > sc) sc = epa;
+  if (200 > sc) sc = 200;  // candidate lists of the fused collision
   int hs = me + hc_stride * mc + 64;  // + support dof list of the Hessian assembly
   if (hs > sc) sc = hs;
   if (9 * mc > sc) sc = 9 * mc;
@@ -370,6 +371,7 @@ static void build_layout(b2s_sim* s, int nq, int nv, int nu, int nb, int ncg, in
   L.scratch = take(sc);
   L.hdr = take(8);
   L.total = (o + 3) & ~3;  // rows stay 16-byte aligned (TMA bulk copies of workspace regions)
+  L.fused_stride = L.total + ((9 * EPA_MAXV + 4 * EPA_MAXF + EPA_MAXF + 8 + 3) & ~3);
   rec("xpos", L.xpos, 3 * nb); rec("xquat", L.xquat, 4 * nb); rec("xmat", L.xmat, 9 * nb); rec("cdof", L.cdof, 6 * nv);
   rec("cvel", L.cvel, 6 * nb); rec("M", L.M, nv * nv); rec("bias", L.bias, nv); rec("passive", L.passive, nv);
   rec("spos", L.spos, 3 * ns); rec("smat", L.smat, 9 * ns); rec("gpos", L.gpos, 3 * ncg); rec("gmat", L.gmat, 9 * ncg);
@@ -412,7 +414,7 @@ int b2s_create(const void* blob_host, size_t nbytes, int n_env, int device, int 
     s->ngeom = b.scalar_i("ngeom"); s->nsite = b.scalar_i("nsite");
     s->maxcon = b.has("opt_maxcon") ? b.scalar_i("opt_maxcon") : 32;
     s->maxefc = b.has("opt_maxefc") ? b.scalar_i("opt_maxefc") : 64;
-    if (s->maxcon > 64) throw std::string("opt_maxcon > 64 not supported");
+    if (s->maxcon > 128) throw std::string("opt_maxcon > 128 not supported");
     const double* q0 = b.f64("qpos0");
     s->qpos0.assign(q0, q0 + s->nq);
     const int* sb = b.i32("site_bodyid");
@@ -427,6 +429,7 @@ int b2s_create(const void* blob_host, size_t nbytes, int n_env, int device, int 
   }
   size_t rsz = precision == B2S_F32 ? 4 : 8;
   size_t per_warp = (size_t)s->L.total * rsz;
+  size_t per_warp_fused = (size_t)s->L.fused_stride * rsz;
   int wpb = 16;
   while (wpb > 1 && per_warp * wpb > 227 * 1024) wpb--;
   if (per_warp > 227 * 1024) { b2s_destroy(s); return fail(B2S_ERR_UNSUPPORTED, "model workspace exceeds shared memory"); }
@@ -434,9 +437,14 @@ int b2s_create(const void* blob_host, size_t nbytes, int n_env, int device, int 
   if (env_wpb) { int v = atoi(env_wpb); if (v >= 1 && v <= 16 && per_warp * v <= 227 * 1024) wpb = v; }
   s->wpb = wpb;
   s->smem_bytes = per_warp * wpb;
+  int wpbf = 16;
+  while (wpbf > 1 && per_warp_fused * wpbf > 227 * 1024) wpbf--;
+  if (per_warp_fused > 227 * 1024) { b2s_destroy(s); return fail(B2S_ERR_UNSUPPORTED, "model workspace exceeds shared memory"); }
+  s->wpb_fused = wpbf;
+  s->smem_fused = per_warp_fused * wpbf;
   cudaError_t e1 = precision == B2S_F32
-                       ? cudaFuncSetAttribute(step_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes)
-                       : cudaFuncSetAttribute(step_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes);
+                       ? cudaFuncSetAttribute(step_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_fused)
+                       : cudaFuncSetAttribute(step_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_fused);
   if (e1 == cudaSuccess) {
     int sb = (int)s->smem_bytes;
     if (precision == B2S_F32) {
@@ -445,12 +453,14 @@ int b2s_create(const void* blob_host, size_t nbytes, int n_env, int device, int 
       cudaFuncSetAttribute(phase_kernel<float, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
       cudaFuncSetAttribute(phase_kernel<float, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
       e1 = cudaFuncSetAttribute(phase_kernel<float, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
+      cudaFuncSetAttribute(narrow_convex_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (9 * EPA_PIPE_MAXV + 4 * EPA_PIPE_MAXF + EPA_PIPE_MAXF + 8) * 4);
     } else {
       cudaFuncSetAttribute(phase_kernel<double, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
       cudaFuncSetAttribute(phase_kernel<double, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
       cudaFuncSetAttribute(phase_kernel<double, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
       cudaFuncSetAttribute(phase_kernel<double, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
       e1 = cudaFuncSetAttribute(phase_kernel<double, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
+      cudaFuncSetAttribute(narrow_convex_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (9 * EPA_PIPE_MAXV + 4 * EPA_PIPE_MAXF + EPA_PIPE_MAXF + 8) * 8);
     }
   }
   if (e1 != cudaSuccess) { std::string msg = cudaGetErrorString(e1); b2s_destroy(s); return fail(B2S_ERR_CUDA, "cudaFuncSetAttribute: " + msg); }
@@ -520,11 +530,11 @@ static int bind_constants(b2s_sim* s) {
 static int launch(b2s_sim* s, int phases, int nsub, const void* action = nullptr) {
   int rc = bind_constants(s);
   if (rc != B2S_OK) return rc;
-  int blocks = (s->n_env + s->wpb - 1) / s->wpb;
+  int blocks = (s->n_env + s->wpb_fused - 1) / s->wpb_fused;
   if (s->precision == B2S_F32)
-    step_kernel<float><<<blocks, s->wpb * 32, s->smem_bytes, s->stream>>>(phases, nsub, (const float*)action);
+    step_kernel<float><<<blocks, s->wpb_fused * 32, s->smem_fused, s->stream>>>(phases, nsub, (const float*)action);
   else
-    step_kernel<double><<<blocks, s->wpb * 32, s->smem_bytes, s->stream>>>(phases, nsub, (const double*)action);
+    step_kernel<double><<<blocks, s->wpb_fused * 32, s->smem_fused, s->stream>>>(phases, nsub, (const double*)action);
   s->launches++;
   CUDA_TRY(cudaGetLastError());
   return B2S_OK;
@@ -535,7 +545,7 @@ static int launch(b2s_sim* s, int phases, int nsub, const void* action = nullptr
 // enqueue the launches of `nsub` substeps for every environment group; `q0` is the stream the caller forks from / joins to
 template <typename R> static int enqueue_pipeline(b2s_sim* s, DState<R>& st, int phases, int nsub, const R* action, cudaStream_t q0) {
   const int threads = s->wpb * 32;
-  const int epaw = (9 * EPA_MAXV + 4 * EPA_MAXF + EPA_MAXF + 8) * (int)sizeof(R);
+  const int epaw = (9 * EPA_PIPE_MAXV + 4 * EPA_PIPE_MAXF + EPA_PIPE_MAXF + 8) * (int)sizeof(R);
   int G = s->ngroups;
   if (G > s->n_env) G = s->n_env;
   CUDA_TRY(cudaEventRecord(s->fork_event, q0));

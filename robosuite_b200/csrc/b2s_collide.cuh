@@ -3,6 +3,7 @@
 // convex pairs (mesh support scans are split across the 32 lanes).  Contacts come out ordered by pair index.
 // Replaces the collision stage of mj_step1 (robosuite/utils/binding_utils.py:1101-1103), SURVEY.md section 8 a1.
 #pragma once
+#include <cstdio>
 #include "b2s_engine.cuh"
 
 template <typename R>
@@ -390,8 +391,11 @@ template <typename R> DEVN int box_box(const Shape<R>& A, const Shape<R>& B, R* 
 
 // ---------------------------------------------------------------------------------------------- GJK / EPA (warp)
 // support point of the core shape in world direction dir; mesh scans are split across lanes, result warp-uniform
-template <typename R> DEVN void support_w(const Shape<R>& s, const R* dir, R* out, int lane) {
+// (the direction travels by value: with a pointer to a caller-side local array nvcc 12.9 merged the stack slots of the
+//  direction and of its negation inside epa(), so one of the two supports was evaluated in the wrong direction)
+template <typename R> DEVN void support_w(const Shape<R>& s, R dx, R dy, R dz, R* out, int lane) {
   R l[3], pnt[3] = {0, 0, 0};
+  const R dir[3] = {dx, dy, dz};
   m3mulTv(l, s.mat, dir);
   switch (s.type) {
     case G_BOX:
@@ -433,9 +437,9 @@ template <typename R> DEV R shape_radius(const Shape<R>& s) { return (s.type == 
 template <typename R> struct SV { R w[3], a[3], b[3]; };
 
 template <typename R> DEV void sv_support(const Shape<R>& A, const Shape<R>& B, const R* dir, SV<R>& o, int lane) {
-  R nd[3] = {-dir[0], -dir[1], -dir[2]};
-  support_w(A, dir, o.a, lane);
-  support_w(B, nd, o.b, lane);
+  const R dx = dir[0], dy = dir[1], dz = dir[2];
+  support_w(A, dx, dy, dz, o.a, lane);
+  support_w(B, -dx, -dy, -dz, o.b, lane);
   v3sub(o.w, o.a, o.b);
 }
 
@@ -564,14 +568,16 @@ DEVN int gjk(const Shape<R>& A, const Shape<R>& B, SV<R>* simplex, int& ns, R& d
   return 0;
 }
 
-#define EPA_MAXV 32
-#define EPA_MAXF 64
+#define EPA_MAXV 96   // polytope capacity (same numbers in the oracle: oracle/o_collide.c)
+#define EPA_MAXF 192
 // EPA polytope lives in this warp's scratch: V[EPA_MAXV][9], Fn[EPA_MAXF][4] (normal, dist), Fi[EPA_MAXF] packed ids
 template <typename R>
-DEVN int epa(const Shape<R>& A, const Shape<R>& B, SV<R>* simplex, int ns, R& depth, R* normal, R* wa, R* wb, R* scratch, int lane) {
+DEVN int epa(const Shape<R>& A, const Shape<R>& B, SV<R>* simplex, int ns, R& depth, R* normal, R* wa, R* wb, R* scratch, int lane,
+             int maxv = EPA_MAXV, int maxf = EPA_MAXF) {
+  // polytope capacity: (EPA_MAXV, EPA_MAXF) inside the fused kernel's scratch, larger in the work-list convex kernel
   R* V = scratch;
-  R* Fn = V + 9 * EPA_MAXV;
-  int* Fi = reinterpret_cast<int*>(Fn + 4 * EPA_MAXF);
+  R* Fn = V + 9 * maxv;
+  int* Fi = reinterpret_cast<int*>(Fn + 4 * maxf);
   int nV = 0, nF = 0;
   SV<R> S[4];
   for (int k = 0; k < ns; k++) S[k] = simplex[k];
@@ -639,7 +645,7 @@ DEVN int epa(const Shape<R>& A, const Shape<R>& B, SV<R>* simplex, int ns, R& de
   __syncwarp();
   int bestf = -1;
   const R epa_tol = sizeof(R) == 4 ? R(1e-6) : R(1e-7);
-  for (int it = 0; it < 40; it++) {
+  for (int it = 0; it < 100; it++) {
     // closest alive face (lane-parallel scan)
     R bd = Lim<R>::big();
     int bf = 0x7fffffff;
@@ -654,9 +660,12 @@ DEVN int epa(const Shape<R>& A, const Shape<R>& B, SV<R>* simplex, int ns, R& de
     SV<R> w;
     sv_support(A, B, fn, w, lane);
     R dw = v3dot(w.w, fn);
-    if (dw - bd < epa_tol || nV >= EPA_MAXV - 1 || nF >= EPA_MAXF - 16) break;
+#ifdef B2S_EPA_TRACE
+    if (lane == 0) printf("dev it %d bf %d bd %.9g dw %.9g nV %d nF %d n %.4f %.4f %.4f\n", it, bf, (double)bd, (double)dw, nV, nF, (double)fn[0], (double)fn[1], (double)fn[2]);
+#endif
+    if (dw - bd < epa_tol || nV >= maxv - 1 || nF >= maxf - 16) break;
     // remove visible faces, build the horizon (sequential, warp-uniform; lane 0 writes)
-    int edges[32];
+    int edges[64];
     int ne = 0;
     for (int f = 0; f < nF; f++) {
       int fi = Fi[f];
@@ -673,18 +682,21 @@ DEVN int epa(const Shape<R>& A, const Shape<R>& B, SV<R>* simplex, int ns, R& de
           int a = vs[k], b = vs[(k + 1) % 3], found = 0;
           for (int q = 0; q < ne; q++)
             if (edges[q] == (b | (a << 8))) { edges[q] = edges[ne - 1]; ne--; found = 1; break; }
-          if (!found && ne < 32) edges[ne++] = a | (b << 8);
+          if (!found && ne < 64) edges[ne++] = a | (b << 8);
         }
       }
     }
     __syncwarp();
+#ifdef B2S_EPA_TRACE
+    if (lane == 0) printf("dev    ne %d\n", ne);
+#endif
     if (ne == 0) break;
     int vi = nV;
     if (lane == 0)
       for (int e = 0; e < 3; e++) { V[9 * vi + e] = w.w[e]; V[9 * vi + 3 + e] = w.a[e]; V[9 * vi + 6 + e] = w.b[e]; }
     nV++;
     __syncwarp();
-    for (int q = 0; q < ne && nF < EPA_MAXF; q++) { mkface(nF, edges[q] & 255, edges[q] >> 8, vi); nF++; }
+    for (int q = 0; q < ne && nF < maxf; q++) { mkface(nF, edges[q] & 255, edges[q] >> 8, vi); nF++; }
     __syncwarp();
   }
   if (bestf < 0) return -1;
@@ -709,7 +721,8 @@ DEVN int epa(const Shape<R>& A, const Shape<R>& B, SV<R>* simplex, int ns, R& de
 }
 
 template <typename R>
-DEVN int convex_convex(const Shape<R>& A, const Shape<R>& B, R* out, int maxn, R* scratch, int lane, R* cache = nullptr) {
+DEVN int convex_convex(const Shape<R>& A, const Shape<R>& B, R* out, int maxn, R* scratch, int lane, R* cache = nullptr,
+                       int maxv = EPA_MAXV, int maxf = EPA_MAXF) {
   SV<R> simplex[4];
   int ns = 0;
   R dist = 0, wa[3], wb[3], n[3], pos[3], pa[3], pb[3];
@@ -726,7 +739,7 @@ DEVN int convex_convex(const Shape<R>& A, const Shape<R>& B, R* out, int maxn, R
     return put(out, 0, maxn, pos, n, dist - ra - rb);
   }
   R depth;
-  if (epa(A, B, simplex, ns, depth, n, wa, wb, scratch, lane) != 0) return 0;
+  if (epa(A, B, simplex, ns, depth, n, wa, wb, scratch, lane, maxv, maxf) != 0) return 0;
   v3addscl(pa, wa, n, ra);
   v3addscl(pb, wb, n, -rb);
   v3add(pos, pa, pb);
@@ -881,8 +894,8 @@ template <typename R> DEVN int collide(Eng<R> e, int& warn, int* dbg3, float* pc
   const WSLayout& L = c_L;
   int lane = e.lane;
   int* cand = reinterpret_cast<int*>(e.p(L.scratch));  // candidate pair indices, analytic first then gjk
-  int* cand_g = cand + 48;
-  const int MAXC = 48;
+  int* cand_g = cand + 96;
+  const int MAXC = 96;
   int na = 0, ng = 0;
   const R* gpos = e.p(L.gpos); const R* gmat = e.p(L.gmat);
   for (int base = 0; base < m.npair; base += 32) {
@@ -965,7 +978,7 @@ template <typename R> DEVN int collide(Eng<R> e, int& warn, int* dbg3, float* pc
   __syncwarp();
   CTICK(9)
   // --- convex candidates: the whole warp per pair (scratch beyond the candidate lists holds the EPA polytope)
-  R* epa_scratch = e.p(L.scratch) + 96;
+  R* epa_scratch = e.ws + L.total;  // the fused kernel appends the EPA polytope area to every warp's workspace
   for (int ci = 0; ci < ng; ci++) {
     int pidx = cand_g[ci];
     int g1 = m.pair_geom[2 * pidx], g2 = m.pair_geom[2 * pidx + 1];
@@ -1003,7 +1016,7 @@ template <typename R> DEVN int collide(Eng<R> e, int& warn, int* dbg3, float* pc
       R rec[7];
       int gi1 = 0, gi2 = 0, key = 0x7fffffff, rank = 0;
       if (c < ncon) {
-        key = cint[5 * c + 4] * 64 + c;
+        key = cint[5 * c + 4] * 256 + c;
         gi1 = cint[5 * c]; gi2 = cint[5 * c + 1];
         rec[0] = cpos[3 * c]; rec[1] = cpos[3 * c + 1]; rec[2] = cpos[3 * c + 2];
         rec[3] = cfr[3 * c]; rec[4] = cfr[3 * c + 1]; rec[5] = cfr[3 * c + 2];
@@ -1018,7 +1031,7 @@ template <typename R> DEVN int collide(Eng<R> e, int& warn, int* dbg3, float* pc
         cpos[3 * rank] = rec[0]; cpos[3 * rank + 1] = rec[1]; cpos[3 * rank + 2] = rec[2];
         cfr[3 * rank] = rec[3]; cfr[3 * rank + 1] = rec[4]; cfr[3 * rank + 2] = rec[5];
         cdist[rank] = rec[6];
-        cint[5 * rank] = gi1; cint[5 * rank + 1] = gi2; cint[5 * rank + 4] = key / 64;
+        cint[5 * rank] = gi1; cint[5 * rank + 1] = gi2; cint[5 * rank + 4] = key / 256;
       }
     } else if (lane == 0) {
       for (int i = 1; i < ncon; i++)

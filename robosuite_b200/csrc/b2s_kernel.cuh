@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(512, 1) step_kernel(int phases, int nsub, cons
   // region, which is what bounds the instruction-cache working set); warps beyond n_env shadow the last env
   bool live = env < s.n_env;
   if (!live) env = s.n_env - 1;
-  Eng<R> e(smem + (size_t)warp * L.total, lane);
+  Eng<R> e(smem + (size_t)warp * L.fused_stride, lane);
   size_t E = env;
   load_row(e.p(L.qpos), s.qpos + E * m.nq, m.nq, lane);
   load_row(e.p(L.qvel), s.qvel + E * m.nv, m.nv, lane);

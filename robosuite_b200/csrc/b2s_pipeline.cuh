@@ -123,6 +123,8 @@ template <typename R> DEV void ws_store(const Eng<R>& e, R* row, const PhaseIO& 
 // A launch covers one group of environments [env0, env0 + nenv); groups run on separate streams so that the tail of one
 // group's kernel (its slowest environment) overlaps with other groups' work.
 struct Grp { int env0, nenv, gid; };
+#define EPA_PIPE_MAXV EPA_MAXV
+#define EPA_PIPE_MAXF EPA_MAXF
 
 // ---- work-list narrow phase --------------------------------------------------------------------------------------
 // analytic pairs: ONE THREAD per candidate pair of any environment (32 different pairs per warp)
@@ -160,7 +162,7 @@ __global__ void __launch_bounds__(256) narrow_convex_kernel(Grp g) {
   int wid = blockIdx.x * wpb + warp;
   if (wid >= s.cl_cnt[2 * g.gid + 1]) return;
   wid += g.env0 * CL_MAXG;
-  const int EPAW = 9 * EPA_MAXV + 4 * EPA_MAXF + EPA_MAXF + 8;
+  const int EPAW = 9 * EPA_PIPE_MAXV + 4 * EPA_PIPE_MAXF + EPA_PIPE_MAXF + 8;
   R* scratch = reinterpret_cast<R*>(smem_raw) + (size_t)warp * EPAW;
   int code = s.cl_listG[wid];
   int env = code >> 12, pidx = code & 4095;
@@ -171,7 +173,8 @@ __global__ void __launch_bounds__(256) narrow_convex_kernel(Grp g) {
   shape_from(g1, row + L.gpos, row + L.gmat, A);
   shape_from(g2, row + L.gpos, row + L.gmat, B);
   R buf[CREC];
-  int n = convex_convex(A, B, buf, 1, scratch, lane, s.gjk_cache ? s.gjk_cache + ((size_t)env * m.npair + pidx) * 3 : (R*)nullptr);
+  int n = convex_convex(A, B, buf, 1, scratch, lane, s.gjk_cache ? s.gjk_cache + ((size_t)env * m.npair + pidx) * 3 : (R*)nullptr,
+                        EPA_PIPE_MAXV, EPA_PIPE_MAXF);
   R* out = s.cl_outG + (size_t)wid * 8;
   if (lane == 0) {
     out[0] = R(n);
@@ -258,7 +261,7 @@ __global__ void __launch_bounds__(512, 1) phase_kernel(int phases, int sub, int 
     e.crb();
     // collision candidates of this environment -> global work lists (slots by warp-aggregated atomics)
     int* cand = reinterpret_cast<int*>(e.p(L.scratch));
-    int* cand_g = cand + 48;
+    int* cand_g = cand + 96;
     int na, ng;
     cull_pairs(e, cand, cand_g, CL_MAXA, CL_MAXG, na, ng);
     if (na > CL_MAXA) { na = CL_MAXA; warn |= 4; }

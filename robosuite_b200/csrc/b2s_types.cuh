@@ -102,6 +102,7 @@ struct WSLayout {
   int J, e_D, e_R, e_aref, e_jar, e_jv, e_force, e_floss, e_int;        // e_int: 2 ints per row (type,id)
   int Ma, grad, search, Mv;
   int scratch, scratch_size;
+  int fused_stride;  // words per warp in the fused kernel = total + EPA polytope area
   int hdr;  // 8 words of per-env integers passed between pipeline phases: ncon, nefc, warn, niter
   int total;
 };

@@ -253,3 +253,89 @@ def test_pipeline_gjk_warm_start_changes_paths_not_results():
     dq = np.abs(a[0] - b[0]).max()
     print("pipeline(warm start) vs fused after 300 substeps: max |dqpos| %.3g" % dq)
     assert dq < 1e-4
+
+
+@pytest.mark.parametrize("name", ["Stack_Panda", "NutAssemblyRound_Panda", "Door_Panda", "PickPlace_Panda", "Lift_Sawyer"])
+def test_engine_parity_other_task_models(name):
+    """engine-level parity (forward + 60 substeps, gravity-compensating torques) on the other BASELINE task models"""
+    import torch
+    from robosuite_b200.engine import BatchedSim
+
+    model = load(name)
+    n = 2
+    rng = np.random.default_rng(0)
+    q = np.tile(model.qpos0, (n, 1))
+    arm = [i for i, nm in enumerate(model.names["joint"]) if nm and nm.startswith("robot0_") and model.jnt_type[i] == 3]
+    init = np.array([0, np.pi / 16.0, 0.00, -np.pi / 2.0 - np.pi / 3.0, 0.00, np.pi - 0.2, np.pi / 4]) if "Panda" in name \
+        else np.array([0, -1.18, 0.00, 2.18, 0.00, 0.57, -1.57])
+    for k, j in enumerate(arm):
+        q[:, model.jnt_qposadr[j]] = init[k] + rng.normal(0, 0.02, n)
+    # free bodies: spread them out (several models park all objects at the same default pose) and lift them a little so
+    # that they drop onto whatever is below them
+    k = 0
+    for j in range(model.njnt):
+        if model.jnt_type[j] == 0:
+            if name.startswith("PickPlace"):  # objects default to the world origin: drop them into the first bin instead
+                a = model.jnt_qposadr[j]
+                q[:, a] = 0.1 + 0.1 * (k - 1.5)
+                q[:, a + 1] = -0.25 + 0.1 * (k - 1.5)
+                q[:, a + 2] = 0.9
+            else:
+                q[:, model.jnt_qposadr[j] + 1] += 0.12 * k - 0.12
+            k += 1
+            q[:, model.jnt_qposadr[j] + 2] += 0.02
+    sim = BatchedSim(model, n, precision="f32", maxcon=96, maxefc=288)
+    sim.qpos.copy_(torch.as_tensor(q, dtype=torch.float32))
+    sim.forward()
+    torch.cuda.synchronize()
+    o = _oracle(model)
+    errs = []
+    ncon_h, cg_h, cd_h = sim.ncon.cpu().numpy(), sim.contact_geom.cpu().numpy(), sim.contact_dist.cpu().numpy()
+    qacc_h, nefc_h = sim.qacc.cpu().numpy(), sim.nefc.cpu().numpy()
+    for e in range(n):
+        o.reset_data(); o.qpos[:] = q[e]; o.forward()
+        # contact sets must agree except for knife-edge contacts (|dist| below fp32 resolution: geoms that touch exactly
+        # in the model, where activation depends on the last bit in any engine)
+        nd = int(ncon_h[e])
+        dev = {}
+        for c in range(nd):
+            dev.setdefault((int(cg_h[e, c, 0]), int(cg_h[e, c, 1])), []).append(float(cd_h[e, c]))
+        ora = {}
+        for c in o.contacts():
+            ora.setdefault((c["geom1"], c["geom2"]), []).append(c["dist"])
+        knife = False
+        for key in set(dev) | set(ora):
+            a, b = dev.get(key, []), ora.get(key, [])
+            if len(a) != len(b):
+                knife = True
+                # a pair present on one side only must be a zero-depth touch; a pair present on both sides may differ in
+                # the NUMBER of manifold points when faces are exactly aligned (clipping keeps / drops boundary vertices)
+                if not a or not b:
+                    assert all(abs(x) < 2e-6 for x in a + b), (name, e, key, a, b)
+        if not knife:
+            assert int(nefc_h[e]) == o.nefc
+            errs.append(np.abs(qacc_h[e] - o.qacc).max() / max(np.abs(o.qacc).max(), 1e-9))
+    assert not errs or max(errs) < 2e-2, (name, errs)  # Door: ~90 stiff rows at rest, fp32 solve
+    # hold the arm with its bias torques, let objects settle for 60 substeps
+    bias = sim.qfrc_bias.clone()
+    ctrl = torch.zeros((n, model.nu), dtype=torch.float32, device=sim.torch_device)
+    for i in range(model.nu):
+        d = int(model.jnt_dofadr[model.actuator_trnid[i]])
+        if model.actuator_biastype[i] == 0:
+            ctrl[:, i] = bias[:, d]
+    sim.ctrl.copy_(ctrl)
+    sim.step(60)
+    torch.cuda.synchronize()
+    assert int(sim.warn.abs().max()) == 0, (name, sim.warn.tolist())
+    qd = sim.qpos.cpu().numpy().astype(np.float64)
+    cn = ctrl.cpu().numpy().astype(np.float64)
+    worst = 0.0
+    for e in range(n):
+        o.reset_data(); o.qpos[:] = q[e]; o.ctrl[:] = cn[e]
+        for _ in range(60):
+            o.step()
+        worst = max(worst, np.abs(qd[e] - o.qpos).max() / np.abs(o.qpos).max())
+    print(name, "forward qacc rel err %.3g (%d of %d envs without knife-edge contacts), 60-substep qpos rel err %.3g" % (
+        max(errs) if errs else float("nan"), len(errs), n, worst))
+    assert worst < (1e-4 if len(errs) == n else 2e-3)
+    sim.close()
