@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -337,8 +338,8 @@ template <typename R> static void build_state(b2s_sim* s, const DModel<R>& m, DS
 static void build_layout(b2s_sim* s, int nq, int nv, int nu, int nb, int ncg, int ns, int mc, int me, int hc_stride) {
   WSLayout& L = s->L;
   int o = 0;
-  auto take = [&](int n) { int r = o; o += (n + 1) & ~1; return r; };  // keep 8-byte alignment for fp32 builds
-  auto rec = [&](const char* name, int off, int n) { s->reg[name] = Region{off, (n + 1) & ~1, 0}; };
+  auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };  // every region 16-byte aligned (TMA bulk copies)
+  auto rec = [&](const char* name, int off, int n) { s->reg[name] = Region{off, (n + 3) & ~3, 0}; };
   // persistent across substeps
   L.qpos = take(nq); L.qvel = take(nv); L.qacc = take(nv); L.qacc_ws = take(nv); L.ctrl = take(nu);
   // live from step1 to the end of the substep (controller, solver, observations read them)
@@ -359,14 +360,14 @@ static void build_layout(b2s_sim* s, int nq, int nv, int nu, int nb, int ncg, in
   L.gpos = take(3 * ncg); L.gmat = take(9 * ncg);
   int uend = o;
   L.J = ubase;
-  if (ubase + me * nv > uend) uend = ubase + ((me * nv + 1) & ~1);
+  if (ubase + me * nv > uend) uend = ubase + ((me * nv + 3) & ~3);
   o = uend;
   int sc = 10 * nb;
   if (200 > sc) sc = 200;  // candidate lists of the fused collision
   int hs = me + hc_stride * mc + 64;  // + support dof list of the Hessian assembly
   if (hs > sc) sc = hs;
   if (9 * mc > sc) sc = 9 * mc;
-  if (sc < 720) sc = 720;  // fused controller work area (336 doubles)
+  if (sc < 672) sc = 672;  // controller work area (336 doubles)
   L.scratch_size = sc;
   L.scratch = take(sc);
   L.hdr = take(8);
@@ -378,11 +379,27 @@ static void build_layout(b2s_sim* s, int nq, int nv, int nu, int nb, int ncg, in
   rec("c_pos", L.c_pos, 3 * mc); rec("c_frame", L.c_frame, 3 * mc); rec("c_dist", L.c_dist, mc); rec("c_fric", L.c_fric, 3 * mc);
   rec("c_int", L.c_int, 5 * mc); rec("e_D", L.e_D, me); rec("e_R", L.e_R, me); rec("e_aref", L.e_aref, me);
   rec("e_floss", L.e_floss, me); rec("e_int", L.e_int, me);
-  s->reg["J"] = Region{L.J, (me * nv + 1) & ~1, 1};
+  s->reg["J"] = Region{L.J, (me * nv + 3) & ~3, 1};
+  // adjacent regions merge into one span (one bulk copy); the dynamic Jacobian span stays on its own
+  auto spans = [&](std::initializer_list<const char*> names, Region* out, int& n, int* words, int* dyn) {
+    std::vector<Region> v;
+    for (const char* nm : names) v.push_back(s->reg[nm]);
+    std::sort(v.begin(), v.end(), [](const Region& a, const Region& b) { return a.off < b.off; });
+    n = 0;
+    if (words) *words = 0;
+    if (dyn) *dyn = 0;
+    for (const Region& r : v) {
+      if (n > 0 && !r.dyn && !out[n - 1].dyn && out[n - 1].off + out[n - 1].len == r.off) out[n - 1].len += r.len;
+      else out[n++] = r;
+    }
+    for (int k = 0; k < n; k++) {
+      if (out[k].dyn) { if (dyn) *dyn = 1; }
+      else if (words) *words += out[k].len;
+    }
+  };
   auto mk = [&](PhaseIO& io, std::initializer_list<const char*> ld, std::initializer_list<const char*> st) {
-    io.nload = io.nstore = 0;
-    for (const char* n : ld) io.load[io.nload++] = s->reg[n];
-    for (const char* n : st) io.store[io.nstore++] = s->reg[n];
+    spans(ld, io.load, io.nload, &io.load_words, &io.load_dyn);
+    spans(st, io.store, io.nstore, nullptr, nullptr);
   };
   mk(s->pio[0], {}, {"xpos", "xquat", "xmat", "cdof", "cvel", "M", "bias", "passive", "spos", "smat", "gpos", "gmat"});
   mk(s->pio[1], {"gpos", "gmat"}, {"c_pos", "c_frame", "c_dist", "c_fric", "c_int"});

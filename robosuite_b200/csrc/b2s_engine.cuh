@@ -31,30 +31,35 @@ DEVN int spd_solve_reg(const R* A, int n, const R* dadd, R dscale, R* x, int lan
   R b = lane < n ? x[row] : R(0);
   R invd = 1;  // 1 / L[lane][lane]
   int bad = 0;
+  // After step j: lanes i > j hold l_ij in a[j]; lane j keeps its row entries a[k], k > j, UNSCALED (u_jk = a[k] * invd is
+  // formed where it is used), which leaves one multiply + shuffle + FMA per trailing entry and no selects.
 #pragma unroll
   for (int j = 0; j < NVP; j++) {
     R d = __shfl_sync(B2S_FULL, a[j], j);
     if (!(d > Lim<R>::minval())) { bad = 1; d = Lim<R>::minval(); }
     R inv = r_rsqrt(d);
     invd = (lane == j) ? inv : invd;
-    a[j] = (lane >= j) ? a[j] * inv : a[j];  // lane i > j: l_ij ; lane j: sqrt(d) ; lanes < j keep their finished u_ij
+    R lj = (lane > j) ? a[j] * inv : R(0);
+    a[j] = (lane > j) ? lj : a[j];
 #pragma unroll
     for (int k = j + 1; k < NVP; k++) {
-      R u = __shfl_sync(B2S_FULL, a[k] * inv, j);  // lane j's scaled row entry: u_jk = l_kj
-      a[k] = (lane == j) ? u : ((lane > j) ? a[k] - a[j] * u : a[k]);
+      R u = __shfl_sync(B2S_FULL, a[k], j) * inv;  // l_kj
+      a[k] -= lj * u;
     }
   }
   // forward: L y = b
 #pragma unroll
   for (int k = 0; k < NVP; k++) {
     R yk = __shfl_sync(B2S_FULL, b * invd, k);
-    b = (lane == k) ? yk : ((lane > k) ? b - a[k] * yk : b);
+    R t = (lane > k) ? a[k] : R(0);
+    b = (lane == k) ? yk : b - t * yk;
   }
-  // backward: L^T x = y   (a[k], k > lane, holds u_lane,k = l_k,lane)
+  // backward: L^T x = y   (u_lane,k = a[k] * invd for k > lane)
 #pragma unroll
   for (int k = NVP - 1; k >= 0; k--) {
     R xk = __shfl_sync(B2S_FULL, b * invd, k);
-    b = (lane == k) ? xk : ((lane < k) ? b - a[k] * xk : b);
+    R t = (lane < k) ? a[k] * invd : R(0);
+    b = (lane == k) ? xk : b - t * xk;
   }
   if (lane < n) x[lane] = b;
   __syncwarp();
@@ -64,6 +69,7 @@ DEVN int spd_solve_reg(const R* A, int n, const R* dadd, R dscale, R* x, int lan
 // Block-diagonal variant: the matrix couples dofs only within kinematic trees (always true for M and M + h D, true for
 // the Newton Hessian when no active contact joins two different moving trees).  Every tree is eliminated at the same
 // time by its own lanes: lane i keeps row i restricted to its tree's columns (NVB = padded size of the largest tree).
+// Lanes whose tree is smaller than the current column see d = 1, l = 0 and shuffle from themselves: no-ops without selects.
 template <typename R, int NVB>
 DEVN int spd_solve_blk(const R* A, int n, const R* dadd, R dscale, R* x, int lane) {
   const DModel<R>& m = cmodel<R>();
@@ -90,24 +96,27 @@ DEVN int spd_solve_blk(const R* A, int n, const R* dadd, R dscale, R* x, int lan
     if (!on) d = 1;
     R inv = r_rsqrt(d);
     invd = (on && li == j) ? inv : invd;
-    a[j] = (on && li >= j) ? a[j] * inv : a[j];
+    R lj = (on && li > j) ? a[j] * inv : R(0);
+    a[j] = (on && li > j) ? lj : a[j];
 #pragma unroll
     for (int k = j + 1; k < NVB; k++) {
-      R u = __shfl_sync(B2S_FULL, a[k] * inv, src);
-      a[k] = !on ? a[k] : ((li == j) ? u : ((li > j) ? a[k] - a[j] * u : a[k]));
+      R u = __shfl_sync(B2S_FULL, a[k], src) * inv;
+      a[k] -= lj * u;
     }
   }
 #pragma unroll
   for (int k = 0; k < NVB; k++) {
     bool on = k < size;
     R yk = __shfl_sync(B2S_FULL, b * invd, on ? base + k : lane);
-    b = !on ? b : ((li == k) ? yk : ((li > k) ? b - a[k] * yk : b));
+    R t = (on && li > k) ? a[k] : R(0);
+    b = (on && li == k) ? yk : b - t * yk;
   }
 #pragma unroll
   for (int k = NVB - 1; k >= 0; k--) {
     bool on = k < size;
     R xk = __shfl_sync(B2S_FULL, b * invd, on ? base + k : lane);
-    b = !on ? b : ((li == k) ? xk : ((li < k) ? b - a[k] * xk : b));
+    R t = (on && li < k) ? a[k] * invd : R(0);
+    b = (on && li == k) ? xk : b - t * xk;
   }
   if (lane < n) x[lane] = b;
   __syncwarp();

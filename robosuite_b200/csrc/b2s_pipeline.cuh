@@ -52,71 +52,40 @@ DEV void tma_store_1d(void* gdst, const void* smem_src, unsigned bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
 }
 
-// 16-byte aligned interior of a region goes through TMA, the (<= 3 word) head and tail through ordinary lane copies
-template <typename R> DEV void span16(int off, int len, int& a0, int& a1) {
-  const int W = 16 / (int)sizeof(R);
-  a0 = (off + W - 1) / W * W;
-  a1 = (off + len) / W * W;
-  if (a1 < a0) a1 = a0;
-}
-
+// Every region of a phase's load / store list is 16-byte aligned in offset and length (build_layout) and adjacent regions
+// are merged into spans on the host, so a phase moves its workspace with a handful of bulk copies: lane k issues span k.
 template <typename R> DEV void ws_load(const Eng<R>& e, const R* row, const PhaseIO& io, int nefc_nv, unsigned long long* bar) {
+  const int W = 16 / (int)sizeof(R);
+  int dynlen = (nefc_nv + W - 1) / W * W;
 #if B2S_TMA
-  unsigned total = 0;
-  for (int k = 0; k < io.nload; k++) {
-    int len = io.load[k].dyn == 1 ? ((nefc_nv + 1) & ~1) : io.load[k].len, a0, a1;
-    span16<R>(io.load[k].off, len, a0, a1);
-    total += (unsigned)(a1 - a0) * sizeof(R);
-  }
-  if (e.lane == 0) {
-    mbar_expect_tx(bar, total);
-    for (int k = 0; k < io.nload; k++) {
-      int len = io.load[k].dyn == 1 ? ((nefc_nv + 1) & ~1) : io.load[k].len, a0, a1;
-      span16<R>(io.load[k].off, len, a0, a1);
-      if (a1 > a0) tma_load_1d(e.ws + a0, row + a0, (unsigned)(a1 - a0) * sizeof(R), bar);
-    }
-  }
-  for (int k = 0; k < io.nload; k++) {
-    int off = io.load[k].off, len = io.load[k].dyn == 1 ? ((nefc_nv + 1) & ~1) : io.load[k].len, a0, a1;
-    span16<R>(off, len, a0, a1);
-    int nh = (a0 < off + len ? a0 : off + len) - off, nt = off + len - a1;
-    if (e.lane < nh) e.ws[off + e.lane] = row[off + e.lane];
-    if (a1 > a0 && e.lane < nt) e.ws[a1 + e.lane] = row[a1 + e.lane];
+  if (e.lane == 0) mbar_expect_tx(bar, (unsigned)(io.load_words + (io.load_dyn ? dynlen : 0)) * (unsigned)sizeof(R));
+  __syncwarp();
+  if (e.lane < io.nload) {
+    Region r = io.load[e.lane];
+    int len = r.dyn == 1 ? dynlen : r.len;
+    if (len > 0) tma_load_1d(e.ws + r.off, row + r.off, (unsigned)len * sizeof(R), bar);
   }
   mbar_wait(bar, 0);
 #else
-  for (int k = 0; k < io.nload; k++) {
-    int len = io.load[k].dyn == 1 ? ((nefc_nv + 1) & ~1) : io.load[k].len;
-    row_copy(e.ws + io.load[k].off, row + io.load[k].off, len, e.lane);
-  }
+  for (int k = 0; k < io.nload; k++) row_copy(e.ws + io.load[k].off, row + io.load[k].off, io.load[k].dyn == 1 ? dynlen : io.load[k].len, e.lane);
 #endif
 }
 template <typename R> DEV void ws_store(const Eng<R>& e, R* row, const PhaseIO& io, int nefc_nv) {
+  const int W = 16 / (int)sizeof(R);
+  int dynlen = (nefc_nv + W - 1) / W * W;
 #if B2S_TMA
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // this lane's generic-proxy writes -> visible to the async proxy
   __syncwarp();
-  if (e.lane == 0) {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the async proxy
-    for (int k = 0; k < io.nstore; k++) {
-      int len = io.store[k].dyn == 1 ? ((nefc_nv + 1) & ~1) : io.store[k].len, a0, a1;
-      span16<R>(io.store[k].off, len, a0, a1);
-      if (a1 > a0) tma_store_1d(row + a0, e.ws + a0, (unsigned)(a1 - a0) * sizeof(R));
-    }
+  if (e.lane < io.nstore) {
+    Region r = io.store[e.lane];
+    int len = r.dyn == 1 ? dynlen : r.len;
+    if (len > 0) tma_store_1d(row + r.off, e.ws + r.off, (unsigned)len * sizeof(R));
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
-  for (int k = 0; k < io.nstore; k++) {
-    int off = io.store[k].off, len = io.store[k].dyn == 1 ? ((nefc_nv + 1) & ~1) : io.store[k].len, a0, a1;
-    span16<R>(off, len, a0, a1);
-    int nh = (a0 < off + len ? a0 : off + len) - off, nt = off + len - a1;
-    if (e.lane < nh) row[off + e.lane] = e.ws[off + e.lane];
-    if (a1 > a0 && e.lane < nt) row[a1 + e.lane] = e.ws[a1 + e.lane];
-  }
-  if (e.lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   __syncwarp();
 #else
-  for (int k = 0; k < io.nstore; k++) {
-    int len = io.store[k].dyn == 1 ? ((nefc_nv + 1) & ~1) : io.store[k].len;
-    row_copy(row + io.store[k].off, e.ws + io.store[k].off, len, e.lane);
-  }
+  for (int k = 0; k < io.nstore; k++) row_copy(row + io.store[k].off, e.ws + io.store[k].off, io.store[k].dyn == 1 ? dynlen : io.store[k].len, e.lane);
 #endif
 }
 

@@ -428,19 +428,23 @@ template <typename R> DEVN int solve(Eng<R> e, int nefc, int ncon, int& warn) {
   __syncwarp();
   R prev_cost = 0;
   int niter = 0;
+  // Ma = M qacc and jar = J qacc - aref are formed once and then moved along the search direction with the step
+  // (Ma += alpha Mv, jar += alpha jv), as the reference engine does
+  for (int i = lane; i < nv; i += 32) {
+    R s = 0;
+    for (int k = 0; k < nv; k++) s += M[i * nv + k] * qacc[k];
+    Ma[i] = s;
+  }
+  for (int r = lane; r < nefc; r += 32) {
+    R s = -aref[r];
+    for (int k = 0; k < nv; k++) s += J[r * nv + k] * qacc[k];
+    jar[r] = s;
+  }
+  __syncwarp();
+  bool stale = false;  // efc_force older than jar?
   for (int iter = 0; iter <= m.iterations; iter++) {
-    for (int i = lane; i < nv; i += 32) {
-      R s = 0;
-      for (int k = 0; k < nv; k++) s += M[i * nv + k] * qacc[k];
-      Ma[i] = s;
-    }
-    for (int r = lane; r < nefc; r += 32) {
-      R s = -aref[r];
-      for (int k = 0; k < nv; k++) s += J[r * nv + k] * qacc[k];
-      jar[r] = s;
-    }
-    __syncwarp();
     R cost = constraint_update(e, nefc, ncon, true);
+    stale = false;
     R gs = 0, gn = 0;
     for (int i = lane; i < nv; i += 32) gs += R(0.5) * (Ma[i] - qs[i]) * (qacc[i] - qas[i]);
     cost += warp_sum(gs);
@@ -551,18 +555,14 @@ template <typename R> DEVN int solve(Eng<R> e, int nefc, int ncon, int& warn) {
       if (hi >= 0 && hi - lo < (sizeof(R) == 4 ? R(1e-7) : R(1e-15)) * r_max(R(1), hi)) break;
       alpha = next;
     }
-    for (int i = lane; i < nv; i += 32) qacc[i] += alpha * search[i];
+    for (int i = lane; i < nv; i += 32) { qacc[i] += alpha * search[i]; Ma[i] += alpha * Mv[i]; }
+    for (int r = lane; r < nefc; r += 32) jar[r] += alpha * jv[r];
+    stale = true;
     __syncwarp();
     if (last) break;
   }
   // --- final forces at the solution
-  for (int r = lane; r < nefc; r += 32) {
-    R s = -aref[r];
-    for (int k = 0; k < nv; k++) s += J[r * nv + k] * qacc[k];
-    jar[r] = s;
-  }
-  __syncwarp();
-  constraint_update(e, nefc, ncon, false);
+  if (stale) constraint_update(e, nefc, ncon, false);
   for (int i = lane; i < nv; i += 32) {
     R s = 0;
     for (int r = 0; r < nefc; r++) s += J[r * nv + i] * force[r];

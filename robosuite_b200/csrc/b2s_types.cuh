@@ -116,7 +116,8 @@ struct Region { int off, len, dyn; };  // dyn: 0 fixed, 1 = nefc*nv words (const
 #define CL_RECA 58
 #define CL_ENVW (2 + 2 * (CL_MAXA + CL_MAXG))
 #define B2S_MAXREG 20
-struct PhaseIO { int nload, nstore; Region load[B2S_MAXREG], store[B2S_MAXREG]; };
+// load / store lists hold merged 16-byte aligned spans; load_words = sum of the fixed spans, load_dyn = list has the Jacobian
+struct PhaseIO { int nload, nstore, load_words, load_dyn; Region load[B2S_MAXREG], store[B2S_MAXREG]; };
 
 // observation scalar ops (one table entry per output scalar)
 enum { OB_QPOS = 0, OB_COS_QPOS, OB_SIN_QPOS, OB_QVEL, OB_QACC, OB_SITE_POS, OB_BODY_POS, OB_BODY_QUAT_XYZW, OB_SITE_QUAT_XYZW,

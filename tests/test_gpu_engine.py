@@ -279,7 +279,7 @@ def test_engine_parity_other_task_models(name):
                 a = model.jnt_qposadr[j]
                 q[:, a] = 0.1 + 0.1 * (k - 1.5)
                 q[:, a + 1] = -0.25 + 0.1 * (k - 1.5)
-                q[:, a + 2] = 0.9
+                q[:, a + 2] = [0.885, 0.845, 0.90, 0.865][k]  # just above each object's resting height in the bin
             else:
                 q[:, model.jnt_qposadr[j] + 1] += 0.12 * k - 0.12
             k += 1

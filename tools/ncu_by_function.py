@@ -8,6 +8,20 @@ import sys
 import tempfile
 
 
+def select_section(rows):
+    """a report with several kernels prints one (Kernel Name, header, rows...) section per kernel: keep the first one
+    whose demangled name contains $NCU_KERNEL_MATCH (default: the first section)"""
+    want = os.environ.get("NCU_KERNEL_MATCH", "")
+    starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+    if not starts:
+        return rows
+    starts.append(len(rows))
+    for a, b in zip(starts[:-1], starts[1:]):
+        if want in rows[a][1]:
+            return rows[a:b]
+    raise SystemExit("no kernel section matches " + want)
+
+
 def main():
     rep, so = sys.argv[1], sys.argv[2]
     kname = sys.argv[3] if len(sys.argv) > 3 else "step_kernelIf"
@@ -22,7 +36,7 @@ def main():
             funcs.append((int(f[1], 16), int(f[2], 0), f[7].split("$")[-1] if "$" in f[7] else "<kernel body>"))
     funcs.sort()
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(io.StringIO(out)))
+    rows = select_section(list(csv.reader(io.StringIO(out))))
     hdr = rows[1]
     ia, ii, ist = hdr.index("Address"), hdr.index("Instructions Executed"), hdr.index("# Samples")
     ino = hdr.index("stall_no_inst")

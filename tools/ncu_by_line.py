@@ -2,6 +2,21 @@
 usage: python tools/ncu_by_line.py <report.ncu-rep> <lib.so> <kernel-substr> <function-substr> [topN]"""
 import csv, io, os, re, subprocess, sys, tempfile, collections
 
+
+def select_section(rows):
+    """a report with several kernels prints one (Kernel Name, header, rows...) section per kernel: keep the first one
+    whose demangled name contains $NCU_KERNEL_MATCH (default: the first section)"""
+    want = os.environ.get("NCU_KERNEL_MATCH", "")
+    starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+    if not starts:
+        return rows
+    starts.append(len(rows))
+    for a, b in zip(starts[:-1], starts[1:]):
+        if want in rows[a][1]:
+            return rows[a:b]
+    raise SystemExit("no kernel section matches " + want)
+
+
 rep, so, kname, fname = sys.argv[1:5]
 topn = int(sys.argv[5]) if len(sys.argv) > 5 else 40
 tmp = tempfile.mkdtemp()
@@ -31,7 +46,7 @@ for l in dis:
     if m:
         addr2[int(m.group(1), 16)] = (cur_fn, cur_line)
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
-rows = list(csv.reader(io.StringIO(out)))
+rows = select_section(list(csv.reader(io.StringIO(out))))
 hdr = rows[1]
 ia, ii = hdr.index("Address"), hdr.index("Instructions Executed")
 base = None
