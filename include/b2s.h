@@ -96,6 +96,14 @@ int b2s_task_config(b2s_sim* sim, int body, int site, const int* left, int nleft
                     const int* obj, int nobj);
 /* optional second object (Stack's cubeB: staged_rewards, manipulation/stack.py:266-312); call after b2s_task_config */
 int b2s_task_config2(b2s_sim* sim, int body2, const int* obj2, int nobj2);
+/* optional per-object grasp flags for multi-object tasks (NutAssembly / PickPlace staged_rewards check the grasp against
+ * the geoms of the still-active objects: manipulation/nut_assembly.py:318-327, pick_place.py:352-361): up to 4 objects,
+ * geoms = concatenated geom id lists, counts[i] = length of list i.  task_out[5] = sum_i 2^i * grasped_i. */
+int b2s_task_objects(b2s_sim* sim, int nobjects, const int* geoms, const int* counts);
+/* task table: n (<= 64) scalars in the observation-table encoding, evaluated after the LAST substep of b2s_env_step into
+ * the array "task_vec" [n_env, n] - the poses reward()/_check_success() read from sim.data after the step
+ * (manipulation/door.py:219-266, nut_assembly.py:247-400, pick_place.py:275-425). Requires b2s_obs_config first. */
+int b2s_task_table(b2s_sim* sim, int n, const int* op, const int* a, const int* b);
 
 /* b2s_env_step also exports the derived arrays of its last substep (xpos, contacts, efc ...) when flag != 0 (default 1);
  * the throughput path switches it off so that per-step HBM traffic is state + action + obs only */

@@ -572,7 +572,7 @@ template <typename R> static int enqueue_pipeline(b2s_sim* s, DState<R>& st, int
     int e0 = (int)((long long)s->n_env * gi / G), e1 = (int)((long long)s->n_env * (gi + 1) / G);
     Grp g{e0, e1 - e0, gi};
     int blocks = (g.nenv + s->wpb - 1) / s->wpb;
-    int nA = g.nenv * CL_MAXA, nG = g.nenv * CL_MAXG;
+    int nA = g.nenv * st.cl_maxa, nG = g.nenv * st.cl_maxg;
     for (int sub = 0; sub < nsub; sub++) {
       CUDA_TRY(cudaMemsetAsync(st.cl_cnt + 2 * gi, 0, 2 * sizeof(int), q));
       phase_kernel<R, 0><<<blocks, threads, s->smem_bytes, q>>>(phases, sub, nsub, action, g);
@@ -601,9 +601,14 @@ template <typename R> static int launch_pipeline_t(b2s_sim* s, DState<R>& st, in
     st.wsg = p;
     size_t ne = (size_t)s->n_env;
     st.cl_cnt = dev_zeros<int>(s, 2 * 64);
-    st.cl_listA = dev_zeros<int>(s, ne * CL_MAXA); st.cl_listG = dev_zeros<int>(s, ne * CL_MAXG);
-    st.cl_outA = dev_zeros<R>(s, ne * CL_MAXA * CL_RECA); st.cl_outG = dev_zeros<R>(s, ne * CL_MAXG * 8);
-    st.cl_env = dev_zeros<int>(s, ne * CL_ENVW);
+    // candidate capacity per environment: small models keep small grids (the narrow-phase grids are sized by these bounds)
+    st.cl_maxa = s->maxcon <= 32 ? 8 : (s->maxcon <= 48 ? 16 : CL_MAXA);
+    st.cl_maxg = s->maxcon <= 32 ? 16 : CL_MAXG;
+    if (const char* v = getenv("B2S_CL_MAXA")) { int x = atoi(v); if (x >= 1 && x <= CL_MAXA) st.cl_maxa = x; }
+    if (const char* v = getenv("B2S_CL_MAXG")) { int x = atoi(v); if (x >= 1 && x <= CL_MAXG) st.cl_maxg = x; }
+    st.cl_listA = dev_zeros<int>(s, ne * st.cl_maxa); st.cl_listG = dev_zeros<int>(s, ne * st.cl_maxg);
+    st.cl_outA = dev_zeros<R>(s, ne * st.cl_maxa * CL_RECA); st.cl_outG = dev_zeros<R>(s, ne * st.cl_maxg * 8);
+    st.cl_env = dev_zeros<int>(s, ne * CL_ENVW(st));
     st.gjk_cache = getenv("B2S_NO_GJK_CACHE") ? nullptr : dev_zeros<R>(s, ne * (size_t)(s->precision == B2S_F32 ? s->mf.npair : s->md.npair) * 3);
     s->action_buf = dev_zeros<R>(s, ne * 16);
     s->dirty = 1;
@@ -759,8 +764,14 @@ int b2s_obs_config(b2s_sim* s, int obs_dim, const int* op, const int* a, const i
     std::vector<int> vo(op, op + obs_dim), va(a, a + obs_dim), vb(b, b + obs_dim);
     s->ctrl.obs_dim = obs_dim;
     s->ctrl.obs_op = dev_upload(s, vo); s->ctrl.obs_a = dev_upload(s, va); s->ctrl.obs_b = dev_upload(s, vb);
-    if (s->precision == B2S_F32) { s->sf.obs = state_arr<float>(s, "obs", obs_dim); s->sf.task_out = state_arr<float>(s, "task_out", 8); }
-    else { s->sd.obs = state_arr<double>(s, "obs", obs_dim); s->sd.task_out = state_arr<double>(s, "task_out", 8); }
+    if (obs_dim > 128) throw std::string("obs_dim > 128 not supported");
+    int* fresh = state_arr_i(s, "obs_fresh", 0);
+    {
+      std::vector<int> ones(s->n_env, 1);
+      if (cudaMemcpy(fresh, ones.data(), sizeof(int) * s->n_env, cudaMemcpyHostToDevice) != cudaSuccess) throw std::string("obs_fresh upload failed");
+    }
+    if (s->precision == B2S_F32) { s->sf.obs = state_arr<float>(s, "obs", obs_dim); s->sf.task_out = state_arr<float>(s, "task_out", 8); s->sf.obs_fresh = fresh; }
+    else { s->sd.obs = state_arr<double>(s, "obs", obs_dim); s->sd.task_out = state_arr<double>(s, "task_out", 8); s->sd.obs_fresh = fresh; }
   } catch (const std::string& e) { return fail(B2S_ERR_CUDA, e); }
   s->has_obs = 1;
   s->dirty = 1;
@@ -776,6 +787,34 @@ int b2s_task_config2(b2s_sim* s, int body2, const int* obj2, int no2) {
     if (k >= 0) mk |= 1ull << k;
   }
   s->ctrl.task_body2 = body2; s->ctrl.mask_obj2 = mk; s->dirty = 1;
+  return B2S_OK;
+}
+
+int b2s_task_table(b2s_sim* s, int n, const int* op, const int* a, const int* b) {
+  if (!s || n <= 0 || n > 64 || !op || !a || !b) return fail(B2S_ERR_ARG, "b2s_task_table: bad argument");
+  CUDA_TRY(cudaSetDevice(s->device));
+  try {
+    std::vector<int> vo(op, op + n), va(a, a + n), vb(b, b + n);
+    s->ctrl.task_dim = n;
+    s->ctrl.task_op = dev_upload(s, vo); s->ctrl.task_a = dev_upload(s, va); s->ctrl.task_b = dev_upload(s, vb);
+    if (s->precision == B2S_F32) s->sf.task_vec = state_arr<float>(s, "task_vec", n);
+    else s->sd.task_vec = state_arr<double>(s, "task_vec", n);
+  } catch (const std::string& e) { return fail(B2S_ERR_CUDA, e); }
+  s->dirty = 1;
+  return B2S_OK;
+}
+
+int b2s_task_objects(b2s_sim* s, int nobjects, const int* geoms, const int* counts) {
+  if (!s || nobjects < 0 || nobjects > 4 || (nobjects > 0 && (!geoms || !counts))) return fail(B2S_ERR_ARG, "b2s_task_objects: bad argument");
+  int o = 0;
+  for (int i = 0; i < 4; i++) s->ctrl.mask_objs[i] = 0;
+  for (int i = 0; i < nobjects; i++)
+    for (int k = 0; k < counts[i]; k++, o++) {
+      if (geoms[o] < 0 || geoms[o] >= s->ngeom) return fail(B2S_ERR_ARG, "b2s_task_objects: geom id out of range");
+      int cg = s->cgid[geoms[o]];
+      if (cg >= 0) s->ctrl.mask_objs[i] |= 1ull << cg;
+    }
+  s->ctrl.n_objs = nobjects; s->dirty = 1;
   return B2S_OK;
 }
 

@@ -214,9 +214,10 @@ DEVN void ctrl_run(Eng<R> e, CtrlState<R>& cs, int env, const R* action) {
     __syncwarp();
     CA d = Lc[j * na + j];
     if (!(d > 1e-300)) { bad = 1; d = 1e-300; }
-    CA inv = 1.0 / sqrt(d);
+    CA inv = rsqrt(d);
     __syncwarp();
-    if (lane >= j && lane < na) Lc[lane * na + j] *= inv;
+    if (lane > j && lane < na) Lc[lane * na + j] *= inv;
+    if (lane == j) Lc[j * na + j] = inv;  // the diagonal keeps 1 / l_jj: the triangular solves multiply instead of divide
     __syncwarp();
   }
   // X = L^-1 J^T (lane = column r of J^T), then Y = L^-T X = M^-1 J^T
@@ -225,7 +226,7 @@ DEVN void ctrl_run(Eng<R> e, CtrlState<R>& cs, int env, const R* action) {
     for (int a = 0; a < na; a++) {
       CA sacc = Jm[lane * na + a];
       for (int k = 0; k < a; k++) sacc -= Lc[a * na + k] * x[k];
-      x[a] = sacc / Lc[a * na + a];
+      x[a] = sacc * Lc[a * na + a];
     }
     for (int a = 0; a < na; a++) X[a * 6 + lane] = x[a];
   }
@@ -245,7 +246,7 @@ DEVN void ctrl_run(Eng<R> e, CtrlState<R>& cs, int env, const R* action) {
     for (int a = na - 1; a >= 0; a--) {
       CA sacc = x[a];
       for (int k = a + 1; k < na; k++) sacc -= Lc[k * na + a] * x[k];
-      x[a] = sacc / Lc[a * na + a];
+      x[a] = sacc * Lc[a * na + a];
     }
     for (int a = 0; a < na; a++) X[a * 6 + lane] = x[a];
   }
@@ -276,9 +277,10 @@ DEVN void ctrl_run(Eng<R> e, CtrlState<R>& cs, int env, const R* action) {
     __syncwarp();
     CA d = Lw[j * 6 + j];
     if (!(d > 1e-300)) { bad = 1; d = 1e-300; }
-    CA inv = 1.0 / sqrt(d);
+    CA inv = rsqrt(d);
     __syncwarp();
-    if (lane >= j && lane < 6) Lw[lane * 6 + j] *= inv;
+    if (lane > j && lane < 6) Lw[lane * 6 + j] *= inv;
+    if (lane == j) Lw[j * 6 + j] = inv;
     __syncwarp();
   }
   if (lane < 6) {
@@ -286,12 +288,12 @@ DEVN void ctrl_run(Eng<R> e, CtrlState<R>& cs, int env, const R* action) {
     for (int a = 0; a < 6; a++) {
       CA sacc = a == lane ? 1.0 : 0.0;
       for (int k = 0; k < a; k++) sacc -= Lw[a * 6 + k] * x[k];
-      x[a] = sacc / Lw[a * 6 + a];
+      x[a] = sacc * Lw[a * 6 + a];
     }
     for (int a = 5; a >= 0; a--) {
       CA sacc = x[a];
       for (int k = a + 1; k < 6; k++) sacc -= Lw[k * 6 + a] * x[k];
-      x[a] = sacc / Lw[a * 6 + a];
+      x[a] = sacc * Lw[a * 6 + a];
     }
     for (int a = 0; a < 6; a++) Lf[a * 6 + lane] = x[a];
   }
@@ -364,31 +366,68 @@ template <typename R> DEV void mat2quat_wpos(const R* M, R* q) {
 // Observation row: one table entry per scalar (MujocoEnv._get_observations, environments/base.py:429-465; sensors
 // robots/robot.py:347-392,412-484 and the task's object observables e.g. manipulation/lift.py:371-397).
 // qpos/qvel/qacc are the freshly integrated values, poses are those of the last step1 (reference staleness).
-template <typename R> DEVN void write_obs(const Eng<R> e, int env) {
+// one scalar of the observation / task tables; `prev` = this environment's previous observation row (lagged entries)
+template <typename R> DEV R table_value(const Eng<R>& e, int op, int a, int b, const R* prev, int fresh) {
   const WSLayout& L = c_L;
+  R v = 0;
+  switch (op) {
+    case OB_QPOS: v = e.p(L.qpos)[a]; break;
+    case OB_COS_QPOS: { R sn, cs; r_sincos(e.p(L.qpos)[a], &sn, &cs); v = cs; break; }
+    case OB_SIN_QPOS: { R sn, cs; r_sincos(e.p(L.qpos)[a], &sn, &cs); v = sn; break; }
+    case OB_QVEL: v = e.p(L.qvel)[a]; break;
+    case OB_QACC: v = e.p(L.qacc)[a]; break;
+    case OB_SITE_POS: v = e.p(L.spos)[3 * a + b]; break;
+    case OB_BODY_POS: v = e.p(L.xpos)[3 * a + b]; break;
+    case OB_BODY_QUAT_XYZW: v = e.p(L.xquat)[4 * a + ((b + 1) & 3)]; break;
+    case OB_SITE_QUAT_XYZW: { R q[4]; mat2quat_wpos(e.p(L.smat) + 9 * a, q); v = q[(b + 1) & 3]; break; }
+    case OB_BODY_MINUS_SITE: v = e.p(L.xpos)[3 * (a >> 8) + b] - e.p(L.spos)[3 * (a & 255) + b]; break;
+    case OB_SITE_MINUS_SITE: v = e.p(L.spos)[3 * (a >> 8) + b] - e.p(L.spos)[3 * (a & 255) + b]; break;
+    case OB_BODY_MINUS_BODY: v = e.p(L.xpos)[3 * (a >> 8) + b] - e.p(L.xpos)[3 * (a & 255) + b]; break;
+    case OB_REL_POS_LAG:
+    case OB_REL_QUAT_LAG: {
+      if (fresh || prev == nullptr) break;
+      int ps = a & 4095, qs = a >> 12, comp = b & 255, site = (b >> 8) & 255, body = (b >> 16) & 255;
+      R Re[9], Ro[9], qo[4] = {prev[qs + 3], prev[qs], prev[qs + 1], prev[qs + 2]};  // cached quaternion is (x, y, z, w)
+      q2mat(Re, e.p(L.xquat) + 4 * body);
+      if (op == OB_REL_POS_LAG) {
+        R d[3] = {prev[ps] - e.p(L.spos)[3 * site], prev[ps + 1] - e.p(L.spos)[3 * site + 1], prev[ps + 2] - e.p(L.spos)[3 * site + 2]}, r[3];
+        m3mulTv(r, Re, d);
+        v = r[comp];
+      } else {
+        R rel[9], q[4];
+        q2mat(Ro, qo);
+        for (int i = 0; i < 3; i++)
+          for (int j = 0; j < 3; j++) rel[3 * i + j] = Re[i] * Ro[j] + Re[3 + i] * Ro[3 + j] + Re[6 + i] * Ro[6 + j];
+        mat2quat_wpos(rel, q);
+        v = q[(comp + 1) & 3];
+      }
+      break;
+    }
+    default: v = 0;
+  }
+  return v;
+}
+
+// `only_fresh`: called from forward() - sample only environments whose observation cache is empty (just reset)
+template <typename R> DEVN void write_obs(const Eng<R> e, int env, bool only_fresh = false) {
   const DState<R>& s = cstate<R>();
   const CtrlCfgDev& cc = c_cc;
   R* out = s.obs + (size_t)env * cc.obs_dim;
-  for (int k = e.lane; k < cc.obs_dim; k += 32) {
-    int op = cc.obs_op[k], a = cc.obs_a[k], b = cc.obs_b[k];
-    R v = 0;
-    switch (op) {
-      case OB_QPOS: v = e.p(L.qpos)[a]; break;
-      case OB_COS_QPOS: { R sn, cs; r_sincos(e.p(L.qpos)[a], &sn, &cs); v = cs; break; }
-      case OB_SIN_QPOS: { R sn, cs; r_sincos(e.p(L.qpos)[a], &sn, &cs); v = sn; break; }
-      case OB_QVEL: v = e.p(L.qvel)[a]; break;
-      case OB_QACC: v = e.p(L.qacc)[a]; break;
-      case OB_SITE_POS: v = e.p(L.spos)[3 * a + b]; break;
-      case OB_BODY_POS: v = e.p(L.xpos)[3 * a + b]; break;
-      case OB_BODY_QUAT_XYZW: v = e.p(L.xquat)[4 * a + ((b + 1) & 3)]; break;
-      case OB_SITE_QUAT_XYZW: { R q[4]; mat2quat_wpos(e.p(L.smat) + 9 * a, q); v = q[(b + 1) & 3]; break; }
-      case OB_BODY_MINUS_SITE: v = e.p(L.xpos)[3 * (a >> 8) + b] - e.p(L.spos)[3 * (a & 255) + b]; break;
-      case OB_SITE_MINUS_SITE: v = e.p(L.spos)[3 * (a >> 8) + b] - e.p(L.spos)[3 * (a & 255) + b]; break;
-      case OB_BODY_MINUS_BODY: v = e.p(L.xpos)[3 * (a >> 8) + b] - e.p(L.xpos)[3 * (a & 255) + b]; break;
-      default: v = 0;
-    }
-    out[k] = v;
+  int fresh = s.obs_fresh[env];
+  if (only_fresh && !fresh) return;
+  R val[4];  // obs_dim <= 128: all values are formed before any is written (lagged entries read the previous sample)
+#pragma unroll
+  for (int it = 0; it < 4; it++) {
+    int k = e.lane + 32 * it;
+    val[it] = k < cc.obs_dim ? table_value(e, cc.obs_op[k], cc.obs_a[k], cc.obs_b[k], out, fresh) : R(0);
   }
+  __syncwarp();
+#pragma unroll
+  for (int it = 0; it < 4; it++) {
+    int k = e.lane + 32 * it;
+    if (k < cc.obs_dim) out[k] = val[it];
+  }
+  if (e.lane == 0 && fresh) s.obs_fresh[env] = 0;
 }
 
 // Task outputs after the last substep (poses / contacts of the last step1, as the reference's reward() sees them:
@@ -399,15 +438,21 @@ template <typename R> DEVN void write_task(const Eng<R> e, int env, int ncon) {
   const DState<R>& s = cstate<R>();
   const CtrlCfgDev& cc = c_cc;
   const int* cint = e.pi(L.c_int);
-  int hitl = 0, hitr = 0, hit2 = 0;
+  int hitl = 0, hitr = 0, hit2 = 0, hl4 = 0, hr4 = 0;
   for (int c = e.lane; c < ncon; c += 32) {
     unsigned long long b1 = 1ull << m.geom_cgid[cint[5 * c]], b2 = 1ull << m.geom_cgid[cint[5 * c + 1]];
+    for (int i = 0; i < cc.n_objs; i++) {
+      bool p1 = b1 & cc.mask_objs[i], p2 = b2 & cc.mask_objs[i];
+      if ((p1 && (b2 & cc.mask_left)) || (p2 && (b1 & cc.mask_left))) hl4 |= 1 << i;
+      if ((p1 && (b2 & cc.mask_right)) || (p2 && (b1 & cc.mask_right))) hr4 |= 1 << i;
+    }
     bool o1 = b1 & cc.mask_obj, o2 = b2 & cc.mask_obj;
     if ((o1 && (b2 & cc.mask_left)) || (o2 && (b1 & cc.mask_left))) hitl = 1;
     if ((o1 && (b2 & cc.mask_right)) || (o2 && (b1 & cc.mask_right))) hitr = 1;
     if ((o1 && (b2 & cc.mask_obj2)) || (o2 && (b1 & cc.mask_obj2))) hit2 = 1;
   }
   hitl = warp_or_i(hitl); hitr = warp_or_i(hitr); hit2 = warp_or_i(hit2);
+  if (cc.n_objs > 0) { hl4 = warp_or_i(hl4); hr4 = warp_or_i(hr4); }
   if (e.lane == 0) {
     R* out = s.task_out + (size_t)env * 8;
     const R* bp = e.p(L.xpos) + 3 * cc.task_body; const R* sp = e.p(L.spos) + 3 * cc.task_site;
@@ -416,8 +461,11 @@ template <typename R> DEVN void write_task(const Eng<R> e, int env, int ncon) {
     out[0] = bp[2]; out[1] = v3norm(d); out[2] = (hitl && hitr) ? R(1) : R(0);
     R hd = 0;
     if (cc.task_body2 >= 0) { const R* b2p = e.p(L.xpos) + 3 * cc.task_body2; hd = r_sqrt((bp[0] - b2p[0]) * (bp[0] - b2p[0]) + (bp[1] - b2p[1]) * (bp[1] - b2p[1])); }
-    out[3] = hd; out[4] = hit2 ? R(1) : R(0); out[5] = 0; out[6] = 0; out[7] = 0;
+    out[3] = hd; out[4] = hit2 ? R(1) : R(0); out[5] = (R)(hl4 & hr4); out[6] = 0; out[7] = 0;
   }
+  // task table: poses the task's reward / success checks read after the step (same scalar ops as the observation table)
+  for (int k = e.lane; k < cc.task_dim; k += 32)
+    s.task_vec[(size_t)env * cc.task_dim + k] = table_value(e, cc.task_op[k], cc.task_a[k], cc.task_b[k], (const R*)nullptr, 0);
 }
 
 // controller.reset_goal + initial joints (osc.py:520-544, controller.py:126-132): goal <- current eef pose (world),

@@ -146,52 +146,67 @@ struct Eng {
         q2mat(xmat + 9 * b, q);
       }
     __syncwarp();
-    // moving bodies, one tree level at a time (parents are complete before children start)
+    // moving bodies.  (1) every body in parallel: its pose relative to the parent frame (lp, lq) including the joint
+    // displacement; (2) one tree level at a time, the short serial part: compose with the finished parent pose;
+    // (3) rotation matrices of all bodies in parallel.
+    R* loc = p(L.scratch);  // 8 words per body: lp[3], lq[4], absolute flag (free joints give world poses directly)
+    for (int b = lane; b < m.nbody; b += 32) {
+      if (m.body_weldid[b] == 0) continue;
+      R lp[3] = {m.body_pos[3 * b], m.body_pos[3 * b + 1], m.body_pos[3 * b + 2]};
+      R lq[4] = {m.body_quat[4 * b], m.body_quat[4 * b + 1], m.body_quat[4 * b + 2], m.body_quat[4 * b + 3]};
+      R absolute = 0;
+      int j = m.body_jntid[b];
+      if (j >= 0) {
+        int t = m.jnt_type[j], qa = m.jnt_qposadr[j];
+        if (t == JNT_FREE) {
+          lp[0] = qpos[qa]; lp[1] = qpos[qa + 1]; lp[2] = qpos[qa + 2];
+          lq[0] = qpos[qa + 3]; lq[1] = qpos[qa + 4]; lq[2] = qpos[qa + 5]; lq[3] = qpos[qa + 6];
+          absolute = 1;
+        } else {
+          R ax[3] = {m.jnt_axis[3 * j], m.jnt_axis[3 * j + 1], m.jnt_axis[3 * j + 2]};
+          R dq = qpos[qa] - m.qpos0[qa];
+          if (t == JNT_SLIDE) {
+            R axp[3];
+            qrot(axp, lq, ax);
+            v3addscl(lp, lp, axp, dq);
+          } else {  // hinge: rotate about the joint anchor (anchor = lp + R(body_quat) jnt_pos stays fixed)
+            R jp[3] = {m.jnt_pos[3 * j], m.jnt_pos[3 * j + 1], m.jnt_pos[3 * j + 2]};
+            R a0[3], a1[3], ql[4], qn[4];
+            qrot(a0, lq, jp);
+            aa2quat(ql, ax, dq);
+            qmul(qn, lq, ql);
+            qrot(a1, qn, jp);
+            lp[0] += a0[0] - a1[0]; lp[1] += a0[1] - a1[1]; lp[2] += a0[2] - a1[2];
+            lq[0] = qn[0]; lq[1] = qn[1]; lq[2] = qn[2]; lq[3] = qn[3];
+          }
+        }
+      }
+      R* o = loc + 8 * b;
+      o[0] = lp[0]; o[1] = lp[1]; o[2] = lp[2]; o[3] = lq[0]; o[4] = lq[1]; o[5] = lq[2]; o[6] = lq[3]; o[7] = absolute;
+    }
+    __syncwarp();
     for (int lev = 1; lev <= m.maxdepth; lev++) {
       for (int b = lane; b < m.nbody; b += 32) {
-        if (m.body_depth[b] != lev) continue;
-        int par = m.body_parentid[b];
-        R pos[3], quat[4], bp[3] = {m.body_pos[3 * b], m.body_pos[3 * b + 1], m.body_pos[3 * b + 2]};
-        R bq[4] = {m.body_quat[4 * b], m.body_quat[4 * b + 1], m.body_quat[4 * b + 2], m.body_quat[4 * b + 3]};
-        m3mulv(pos, xmat + 9 * par, bp);
-        v3add(pos, pos, xpos + 3 * par);
-        qmul(quat, xquat + 4 * par, bq);
-        int j = m.body_jntid[b];
-        if (j >= 0) {
-          int t = m.jnt_type[j], qa = m.jnt_qposadr[j];
-          if (t == JNT_FREE) {
-            pos[0] = qpos[qa]; pos[1] = qpos[qa + 1]; pos[2] = qpos[qa + 2];
-            quat[0] = qpos[qa + 3]; quat[1] = qpos[qa + 4]; quat[2] = qpos[qa + 5]; quat[3] = qpos[qa + 6];
-          } else {
-            R ax[3] = {m.jnt_axis[3 * j], m.jnt_axis[3 * j + 1], m.jnt_axis[3 * j + 2]};
-            R jp[3] = {m.jnt_pos[3 * j], m.jnt_pos[3 * j + 1], m.jnt_pos[3 * j + 2]};
-            R dq = qpos[qa] - m.qpos0[qa];
-            if (t == JNT_SLIDE) {
-              R M9[9], axw[3];
-              q2mat(M9, quat);
-              m3mulv(axw, M9, ax);
-              v3addscl(pos, pos, axw, dq);
-            } else {  // hinge
-              R M9[9], anchor[3], off[3], ql[4], qn[4];
-              q2mat(M9, quat);
-              m3mulv(anchor, M9, jp);
-              v3add(anchor, anchor, pos);
-              aa2quat(ql, ax, dq);
-              qmul(qn, quat, ql);
-              quat[0] = qn[0]; quat[1] = qn[1]; quat[2] = qn[2]; quat[3] = qn[3];
-              q2mat(M9, quat);
-              m3mulv(off, M9, jp);
-              v3sub(pos, anchor, off);
-            }
-          }
+        if (m.body_depth[b] != lev || m.body_weldid[b] == 0) continue;
+        const R* o = loc + 8 * b;
+        R pos[3] = {o[0], o[1], o[2]}, quat[4] = {o[3], o[4], o[5], o[6]};
+        if (o[7] == R(0)) {
+          int par = m.body_parentid[b];
+          R t[3];
+          qrot(t, xquat + 4 * par, pos);
+          v3add(pos, t, xpos + 3 * par);
+          R lq[4] = {quat[0], quat[1], quat[2], quat[3]};
+          qmul(quat, xquat + 4 * par, lq);
         }
         qnormalize(quat);
         xpos[3 * b] = pos[0]; xpos[3 * b + 1] = pos[1]; xpos[3 * b + 2] = pos[2];
         xquat[4 * b] = quat[0]; xquat[4 * b + 1] = quat[1]; xquat[4 * b + 2] = quat[2]; xquat[4 * b + 3] = quat[3];
-        q2mat(xmat + 9 * b, quat);
       }
       __syncwarp();
     }
+    for (int b = lane; b < m.nbody; b += 32)
+      if (m.body_weldid[b] != 0) q2mat(xmat + 9 * b, xquat + 4 * b);
+    __syncwarp();
     // per body: inertial frame origin + spatial inertia about the world origin
     R* xipos = p(L.xipos); R* cinert = p(L.cinert);
     for (int b = lane; b < m.nbody; b += 32) {

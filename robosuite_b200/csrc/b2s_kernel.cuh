@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(512, 1) step_kernel(int phases, int nsub, cons
       TICK(7)
     }
     if (live && (phases & PH_OBS) && c_cc.obs_dim > 0) {
-      if (sub == 0) write_obs(e, env);
+      if (sub == 0) write_obs(e, env, (phases & PH_NOINTEGRATE) != 0);
       if (sub == nsub - 1) write_task(e, env, ncon);
     }
     __syncwarp();

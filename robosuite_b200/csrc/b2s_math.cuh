@@ -59,6 +59,14 @@ template <typename R> DEV void qmul(R* r, const R* a, const R* b) {
   R z = a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0];
   r[0] = w; r[1] = x; r[2] = y; r[3] = z;
 }
+// v rotated by the unit quaternion q:  v + 2 w (u x v) + 2 u x (u x v)
+template <typename R> DEV void qrot(R* r, const R* q, const R* v) {
+  R t[3] = {R(2) * (q[2] * v[2] - q[3] * v[1]), R(2) * (q[3] * v[0] - q[1] * v[2]), R(2) * (q[1] * v[1] - q[2] * v[0])};
+  R x = v[0] + q[0] * t[0] + (q[2] * t[2] - q[3] * t[1]);
+  R y = v[1] + q[0] * t[1] + (q[3] * t[0] - q[1] * t[2]);
+  R z = v[2] + q[0] * t[2] + (q[1] * t[1] - q[2] * t[0]);
+  r[0] = x; r[1] = y; r[2] = z;
+}
 template <typename R> DEV void qnormalize(R* q) {
   R n = r_sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
   if (n < Lim<R>::minval()) { q[0] = 1; q[1] = q[2] = q[3] = 0; return; }

@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(128) narrow_analytic_kernel(Grp g) {
   const WSLayout& L = c_L;
   int tid = blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= s.cl_cnt[2 * g.gid]) return;
-  tid += g.env0 * CL_MAXA;  // this group's slice of the candidate list / output slots
+  tid += g.env0 * s.cl_maxa;  // this group's slice of the candidate list / output slots
   int code = s.cl_listA[tid];
   int env = code >> 12, pidx = code & 4095;
   const R* row = s.wsg + (size_t)env * L.total;
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(256) narrow_convex_kernel(Grp g) {
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   int wid = blockIdx.x * wpb + warp;
   if (wid >= s.cl_cnt[2 * g.gid + 1]) return;
-  wid += g.env0 * CL_MAXG;
+  wid += g.env0 * s.cl_maxg;
   const int EPAW = 9 * EPA_PIPE_MAXV + 4 * EPA_PIPE_MAXF + EPA_PIPE_MAXF + 8;
   R* scratch = reinterpret_cast<R*>(smem_raw) + (size_t)warp * EPAW;
   int code = s.cl_listG[wid];
@@ -157,22 +157,43 @@ template <typename R> DEVN int gather_contacts(Eng<R> e, int env, int& warn) {
   const DState<R>& s = cstate<R>();
   const WSLayout& L = c_L;
   int lane = e.lane;
-  const int* tab = s.cl_env + (size_t)env * CL_ENVW;
-  int na = tab[0], ng = tab[1], nc = na + ng;  // nc <= 24 <= 32 lanes
-  int pair = 0x7fffffff, slot = 0, isg = 0, n = 0;
-  if (lane < na) { pair = tab[2 + 2 * lane]; slot = tab[3 + 2 * lane]; n = (int)s.cl_outA[(size_t)slot * CL_RECA]; }
-  else if (lane < nc) { int k = lane - na; isg = 1; pair = tab[2 + 2 * (CL_MAXA + k)]; slot = tab[3 + 2 * (CL_MAXA + k)]; n = (int)s.cl_outG[(size_t)slot * 8]; }
-  // contact offset = contacts of candidates with a smaller pair index
-  int off = 0;
-  for (int o = 0; o < nc; o++) {
-    int op = __shfl_sync(B2S_FULL, pair, o), on = __shfl_sync(B2S_FULL, n, o);
-    if (op < pair) off += on;
+  const int* tab = s.cl_env + (size_t)env * CL_ENVW(s);
+  int na = tab[0], ng = tab[1], nc = na + ng;  // nc <= CL_MAXA + CL_MAXG = 96: up to IT candidates per lane
+  const int IT = 3;
+  int nchunk = (nc + 31) >> 5;
+  int pairv[IT], slotv[IT], isgv[IT], cntv[IT], offv[IT];
+#pragma unroll
+  for (int it = 0; it < IT; it++) {
+    int j = lane + 32 * it;
+    pairv[it] = 0x7fffffff; slotv[it] = 0; isgv[it] = 0; cntv[it] = 0; offv[it] = 0;
+    if (j < na) { pairv[it] = tab[2 + 2 * j]; slotv[it] = tab[3 + 2 * j]; cntv[it] = (int)s.cl_outA[(size_t)slotv[it] * CL_RECA]; }
+    else if (j < nc) {
+      int k = j - na;
+      isgv[it] = 1; pairv[it] = tab[2 + 2 * (s.cl_maxa + k)]; slotv[it] = tab[3 + 2 * (s.cl_maxa + k)];
+      cntv[it] = (int)s.cl_outG[(size_t)slotv[it] * 8];
+    }
   }
-  int total = warp_sum_i(lane < nc ? n : 0);
+  // contact offset = contacts of candidates with a smaller pair index
+  int total = 0;
+#pragma unroll
+  for (int it2 = 0; it2 < IT; it2++) {
+    if (it2 >= nchunk) break;
+    int lim = nc - 32 * it2 < 32 ? nc - 32 * it2 : 32;
+    for (int o = 0; o < lim; o++) {
+      int op = __shfl_sync(B2S_FULL, pairv[it2], o), on = __shfl_sync(B2S_FULL, cntv[it2], o);
+      total += on;
+#pragma unroll
+      for (int it = 0; it < IT; it++)
+        if (op < pairv[it]) offv[it] += on;
+    }
+  }
   R* cpos = e.p(L.c_pos); R* cfr = e.p(L.c_frame); R* cdist = e.p(L.c_dist);
   int* cint = e.pi(L.c_int);
-  if (lane < nc) {
-    const R* rec = isg ? s.cl_outG + (size_t)slot * 8 + 1 : s.cl_outA + (size_t)slot * CL_RECA + 1;
+#pragma unroll
+  for (int it = 0; it < IT; it++) {
+    if (lane + 32 * it >= nc) continue;
+    int pair = pairv[it], slot = slotv[it], n = cntv[it], off = offv[it];
+    const R* rec = isgv[it] ? s.cl_outG + (size_t)slot * 8 + 1 : s.cl_outA + (size_t)slot * CL_RECA + 1;
     int g1 = m.pair_geom[2 * pair], g2 = m.pair_geom[2 * pair + 1];
     if (m.geom_type[g1] > m.geom_type[g2]) { int t = g1; g1 = g2; g2 = t; }
     for (int k = 0; k < n; k++) {
@@ -232,20 +253,20 @@ __global__ void __launch_bounds__(512, 1) phase_kernel(int phases, int sub, int 
     int* cand = reinterpret_cast<int*>(e.p(L.scratch));
     int* cand_g = cand + 96;
     int na, ng;
-    cull_pairs(e, cand, cand_g, CL_MAXA, CL_MAXG, na, ng);
-    if (na > CL_MAXA) { na = CL_MAXA; warn |= 4; }
-    if (ng > CL_MAXG) { ng = CL_MAXG; warn |= 4; }
+    cull_pairs(e, cand, cand_g, s.cl_maxa, s.cl_maxg, na, ng);
+    if (na > s.cl_maxa) { na = s.cl_maxa; warn |= 4; }
+    if (ng > s.cl_maxg) { ng = s.cl_maxg; warn |= 4; }
     int baseA = 0, baseG = 0;
     if (lane == 0) {
-      if (na) baseA = g.env0 * CL_MAXA + atomicAdd(s.cl_cnt + 2 * g.gid, na);
-      if (ng) baseG = g.env0 * CL_MAXG + atomicAdd(s.cl_cnt + 2 * g.gid + 1, ng);
+      if (na) baseA = g.env0 * s.cl_maxa + atomicAdd(s.cl_cnt + 2 * g.gid, na);
+      if (ng) baseG = g.env0 * s.cl_maxg + atomicAdd(s.cl_cnt + 2 * g.gid + 1, ng);
     }
     baseA = __shfl_sync(B2S_FULL, baseA, 0);
     baseG = __shfl_sync(B2S_FULL, baseG, 0);
-    int* tab = s.cl_env + E * CL_ENVW;
+    int* tab = s.cl_env + E * CL_ENVW(s);
     if (lane == 0) { tab[0] = na; tab[1] = ng; }
-    if (lane < na) { s.cl_listA[baseA + lane] = (env << 12) | cand[lane]; tab[2 + 2 * lane] = cand[lane]; tab[3 + 2 * lane] = baseA + lane; }
-    if (lane < ng) { s.cl_listG[baseG + lane] = (env << 12) | cand_g[lane]; tab[2 + 2 * (CL_MAXA + lane)] = cand_g[lane]; tab[3 + 2 * (CL_MAXA + lane)] = baseG + lane; }
+    for (int i = lane; i < na; i += 32) { s.cl_listA[baseA + i] = (env << 12) | cand[i]; tab[2 + 2 * i] = cand[i]; tab[3 + 2 * i] = baseA + i; }
+    for (int i = lane; i < ng; i += 32) { s.cl_listG[baseG + i] = (env << 12) | cand_g[i]; tab[2 + 2 * (s.cl_maxa + i)] = cand_g[i]; tab[3 + 2 * (s.cl_maxa + i)] = baseG + i; }
     hdr[0] = 0; hdr[1] = 0;
     if (lane == 0) { hdr[2] = warn; reinterpret_cast<int*>(row + L.hdr)[2] = warn; }
   } else if (PH == 1) {
@@ -273,7 +294,7 @@ __global__ void __launch_bounds__(512, 1) phase_kernel(int phases, int sub, int 
       if (e.euler(&time)) warn |= 2;
     }
     if ((phases & PH_OBS) && c_cc.obs_dim > 0) {
-      if (sub == 0) write_obs(e, env);
+      if (sub == 0) write_obs(e, env, (phases & PH_NOINTEGRATE) != 0);
       if (sub == nsub - 1) write_task(e, env, ncon);
     }
     for (int i = lane; i < m.nq; i += 32) s.qpos[E * m.nq + i] = e.p(L.qpos)[i];

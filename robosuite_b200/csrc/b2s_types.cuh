@@ -81,12 +81,15 @@ struct DState {
   R* wsg;          // [n_env, L.total] global workspace rows (pipeline mode)
   // pipeline-mode collision work lists (candidate pairs of ALL environments, compacted with atomics)
   int* cl_cnt;     // [2] number of analytic / convex candidates this substep
-  int* cl_listA;   // [n_env * CL_MAXA] env << 12 | pair
-  int* cl_listG;   // [n_env * CL_MAXG]
-  R* cl_outA;      // [n_env * CL_MAXA][CL_RECA] count + 8 x (pos3 normal3 dist)
-  R* cl_outG;      // [n_env * CL_MAXG][8]       count + (pos3 normal3 dist)
+  int cl_maxa, cl_maxg;  // per-environment candidate capacity of the two work lists
+  int* cl_listA;   // [n_env * cl_maxa] env << 12 | pair
+  int* cl_listG;   // [n_env * cl_maxg]
+  R* cl_outA;      // [n_env * cl_maxa][CL_RECA] count + 8 x (pos3 normal3 dist)
+  R* cl_outG;      // [n_env * cl_maxg][8]       count + (pos3 normal3 dist)
   R* gjk_cache;    // [n_env][npair][3] last separating direction of each convex pair (GJK warm start)
-  int* cl_env;     // [n_env][2 + 2 * (CL_MAXA + CL_MAXG)] na, ng, then (pair, slot) of each candidate
+  int* cl_env;     // [n_env][2 + 2 * (cl_maxa + cl_maxg)] na, ng, then (pair, slot) of each candidate
+  int* obs_fresh;  // [n_env] 1 = observation cache empty (set at reset, cleared by the first sample)
+  R* task_vec;     // [n_env, task_dim] task table values after the last substep
   R* task_out;     // [n_env, 8]: body height, |grip site - body|, grasp flag, horizontal |body - body2|, obj-obj2 contact flag
 };
 
@@ -111,23 +114,29 @@ struct WSLayout {
 // from / to the per-environment global workspace row (L2 resident).
 struct Region { int off, len, dyn; };  // dyn: 0 fixed, 1 = nefc*nv words (constraint Jacobian)
 #define B2S_NPHASE 5
-#define CL_MAXA 8
-#define CL_MAXG 16
+#define CL_MAXA 64  // hard upper bounds of the per-environment candidate counts (analytic / convex pairs);
+#define CL_MAXG 32  // the run-time caps DState::cl_maxa / cl_maxg are chosen per model (b2s_capi.cu)
 #define CL_RECA 58
-#define CL_ENVW (2 + 2 * (CL_MAXA + CL_MAXG))
+#define CL_ENVW(s) (2 + 2 * ((s).cl_maxa + (s).cl_maxg))
 #define B2S_MAXREG 20
 // load / store lists hold merged 16-byte aligned spans; load_words = sum of the fixed spans, load_dyn = list has the Jacobian
 struct PhaseIO { int nload, nstore, load_words, load_dyn; Region load[B2S_MAXREG], store[B2S_MAXREG]; };
 
 // observation scalar ops (one table entry per output scalar)
 enum { OB_QPOS = 0, OB_COS_QPOS, OB_SIN_QPOS, OB_QVEL, OB_QACC, OB_SITE_POS, OB_BODY_POS, OB_BODY_QUAT_XYZW, OB_SITE_QUAT_XYZW,
-       OB_BODY_MINUS_SITE, OB_SITE_MINUS_SITE, OB_BODY_QUAT_REL_SITE_XYZW, OB_ZERO, OB_BODY_MINUS_BODY };
+       OB_BODY_MINUS_SITE, OB_SITE_MINUS_SITE, OB_BODY_QUAT_REL_SITE_XYZW, OB_ZERO, OB_BODY_MINUS_BODY,
+       // object pose in the gripper frame from the object pose of the PREVIOUS observation sample (the reference evaluates
+       // `{obj}_to_eef_pos/quat` before `{obj}_pos/quat` in the same pass: manipulation_env.py:268-329) and the current
+       // hand pose; zeros on the first sample after a reset.  a = pos_slot | quat_slot << 12, b = k | site << 8 | body << 16
+       OB_REL_POS_LAG, OB_REL_QUAT_LAG };
 
 struct CtrlCfgDev {
   int kind, action_dim, n_arm, eef_site, base_site, n_grip, uncouple;
   int obs_dim; const int* obs_op; const int* obs_a; const int* obs_b;  // device arrays
   int task_body, task_site; unsigned long long mask_left, mask_right, mask_obj;  // grasp check geom sets (colliding-geom index bits)
   int task_body2; unsigned long long mask_obj2;  // second object (Stack: cubeB), -1 / 0 when unused
+  int n_objs; unsigned long long mask_objs[4];   // per-object grasp flags (multi-object tasks)
+  int task_dim; const int* task_op; const int* task_a; const int* task_b;  // task table (device arrays)
   // JOINT_VELOCITY part controller (controllers/parts/generic/joint_vel.py)
   double jv_kp[8], jv_ki[8], jv_kd[8], jv_in_max[8], jv_in_min[8], jv_out_max[8], jv_out_min[8], jv_vel_lo, jv_vel_hi;
   int jv_use_vel_limits, jv_torque_comp;

@@ -60,6 +60,8 @@ def lib():
         L.b2s_obs_config.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.b2s_task_config.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.b2s_task_config2.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        L.b2s_task_objects.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.b2s_task_table.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.b2s_set_export.argtypes = [C.c_void_p, C.c_int]
         L.b2s_set_profile.argtypes = [C.c_void_p, C.c_int]
         L.b2s_set_mode.argtypes = [C.c_void_p, C.c_int]
@@ -195,6 +197,18 @@ class BatchedSim:
     def task_config2(self, body2, obj2):
         obj2 = np.ascontiguousarray(obj2, dtype=np.int32)
         self._check(self._L.b2s_task_config2(self._h, int(body2), obj2.ctypes.data, len(obj2)))
+
+    def task_table(self, rows):
+        """rows: [(op, a, b), ...] in the observation-table encoding -> array `task_vec` [n_env, len(rows)]"""
+        arr = np.ascontiguousarray(rows, dtype=np.int32).reshape(-1, 3)
+        op, a, b = (np.ascontiguousarray(arr[:, k]) for k in range(3))
+        self._check(self._L.b2s_task_table(self._h, len(op), op.ctypes.data, a.ctypes.data, b.ctypes.data))
+
+    def task_objects(self, geom_lists):
+        """per-object grasp flags (task_out[:, 5] = bit i set when object i is grasped); at most 4 objects"""
+        flat = np.ascontiguousarray([g for l in geom_lists for g in l], dtype=np.int32)
+        cnt = np.ascontiguousarray([len(l) for l in geom_lists], dtype=np.int32)
+        self._check(self._L.b2s_task_objects(self._h, len(geom_lists), flat.ctypes.data, cnt.ctypes.data))
 
     def set_export(self, flag):
         """whether b2s_env_step also writes the derived arrays (xpos, contacts, ...) of its last substep to HBM"""

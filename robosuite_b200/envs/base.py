@@ -24,7 +24,8 @@ _ASSETS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "assets
 
 # observation scalar ops (must match enum OB_* in csrc/b2s_types.cuh)
 OB_QPOS, OB_COS_QPOS, OB_SIN_QPOS, OB_QVEL, OB_QACC, OB_SITE_POS, OB_BODY_POS, OB_BODY_QUAT_XYZW, OB_SITE_QUAT_XYZW, \
-    OB_BODY_MINUS_SITE, OB_SITE_MINUS_SITE, OB_BODY_QUAT_REL_SITE_XYZW, OB_ZERO, OB_BODY_MINUS_BODY = range(14)
+    OB_BODY_MINUS_SITE, OB_SITE_MINUS_SITE, OB_BODY_QUAT_REL_SITE_XYZW, OB_ZERO, OB_BODY_MINUS_BODY, OB_REL_POS_LAG, \
+    OB_REL_QUAT_LAG = range(16)
 
 
 def register_env(cls):
@@ -60,6 +61,14 @@ class ObsBuilder:
     def add(self, name, modality, rows):
         self.items.append((name, modality, rows))
 
+    def add_rel_pose(self, obj_key, eef_site, eef_body, modality, pf="robot0_"):
+        """`{obj}_to_{pf}eef_pos` (3) and `{obj}_to_{pf}eef_quat` (4): pose of the object in the gripper frame, from the
+        `{obj}_pos` / `{obj}_quat` values of the previous sample (manipulation_env.py:268-329).  The slots of those two
+        observables are resolved in tables(), so they may be added afterwards, as the reference orders them."""
+        b = (eef_site << 8) | (eef_body << 16)
+        self.items.append((f"{obj_key}_to_{pf}eef_pos", modality, [("lagpos", obj_key, b | k) for k in range(3)]))
+        self.items.append((f"{obj_key}_to_{pf}eef_quat", modality, [("lagquat", obj_key, b | k) for k in range(4)]))
+
     def tables(self):
         """rows ordered modality by modality (first-seen order), as _get_observations concatenates them"""
         mods = []
@@ -75,12 +84,19 @@ class ObsBuilder:
                 slices[name] = (len(ops), len(ops) + len(rows))
                 ops += rows
             mod_slices[mod + "-state"] = (start, len(ops))
+        for i, row in enumerate(ops):
+            if row[0] in ("lagpos", "lagquat"):
+                ps, qs = slices[row[1] + "_pos"][0], slices[row[1] + "_quat"][0]
+                ops[i] = (OB_REL_POS_LAG if row[0] == "lagpos" else OB_REL_QUAT_LAG, ps | (qs << 12), row[2])
         arr = np.array(ops, dtype=np.int32).reshape(-1, 3)
         return arr[:, 0], arr[:, 1], arr[:, 2], slices, mod_slices
 
 
 class BatchedMujocoEnv:
     """N copies of one task on one GPU.  All returned arrays are torch.cuda tensors with leading dim N."""
+
+    maxcon = None  # per-environment contact / constraint-row capacity (None: engine defaults 32 / 64); overflow sets warn bit 4
+    maxefc = None
 
     def __init__(self, robots="Panda", num_envs=1, device=0, controller_configs=None, control_freq=20, horizon=500,
                  ignore_done=False, reward_scale=1.0, reward_shaping=False, use_object_obs=True, seed=None,
@@ -109,7 +125,8 @@ class BatchedMujocoEnv:
         if control_freq <= 0:
             raise ValueError("Control frequency {} is invalid".format(control_freq))
         self.n_substeps = int(self.control_timestep / self.model_timestep)
-        self.sim = BatchedSim(self.model, self.num_envs, device=device, precision=precision)
+        caps = {k: v for k, v in (("maxcon", kwargs.get("maxcon", self.maxcon)), ("maxefc", kwargs.get("maxefc", self.maxefc))) if v}
+        self.sim = BatchedSim(self.model, self.num_envs, device=device, precision=precision, **caps)
         self.device = self.sim.torch_device
         self.dtype = self.sim.dtype
         self.composite_controller_config = cc.load_composite_controller_config(controller_configs, self.robot_name)
@@ -171,6 +188,38 @@ class BatchedMujocoEnv:
     def _setup_task(self):
         pass
 
+    def _robot_reset_qpos(self, n):
+        """[n, nq] float64 qpos0 with the arm at init_qpos + noise and the gripper at its init pose
+        (robots/robot.py:247-259, gripper init_qpos)"""
+        import torch
+
+        from .lift import GRIPPER_INIT_QPOS, PANDA_INIT_QPOS, SAWYER_INIT_QPOS
+
+        dev = self.device
+        q = torch.as_tensor(self.model.qpos0, device=dev, dtype=torch.float64).repeat(n, 1)
+        init = PANDA_INIT_QPOS if self.robot_name == "Panda" else SAWYER_INIT_QPOS
+        mag = float(self.initialization_noise["magnitude"])
+        if self.initialization_noise["type"] == "gaussian":
+            noise = torch.randn((n, len(init)), generator=self.rng, device=dev, dtype=torch.float64) * mag
+        else:
+            noise = (torch.rand((n, len(init)), generator=self.rng, device=dev, dtype=torch.float64) * 2 - 1) * mag
+        q[:, self._ref_joint_pos_indexes] = torch.as_tensor(init, device=dev) + noise
+        q[:, self._ref_gripper_joint_pos_indexes] = torch.as_tensor(GRIPPER_INIT_QPOS[self.robot_name], device=dev, dtype=torch.float64)
+        return q
+
+    @staticmethod
+    def _place_free_body(q, adr, x, y, z, yaw):
+        """free-joint qpos <- position + rotation about z"""
+        import torch
+
+        q[:, adr] = x
+        q[:, adr + 1] = y
+        q[:, adr + 2] = z
+        q[:, adr + 3] = torch.cos(yaw / 2)
+        q[:, adr + 4] = 0
+        q[:, adr + 5] = 0
+        q[:, adr + 6] = torch.sin(yaw / 2)
+
     def _sample_reset_state(self, n):
         raise NotImplementedError
 
@@ -223,6 +272,7 @@ class BatchedMujocoEnv:
             self.sim.time[idx] = 0
             self.timestep[idx] = 0
             self.done[idx] = False
+            self.sim.obs_fresh[idx] = 1  # observation cache emptied (environments/base.py:332-335)
         if mask is None:
             self._max_steps_since_reset = 0
         self.sim.forward()

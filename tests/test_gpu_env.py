@@ -143,3 +143,105 @@ def test_stack_sawyer_joint_velocity_env_parity():
         r_reach = (1 - np.tanh(10 * dist)) * 0.25
         assert abs(float(rew[e]) * 2.0 - r_reach) < 5e-3 or float(rew[e]) * 2.0 >= r_reach - 5e-3
     env.close()
+
+
+def _quat_xyzw_wpos_from_mat(M):
+    """T.mat2quat semantics (transform_utils.py:317-355): unit quaternion of M with w >= 0, (x, y, z, w)"""
+    from scipy.spatial.transform import Rotation
+
+    q = Rotation.from_matrix(M).as_quat()  # x, y, z, w
+    return -q if q[3] < 0 else q
+
+
+def _quat2mat_wxyz(q):
+    w, x, y, z = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                     [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                     [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+
+
+def _object_obs(env, o, cache, task):
+    """object-state row from oracle arrays with the reference's sensor ORDER semantics: `{obj}_to_eef_pos/quat` are
+    evaluated before `{obj}_pos/quat` and read the cached values of the previous sample (zeros on an empty cache)"""
+    eef_pos = o.site_xpos[env.eef_site_id].copy()
+    Re = _quat2mat_wxyz(o.xquat[env.eef_body_id])
+    out = []
+    if task == "Door":
+        d, h = o.xpos[env.door_body_id], o.site_xpos[env.door_handle_site_id]
+        out = [d, h, [o.qpos[env.hinge_qpos_addr]], d - eef_pos, h - eef_pos, [o.qpos[env.handle_qpos_addr]]]
+        return np.concatenate(out)
+    names = [env.nut_names[i] for i in env.active] if task.startswith("Nut") else list(env.obj_names)
+    for nme in names:
+        b = env.obj_body_id[nme]
+        if nme in cache:
+            p_prev, q_prev = cache[nme]  # q xyzw
+            rel_pos = Re.T @ (p_prev - eef_pos)
+            Ro = _quat2mat_wxyz(q_prev[[3, 0, 1, 2]])
+            rel_q = _quat_xyzw_wpos_from_mat(Re.T @ Ro)
+        else:
+            rel_pos, rel_q = np.zeros(3), np.zeros(4)
+        p, q = o.xpos[b].copy(), o.xquat[b][[1, 2, 3, 0]].copy()
+        cache[nme] = (p, q)
+        out += [rel_pos, rel_q, p, q]
+    return np.concatenate(out)
+
+
+@pytest.mark.parametrize("task,obs_dim", [("Door", 64), ("NutAssemblyRound", 64), ("PickPlace", 106)])
+def test_other_task_envs_obs_and_reward(task, obs_dim):
+    """Door / NutAssemblyRound / PickPlace through the env API: observation layout incl. the one-sample lag of the
+    object-in-gripper poses, state parity after 3 control steps, sparse/shaped reward pieces from the oracle poses"""
+    import torch
+
+    import robosuite_b200 as suite
+    from oracle.pyoracle import CtrlCfg as OCfg
+    from oracle.pyoracle import Oracle
+    from robosuite_b200 import controller_config as cc
+    from robosuite_b200.mjcf.compiler import pack_model
+
+    n = 3
+    env = suite.make(task, robots="Panda", num_envs=n, seed=11, horizon=50, reward_shaping=True)
+    assert env.action_dim == 7 and env.obs_dim == obs_dim, (env.action_dim, env.obs_dim)
+    model = env.model
+    q0 = env.sim.qpos.cpu().numpy().astype(np.float64)
+    oracles, caches = [], []
+    for e in range(n):
+        o = Oracle(pack_model(model))
+        o.ctrl_setup(cc.resolve(model, cc.default_composite_config(), OCfg))
+        o.qpos[:] = q0[e]; o.forward(); o.ctrl_reset()
+        oracles.append(o); caches.append({})
+    flat = env.flat_obs().cpu().numpy().astype(np.float64)
+    for e in range(n):
+        exp = _object_obs(env, oracles[e], caches[e], task)
+        assert np.abs(flat[e, 50:] - exp).max() < 2e-5, (task, "reset", np.abs(flat[e, 50:] - exp).argmax())
+    rng = np.random.default_rng(1)
+    for t in range(3):
+        act = rng.uniform(-1, 1, size=(n, 7))
+        obs, rew, done, info = env.step(torch.as_tensor(act))
+        flat = env.flat_obs().cpu().numpy().astype(np.float64)
+        for e in range(n):
+            o = oracles[e]
+            o.step1(); o.ctrl_run(act[e]); o.step2()
+            exp = _object_obs(env, o, caches[e], task)
+            for _ in range(24):
+                o.step1(); o.ctrl_run(None); o.step2()
+            err = np.abs(flat[e, 50:] - exp)
+            # (PickPlace: mesh objects settling on the bin floor amplify fp32 rounding in their orientation)
+            assert err.max() < (3e-3 if task == "PickPlace" else 1e-3), (task, t, e, int(err.argmax()), float(err.max()))
+            # reaching term of the shaped reward from the oracle's poses after the step
+            eef = o.site_xpos[env.eef_site_id]
+            if task == "Door":
+                expect = 0.25 * (1 - np.tanh(10 * np.linalg.norm(o.site_xpos[env.door_handle_site_id] - eef))) \
+                    + np.clip(0.25 * abs(o.qpos[env.handle_qpos_addr] / (0.5 * np.pi)), -0.25, 0.25)
+                assert abs(float(rew[e]) - expect) < 2e-3, (float(rew[e]), expect)
+            elif task.startswith("Nut"):
+                d = min(np.linalg.norm(o.site_xpos[s] - eef) for s in env.object_site_ids)
+                assert float(rew[e]) >= (1 - np.tanh(10 * d)) * 0.1 - 2e-3
+            else:
+                d = min(np.linalg.norm(o.xpos[env.obj_body_id[nm]] - eef) for nm in env.obj_names)
+                assert float(rew[e]) * 4.0 >= (1 - np.tanh(10 * d)) * 0.1 - 2e-3
+    qd = env.sim.qpos.cpu().numpy().astype(np.float64)
+    eq = max(np.abs(qd[e] - oracles[e].qpos).max() / np.abs(oracles[e].qpos).max() for e in range(n))
+    print(task, "75 substeps through the env API: qpos rel err %.3g, warn %s" % (eq, env.sim.warn.tolist()))
+    assert eq < 2e-3
+    assert int(env.sim.warn.abs().max()) == 0
+    env.close()
