@@ -21,7 +21,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-ENVS_PER_GPU = 4096
+ENVS_PER_GPU = int(os.environ.get("B2S_BENCH_ENVS", "4096"))  # BASELINE.json configs[1]; the override is for scaling experiments only
 N_SUBSTEPS = 25
 METRIC = "env-steps/sec (device-timed) Panda-Lift OSC_POSE @4096 envs per GPU"
 WORKLOAD = "4096 Panda Lift envs, OSC_POSE, fp32, random actions, 1xB200 (BASELINE.json configs[1]); weak-scaled: 4096 envs per GPU"

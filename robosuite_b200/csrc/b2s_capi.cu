@@ -66,6 +66,10 @@ struct b2s_sim {
   std::vector<double> qpos0;
   std::vector<int> site_bodyid, cgid;
   int has_obs = 0, export_env_step = 1, dirty = 1, profile = 0, mode = 0, worklist = 1, ngroups = 4;
+  int timeline = 0, debug_skip = 0;  // B2S_DEBUG_SKIP: bit 0 / 1 = leave out the analytic / convex narrow-phase launch (timing experiments)
+  struct TlEv { int group, type; cudaEvent_t ev; };
+  std::vector<TlEv> tl_events;
+  int merge_tail = 1;  // pipeline: constraint rows + controller + solve in ONE launch (B2S_MERGE_TAIL)
   std::vector<cudaStream_t> gstreams;
   std::vector<cudaEvent_t> gevents;
   cudaEvent_t fork_event = nullptr, in_event = nullptr, out_event = nullptr;
@@ -405,6 +409,7 @@ static void build_layout(b2s_sim* s, int nq, int nv, int nu, int nb, int ncg, in
   mk(s->pio[1], {"gpos", "gmat"}, {"c_pos", "c_frame", "c_dist", "c_fric", "c_int"});
   mk(s->pio[2], {"cdof"}, {"J", "e_D", "e_R", "e_aref", "e_floss", "e_int", "c_int", "c_fric", "c_dist"});
   mk(s->pio[3], {"cdof", "cvel", "M", "bias", "spos", "smat"}, {});
+  mk(s->pio[5], {"cdof", "cvel", "M", "bias", "passive", "xpos", "xquat", "spos", "smat"}, {});
   mk(s->pio[4], {"M", "bias", "passive", "J", "e_D", "e_R", "e_aref", "e_floss", "e_int", "c_fric", "c_int", "c_dist", "xpos", "xquat", "spos", "smat"}, {});
 }
 
@@ -469,15 +474,17 @@ int b2s_create(const void* blob_host, size_t nbytes, int n_env, int device, int 
       cudaFuncSetAttribute(phase_kernel<float, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
       cudaFuncSetAttribute(phase_kernel<float, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
       cudaFuncSetAttribute(phase_kernel<float, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
+      cudaFuncSetAttribute(phase_kernel<float, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
       e1 = cudaFuncSetAttribute(phase_kernel<float, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
-      cudaFuncSetAttribute(narrow_convex_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (9 * EPA_PIPE_MAXV + 4 * EPA_PIPE_MAXF + EPA_PIPE_MAXF + 8) * 4);
+      cudaFuncSetAttribute(narrow_convex_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (9 * EPA_PIPE_MAXV + 4 * EPA_PIPE_MAXF + EPA_PIPE_MAXF + 8) * 4);
     } else {
       cudaFuncSetAttribute(phase_kernel<double, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
       cudaFuncSetAttribute(phase_kernel<double, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
       cudaFuncSetAttribute(phase_kernel<double, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
       cudaFuncSetAttribute(phase_kernel<double, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
+      cudaFuncSetAttribute(phase_kernel<double, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
       e1 = cudaFuncSetAttribute(phase_kernel<double, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
-      cudaFuncSetAttribute(narrow_convex_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (9 * EPA_PIPE_MAXV + 4 * EPA_PIPE_MAXF + EPA_PIPE_MAXF + 8) * 8);
+      cudaFuncSetAttribute(narrow_convex_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (9 * EPA_PIPE_MAXV + 4 * EPA_PIPE_MAXF + EPA_PIPE_MAXF + 8) * 8);
     }
   }
   if (e1 != cudaSuccess) { std::string msg = cudaGetErrorString(e1); b2s_destroy(s); return fail(B2S_ERR_CUDA, "cudaFuncSetAttribute: " + msg); }
@@ -573,15 +580,36 @@ template <typename R> static int enqueue_pipeline(b2s_sim* s, DState<R>& st, int
     Grp g{e0, e1 - e0, gi};
     int blocks = (g.nenv + s->wpb - 1) / s->wpb;
     int nA = g.nenv * st.cl_maxa, nG = g.nenv * st.cl_maxg;
+    const int cvx_blocks = 148 * 24;
+    // B2S_TIMELINE=1 (with B2S_NO_GRAPH=1): timing events between the launches, per-kernel means on stderr (debug aid)
+    auto mark = [&](int type) {
+      if (!s->timeline) return;
+      cudaEvent_t ev; cudaEventCreate(&ev); cudaEventRecord(ev, q);
+      s->tl_events.push_back({gi, type, ev});
+    };
     for (int sub = 0; sub < nsub; sub++) {
-      CUDA_TRY(cudaMemsetAsync(st.cl_cnt + 2 * gi, 0, 2 * sizeof(int), q));
+      mark(0);
+      CUDA_TRY(cudaMemsetAsync(st.cl_cnt + 4 * gi, 0, 4 * sizeof(int), q));
+      mark(1);
       phase_kernel<R, 0><<<blocks, threads, s->smem_bytes, q>>>(phases, sub, nsub, action, g);
+      mark(2);
       // upper bounds of the candidate counts size the grids; threads / warps beyond the device-side count exit at once
-      narrow_analytic_kernel<R><<<(nA + 127) / 128, 128, 0, q>>>(g);
-      narrow_convex_kernel<R><<<(nG + 7) / 8, 256, 8 * epaw, q>>>(g);
-      phase_kernel<R, 2><<<blocks, threads, s->smem_bytes, q>>>(phases, sub, nsub, action, g);
-      if (phases & PH_CTRL) phase_kernel<R, 3><<<blocks, threads, s->smem_bytes, q>>>(phases, sub, nsub, action, g);
-      phase_kernel<R, 4><<<blocks, threads, s->smem_bytes, q>>>(phases, sub, nsub, action, g);
+      if (!(s->debug_skip & 1)) narrow_analytic_kernel<R><<<(nA + 127) / 128, 128, 0, q>>>(g);
+      mark(3);
+      // one warp per block (its EPA polytope is the block's shared memory), work items claimed through an atomic counter
+      if (!(s->debug_skip & 2)) narrow_convex_kernel<R><<<nG < cvx_blocks ? nG : cvx_blocks, 32, epaw, q>>>(g);
+      mark(4);
+      if (s->merge_tail) {
+        phase_kernel<R, 5><<<blocks, threads, s->smem_bytes, q>>>(phases, sub, nsub, action, g);
+        mark(5);
+      } else {
+        phase_kernel<R, 2><<<blocks, threads, s->smem_bytes, q>>>(phases, sub, nsub, action, g);
+        mark(5);
+        if (phases & PH_CTRL) phase_kernel<R, 3><<<blocks, threads, s->smem_bytes, q>>>(phases, sub, nsub, action, g);
+        mark(6);
+        phase_kernel<R, 4><<<blocks, threads, s->smem_bytes, q>>>(phases, sub, nsub, action, g);
+        mark(7);
+      }
     }
     if (G > 1) {
       CUDA_TRY(cudaEventRecord(s->gevents[gi], q));
@@ -600,7 +628,7 @@ template <typename R> static int launch_pipeline_t(b2s_sim* s, DState<R>& st, in
     s->allocs.push_back(p);
     st.wsg = p;
     size_t ne = (size_t)s->n_env;
-    st.cl_cnt = dev_zeros<int>(s, 2 * 64);
+    st.cl_cnt = dev_zeros<int>(s, 4 * 64);
     // candidate capacity per environment: small models keep small grids (the narrow-phase grids are sized by these bounds)
     st.cl_maxa = s->maxcon <= 32 ? 8 : (s->maxcon <= 48 ? 16 : CL_MAXA);
     st.cl_maxg = s->maxcon <= 32 ? 16 : CL_MAXG;
@@ -634,6 +662,22 @@ template <typename R> static int launch_pipeline_t(b2s_sim* s, DState<R>& st, in
   if (!s->use_graph) {
     rc = enqueue_pipeline<R>(s, st, phases, nsub, action, s->stream);
     s->launches += launches_per_call;
+    if (s->timeline && rc == B2S_OK) {
+      cudaStreamSynchronize(s->stream);
+      static const char* names[8] = {"(prev->memset)", "memset", "P0", "narrowA", "narrowG", "P2|P5", "P3", "P4"};
+      double sum[8] = {0}; int cnt[8] = {0};
+      for (size_t i = 1; i < s->tl_events.size(); i++) {
+        auto &a = s->tl_events[i - 1], &b = s->tl_events[i];
+        if (a.group != b.group) continue;
+        float ms = 0; cudaEventElapsedTime(&ms, a.ev, b.ev);
+        sum[b.type] += ms; cnt[b.type]++;
+      }
+      double tot = 0;
+      for (int k = 0; k < 8; k++) if (cnt[k]) { fprintf(stderr, "[timeline] %-16s n=%4d mean %8.1f us\n", names[k], cnt[k], 1e3 * sum[k] / cnt[k]); tot += sum[k]; }
+      fprintf(stderr, "[timeline] sum over one call %.3f ms (all groups)\n", tot);
+      for (auto& t : s->tl_events) cudaEventDestroy(t.ev);
+      s->tl_events.clear();
+    }
     return rc;
   }
   // CUDA-graph replay: the launch sequence of one call (G groups x nsub substeps x 6 kernels) is captured once per
@@ -680,6 +724,9 @@ int b2s_set_mode(b2s_sim* s, int mode) {
   const char* eg = getenv("B2S_GROUPS");
   if (eg) { int v = atoi(eg); if (v >= 1 && v <= 64) s->ngroups = v; }
   if (getenv("B2S_NO_GRAPH")) s->use_graph = 0;
+  if (const char* ds = getenv("B2S_DEBUG_SKIP")) s->debug_skip = atoi(ds);
+  if (getenv("B2S_TIMELINE")) { s->timeline = 1; s->use_graph = 0; }
+  if (const char* mt = getenv("B2S_MERGE_TAIL")) s->merge_tail = atoi(mt) != 0;
   return B2S_OK;
 }
 

@@ -644,7 +644,8 @@ DEVN int epa(const Shape<R>& A, const Shape<R>& B, SV<R>* simplex, int ns, R& de
   nF = 4;
   __syncwarp();
   int bestf = -1;
-  const R epa_tol = sizeof(R) == 4 ? R(1e-6) : R(1e-7);
+  const R epa_tol = sizeof(R) == 4 ? R(2e-6) : R(1e-7);
+  const R vis_tol = sizeof(R) == 4 ? R(2e-7) : R(1e-12);  // fp32: above the rounding noise of the plane distances
   for (int it = 0; it < 100; it++) {
     // closest alive face (lane-parallel scan)
     R bd = Lim<R>::big();
@@ -664,20 +665,27 @@ DEVN int epa(const Shape<R>& A, const Shape<R>& B, SV<R>* simplex, int ns, R& de
     if (lane == 0) printf("dev it %d bf %d bd %.9g dw %.9g nV %d nF %d n %.4f %.4f %.4f\n", it, bf, (double)bd, (double)dw, nV, nF, (double)fn[0], (double)fn[1], (double)fn[2]);
 #endif
     if (dw - bd < epa_tol || nV >= maxv - 1 || nF >= maxf - 16) break;
-    // remove visible faces, build the horizon (sequential, warp-uniform; lane 0 writes)
+    // remove the faces visible from w and build the horizon.  Visibility is tested lane-parallel (32 faces at a time);
+    // the few visible faces are then processed in increasing face order by the whole warp (same order as a serial scan).
     int edges[64];
     int ne = 0;
-    for (int f = 0; f < nF; f++) {
-      int fi = Fi[f];
-      if (!(fi >> 24)) continue;
-      int va = fi & 255, vb = (fi >> 8) & 255, vc = (fi >> 16) & 255;
-      R e3[3];
-      v3sub(e3, w.w, V + 9 * va);
-      R vis = Fn[4 * f] * e3[0] + Fn[4 * f + 1] * e3[1] + Fn[4 * f + 2] * e3[2];
-      if (vis > R(1e-12)) {
-        __syncwarp();
-        if (lane == 0) Fi[f] = fi & 0xffffff;
-        int vs[3] = {va, vb, vc};
+    for (int base = 0; base < nF; base += 32) {
+      int f = base + lane, fi = 0;
+      bool vis = false;
+      if (f < nF) {
+        fi = Fi[f];
+        if (fi >> 24) {
+          const R* va = V + 9 * (fi & 255);
+          vis = Fn[4 * f] * (w.w[0] - va[0]) + Fn[4 * f + 1] * (w.w[1] - va[1]) + Fn[4 * f + 2] * (w.w[2] - va[2]) > vis_tol;
+        }
+      }
+      unsigned mask = __ballot_sync(B2S_FULL, vis);
+      while (mask) {
+        int l = __ffs(mask) - 1;
+        mask &= mask - 1;
+        int fv = __shfl_sync(B2S_FULL, fi, l);
+        if (lane == 0) Fi[base + l] = fv & 0xffffff;
+        int vs[3] = {fv & 255, (fv >> 8) & 255, (fv >> 16) & 255};
         for (int k = 0; k < 3; k++) {
           int a = vs[k], b = vs[(k + 1) % 3], found = 0;
           for (int q = 0; q < ne; q++)
@@ -696,9 +704,26 @@ DEVN int epa(const Shape<R>& A, const Shape<R>& B, SV<R>* simplex, int ns, R& de
       for (int e = 0; e < 3; e++) { V[9 * vi + e] = w.w[e]; V[9 * vi + 3 + e] = w.a[e]; V[9 * vi + 6 + e] = w.b[e]; }
     nV++;
     __syncwarp();
-    for (int q = 0; q < ne && nF < maxf; q++) { mkface(nF, edges[q] & 255, edges[q] >> 8, vi); nF++; }
+    // new faces (horizon edge, w): one lane per face
+    int nnew = ne < maxf - nF ? ne : maxf - nF;
+    for (int q = lane; q < nnew; q += 32) {
+      int a = edges[q] & 255, b = edges[q] >> 8, f = nF + q;
+      R ab[3], ac[3], nn[3];
+      v3sub(ab, V + 9 * b, V + 9 * a);
+      v3sub(ac, V + 9 * vi, V + 9 * a);
+      v3cross(nn, ab, ac);
+      R len = v3norm(nn), d;
+      if (len < R(1e-30)) { d = Lim<R>::big(); nn[0] = 1; nn[1] = 0; nn[2] = 0; }
+      else { v3scl(nn, nn, R(1) / len); d = v3dot(nn, V + 9 * a); }
+      Fn[4 * f] = nn[0]; Fn[4 * f + 1] = nn[1]; Fn[4 * f + 2] = nn[2]; Fn[4 * f + 3] = d;
+      Fi[f] = a | (b << 8) | (vi << 16) | (1 << 24);
+    }
+    nF += nnew;
     __syncwarp();
   }
+#ifdef B2S_CVX_STATS
+  if (lane == 0 && (nF >= maxf - 16 || nV >= maxv - 1)) printf("EPA cap: nV %d nF %d types %d %d depth %.6g\n", nV, nF, A.type, B.type, (double)(bestf >= 0 ? Fn[4 * bestf + 3] : -1));
+#endif
   if (bestf < 0) return -1;
   int fi = Fi[bestf];
   int ia = fi & 255, ib = (fi >> 8) & 255, ic = (fi >> 16) & 255;

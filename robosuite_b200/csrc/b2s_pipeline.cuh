@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(128) narrow_analytic_kernel(Grp g) {
   const DState<R>& s = cstate<R>();
   const WSLayout& L = c_L;
   int tid = blockIdx.x * blockDim.x + threadIdx.x;
-  if (tid >= s.cl_cnt[2 * g.gid]) return;
+  if (tid >= s.cl_cnt[4 * g.gid]) return;
   tid += g.env0 * s.cl_maxa;  // this group's slice of the candidate list / output slots
   int code = s.cl_listA[tid];
   int env = code >> 12, pidx = code & 4095;
@@ -120,34 +120,41 @@ __global__ void __launch_bounds__(128) narrow_analytic_kernel(Grp g) {
   for (int k = 0; k < n * CREC; k++) out[1 + k] = buf[k];
 }
 
-// convex pairs: ONE WARP per candidate pair (mesh support scans split over the lanes); EPA polytope in shared memory
+// convex pairs: ONE WARP per candidate pair (mesh support scans split over the lanes).  A block is one warp and owns one EPA
+// polytope in shared memory (7.3 KB fp32 -> ~30 resident warps per SM); warps claim work items through an atomic counter, so
+// the few expensive pairs (penetrating meshes: tens of EPA expansions) never hold idle neighbours resident.
 template <typename R>
-__global__ void __launch_bounds__(256) narrow_convex_kernel(Grp g) {
+__global__ void __launch_bounds__(32) narrow_convex_kernel(Grp g) {
   const DModel<R>& m = cmodel<R>();
   const DState<R>& s = cstate<R>();
   const WSLayout& L = c_L;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-  int wid = blockIdx.x * wpb + warp;
-  if (wid >= s.cl_cnt[2 * g.gid + 1]) return;
-  wid += g.env0 * s.cl_maxg;
-  const int EPAW = 9 * EPA_PIPE_MAXV + 4 * EPA_PIPE_MAXF + EPA_PIPE_MAXF + 8;
-  R* scratch = reinterpret_cast<R*>(smem_raw) + (size_t)warp * EPAW;
-  int code = s.cl_listG[wid];
-  int env = code >> 12, pidx = code & 4095;
-  const R* row = s.wsg + (size_t)env * L.total;
-  int g1 = m.pair_geom[2 * pidx], g2 = m.pair_geom[2 * pidx + 1];
-  if (m.geom_type[g1] > m.geom_type[g2]) { int t = g1; g1 = g2; g2 = t; }
-  Shape<R> A, B;
-  shape_from(g1, row + L.gpos, row + L.gmat, A);
-  shape_from(g2, row + L.gpos, row + L.gmat, B);
-  R buf[CREC];
-  int n = convex_convex(A, B, buf, 1, scratch, lane, s.gjk_cache ? s.gjk_cache + ((size_t)env * m.npair + pidx) * 3 : (R*)nullptr,
-                        EPA_PIPE_MAXV, EPA_PIPE_MAXF);
-  R* out = s.cl_outG + (size_t)wid * 8;
-  if (lane == 0) {
-    out[0] = R(n);
-    for (int k = 0; k < CREC; k++) out[1 + k] = n ? buf[k] : R(0);
+  int lane = threadIdx.x & 31;
+  R* scratch = reinterpret_cast<R*>(smem_raw);
+  const int cnt = s.cl_cnt[4 * g.gid + 1];
+  while (true) {
+    int item = 0;
+    if (lane == 0) item = atomicAdd(s.cl_cnt + 4 * g.gid + 3, 1);
+    item = __shfl_sync(B2S_FULL, item, 0);
+    if (item >= cnt) break;
+    int wid = item + g.env0 * s.cl_maxg;
+    int code = s.cl_listG[wid];
+    int env = code >> 12, pidx = code & 4095;
+    const R* row = s.wsg + (size_t)env * L.total;
+    int g1 = m.pair_geom[2 * pidx], g2 = m.pair_geom[2 * pidx + 1];
+    if (m.geom_type[g1] > m.geom_type[g2]) { int t = g1; g1 = g2; g2 = t; }
+    Shape<R> A, B;
+    shape_from(g1, row + L.gpos, row + L.gmat, A);
+    shape_from(g2, row + L.gpos, row + L.gmat, B);
+    R buf[CREC];
+    int n = convex_convex(A, B, buf, 1, scratch, lane, s.gjk_cache ? s.gjk_cache + ((size_t)env * m.npair + pidx) * 3 : (R*)nullptr,
+                          EPA_PIPE_MAXV, EPA_PIPE_MAXF);
+    R* out = s.cl_outG + (size_t)wid * 8;
+    if (lane == 0) {
+      out[0] = R(n);
+      for (int k = 0; k < CREC; k++) out[1 + k] = n ? buf[k] : R(0);
+    }
+    __syncwarp();
   }
 }
 
@@ -212,7 +219,8 @@ template <typename R> DEVN int gather_contacts(Eng<R> e, int env, int& warn) {
   return total;
 }
 
-// PH: 0 kinematics+velocity+crb, 1 collision, 2 constraint rows, 3 controller, 4 actuation+solve+integrate(+obs)
+// PH: 0 kinematics+velocity+crb, 1 collision, 2 constraint rows, 3 controller, 4 actuation+solve+integrate(+obs),
+//     5 = 2 + 3 + 4 in one launch (constraint rows, Jacobian and controller output never leave shared memory)
 template <typename R, int PH>
 __global__ void __launch_bounds__(512, 1) phase_kernel(int phases, int sub, int nsub, const R* action, Grp g) {
   const DModel<R>& m = cmodel<R>();
@@ -236,14 +244,14 @@ __global__ void __launch_bounds__(512, 1) phase_kernel(int phases, int sub, int 
     if (lane < 8) hdr[lane] = reinterpret_cast<const int*>(row + L.hdr)[lane];
     __syncwarp();
   }
-  int ncon = PH >= 2 ? hdr[0] : 0, nefc = PH >= 3 ? hdr[1] : 0, warn = PH >= 2 ? hdr[2] : 0;
+  int ncon = PH >= 2 ? hdr[0] : 0, nefc = (PH == 3 || PH == 4) ? hdr[1] : 0, warn = PH >= 2 ? hdr[2] : 0;
   ws_load(e, row, io, nefc * m.nv, &mbar[warp]);
-  if (PH == 0 || PH == 2 || PH == 3 || PH == 4) {
+  if (PH == 0 || PH >= 2) {
     load_row(e.p(L.qpos), s.qpos + E * m.nq, m.nq, lane);
     load_row(e.p(L.qvel), s.qvel + E * m.nv, m.nv, lane);
   }
-  if (PH == 3 || PH == 4) load_row(e.p(L.ctrl), s.ctrl + E * m.nu, m.nu, lane);
-  if (PH == 4) load_row(e.p(L.qacc_ws), s.qacc_ws + E * m.nv, m.nv, lane);
+  if (PH >= 3) load_row(e.p(L.ctrl), s.ctrl + E * m.nu, m.nu, lane);
+  if (PH >= 4) load_row(e.p(L.qacc_ws), s.qacc_ws + E * m.nv, m.nv, lane);
   __syncwarp();
   if (PH == 0) {
     e.kinematics();
@@ -258,8 +266,8 @@ __global__ void __launch_bounds__(512, 1) phase_kernel(int phases, int sub, int 
     if (ng > s.cl_maxg) { ng = s.cl_maxg; warn |= 4; }
     int baseA = 0, baseG = 0;
     if (lane == 0) {
-      if (na) baseA = g.env0 * s.cl_maxa + atomicAdd(s.cl_cnt + 2 * g.gid, na);
-      if (ng) baseG = g.env0 * s.cl_maxg + atomicAdd(s.cl_cnt + 2 * g.gid + 1, ng);
+      if (na) baseA = g.env0 * s.cl_maxa + atomicAdd(s.cl_cnt + 4 * g.gid, na);
+      if (ng) baseG = g.env0 * s.cl_maxg + atomicAdd(s.cl_cnt + 4 * g.gid + 1, ng);
     }
     baseA = __shfl_sync(B2S_FULL, baseA, 0);
     baseG = __shfl_sync(B2S_FULL, baseG, 0);
@@ -274,18 +282,22 @@ __global__ void __launch_bounds__(512, 1) phase_kernel(int phases, int sub, int 
     ncon = collide(e, warn, dbgc);
     if (lane == 0) { hdr[0] = ncon; hdr[1] = 0; hdr[2] = warn; hdr[3] = 0; }
     __syncwarp();
-  } else if (PH == 2) {
+  }
+  if (PH == 2 || PH == 5) {
     if (phases & PH_WORKLIST) ncon = gather_contacts(e, env, warn);
     nefc = make_constraint(e, ncon, warn);
     if (lane == 0) { hdr[0] = ncon; hdr[1] = nefc; hdr[2] = warn; }
     __syncwarp();
-  } else if (PH == 3) {
+  }
+  if (PH == 3 || (PH == 5 && (phases & PH_CTRL))) {
     CtrlState<R> cs;
     ctrl_load(e, cs, env);
     ctrl_run(e, cs, env, sub == 0 ? action : (const R*)nullptr);
     for (int i = lane; i < m.nu; i += 32) s.ctrl[E * m.nu + i] = e.p(L.ctrl)[i];
     if (sub == 0) ctrl_store(e, cs, env);
-  } else {
+    __syncwarp();
+  }
+  if (PH == 4 || PH == 5) {
     R time = s.time[env];
     e.actuation((R*)nullptr);
     if (e.acceleration()) warn |= 1;

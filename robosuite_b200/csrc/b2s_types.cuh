@@ -80,7 +80,7 @@ struct DState {
   int* dbg;        // [n_env, 4] analytic candidates, convex candidates, EPA calls, reserved
   R* wsg;          // [n_env, L.total] global workspace rows (pipeline mode)
   // pipeline-mode collision work lists (candidate pairs of ALL environments, compacted with atomics)
-  int* cl_cnt;     // [2] number of analytic / convex candidates this substep
+  int* cl_cnt;     // per group [4]: number of analytic / convex candidates this substep, (spare), next convex work item
   int cl_maxa, cl_maxg;  // per-environment candidate capacity of the two work lists
   int* cl_listA;   // [n_env * cl_maxa] env << 12 | pair
   int* cl_listG;   // [n_env * cl_maxg]
@@ -113,7 +113,7 @@ struct WSLayout {
 // Pipeline mode: the substep is split into phase kernels; each phase loads / stores these workspace regions
 // from / to the per-environment global workspace row (L2 resident).
 struct Region { int off, len, dyn; };  // dyn: 0 fixed, 1 = nefc*nv words (constraint Jacobian)
-#define B2S_NPHASE 5
+#define B2S_NPHASE 6
 #define CL_MAXA 64  // hard upper bounds of the per-environment candidate counts (analytic / convex pairs);
 #define CL_MAXG 32  // the run-time caps DState::cl_maxa / cl_maxg are chosen per model (b2s_capi.cu)
 #define CL_RECA 58
