@@ -415,6 +415,32 @@ static void build_layout(b2s_sim* s, int nq, int nv, int nu, int nb, int ncg, in
 
 static b2s_sim* g_owner[64] = {nullptr};
 
+// The phase / narrow-phase kernels need different amounts of per-thread local memory (stack).  By default the driver shrinks the
+// local-memory pool after a launch and grows it again for the next kernel that needs more - a device-wide reallocation worth
+// ~200 us in front of every narrow_convex launch.  Ask the context to keep the pool at its high-water mark
+// (cudaDeviceLmemResizeToMax / CU_CTX_LMEM_RESIZE_TO_MAX); works on the already-initialised primary context torch created.
+static void keep_local_memory_pool() {
+  unsigned flags = 0;
+  if (cudaGetDeviceFlags(&flags) == cudaSuccess && (flags & cudaDeviceLmemResizeToMax)) return;
+  const char* how = "unchanged";
+  if (cudaSetDeviceFlags((flags & cudaDeviceMask) | cudaDeviceLmemResizeToMax) == cudaSuccess) how = "cudaSetDeviceFlags";
+  else {
+    cudaGetLastError();
+    typedef int (*get_fn)(unsigned*);
+    typedef int (*set_fn)(unsigned);
+    void *fg = nullptr, *fs = nullptr;
+    cudaDriverEntryPointQueryResult q1, q2;
+    if (cudaGetDriverEntryPoint("cuCtxGetFlags", &fg, cudaEnableDefault, &q1) == cudaSuccess &&
+        cudaGetDriverEntryPoint("cuCtxSetFlags", &fs, cudaEnableDefault, &q2) == cudaSuccess && fg && fs) {
+      unsigned cf = 0;
+      if (((get_fn)fg)(&cf) == 0 && ((set_fn)fs)(cf | 0x10u /* CU_CTX_LMEM_RESIZE_TO_MAX */) == 0) how = "cuCtxSetFlags";
+    }
+    cudaGetLastError();
+  }
+  if (getenv("B2S_VERBOSE")) fprintf(stderr, "[b2s] local-memory pool kept at high-water mark: %s\n", how);
+}
+
+
 // ------------------------------------------------------------------------------------------------ API
 extern "C" {
 
@@ -428,6 +454,7 @@ int b2s_create(const void* blob_host, size_t nbytes, int n_env, int device, int 
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(B2S_ERR_CUDA, "b2s_create: no CUDA device available (this library has no CPU fallback)");
   CUDA_TRY(cudaSetDevice(device));
+  if (!getenv("B2S_NO_LMEM_FLAG")) keep_local_memory_pool();
   b2s_sim* s = new b2s_sim();
   s->n_env = n_env; s->device = device; s->precision = precision;
   Blob b{(const char*)blob_host, nbytes};

@@ -245,3 +245,28 @@ def test_other_task_envs_obs_and_reward(task, obs_dim):
     assert eq < 2e-3
     assert int(env.sim.warn.abs().max()) == 0
     env.close()
+
+
+def test_batched_gym_wrapper_autoreset():
+    """GymWrapper semantics (wrappers/gym_wrapper.py:26-180) on the batch: key order, 5-tuple, reset inside step"""
+    import torch
+
+    import robosuite_b200 as suite
+    from robosuite_b200.wrappers import BatchedGymWrapper
+
+    n = 4
+    env = BatchedGymWrapper(suite.make("Lift", robots="Panda", num_envs=n, seed=2, horizon=3))
+    obs, info = env.reset(seed=7)
+    assert obs.shape == (n, 60) and info == {}
+    d = env.env._get_observations()
+    assert torch.equal(obs[:, :10], d["object-state"]) and torch.equal(obs[:, 10:], d["robot0_proprio-state"])
+    for t in range(3):
+        obs, rew, term, trunc, info = env.step(torch.zeros((n, 7), device=obs.device))
+        assert rew.shape == (n,) and term.shape == (n,) and not bool(trunc.any())
+    assert bool(term.all()) and "final_observation" in info
+    assert int(env.env.timestep.max()) == 0 and not bool(env.env.done.any())  # every environment started a new episode
+    # the observation handed back is the reset observation: cube back on the table
+    assert torch.allclose(obs[:, 2], torch.full((n,), 0.83, device=obs.device), atol=5e-3)
+    obs, rew, term, trunc, info = env.step(torch.zeros((n, 7), device=obs.device))  # stepping continues without an explicit reset
+    assert not bool(term.any())
+    env.close()
