@@ -254,13 +254,33 @@ def run_gpu(args):
         if world > 1:
             dist.destroy_process_group()
         return
-    # ---- roofline of the dominant (only) kernel: algorithmic HBM bytes per launch / launch duration
+    # ---- roofline of the dominant kernel.  Pipeline mode: the merged tail kernel phase_kernel<R,5> (73 % of the summed
+    # kernel time, profiles/r01_pipeline_summary.md); its launch duration is measured live with CUDA events on the launching
+    # stream in a short eager pass (the timed region above replays a CUDA graph, which events cannot subdivide).
+    # Algorithmic bytes of ONE launch = environments per launch x per-substep state round trip (SURVEY.md section 8d:
+    # B_substep = 2*4*S, here counted from the arrays the kernel really reads/writes in HBM).
     m = env.model
     per_env_in = (m.nq + 3 * m.nv + m.nu + 1 + 3 + 9 + 4 + 8 + env.action_dim) * esz
     per_env_out = (m.nq + 3 * m.nv + m.nu + 1 + 3 + 9 + 4 + env.obs_dim + 4 + 8) * esz + 4
-    alg_bytes = N * (per_env_in + per_env_out)
     peak, how = _peaks()
-    achieved = alg_bytes / (ms / K * 1e-3) / 1e9
+    step_bytes = N * (per_env_in + per_env_out)
+    achieved_step = step_bytes / (ms / K * 1e-3) / 1e9
+    kernel, launch_us, envs_per_launch = "step_kernel", ms / K * 1e3, N
+    alg_bytes = step_bytes
+    if args.mode == 1:
+        sim.timeline(1)
+        tl = []
+        for i in range(2):
+            sim.env_step(actions[W + i], N_SUBSTEPS)
+            tl.append(sim.timeline(-1))
+        sim.timeline(0)
+        mean_us, cnt = tl[-1]
+        groups = max(1, cnt[5] // N_SUBSTEPS)
+        kernel, launch_us, envs_per_launch = "phase_kernel<float,5> (rows+controller+solve+integrate)", mean_us[5], N // groups
+        sub_in = (m.nq + 2 * m.nv + m.nu + 1 + 3 + 9 + 4) * esz   # qpos qvel qacc_ws ctrl time + controller state
+        sub_out = (m.nq + 3 * m.nv + m.nu + 1) * esz                # qpos qvel qacc qacc_ws ctrl time
+        alg_bytes = envs_per_launch * (sub_in + sub_out)
+    achieved = alg_bytes / (launch_us * 1e-6) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
@@ -286,9 +306,11 @@ def run_gpu(args):
                    "preroll_steps": args.preroll, "kernel_mode": "pipeline" if args.mode else "fused",
                    "multi_gpu": "env shards independent; NCCL: model broadcast at start" + (", obs all-gather per step (e2e loop)" if args.allgather_obs else "")},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": how,
-                     "note": "fused 25-substep kernel keeps state on chip: algorithmic HBM traffic is tiny, the kernel is "
-                             "issue/latency bound (see DESIGN.md section 5)"},
+                     "traffic": traffic, "peak_source": how, "kernel": kernel, "launch_us": launch_us,
+                     "envs_per_launch": envs_per_launch, "alg_bytes_per_launch": alg_bytes,
+                     "whole_step": {"achieved": achieved_step, "frac": achieved_step / peak, "alg_bytes": step_bytes},
+                     "note": "per-environment state stays in shared memory / L2 between phases: algorithmic HBM traffic is tiny, "
+                             "the kernels are latency / instruction-fetch bound (DESIGN.md section 5)"},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),

@@ -121,6 +121,11 @@ int b2s_set_profile(b2s_sim* sim, int flag);
 
 /* number of kernels this handle has launched since creation (bench.py "gpu_launches") */
 int64_t b2s_launch_count(const b2s_sim* sim);
+/* Measurement aid (pipeline mode): enable = 1 switches b2s_env_step / b2s_step to eager launches bracketed by timing events,
+ * enable = 0 back to CUDA-graph replay, enable < 0 only reads.  mean_us / count (may be NULL) receive, for the LAST call made
+ * while enabled, the mean event-to-event interval per launch kind: [1] counter memset, [2] phase 0, [3] analytic narrow phase,
+ * [4] convex narrow phase, [5] merged tail phase (or phase 2), [6] phase 3, [7] phase 4. */
+int b2s_timeline(b2s_sim* sim, int enable, double mean_us[8], int count[8]);
 
 #ifdef __cplusplus
 }

@@ -69,6 +69,7 @@ struct b2s_sim {
   int timeline = 0, debug_skip = 0;  // B2S_DEBUG_SKIP: bit 0 / 1 = leave out the analytic / convex narrow-phase launch (timing experiments)
   struct TlEv { int group, type; cudaEvent_t ev; };
   std::vector<TlEv> tl_events;
+  double tl_mean_us[8] = {0}; int tl_count[8] = {0};
   int merge_tail = 1;  // pipeline: constraint rows + controller + solve in ONE launch (B2S_MERGE_TAIL)
   std::vector<cudaStream_t> gstreams;
   std::vector<cudaEvent_t> gevents;
@@ -542,6 +543,17 @@ int b2s_set_stream(b2s_sim* s, void* stream) {
   return B2S_OK;
 }
 
+int b2s_timeline(b2s_sim* s, int enable, double mean_us[8], int count[8]) {
+  if (!s) return fail(B2S_ERR_ARG, "null handle");
+  if (mean_us) for (int k = 0; k < 8; k++) mean_us[k] = s->tl_mean_us[k];
+  if (count) for (int k = 0; k < 8; k++) count[k] = s->tl_count[k];
+  if (enable >= 0) {
+    s->timeline = enable ? (getenv("B2S_TIMELINE") ? 2 : 1) : 0;
+    s->use_graph = enable ? 0 : (getenv("B2S_NO_GRAPH") ? 0 : 1);
+  }
+  return B2S_OK;
+}
+
 int b2s_set_profile(b2s_sim* s, int flag) { if (!s) return fail(B2S_ERR_ARG, "null handle"); s->profile = flag != 0; return B2S_OK; }
 
 int b2s_set_export(b2s_sim* s, int flag) { if (!s) return fail(B2S_ERR_ARG, "null handle"); s->export_env_step = flag != 0; return B2S_OK; }
@@ -700,8 +712,12 @@ template <typename R> static int launch_pipeline_t(b2s_sim* s, DState<R>& st, in
         sum[b.type] += ms; cnt[b.type]++;
       }
       double tot = 0;
-      for (int k = 0; k < 8; k++) if (cnt[k]) { fprintf(stderr, "[timeline] %-16s n=%4d mean %8.1f us\n", names[k], cnt[k], 1e3 * sum[k] / cnt[k]); tot += sum[k]; }
-      fprintf(stderr, "[timeline] sum over one call %.3f ms (all groups)\n", tot);
+      for (int k = 0; k < 8; k++) {
+        s->tl_mean_us[k] = cnt[k] ? 1e3 * sum[k] / cnt[k] : 0.0; s->tl_count[k] = cnt[k];
+        if (cnt[k]) tot += sum[k];
+        if (cnt[k] && s->timeline > 1) fprintf(stderr, "[timeline] %-16s n=%4d mean %8.1f us\n", names[k], cnt[k], s->tl_mean_us[k]);
+      }
+      if (s->timeline > 1) fprintf(stderr, "[timeline] sum over one call %.3f ms (all groups)\n", tot);
       for (auto& t : s->tl_events) cudaEventDestroy(t.ev);
       s->tl_events.clear();
     }
@@ -752,7 +768,7 @@ int b2s_set_mode(b2s_sim* s, int mode) {
   if (eg) { int v = atoi(eg); if (v >= 1 && v <= 64) s->ngroups = v; }
   if (getenv("B2S_NO_GRAPH")) s->use_graph = 0;
   if (const char* ds = getenv("B2S_DEBUG_SKIP")) s->debug_skip = atoi(ds);
-  if (getenv("B2S_TIMELINE")) { s->timeline = 1; s->use_graph = 0; }
+  if (getenv("B2S_TIMELINE")) { s->timeline = 2; s->use_graph = 0; }
   if (const char* mt = getenv("B2S_MERGE_TAIL")) s->merge_tail = atoi(mt) != 0;
   return B2S_OK;
 }

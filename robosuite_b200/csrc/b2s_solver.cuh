@@ -3,6 +3,12 @@
 // Replaces the constraint stage of mj_step1 and the solve of mj_step2 (robosuite/utils/binding_utils.py:1101-1107),
 // SURVEY.md section 8 rows a1/a7 and Appendix C.
 #pragma once
+// B2S_LOOP: loops of the solver keep their rolled form when B2S_SMALL_CODE is set (instruction-cache footprint experiments)
+#ifdef B2S_SMALL_CODE
+#define B2S_LOOP _Pragma("unroll 1")
+#else
+#define B2S_LOOP
+#endif
 #include "b2s_collide.cuh"
 
 #define B2S_MINIMP 0.0001
@@ -50,8 +56,10 @@ template <typename R> DEVN int make_constraint(Eng<R> e, int ncon, int& warn, fl
   const R* qpos = e.p(L.qpos); const R* qvel = e.p(L.qvel);
   int nefc = 0;
   // --- friction-loss rows (static list)
+  B2S_LOOP
   for (int r = lane; r < m.nfl; r += 32) {
     int dof = m.fl_dof[r];
+    B2S_LOOP
     for (int i = 0; i < nv; i++) J[r * nv + i] = i == dof ? R(1) : R(0);
     eint[r] = C_FRICTION | (dof << 8);
     epos[r] = 0;
@@ -59,6 +67,7 @@ template <typename R> DEVN int make_constraint(Eng<R> e, int ncon, int& warn, fl
   }
   nefc = m.nfl;
   // --- joint limits
+  B2S_LOOP
   for (int base = 0; base < m.nlim; base += 32) {
     int k = base + lane, act = 0, j = 0, side = 0;
     R dist = 0;
@@ -74,6 +83,7 @@ template <typename R> DEVN int make_constraint(Eng<R> e, int ncon, int& warn, fl
       int r = nefc + __popc(mask & ((1u << lane) - 1));
       if (r < m.maxefc) {
         int dof = m.jnt_dofadr[j];
+        B2S_LOOP
         for (int i = 0; i < nv; i++) J[r * nv + i] = i == dof ? R(-side) : R(0);
         eint[r] = C_LIMIT | (j << 8);
         epos[r] = dist;
@@ -87,6 +97,7 @@ template <typename R> DEVN int make_constraint(Eng<R> e, int ncon, int& warn, fl
   int* cint = e.pi(L.c_int);
   const R* cdist = e.p(L.c_dist);
   int first_contact_row = nefc;
+  B2S_LOOP
   for (int base = 0; base < ncon; base += 32) {
     int c = base + lane, dim = 0;
     if (c < ncon && cdist[c] < 0) dim = cint[5 * c + 2];
@@ -106,16 +117,20 @@ template <typename R> DEVN int make_constraint(Eng<R> e, int ncon, int& warn, fl
   // recompute exact nefc as end of the last placed contact
   {
     int last = first_contact_row;
+    B2S_LOOP
     for (int c = lane; c < ncon; c += 32)
       if (cint[5 * c + 3] >= 0) last = max(last, cint[5 * c + 3] + cint[5 * c + 2]);
+    B2S_LOOP
     for (int o = 16; o > 0; o >>= 1) last = max(last, __shfl_xor_sync(B2S_FULL, last, o));
     nefc = last;
   }
   // row headers of contact rows
+  B2S_LOOP
   for (int c = lane; c < ncon; c += 32) {
     int adr = cint[5 * c + 3];
     if (adr < 0) continue;
     int dim = cint[5 * c + 2];
+    B2S_LOOP
     for (int k = 0; k < dim; k++) {
       eint[adr + k] = (dim == 1 ? C_FRICTIONLESS : C_ELLIPTIC) | (c << 8);
       epos[adr + k] = k == 0 ? cdist[c] : R(0);
@@ -128,6 +143,7 @@ template <typename R> DEVN int make_constraint(Eng<R> e, int ncon, int& warn, fl
   {
     R* fr = e.p(L.scratch);
     const R* cn = e.p(L.c_frame);
+    B2S_LOOP
     for (int c = lane; c < ncon; c += 32) {
       R f9[9] = {cn[3 * c], cn[3 * c + 1], cn[3 * c + 2], 0, 0, 0, 0, 0, 0};
       make_frame(f9);
@@ -140,6 +156,7 @@ template <typename R> DEVN int make_constraint(Eng<R> e, int ncon, int& warn, fl
   {
     const R* cdof = e.p(L.cdof); const R* cpos = e.p(L.c_pos); const R* cfr = e.p(L.scratch);
     int nrows = nefc - first_contact_row;
+    B2S_LOOP
     for (int w = lane; w < nrows * nv; w += 32) {
       int r = first_contact_row + w / nv, i = w % nv;
       int c = eint[r] >> 8, k = r - cint[5 * c + 3];
@@ -163,18 +180,22 @@ template <typename R> DEVN int make_constraint(Eng<R> e, int ncon, int& warn, fl
   MTICK(7)
   // per row: velocity, impedance, regularisation, reference acceleration
   R* ejv = e.p(L.e_jv);  // borrow: holds imp of each row until the cone pass
+  B2S_LOOP
   for (int r = lane; r < nefc; r += 32) {
     R vel = 0;
+    B2S_LOOP
     for (int i = 0; i < nv; i++) vel += J[r * nv + i] * qvel[i];
     int type = eint[r] & 255, id = eint[r] >> 8;
     R solref[2], solimp[5], diag;
     int first = 1;
     if (type == C_FRICTION) {
       solref[0] = m.dof_solref[2 * id]; solref[1] = m.dof_solref[2 * id + 1];
+      B2S_LOOP
       for (int q = 0; q < 5; q++) solimp[q] = m.dof_solimp[5 * id + q];
       diag = m.dof_invweight0[id];
     } else if (type == C_LIMIT) {
       solref[0] = m.jnt_solref[2 * id]; solref[1] = m.jnt_solref[2 * id + 1];
+      B2S_LOOP
       for (int q = 0; q < 5; q++) solimp[q] = m.jnt_solimp[5 * id + q];
       diag = m.dof_invweight0[m.jnt_dofadr[id]];
     } else {
@@ -192,6 +213,7 @@ template <typename R> DEVN int make_constraint(Eng<R> e, int ncon, int& warn, fl
       R r10 = m.geom_solref[2 * g1], r11 = m.geom_solref[2 * g1 + 1], r20 = m.geom_solref[2 * g2], r21 = m.geom_solref[2 * g2 + 1];
       if (p1 != p2 || (r10 > 0 && r20 > 0)) { solref[0] = mix * r10 + (1 - mix) * r20; solref[1] = mix * r11 + (1 - mix) * r21; }
       else { solref[0] = r_min(r10, r20); solref[1] = r_min(r11, r21); }
+      B2S_LOOP
       for (int q = 0; q < 5; q++) solimp[q] = mix * m.geom_solimp[5 * g1 + q] + (1 - mix) * m.geom_solimp[5 * g2 + q];
     }
     R pos = epos[r];
@@ -210,6 +232,7 @@ template <typename R> DEVN int make_constraint(Eng<R> e, int ncon, int& warn, fl
   MTICK(8)
   // elliptic cones: friction-row regularisation and cone coefficient mu
   const R* cfric = e.p(L.c_fric);
+  B2S_LOOP
   for (int c = lane; c < ncon; c += 32) {
     int adr = cint[5 * c + 3], dim = cint[5 * c + 2];
     if (adr < 0 || dim < 3) continue;
@@ -217,11 +240,13 @@ template <typename R> DEVN int make_constraint(Eng<R> e, int ncon, int& warn, fl
     R R0 = eR[adr];
     R R1 = R0 / r_max(Lim<R>::minval(), m.impratio);
     eR[adr + 1] = R1;
+    B2S_LOOP
     for (int k = 2; k < dim; k++) { R fk = row_friction(cfric + 3 * c, k); eR[adr + k] = R1 * f0 * f0 / (fk * fk); }
     efl[adr] = f0 * r_sqrt(R1 / R0);  // cone coefficient mu, kept in the (otherwise unused) frictionloss slot
   }
   __syncwarp();
   MTICK(9)
+  B2S_LOOP
   for (int r = lane; r < nefc; r += 32) eD[r] = R(1) / eR[r];
   __syncwarp();
   MTICK(10)
@@ -246,8 +271,10 @@ DEVN R constraint_update(Eng<R> e, int nefc, int ncon, bool hess) {
   int nsimple = m.nfl;
   // simple rows up to the first contact row
   int first_contact_row = nefc;
+  B2S_LOOP
   for (int c = 0; c < ncon; c++) { int a = cint[5 * c + 3]; if (a >= 0) { first_contact_row = a; break; } }
   (void)nsimple;
+  B2S_LOOP
   for (int r = lane; r < first_contact_row; r += 32) {
     int type = eint[r] & 255;
     R x = jar[r], D = eD[r], a = 0, f;
@@ -264,6 +291,7 @@ DEVN R constraint_update(Eng<R> e, int nefc, int ncon, bool hess) {
     if (hess) act[r] = a;
   }
   const R* cfric = e.p(L.c_fric);
+  B2S_LOOP
   for (int c = lane; c < ncon; c += 32) {
     int adr = cint[5 * c + 3];
     if (adr < 0) continue;
@@ -279,12 +307,15 @@ DEVN R constraint_update(Eng<R> e, int nefc, int ncon, bool hess) {
     fr[0] = mu;
     U[0] = jar[adr] * mu;
     R TT = 0;
+    B2S_LOOP
     for (int k = 1; k < dim; k++) { fr[k] = row_friction(cfric + 3 * c, k); U[k] = jar[adr + k] * fr[k]; TT += U[k] * U[k]; }
     R N = U[0], T = r_sqrt(TT);
     if (N >= mu * T || (T <= 0 && N >= 0)) {
+      B2S_LOOP
       for (int k = 0; k < dim; k++) { force[adr + k] = 0; if (hess) act[adr + k] = 0; }
       if (hess) Hc[m.hc_stride * c] = -1;
     } else if (mu * N + T <= 0 || (T <= 0 && N < 0)) {
+      B2S_LOOP
       for (int k = 0; k < dim; k++) {
         R Dk = eD[adr + k], x = jar[adr + k];
         force[adr + k] = -Dk * x;
@@ -298,14 +329,19 @@ DEVN R constraint_update(Eng<R> e, int nefc, int ncon, bool hess) {
       cost += R(0.5) * Dm * NT * NT;
       R f0 = -Dm * NT * mu;
       force[adr] = f0;
+      B2S_LOOP
       for (int k = 1; k < dim; k++) force[adr + k] = -f0 / T * U[k] * fr[k];
       if (hess) {
+        B2S_LOOP
         for (int k = 0; k < dim; k++) act[adr + k] = 0;
         R* h = Hc + m.hc_stride * c;
         R invT = R(1) / T;
         h[0] = Dm * fr[0] * fr[0];
+        B2S_LOOP
         for (int k = 1; k < dim; k++) h[k] = h[k * dim] = -Dm * mu * U[k] * invT * fr[0] * fr[k];
+        B2S_LOOP
         for (int a = 1; a < dim; a++)
+          B2S_LOOP
           for (int b = 1; b < dim; b++) {
             R v = Dm * mu * mu * U[a] * U[b] * invT * invT - Dm * NT * mu * ((a == b ? invT : R(0)) - U[a] * U[b] * invT * invT * invT);
             h[a * dim + b] = v * fr[a] * fr[b];
@@ -329,6 +365,7 @@ DEVN void ls_eval(Eng<R> e, int nefc, int ncon, int first_contact_row, R alpha, 
   const int* eint = e.pi(L.e_int); const int* cint = e.pi(L.c_int);
   const R* cfric = e.p(L.c_fric);
   R g = 0, h = 0;
+  B2S_LOOP
   for (int r = lane; r < first_contact_row; r += 32) {
     R x = jar[r] + alpha * jv[r], v = jv[r], D = eD[r];
     if ((eint[r] & 255) == C_FRICTION) {
@@ -338,6 +375,7 @@ DEVN void ls_eval(Eng<R> e, int nefc, int ncon, int first_contact_row, R alpha, 
       else { g += D * x * v; h += D * v * v; }
     } else if (x < 0) { g += D * x * v; h += D * v * v; }
   }
+  B2S_LOOP
   for (int c = lane; c < ncon; c += 32) {
     int adr = cint[5 * c + 3];
     if (adr < 0) continue;
@@ -346,6 +384,7 @@ DEVN void ls_eval(Eng<R> e, int nefc, int ncon, int first_contact_row, R alpha, 
     if (dim == 1) { if (x0 < 0) { g += eD[adr] * x0 * v0; h += eD[adr] * v0 * v0; } continue; }
     R mu = efl[adr];
     R N = x0 * mu, Nd = v0 * mu, TT = 0, UV = 0, VV = 0;
+    B2S_LOOP
     for (int k = 1; k < dim; k++) {
       R fk = row_friction(cfric + 3 * c, k);
       R u = (jar[adr + k] + alpha * jv[adr + k]) * fk, w = jv[adr + k] * fk;
@@ -354,6 +393,7 @@ DEVN void ls_eval(Eng<R> e, int nefc, int ncon, int first_contact_row, R alpha, 
     R T = r_sqrt(TT);
     if (N >= mu * T || (T <= 0 && N >= 0)) {
     } else if (mu * N + T <= 0 || (T <= 0 && N < 0)) {
+      B2S_LOOP
       for (int k = 0; k < dim; k++) {
         R xk = jar[adr + k] + alpha * jv[adr + k], vk = jv[adr + k], Dk = eD[adr + k];
         g += Dk * xk * vk; h += Dk * vk * vk;
@@ -379,6 +419,7 @@ template <typename R> DEVN int solve(Eng<R> e, int nefc, int ncon, int& warn) {
   R* qacc = e.p(L.qacc); R* qcon = e.p(L.qcon);
   const R* qs = e.p(L.qsmooth); const R* qas = e.p(L.qaccs);
   if (nefc == 0) {
+    B2S_LOOP
     for (int i = lane; i < nv; i += 32) { qacc[i] = qas[i]; qcon[i] = 0; }
     __syncwarp();
     return 0;
@@ -391,9 +432,11 @@ template <typename R> DEVN int solve(Eng<R> e, int nefc, int ncon, int& warn) {
   R* act = e.p(L.scratch); R* Hcb = e.p(L.scratch) + m.maxefc;
   R scale = R(1) / (m.meaninertia * R(nv > 1 ? nv : 1));
   int first_contact_row = nefc;
+  B2S_LOOP
   for (int c = 0; c < ncon; c++) { int a = cint[5 * c + 3]; if (a >= 0) { first_contact_row = a; break; } }
   // does any constraint couple two different moving trees?  (then the Hessian is not block diagonal)
   bool cross_tree = false;
+  B2S_LOOP
   for (int c = 0; c < ncon; c++) {
     if (cint[5 * c + 3] < 0) continue;
     int t1 = m.body_treeid[m.geom_bodyid[cint[5 * c]]], t2 = m.body_treeid[m.geom_bodyid[cint[5 * c + 1]]];
@@ -402,10 +445,13 @@ template <typename R> DEVN int solve(Eng<R> e, int nefc, int ncon, int& warn) {
 
   // --- warm start: previous qacc unless the unconstrained acceleration is cheaper
   R cost_ws = 0, cost_sm = 0;
+  B2S_LOOP
   for (int pass = 0; pass < 2; pass++) {
     const R* q = pass == 0 ? e.p(L.qacc_ws) : qas;
+    B2S_LOOP
     for (int r = lane; r < nefc; r += 32) {
       R s = -aref[r];
+      B2S_LOOP
       for (int k = 0; k < nv; k++) s += J[r * nv + k] * q[k];
       jar[r] = s;
     }
@@ -413,8 +459,10 @@ template <typename R> DEVN int solve(Eng<R> e, int nefc, int ncon, int& warn) {
     R cc = constraint_update(e, nefc, ncon, false);
     if (pass == 0) {
       R gs = 0;
+      B2S_LOOP
       for (int i = lane; i < nv; i += 32) {
         R s = 0;
+        B2S_LOOP
         for (int k = 0; k < nv; k++) s += M[i * nv + k] * q[k];
         gs += R(0.5) * (s - qs[i]) * (q[i] - qas[i]);
       }
@@ -423,6 +471,7 @@ template <typename R> DEVN int solve(Eng<R> e, int nefc, int ncon, int& warn) {
   }
   {
     const R* q = cost_ws < cost_sm ? e.p(L.qacc_ws) : qas;
+    B2S_LOOP
     for (int i = lane; i < nv; i += 32) qacc[i] = q[i];
   }
   __syncwarp();
@@ -430,26 +479,34 @@ template <typename R> DEVN int solve(Eng<R> e, int nefc, int ncon, int& warn) {
   int niter = 0;
   // Ma = M qacc and jar = J qacc - aref are formed once and then moved along the search direction with the step
   // (Ma += alpha Mv, jar += alpha jv), as the reference engine does
+  B2S_LOOP
   for (int i = lane; i < nv; i += 32) {
     R s = 0;
+    B2S_LOOP
     for (int k = 0; k < nv; k++) s += M[i * nv + k] * qacc[k];
     Ma[i] = s;
   }
+  B2S_LOOP
   for (int r = lane; r < nefc; r += 32) {
     R s = -aref[r];
+    B2S_LOOP
     for (int k = 0; k < nv; k++) s += J[r * nv + k] * qacc[k];
     jar[r] = s;
   }
   __syncwarp();
   bool stale = false;  // efc_force older than jar?
+  B2S_LOOP
   for (int iter = 0; iter <= m.iterations; iter++) {
     R cost = constraint_update(e, nefc, ncon, true);
     stale = false;
     R gs = 0, gn = 0;
+    B2S_LOOP
     for (int i = lane; i < nv; i += 32) gs += R(0.5) * (Ma[i] - qs[i]) * (qacc[i] - qas[i]);
     cost += warp_sum(gs);
+    B2S_LOOP
     for (int i = lane; i < nv; i += 32) {
       R s = Ma[i] - qs[i];
+      B2S_LOOP
       for (int r = 0; r < nefc; r++) s -= J[r * nv + i] * force[r];
       grad[i] = s;
       gn += s * s;
@@ -468,8 +525,10 @@ template <typename R> DEVN int solve(Eng<R> e, int nefc, int ncon, int& warn) {
     // --- Hessian H = M + J^T act J + cone blocks, exploiting row structure:
     //   friction-loss / limit rows are +-unit vectors -> diagonal terms only;
     //   a contact's rows touch only the dofs that move exactly one of its two bodies -> entries on that support only
+    B2S_LOOP
     for (int k = lane; k < nv * nv; k += 32) H[k] = M[k];
     __syncwarp();
+    B2S_LOOP
     for (int r = lane; r < first_contact_row; r += 32) {
       R d = act[r];
       if (d != 0) {
@@ -481,6 +540,7 @@ template <typename R> DEVN int solve(Eng<R> e, int nefc, int ncon, int& warn) {
     __syncwarp();
     {
       int* dofs = reinterpret_cast<int*>(Hcb + m.hc_stride * m.maxcon);
+      B2S_LOOP
       for (int c = 0; c < ncon; c++) {
         int adr = cint[5 * c + 3];
         if (adr < 0) continue;
@@ -488,14 +548,17 @@ template <typename R> DEVN int solve(Eng<R> e, int nefc, int ncon, int& warn) {
         const R* h = Hcb + m.hc_stride * c;
         bool cone = h[0] >= 0;
         bool any = cone;
+        B2S_LOOP
         for (int k = 0; k < dim && !any; k++) any = act[adr + k] != 0;
         if (!any) continue;
         unsigned long long mask = m.body_dofmask[m.geom_bodyid[cint[5 * c]]] ^ m.body_dofmask[m.geom_bodyid[cint[5 * c + 1]]];
         int ns = __popcll(mask);
+        B2S_LOOP
         for (int i = lane; i < nv; i += 32)
           if ((mask >> i) & 1ull) dofs[__popcll(mask & ((1ull << i) - 1ull))] = i;
         __syncwarp();
         int ne = ns * (ns + 1) / 2;
+        B2S_LOOP
         for (int w = lane; w < ne; w += 32) {
           int ia = (int)((r_sqrt(R(8 * w + 1)) - R(1)) * R(0.5));
           while ((ia + 1) * (ia + 2) / 2 <= w) ia++;
@@ -504,12 +567,15 @@ template <typename R> DEVN int solve(Eng<R> e, int nefc, int ncon, int& warn) {
           int a = dofs[ia], b = dofs[ib];
           R sacc = 0;
           if (cone) {
+            B2S_LOOP
             for (int x = 0; x < dim; x++) {
               R t = 0;
+              B2S_LOOP
               for (int y = 0; y < dim; y++) t += h[x * dim + y] * J[(adr + y) * nv + b];
               sacc += J[(adr + x) * nv + a] * t;
             }
           } else {
+            B2S_LOOP
             for (int k = 0; k < dim; k++) sacc += act[adr + k] * J[(adr + k) * nv + a] * J[(adr + k) * nv + b];
           }
           H[a * nv + b] += sacc;
@@ -518,21 +584,26 @@ template <typename R> DEVN int solve(Eng<R> e, int nefc, int ncon, int& warn) {
         __syncwarp();
       }
     }
+    B2S_LOOP
     for (int i = lane; i < nv; i += 32) search[i] = -grad[i];
     __syncwarp();
     if (e.spd_solve(H, nv, (const R*)nullptr, R(0), search, H, !cross_tree)) { warn |= 16; break; }
     // --- exact line search
     R q1 = 0, q2 = 0;
+    B2S_LOOP
     for (int i = lane; i < nv; i += 32) {
       R s = 0;
+      B2S_LOOP
       for (int k = 0; k < nv; k++) s += M[i * nv + k] * search[k];
       Mv[i] = s;
       q1 += search[i] * (Ma[i] - qs[i]);
       q2 += search[i] * s;
     }
     R quad1 = warp_sum(q1), quad2 = warp_sum(q2);
+    B2S_LOOP
     for (int r = lane; r < nefc; r += 32) {
       R s = 0;
+      B2S_LOOP
       for (int k = 0; k < nv; k++) s += J[r * nv + k] * search[k];
       jv[r] = s;
     }
@@ -545,6 +616,7 @@ template <typename R> DEVN int solve(Eng<R> e, int nefc, int ncon, int& warn) {
     bool last = R(0.5) * scale * (-d1) < m.tolerance || R(0.5) * (-d1) < noise;
     R gtol = (sizeof(R) == 4 ? R(1e-3) : R(1e-12)) * r_abs(d1);
     alpha = -d1 / d2;
+    B2S_LOOP
     for (int ls = 0; ls < (sizeof(R) == 4 ? 20 : 100); ls++) {
       ls_eval(e, nefc, ncon, first_contact_row, alpha, quad1, quad2, d1, d2);
       if (r_abs(d1) <= gtol) break;
@@ -555,7 +627,9 @@ template <typename R> DEVN int solve(Eng<R> e, int nefc, int ncon, int& warn) {
       if (hi >= 0 && hi - lo < (sizeof(R) == 4 ? R(1e-7) : R(1e-15)) * r_max(R(1), hi)) break;
       alpha = next;
     }
+    B2S_LOOP
     for (int i = lane; i < nv; i += 32) { qacc[i] += alpha * search[i]; Ma[i] += alpha * Mv[i]; }
+    B2S_LOOP
     for (int r = lane; r < nefc; r += 32) jar[r] += alpha * jv[r];
     stale = true;
     __syncwarp();
@@ -563,8 +637,10 @@ template <typename R> DEVN int solve(Eng<R> e, int nefc, int ncon, int& warn) {
   }
   // --- final forces at the solution
   if (stale) constraint_update(e, nefc, ncon, false);
+  B2S_LOOP
   for (int i = lane; i < nv; i += 32) {
     R s = 0;
+    B2S_LOOP
     for (int r = 0; r < nefc; r++) s += J[r * nv + i] * force[r];
     qcon[i] = s;
   }

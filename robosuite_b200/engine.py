@@ -61,6 +61,7 @@ def lib():
         L.b2s_task_config.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.b2s_task_config2.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.b2s_task_objects.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.b2s_timeline.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.b2s_task_table.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.b2s_set_export.argtypes = [C.c_void_p, C.c_int]
         L.b2s_set_profile.argtypes = [C.c_void_p, C.c_int]
@@ -217,6 +218,13 @@ class BatchedSim:
     def set_mode(self, mode):
         """0 = fused single kernel, 1 = pipelined phase kernels (identical results)"""
         self._check(self._L.b2s_set_mode(self._h, int(mode)))
+
+    def timeline(self, enable=-1):
+        """(mean_us[8], count[8]) of the last timed call; enable=1/0 switches event-timed eager launches on/off"""
+        m = (C.c_double * 8)()
+        n = (C.c_int * 8)()
+        self._check(self._L.b2s_timeline(self._h, int(enable), m, n))
+        return list(m), list(n)
 
     def set_profile(self, flag):
         self._check(self._L.b2s_set_profile(self._h, int(bool(flag))))
