@@ -80,6 +80,7 @@ void o_make_constraint(const OModel* m, OData* d) {
     o_jac(m, d, jp2, jr2, con->pos, b2);
     int dim = con->dim;
     int type = dim == 1 ? O_CNSTR_CONTACT_FRICTIONLESS : O_CNSTR_CONTACT_ELLIPTIC;
+    if (d->nefc + dim > O_MAXEFC) { d->warn_flags |= 8; break; } /* a contact enters with all of its rows or not at all */
     for (int k = 0; k < dim; k++) {
       int r = add_row(d, nv, type, c, k == 0 ? con->dist : 0.0, 0, 0);
       if (r < 0) break;

@@ -281,6 +281,32 @@ class BatchedMujocoEnv:
         self.cur_time = 0.0
         return self._get_observations()
 
+    def reset_to(self, qpos, qvel=None):
+        """Put every environment into the given state and do what reset() does afterwards (forward, controllers rebuilt,
+        observation cache emptied and force-updated): `set_state` + the tail of environments/base.py:277-347.
+        qpos: [nq] or [N, nq]"""
+        import torch
+
+        q = torch.as_tensor(np.asarray(qpos), dtype=self.dtype, device=self.device)
+        self.sim.qpos[:] = q if q.ndim == 2 else q.unsqueeze(0).expand(self.num_envs, -1)
+        if qvel is None:
+            self.sim.qvel[:] = 0
+        else:
+            v = torch.as_tensor(np.asarray(qvel), dtype=self.dtype, device=self.device)
+            self.sim.qvel[:] = v if v.ndim == 2 else v.unsqueeze(0).expand(self.num_envs, -1)
+        self.sim.qacc[:] = 0
+        self.sim.qacc_warmstart[:] = 0
+        self.sim.ctrl[:] = 0
+        self.sim.time[:] = 0
+        self.timestep[:] = 0
+        self.done[:] = False
+        self.sim.obs_fresh[:] = 1
+        self._max_steps_since_reset = 0
+        self.sim.forward()
+        self.sim.ctrl_reset(None)
+        self.cur_time = 0.0
+        return self._get_observations()
+
     def step(self, action):
         """One control step = n_substeps x {step1, controller, step2} in one kernel launch (base.py:467-521)."""
         import torch
