@@ -416,13 +416,13 @@ template <typename R> DEVN void write_obs(const Eng<R> e, int env, bool only_fre
   int fresh = s.obs_fresh[env];
   if (only_fresh && !fresh) return;
   R val[4];  // obs_dim <= 128: all values are formed before any is written (lagged entries read the previous sample)
-#pragma unroll
-  for (int it = 0; it < 4; it++) {
+#pragma unroll 1
+  for (int it = 0; it < 4; it++) {  // rolled: table_value is large and runs once per control step
     int k = e.lane + 32 * it;
     val[it] = k < cc.obs_dim ? table_value(e, cc.obs_op[k], cc.obs_a[k], cc.obs_b[k], out, fresh) : R(0);
   }
   __syncwarp();
-#pragma unroll
+#pragma unroll 1
   for (int it = 0; it < 4; it++) {
     int k = e.lane + 32 * it;
     if (k < cc.obs_dim) out[k] = val[it];

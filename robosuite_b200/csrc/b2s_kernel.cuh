@@ -155,8 +155,10 @@ __global__ void __launch_bounds__(512, 1) step_kernel(int phases, int nsub, cons
       TICK(7)
     }
     if (live && (phases & PH_OBS) && c_cc.obs_dim > 0) {
-      if (sub == 0) write_obs(e, env, (phases & PH_NOINTEGRATE) != 0);
-      if (sub == nsub - 1) write_task(e, env, ncon);
+      // The reference's observables sample on the LAST substep of a control step: reset()'s forced update already
+      // advances their period timer by one model timestep (utils/observables.py:214-259, environments/base.py:418-427),
+      // so the period closes after substep 24 and the next update - substep 25 - takes the sample.
+      if (sub == nsub - 1) { write_obs(e, env, (phases & PH_NOINTEGRATE) != 0); write_task(e, env, ncon); }
     }
     __syncwarp();
   }

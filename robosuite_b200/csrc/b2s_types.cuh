@@ -23,7 +23,7 @@ enum {
   PH_POLICY = 32,    // first substep of a control step: consume `action` (set_goal)
   PH_PROFILE = 128,  // accumulate per-phase clock() cycles per environment into `prof`
   PH_WORKLIST = 256, // pipeline mode: collision narrow phase runs as global work-list kernels
-  PH_OBS = 64        // write the observation row (after substep 0) and the task outputs (after the last substep)
+  PH_OBS = 64        // write the observation row and the task outputs (after the last substep)
 };
 
 template <typename R>

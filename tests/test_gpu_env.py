@@ -68,11 +68,9 @@ def test_env_api_and_obs_parity():
         flat = env.flat_obs().cpu().numpy().astype(np.float64)
         for e in range(n):
             o = oracles[e]
-            # first substep, then sample (observables.py:230-240), then the remaining 24
-            o.step1(); o.ctrl_run(act[e]); o.step2()
+            # observables sample on the last substep of the control step (poses of its step1, qpos/qvel after its step2)
+            o.env_step(act[e], 25)
             exp = _expected_obs(model, o, env)
-            for _ in range(24):
-                o.step1(); o.ctrl_run(None); o.step2()
             err = np.abs(flat[e] - exp)
             err[28:35] /= max(1.0, np.abs(exp[28:35]).max())  # joint_acc: relative
             assert err.max() < 5e-4, (t, e, err.argmax(), err.max())
@@ -220,10 +218,8 @@ def test_other_task_envs_obs_and_reward(task, obs_dim):
         flat = env.flat_obs().cpu().numpy().astype(np.float64)
         for e in range(n):
             o = oracles[e]
-            o.step1(); o.ctrl_run(act[e]); o.step2()
+            o.env_step(act[e], 25)
             exp = _object_obs(env, o, caches[e], task)
-            for _ in range(24):
-                o.step1(); o.ctrl_run(None); o.step2()
             err = np.abs(flat[e, 50:] - exp)
             # (PickPlace: mesh objects settling on the bin floor amplify fp32 rounding in their orientation)
             assert err.max() < (3e-3 if task == "PickPlace" else 1e-3), (task, t, e, int(err.argmax()), float(err.max()))
