@@ -697,7 +697,8 @@ template <typename R> static int launch_pipeline_t(b2s_sim* s, DState<R>& st, in
     CUDA_TRY(cudaEventCreateWithFlags(&s->out_event, cudaEventDisableTiming));
     CUDA_TRY(cudaStreamCreateWithFlags(&s->pstream, cudaStreamNonBlocking));
   }
-  int launches_per_call = G * nsub * ((phases & PH_CTRL) ? 6 : 5);
+  // kernels per group-substep: phase 0, analytic + convex narrow phase, then the merged tail (or phases 2, [3], 4)
+  int launches_per_call = G * nsub * (3 + (s->merge_tail ? 1 : ((phases & PH_CTRL) ? 3 : 2)));
   if (!s->use_graph) {
     rc = enqueue_pipeline<R>(s, st, phases, nsub, action, s->stream);
     s->launches += launches_per_call;

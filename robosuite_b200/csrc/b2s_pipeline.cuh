@@ -231,7 +231,14 @@ __global__ void __launch_bounds__(512, 1) phase_kernel(int phases, int sub, int 
   R* smem = reinterpret_cast<R*>(smem_raw);
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   int env = blockIdx.x * wpb + warp;
-  if (env >= g.nenv) return;
+#ifndef B2S_TAIL_BARRIERS
+#define B2S_TAIL_BARRIERS 0  // block barriers between the sub-phases of the merged tail kernel (instruction-cache locality)
+#endif
+#define TAIL_BAR(level) if (PH == 5 && B2S_TAIL_BARRIERS >= level) __syncthreads();
+  if (env >= g.nenv) {  // warps past the end of the group still take part in the block barriers
+    TAIL_BAR(1) TAIL_BAR(2) TAIL_BAR(3) TAIL_BAR(4)
+    return;
+  }
   env += g.env0;
   __shared__ unsigned long long mbar[16];  // one transaction barrier per warp (TMA loads of its workspace regions)
   if (lane == 0) mbar_init(&mbar[warp]);
@@ -289,6 +296,7 @@ __global__ void __launch_bounds__(512, 1) phase_kernel(int phases, int sub, int 
     if (lane == 0) { hdr[0] = ncon; hdr[1] = nefc; hdr[2] = warn; }
     __syncwarp();
   }
+  TAIL_BAR(1)
   if (PH == 3 || (PH == 5 && (phases & PH_CTRL))) {
     CtrlState<R> cs;
     ctrl_load(e, cs, env);
@@ -297,11 +305,14 @@ __global__ void __launch_bounds__(512, 1) phase_kernel(int phases, int sub, int 
     if (sub == 0) ctrl_store(e, cs, env);
     __syncwarp();
   }
+  TAIL_BAR(2)
   if (PH == 4 || PH == 5) {
     R time = s.time[env];
     e.actuation((R*)nullptr);
     if (e.acceleration()) warn |= 1;
+    TAIL_BAR(3)
     solve(e, nefc, ncon, warn);
+    TAIL_BAR(4)
     if (!(phases & PH_NOINTEGRATE)) {
       if (e.euler(&time)) warn |= 2;
     }
