@@ -86,43 +86,52 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
-def cpu_oracle_rate(n_env, n_steps, threads):
-    """env-steps/s of the oracle port (fp64 C, oracle/) of the same path on `threads` host threads; each thread owns
-    independent environments (the reference runs one env per process: SURVEY.md section 2.1)."""
-    import numpy as np
+class CpuArm:
+    """The oracle port (fp64 C, oracle/) of the same path on `threads` host threads; each thread owns independent
+    environments (the reference runs one env per process: SURVEY.md section 2.1).  Same measurement protocol as the GPU
+    arm: `preroll` untimed control steps of random actions first (steady-state contact load), then timed chunks."""
 
-    from oracle.pyoracle import CtrlCfg, Oracle
-    from robosuite_b200 import controller_config as cc
-    from robosuite_b200.mjcf.compiler import load_model, pack_model
-    from tests.util import lift_states
+    def __init__(self, n_env, threads, preroll):
+        import numpy as np
 
-    model = load_model(os.path.join(ROOT, "robosuite_b200", "assets", "models", "Lift_Panda.npz"))
-    blob = pack_model(model)
-    q, _ = lift_states(model, n_env, seed=0)
-    rng = np.random.default_rng(0)
-    actions = rng.uniform(-1, 1, size=(n_steps, n_env, 7))
-    sims = []
-    for e in range(n_env):
-        o = Oracle(blob)
-        o.ctrl_setup(cc.resolve(model, cc.default_composite_config(), CtrlCfg))
-        o.qpos[:] = q[e]
-        o.forward()
-        o.ctrl_reset()
-        sims.append(o)
+        from oracle.pyoracle import CtrlCfg, Oracle
+        from robosuite_b200 import controller_config as cc
+        from robosuite_b200.mjcf.compiler import load_model, pack_model
+        from tests.util import lift_states
 
-    def work(tid):
-        for e in range(tid, n_env, threads):
-            for t in range(n_steps):
-                sims[e].env_step(actions[t, e], N_SUBSTEPS)
+        model = load_model(os.path.join(ROOT, "robosuite_b200", "assets", "models", "Lift_Panda.npz"))
+        blob = pack_model(model)
+        q, _ = lift_states(model, n_env, seed=0)
+        self.n_env, self.threads = n_env, threads
+        self.rng = np.random.default_rng(0)
+        self.sims = []
+        for e in range(n_env):
+            o = Oracle(blob)
+            o.ctrl_setup(cc.resolve(model, cc.default_composite_config(), CtrlCfg))
+            o.qpos[:] = q[e]
+            o.forward()
+            o.ctrl_reset()
+            self.sims.append(o)
+        self.preroll_s = self.run(preroll)[1] if preroll > 0 else 0.0
 
-    t0 = time.perf_counter()
-    ths = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
-    for t in ths:
-        t.start()
-    for t in ths:
-        t.join()
-    dt = time.perf_counter() - t0
-    return n_env * n_steps / dt, dt
+    def run(self, n_steps):
+        """n_steps more control steps on every environment -> (env-steps/s, seconds)"""
+        actions = self.rng.uniform(-1, 1, size=(n_steps, self.n_env, 7))
+        sims, n_env, threads = self.sims, self.n_env, self.threads
+
+        def work(tid):
+            for e in range(tid, n_env, threads):
+                for t in range(n_steps):
+                    sims[e].env_step(actions[t, e], N_SUBSTEPS)
+
+        t0 = time.perf_counter()
+        ths = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        dt = time.perf_counter() - t0
+        return n_env * n_steps / dt, dt
 
 
 def run_reference(args):
@@ -131,16 +140,18 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     n_env = max(cores, 8)
-    per_step = 16  # control steps per env per bench "step" (bounded sample of the workload)
+    per_step = 8  # control steps per env per bench "step" (bounded sample of the workload)
+    arm = CpuArm(n_env, cores, args.preroll)  # same protocol as the GPU arm: untimed pre-roll into the steady-state regime
     rates = []
     for i in range(args.warmup + args.steps):
-        r, dt = cpu_oracle_rate(n_env, per_step, cores)
+        r, dt = arm.run(per_step)
         if i >= args.warmup:
             rates.append((r, dt))
     total_steps = sum(n_env * per_step for _ in rates)
     total_t = sum(dt for _, dt in rates)
     value = total_steps / total_t
-    sample = f"{n_env} Lift envs x {per_step} control steps per bench step, {cores} threads, oracle port (fp64 C) incl. OSC controller"
+    sample = (f"{n_env} Lift envs x {per_step} control steps per bench step after {args.preroll} untimed pre-roll steps "
+              f"({arm.preroll_s:.1f}s), {cores} threads, oracle port (fp64 C) incl. OSC controller")
     out = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_t / max(len(rates), 1),
@@ -293,10 +304,12 @@ def run_gpu(args):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        n_env, n_steps = max(cores, 8) * 2, 150
-        r, dtc = cpu_oracle_rate(n_env, n_steps, cores)
+        n_env, n_steps = max(cores, 8) * 2, 50
+        arm = CpuArm(n_env, cores, args.preroll)
+        r, dtc = arm.run(n_steps)
         cpu = {"value": r, "unit": "env-steps/s", "cores": cores, "kind": "port",
-               "sample": f"{n_env} Lift envs x {n_steps} control steps ({dtc:.1f}s), oracle port (fp64 C) incl. OSC, {cores} threads"}
+               "sample": f"{n_env} Lift envs x {n_steps} control steps ({dtc:.1f}s) after {args.preroll} untimed pre-roll steps "
+                         f"({arm.preroll_s:.1f}s), oracle port (fp64 C) incl. OSC, {cores} threads"}
     out = {
         "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
