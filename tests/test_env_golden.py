@@ -22,13 +22,13 @@ def _golden():
 
 
 def _model(task, G):
-    m = load(task + "_Panda")
+    m = load(task + "_Panda" if "_" not in task else task)
     m.body_pos[:] = G[task + "/body_pos"]   # the reference writes sampled placements into the model (Door, visual objects)
     m.body_quat[:] = G[task + "/body_quat"]
     return m
 
 
-@pytest.mark.parametrize("task", TASKS)
+@pytest.mark.parametrize("task", TASKS + ["Lift_Sawyer", "Stack_Sawyer"])
 def test_oracle_env_step_matches_reference_stack(task):
     """150 substeps of {step1, reference controllers, step2} vs the oracle's C controller + loop: <= 1e-6 on qpos
     (the residual is the reference's float32 round trip in transform_utils.quat2mat)"""
@@ -40,7 +40,9 @@ def test_oracle_env_step_matches_reference_stack(task):
     G = _golden()
     m = _model(task, G)
     o = Oracle(pack_model(m))
-    o.ctrl_setup(cc.resolve(m, cc.default_composite_config(), OCfg))
+    sawyer = task.endswith("Sawyer")
+    cfg = cc.load_composite_controller_config(None, "Sawyer") if sawyer else cc.default_composite_config()
+    o.ctrl_setup(cc.resolve(m, cfg, OCfg, gripper="rethink" if sawyer else "panda"))
     o.qpos[:] = G[task + "/qpos0"]
     o.forward()
     o.ctrl_reset()
@@ -88,3 +90,30 @@ def test_env_api_matches_reference_stack(task):
     assert worst_q < (2e-3 if task == "PickPlace" else 1e-4)
     assert int(env.sim.warn.abs().max()) == 0
     env.close()
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/robosuite"), reason="needs the reference checkout (build container only)")
+def test_reference_stack_runs_on_the_shim_and_reproduces_the_golden_file():
+    """regenerate the first two Lift steps with the unmodified reference stack on oracle/mujoco_shim (subprocess: the shim
+    shadows the `mujoco` module name) and compare with the committed vectors"""
+    import subprocess
+    import sys
+
+    code = (
+        "import sys, numpy as np\n"
+        f"sys.path.insert(0, {os.path.join(ROOT, 'tools')!r})\n"
+        "import gen_env_golden as g\n"
+        "g.install()\n"
+        "rec = g.run('Lift', 'Panda', steps=2)\n"
+        "np.save(sys.argv[1], np.concatenate([rec['qpos'].ravel(), rec['obs_object'].ravel(), rec['reward'].ravel()]))\n")
+    out = os.path.join(ROOT, "tests", "golden", "_regen_check.npy")
+    try:
+        r = subprocess.run([sys.executable, "-c", code, out], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        got = np.load(out)
+    finally:
+        if os.path.exists(out):
+            os.remove(out)
+    G = _golden()
+    ref = np.concatenate([G["Lift/qpos"][:2].ravel(), G["Lift/obs_object"][:2].ravel(), G["Lift/reward"][:2].ravel()])
+    assert np.abs(got - ref).max() < 1e-12

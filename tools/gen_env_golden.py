@@ -54,9 +54,10 @@ def run(task, robot, steps=6, seed=0, **kw):
 if __name__ == "__main__":
     install()
     out = {}
-    for task, robot in [("Lift", "Panda"), ("Door", "Panda"), ("NutAssemblyRound", "Panda"), ("PickPlace", "Panda"), ("Stack", "Panda")]:
+    for task, robot in [("Lift", "Panda"), ("Door", "Panda"), ("NutAssemblyRound", "Panda"), ("PickPlace", "Panda"), ("Stack", "Panda"),
+                        ("Lift", "Sawyer"), ("Stack", "Sawyer")]:
         rec = run(task, robot)
         for k, v in rec.items():
-            out[f"{task}/{k}"] = np.array(v)
+            out[f"{task}/{k}" if robot == "Panda" else f"{task}_{robot}/{k}"] = np.array(v)
         print(task, "object-state", rec["obs_object"].shape, "proprio", rec["obs_proprio"].shape, "reward", np.round(rec["reward"], 4))
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "env_golden.npz"), **out)
