@@ -139,6 +139,8 @@ void o_ctrl_reset(const OModel* m, const OData* d, const OCtrlCfg* c, OCtrlState
   memset(s->jv_goal, 0, sizeof s->jv_goal); memset(s->jv_last_err, 0, sizeof s->jv_last_err);
   memset(s->jv_summed, 0, sizeof s->jv_summed); memset(s->jv_derr, 0, sizeof s->jv_derr);
   s->jv_ptr = 4; s->jv_size = 0; s->jv_saturated = 0;
+  if (c->kind == 3) /* JointPositionController.reset_goal: goal <- current joint positions */
+    for (int i = 0; i < c->n_arm; i++) s->jv_goal[i] = d->qpos[c->arm_qpos[i]];
 }
 
 static void grip_run(const OModel* m, OData* d, const OCtrlCfg* c, OCtrlState* s, const double* action, int grip_index) {
@@ -192,9 +194,59 @@ static void jv_run(const OModel* m, OData* d, const OCtrlCfg* c, OCtrlState* s, 
   grip_run(m, d, c, s, action, na);
 }
 
+/* scale_action of the joint-space controllers (controller.py:149-168) with the per-joint limits kept in the jv_* fields */
+static double joint_scale(const OCtrlCfg* c, int k, double a) {
+  a = fmin(fmax(a, c->jv_in_min[k]), c->jv_in_max[k]);
+  double scale = fabs(c->jv_out_max[k] - c->jv_out_min[k]) / fabs(c->jv_in_max[k] - c->jv_in_min[k]);
+  return (a - 0.5 * (c->jv_in_max[k] + c->jv_in_min[k])) * scale + 0.5 * (c->jv_out_max[k] + c->jv_out_min[k]);
+}
+
+/* JointPositionController (joint_pos.py:160-262), input_type "delta", impedance_mode "fixed", no interpolator:
+ * goal_qpos = joint_pos + scaled delta at policy steps; torque = M_arm (kp e - kd qvel) + qfrc_bias, clipped.
+ * kp / kd live in jv_kp / jv_kd, the goal in jv_goal. */
+static void jp_run(const OModel* m, OData* d, const OCtrlCfg* c, OCtrlState* s, const double* action) {
+  int na = c->n_arm, nv = m->nv;
+  if (action)
+    for (int k = 0; k < na; k++) s->jv_goal[k] = d->qpos[c->arm_qpos[k]] + joint_scale(c, k, action[k]);
+  double des[8];
+  for (int k = 0; k < na; k++)
+    des[k] = (s->jv_goal[k] - d->qpos[c->arm_qpos[k]]) * c->jv_kp[k] - d->qvel[c->arm_dof[k]] * c->jv_kd[k];
+  for (int a = 0; a < na; a++) {
+    double tau = 0;
+    if (c->jv_torque_comp) {
+      for (int b = 0; b < na; b++) tau += d->M[c->arm_dof[a] * nv + c->arm_dof[b]] * des[b];
+      tau += d->qfrc_bias[c->arm_dof[a]];
+    } else tau = des[a];
+    int u = c->arm_act[a];
+    s->torques[a] = tau;
+    d->ctrl[u] = fmin(fmax(tau, m->actuator_ctrlrange[2 * u]), m->actuator_ctrlrange[2 * u + 1]);
+  }
+  grip_run(m, d, c, s, action, na);
+}
+
+/* JointTorqueController (joint_tor.py:112-160): goal_torque = clip(scaled action, actuator limits) at policy steps;
+ * torque = goal_torque + qfrc_bias, clipped.  The goal lives in jv_goal. */
+static void jt_run(const OModel* m, OData* d, const OCtrlCfg* c, OCtrlState* s, const double* action) {
+  int na = c->n_arm;
+  if (action)
+    for (int k = 0; k < na; k++) {
+      int u = c->arm_act[k];
+      s->jv_goal[k] = fmin(fmax(joint_scale(c, k, action[k]), m->actuator_ctrlrange[2 * u]), m->actuator_ctrlrange[2 * u + 1]);
+    }
+  for (int k = 0; k < na; k++) {
+    int u = c->arm_act[k];
+    double tau = s->jv_goal[k] + (c->jv_torque_comp ? d->qfrc_bias[c->arm_dof[k]] : 0.0);
+    s->torques[k] = tau;
+    d->ctrl[u] = fmin(fmax(tau, m->actuator_ctrlrange[2 * u]), m->actuator_ctrlrange[2 * u + 1]);
+  }
+  grip_run(m, d, c, s, action, na);
+}
+
 /* one controller evaluation between step1 and step2; action != NULL on policy steps */
 void o_ctrl_run(const OModel* m, OData* d, const OCtrlCfg* c, OCtrlState* s, const double* action) {
   if (c->kind == 2) { jv_run(m, d, c, s, action); return; }
+  if (c->kind == 3) { jp_run(m, d, c, s, action); return; }
+  if (c->kind == 4) { jt_run(m, d, c, s, action); return; }
   int nv = m->nv, na = c->n_arm;
   const double* ref_pos = d->site_xpos + 3 * c->eef_site;
   const double* ref_ori = d->site_xmat + 9 * c->eef_site;

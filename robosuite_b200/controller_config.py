@@ -52,9 +52,18 @@ _DEFAULT_JOINT_VELOCITY = {"type": "JOINT_VELOCITY", "input_max": 1, "input_min"
                            "kp": 3.0, "velocity_limits": [-1, 1], "interpolation": None, "ramp_ratio": 0.2}
 
 
+# controllers/config/default/parts/joint_position.json, joint_torque.json
+_DEFAULT_JOINT_POSITION = {"type": "JOINT_POSITION", "input_max": 1, "input_min": -1, "output_max": 0.05, "output_min": -0.05,
+                           "kp": 50, "damping_ratio": 1, "impedance_mode": "fixed", "kp_limits": [0, 300],
+                           "damping_ratio_limits": [0, 10], "qpos_limits": None, "interpolation": None, "ramp_ratio": 0.2}
+_DEFAULT_JOINT_TORQUE = {"type": "JOINT_TORQUE", "input_max": 1, "input_min": -1, "output_max": 0.1, "output_min": -0.1,
+                         "torque_limits": None, "interpolation": None, "ramp_ratio": 0.2}
+
+
 def load_part_controller_config(default_controller="OSC_POSE"):
     """suite.load_part_controller_config(default_controller=...) (controllers/parts/controller_factory.py:16-70)"""
-    table = {"OSC_POSE": _DEFAULT_OSC_POSE, "JOINT_VELOCITY": _DEFAULT_JOINT_VELOCITY}
+    table = {"OSC_POSE": _DEFAULT_OSC_POSE, "JOINT_VELOCITY": _DEFAULT_JOINT_VELOCITY,
+             "JOINT_POSITION": _DEFAULT_JOINT_POSITION, "JOINT_TORQUE": _DEFAULT_JOINT_TORQUE}
     if default_controller not in table:
         raise NotImplementedError(f"part controller {default_controller} is not implemented")
     return dict(table[default_controller])
@@ -77,8 +86,16 @@ def resolve(model, composite_cfg, cfg_struct_cls, robot_prefix="robot0_", grippe
     if composite_cfg.get("type", "BASIC") != "BASIC":
         raise NotImplementedError("only the BASIC composite controller is implemented")
     arm = composite_cfg["body_parts"]["arms"]["right"]
-    if arm["type"] not in ("OSC_POSE", "JOINT_VELOCITY"):
+    if arm["type"] not in ("OSC_POSE", "JOINT_VELOCITY", "JOINT_POSITION", "JOINT_TORQUE"):
         raise NotImplementedError(f"arm controller type {arm['type']} not implemented in the fused path")
+    if arm["type"] in ("JOINT_POSITION", "JOINT_TORQUE") and cfg_struct_cls.__module__.startswith("robosuite_b200"):
+        # the CPU oracle has these two (pinned against the reference stack); the device kernels do not yet
+        raise NotImplementedError(f"arm controller type {arm['type']} is not implemented on the device yet")
+    if arm["type"] == "JOINT_POSITION" and (arm.get("impedance_mode", "fixed") != "fixed" or arm.get("input_type", "delta") != "delta"
+                                            or arm.get("qpos_limits") is not None):
+        raise NotImplementedError("JOINT_POSITION: fixed impedance, delta inputs, no qpos_limits")
+    if arm["type"] == "JOINT_TORQUE" and arm.get("torque_limits") is not None:
+        raise NotImplementedError("JOINT_TORQUE: torque_limits other than the actuator limits are not implemented")
     if arm["type"] == "OSC_POSE" and (arm.get("impedance_mode", "fixed") != "fixed" or arm.get("input_type", "delta") != "delta"
                                       or arm.get("input_ref_frame", "base") != "base" or arm.get("interpolation") is not None):
         raise NotImplementedError("fused OSC path implements fixed impedance, delta inputs in the base frame")
@@ -88,7 +105,7 @@ def resolve(model, composite_cfg, cfg_struct_cls, robot_prefix="robot0_", grippe
     # arm joints: the robot's own hinge joints (robots/robot.py:302-332 collects them through the robot model)
     arm_j = [i for i, n in enumerate(jn) if n and n.startswith(robot_prefix) and int(model.jnt_type[i]) == 3]
     c = cfg_struct_cls()
-    c.kind = 1 if arm["type"] == "OSC_POSE" else 2
+    c.kind = {"OSC_POSE": 1, "JOINT_VELOCITY": 2, "JOINT_POSITION": 3, "JOINT_TORQUE": 4}[arm["type"]]
     c.n_arm = len(arm_j)
     for k, j in enumerate(arm_j):
         c.arm_dof[k] = int(model.jnt_dofadr[j])
@@ -104,6 +121,22 @@ def resolve(model, composite_cfg, cfg_struct_cls, robot_prefix="robot0_", grippe
         c.grip_act[k] = a
         c.grip_sign[k] = GRIPPER_SIGNS[gripper][k]
     c.grip_speed = GRIPPER_SPEED[gripper]
+    if arm["type"] in ("JOINT_POSITION", "JOINT_TORQUE"):
+        # per-joint scaling in the jv_in/out fields, gains in jv_kp / jv_kd (joint_pos.py:124-137: kd = 2 sqrt(kp) damping_ratio)
+        n = c.n_arm
+        c.action_dim = n + 1
+        imax, imin = _arr(arm.get("input_max", 1), n), _arr(arm.get("input_min", -1), n)
+        omax, omin = _arr(arm.get("output_max", 0.05), n), _arr(arm.get("output_min", -0.05), n)
+        kp = _arr(arm.get("kp", 50), n)
+        kd = _arr(arm["kd"], n) if arm.get("kd") is not None else 2 * np.sqrt(kp) * _arr(arm.get("damping_ratio", 1), n)
+        for k in range(n):
+            c.jv_kp[k], c.jv_ki[k], c.jv_kd[k] = kp[k], 0.0, kd[k]
+            c.jv_in_max[k], c.jv_in_min[k], c.jv_out_max[k], c.jv_out_min[k] = imax[k], imin[k], omax[k], omin[k]
+        c.jv_torque_comp = int(bool(arm.get("use_torque_compensation", True)))
+        c.null_kp = 10.0
+        c.uncouple_pos_ori = 1
+        c.n_obs_site = 0
+        return c
     if arm["type"] == "JOINT_VELOCITY":
         n = c.n_arm
         c.action_dim = n + 1

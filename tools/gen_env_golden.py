@@ -30,8 +30,14 @@ def install():
     sys.path.insert(0, REF)
 
 
-def run(task, robot, steps=6, seed=0, **kw):
+def run(task, robot, steps=6, seed=0, controller=None, **kw):
     import robosuite as suite
+
+    if controller is not None:  # the way demos/demo_control.py:99-103 selects a part controller
+        from robosuite.controllers.composite.composite_controller_factory import refactor_composite_controller_config
+
+        part = suite.load_part_controller_config(default_controller=controller)
+        kw["controller_configs"] = refactor_composite_controller_config(part, robot, ["right", "left"])
 
     env = suite.make(task, robots=robot, has_renderer=False, has_offscreen_renderer=False, use_camera_obs=False,
                      hard_reset=False, reward_shaping=True, control_freq=20, seed=seed, **kw)
@@ -60,4 +66,9 @@ if __name__ == "__main__":
         for k, v in rec.items():
             out[f"{task}/{k}" if robot == "Panda" else f"{task}_{robot}/{k}"] = np.array(v)
         print(task, "object-state", rec["obs_object"].shape, "proprio", rec["obs_proprio"].shape, "reward", np.round(rec["reward"], 4))
+    for ctrl in ("JOINT_POSITION", "JOINT_TORQUE"):
+        rec = run("Lift", "Panda", controller=ctrl)
+        for k, v in rec.items():
+            out[f"Lift_{ctrl}/{k}"] = np.array(v)
+        print("Lift", ctrl, "reward", np.round(rec["reward"], 4))
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "env_golden.npz"), **out)
