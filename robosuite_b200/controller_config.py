@@ -88,9 +88,6 @@ def resolve(model, composite_cfg, cfg_struct_cls, robot_prefix="robot0_", grippe
     arm = composite_cfg["body_parts"]["arms"]["right"]
     if arm["type"] not in ("OSC_POSE", "JOINT_VELOCITY", "JOINT_POSITION", "JOINT_TORQUE"):
         raise NotImplementedError(f"arm controller type {arm['type']} not implemented in the fused path")
-    if arm["type"] in ("JOINT_POSITION", "JOINT_TORQUE") and cfg_struct_cls.__module__.startswith("robosuite_b200"):
-        # the CPU oracle has these two (pinned against the reference stack); the device kernels do not yet
-        raise NotImplementedError(f"arm controller type {arm['type']} is not implemented on the device yet")
     if arm["type"] == "JOINT_POSITION" and (arm.get("impedance_mode", "fixed") != "fixed" or arm.get("input_type", "delta") != "delta"
                                             or arm.get("qpos_limits") is not None):
         raise NotImplementedError("JOINT_POSITION: fixed impedance, delta inputs, no qpos_limits")

@@ -806,7 +806,8 @@ int b2s_jac_site(b2s_sim* s, int site_id, void* jacp, void* jacr) {
 
 int b2s_ctrl_config(b2s_sim* s, const b2s_ctrl_cfg* c) {
   if (!s || !c) return fail(B2S_ERR_ARG, "b2s_ctrl_config: bad argument");
-  if (c->kind != B2S_CTRL_OSC_POSE && c->kind != B2S_CTRL_JOINT_VELOCITY && c->kind != B2S_CTRL_NONE)
+  if (c->kind != B2S_CTRL_OSC_POSE && c->kind != B2S_CTRL_JOINT_VELOCITY && c->kind != B2S_CTRL_JOINT_POSITION &&
+      c->kind != B2S_CTRL_JOINT_TORQUE && c->kind != B2S_CTRL_NONE)
     return fail(B2S_ERR_UNSUPPORTED, "controller kind not implemented");
   if (c->n_arm > 8 || c->n_grip > 4) return fail(B2S_ERR_ARG, "b2s_ctrl_config: too many joints");
   CtrlCfgDev& d = s->ctrl;

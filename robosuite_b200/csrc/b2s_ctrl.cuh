@@ -59,6 +59,56 @@ template <typename R> DEV void delta_rotmat(R* Rm, const R* aa) {
 // JointVelocityController (robosuite/controllers/parts/generic/joint_vel.py:129-209): PID on joint velocity with a
 // 5-sample derivative ring, anti-windup, + qfrc_bias; the constructor line :127 (assignment to a read-only property)
 // is read as the sibling controllers spell it (`use_torque_compensation`, joint_tor.py:109).  One lane per joint.
+// JointPositionController (joint_pos.py:160-262; kind 3: goal_qpos = q + scaled delta at policy steps, torque =
+// M_arm (kp e - kd qvel) + qfrc_bias) and JointTorqueController (joint_tor.py:112-160; kind 4: goal torque = clipped scaled
+// action, torque = goal + qfrc_bias).  One lane per joint; the goal lives in the first 8 words of the jv_state row.
+template <typename R>
+DEVN void ctrl_run_joint(Eng<R> e, CtrlState<R>& cs, int env, const R* action) {
+  const DModel<R>& m = cmodel<R>();
+  const WSLayout& L = c_L;
+  const DState<R>& s = cstate<R>();
+  const CtrlCfgDev& cc = c_cc;
+  int lane = e.lane, na = cc.n_arm, nv = m.nv;
+  R* st = s.jv_state + (size_t)env * 72;
+  R* ctrl = e.p(L.ctrl);
+  int k = lane < na ? lane : 0, dof = cc.arm_dof[k], u = cc.arm_act[k];
+  R goal = st[k];
+  if (action && lane < na) {
+    R a = r_clamp(action[(size_t)env * cc.action_dim + k], (R)cc.jv_in_min[k], (R)cc.jv_in_max[k]);
+    R scale = (R)(fabs(cc.jv_out_max[k] - cc.jv_out_min[k]) / fabs(cc.jv_in_max[k] - cc.jv_in_min[k]));
+    R sc = (a - (R)(0.5 * (cc.jv_in_max[k] + cc.jv_in_min[k]))) * scale + (R)(0.5 * (cc.jv_out_max[k] + cc.jv_out_min[k]));
+    goal = cc.kind == 3 ? e.p(L.qpos)[cc.arm_qpos[k]] + sc : r_clamp(sc, m.act_ctrlrange[2 * u], m.act_ctrlrange[2 * u + 1]);
+    st[k] = goal;
+  }
+  R tau;
+  if (cc.kind == 3) {
+    R des = lane < na ? (goal - e.p(L.qpos)[cc.arm_qpos[k]]) * (R)cc.jv_kp[k] - e.p(L.qvel)[dof] * (R)cc.jv_kd[k] : R(0);
+    tau = 0;
+    for (int b = 0; b < na; b++) {
+      R db = __shfl_sync(B2S_FULL, des, b);
+      tau += e.p(L.M)[dof * nv + cc.arm_dof[b]] * db;
+    }
+    tau = cc.jv_torque_comp ? tau + e.p(L.bias)[dof] : des;
+  } else {
+    tau = goal + (cc.jv_torque_comp ? e.p(L.bias)[dof] : R(0));
+  }
+  if (lane < na) {
+    s.ctrl_torque[(size_t)env * 8 + k] = tau;
+    ctrl[u] = r_clamp(tau, m.act_ctrlrange[2 * u], m.act_ctrlrange[2 * u + 1]);
+  }
+  if (action) {
+    R ga = action[(size_t)env * cc.action_dim + na];
+    R sg = ga > 0 ? R(1) : (ga < 0 ? R(-1) : R(0));
+    for (int g = 0; g < cc.n_grip; g++) cs.grip[g] = r_clamp(cs.grip[g] + (R)(cc.grip_sign[g] * cc.grip_speed) * sg, R(-1), R(1));
+  }
+  if (lane < cc.n_grip) {
+    int ug = cc.grip_act[lane];
+    R lo = m.act_ctrlrange[2 * ug], hi = m.act_ctrlrange[2 * ug + 1];
+    ctrl[ug] = r_clamp(R(0.5) * (hi + lo) + R(0.5) * (hi - lo) * cs.grip[lane], lo, hi);
+  }
+  __syncwarp();
+}
+
 template <typename R>
 DEVN void ctrl_run_jv(Eng<R> e, CtrlState<R>& cs, int env, const R* action) {
   const DModel<R>& m = cmodel<R>();
@@ -121,6 +171,7 @@ DEVN void ctrl_run(Eng<R> e, CtrlState<R>& cs, int env, const R* action) {
   const DState<R>& s = cstate<R>();
   const CtrlCfgDev& cc = c_cc;
   if (cc.kind == 2) { ctrl_run_jv(e, cs, env, action); return; }
+  if (cc.kind == 3 || cc.kind == 4) { ctrl_run_joint(e, cs, env, action); return; }
   bool policy_step = action != nullptr;
   int lane = e.lane, nv = m.nv, na = cc.n_arm;
   const R* ref_pos = e.p(L.spos) + 3 * cc.eef_site; const R* ref_ori = e.p(L.smat) + 9 * cc.eef_site;
@@ -484,4 +535,6 @@ __global__ void ctrl_reset_kernel(const uint8_t* mask) {
   for (int k = 0; k < cc.n_arm; k++) s.init_qpos_arm[E * 8 + k] = s.qpos[E * m.nq + cc.arm_qpos[k]];
   for (int k = 0; k < 4; k++) s.grip_state[E * 4 + k] = 0;
   for (int k = 0; k < 72; k++) s.jv_state[E * 72 + k] = k == 64 ? R(4) : R(0);  // ring pointer starts at length - 1
+  if (cc.kind == 3)  // JointPositionController.reset_goal: goal <- current joint positions
+    for (int k = 0; k < cc.n_arm; k++) s.jv_state[E * 72 + k] = s.qpos[E * m.nq + cc.arm_qpos[k]];
 }

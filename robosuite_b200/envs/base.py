@@ -238,7 +238,7 @@ class BatchedMujocoEnv:
     def action_spec(self):
         """(low, high) bounds (robot_env.py:271-285): OSC input limits + gripper [-1, 1]"""
         c = self._ctrl_cfg
-        if c.kind == 2:
+        if c.kind in (2, 3, 4):  # joint-space controllers: per-joint input limits
             n = c.n_arm
             return (np.array(list(c.jv_in_min)[:n] + [-1.0] * (c.action_dim - n)),
                     np.array(list(c.jv_in_max)[:n] + [1.0] * (c.action_dim - n)))

@@ -54,7 +54,7 @@ def test_oracle_env_step_matches_reference_stack(task):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("task", TASKS)
+@pytest.mark.parametrize("task", TASKS + ["Lift_JOINT_POSITION", "Lift_JOINT_TORQUE"])
 def test_env_api_matches_reference_stack(task):
     """observations (layout, order, sampling instant, lagged object-in-gripper poses), rewards and state after every control
     step, fp32 engine vs the reference stack on the fp64 oracle"""
@@ -65,7 +65,12 @@ def test_env_api_matches_reference_stack(task):
     G = _golden()
     m = _model(task, G)
     n = 2
-    env = suite.make(task, robots="Panda", num_envs=n, seed=0, horizon=1000, reward_shaping=True, model=m)
+    kw = {}
+    if "JOINT" in task:
+        from robosuite_b200 import controller_config as cc
+
+        kw["controller_configs"] = cc.refactor_composite_controller_config(cc.load_part_controller_config(task.split("_", 1)[1]), "Panda", ["right"])
+    env = suite.make(task.split("_")[0], robots="Panda", num_envs=n, seed=0, horizon=1000, reward_shaping=True, model=m, **kw)
     obs = env.reset_to(G[task + "/qpos0"])
     for key, ref in (("object-state", G[task + "/obs0_object"]), ("robot0_proprio-state", G[task + "/obs0_proprio"])):
         got = obs[key].cpu().numpy().astype(np.float64)
