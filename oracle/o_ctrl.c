@@ -254,8 +254,11 @@ void o_ctrl_run(const OModel* m, OData* d, const OCtrlCfg* c, OCtrlState* s, con
   const double* org_ori = d->site_xmat + 9 * c->base_site;
   if (action) {
     /* scale_action: clip to [input_min, input_max], affine map to [output_min, output_max] */
-    double sd[6];
-    for (int k = 0; k < 6; k++) {
+    /* OSC_POSITION (kind 5, osc.py:152-166, 259-270): 3-dim arm action, the orientation part of the delta is zero, so every
+     * policy step re-anchors goal_ori to the current orientation */
+    double sd[6] = {0, 0, 0, 0, 0, 0};
+    int od = c->kind == 5 ? 3 : 6;
+    for (int k = 0; k < od; k++) {
       double a = fmin(fmax(action[k], c->input_min[k]), c->input_max[k]);
       double scale = fabs(c->output_max[k] - c->output_min[k]) / fabs(c->input_max[k] - c->input_min[k]);
       sd[k] = (a - 0.5 * (c->input_max[k] + c->input_min[k])) * scale + 0.5 * (c->output_max[k] + c->output_min[k]);
@@ -271,7 +274,7 @@ void o_ctrl_run(const OModel* m, OData* d, const OCtrlCfg* c, OCtrlState* s, con
     m3_mul(s->goal_ori, Rd, cur);
     /* gripper: format_action integrates sign(a)*speed into current_action, clipped to [-1,1] */
     for (int g = 0; g < c->n_grip; g++) {
-      double a = action[6];
+      double a = action[od];
       double sg = a > 0 ? 1.0 : (a < 0 ? -1.0 : 0.0);
       s->grip_action[g] = fmin(fmax(s->grip_action[g] + c->grip_sign[g] * c->grip_speed * sg, -1.0), 1.0);
     }

@@ -52,6 +52,11 @@ _DEFAULT_JOINT_VELOCITY = {"type": "JOINT_VELOCITY", "input_max": 1, "input_min"
                            "kp": 3.0, "velocity_limits": [-1, 1], "interpolation": None, "ramp_ratio": 0.2}
 
 
+# controllers/config/default/parts/osc_position.json
+_DEFAULT_OSC_POSITION = {"type": "OSC_POSITION", "input_max": 1, "input_min": -1, "output_max": [0.05, 0.05, 0.05],
+                         "output_min": [-0.05, -0.05, -0.05], "kp": 150, "damping_ratio": 1, "impedance_mode": "fixed",
+                         "kp_limits": [0, 300], "damping_ratio_limits": [0, 10], "position_limits": None, "input_type": "delta",
+                         "input_ref_frame": "base", "interpolation": None, "ramp_ratio": 0.2}
 # controllers/config/default/parts/joint_position.json, joint_torque.json
 _DEFAULT_JOINT_POSITION = {"type": "JOINT_POSITION", "input_max": 1, "input_min": -1, "output_max": 0.05, "output_min": -0.05,
                            "kp": 50, "damping_ratio": 1, "impedance_mode": "fixed", "kp_limits": [0, 300],
@@ -62,7 +67,7 @@ _DEFAULT_JOINT_TORQUE = {"type": "JOINT_TORQUE", "input_max": 1, "input_min": -1
 
 def load_part_controller_config(default_controller="OSC_POSE"):
     """suite.load_part_controller_config(default_controller=...) (controllers/parts/controller_factory.py:16-70)"""
-    table = {"OSC_POSE": _DEFAULT_OSC_POSE, "JOINT_VELOCITY": _DEFAULT_JOINT_VELOCITY,
+    table = {"OSC_POSE": _DEFAULT_OSC_POSE, "OSC_POSITION": _DEFAULT_OSC_POSITION, "JOINT_VELOCITY": _DEFAULT_JOINT_VELOCITY,
              "JOINT_POSITION": _DEFAULT_JOINT_POSITION, "JOINT_TORQUE": _DEFAULT_JOINT_TORQUE}
     if default_controller not in table:
         raise NotImplementedError(f"part controller {default_controller} is not implemented")
@@ -86,14 +91,14 @@ def resolve(model, composite_cfg, cfg_struct_cls, robot_prefix="robot0_", grippe
     if composite_cfg.get("type", "BASIC") != "BASIC":
         raise NotImplementedError("only the BASIC composite controller is implemented")
     arm = composite_cfg["body_parts"]["arms"]["right"]
-    if arm["type"] not in ("OSC_POSE", "JOINT_VELOCITY", "JOINT_POSITION", "JOINT_TORQUE"):
+    if arm["type"] not in ("OSC_POSE", "OSC_POSITION", "JOINT_VELOCITY", "JOINT_POSITION", "JOINT_TORQUE"):
         raise NotImplementedError(f"arm controller type {arm['type']} not implemented in the fused path")
     if arm["type"] == "JOINT_POSITION" and (arm.get("impedance_mode", "fixed") != "fixed" or arm.get("input_type", "delta") != "delta"
                                             or arm.get("qpos_limits") is not None):
         raise NotImplementedError("JOINT_POSITION: fixed impedance, delta inputs, no qpos_limits")
     if arm["type"] == "JOINT_TORQUE" and arm.get("torque_limits") is not None:
         raise NotImplementedError("JOINT_TORQUE: torque_limits other than the actuator limits are not implemented")
-    if arm["type"] == "OSC_POSE" and (arm.get("impedance_mode", "fixed") != "fixed" or arm.get("input_type", "delta") != "delta"
+    if arm["type"] in ("OSC_POSE", "OSC_POSITION") and (arm.get("impedance_mode", "fixed") != "fixed" or arm.get("input_type", "delta") != "delta"
                                       or arm.get("input_ref_frame", "base") != "base" or arm.get("interpolation") is not None):
         raise NotImplementedError("fused OSC path implements fixed impedance, delta inputs in the base frame")
     if arm.get("interpolation") is not None:
@@ -102,7 +107,8 @@ def resolve(model, composite_cfg, cfg_struct_cls, robot_prefix="robot0_", grippe
     # arm joints: the robot's own hinge joints (robots/robot.py:302-332 collects them through the robot model)
     arm_j = [i for i, n in enumerate(jn) if n and n.startswith(robot_prefix) and int(model.jnt_type[i]) == 3]
     c = cfg_struct_cls()
-    c.kind = {"OSC_POSE": 1, "JOINT_VELOCITY": 2, "JOINT_POSITION": 3, "JOINT_TORQUE": 4}[arm["type"]]
+    # kind 5 (OSC_POSITION) exists in the CPU oracle only so far: b2s_ctrl_config rejects it on the device
+    c.kind = {"OSC_POSE": 1, "JOINT_VELOCITY": 2, "JOINT_POSITION": 3, "JOINT_TORQUE": 4, "OSC_POSITION": 5}[arm["type"]]
     c.n_arm = len(arm_j)
     for k, j in enumerate(arm_j):
         c.arm_dof[k] = int(model.jnt_dofadr[j])
@@ -155,10 +161,16 @@ def resolve(model, composite_cfg, cfg_struct_cls, robot_prefix="robot0_", grippe
         c.uncouple_pos_ori = 1
         c.n_obs_site = 0
         return c
-    c.action_dim = 6 + 1
+    od = 3 if arm["type"] == "OSC_POSITION" else 6
+    c.action_dim = od + 1
     kp, dr = _arr6(arm["kp"]), _arr6(arm["damping_ratio"])
-    imax, imin = _arr6(arm["input_max"]), _arr6(arm["input_min"])
-    omax, omin = _arr6(arm["output_max"]), _arr6(arm["output_min"])
+
+    def _lim(v):  # OSC_POSITION carries 3-vectors (osc.py:165): pad the unused orientation slots
+        a = np.asarray(v, dtype=np.float64)
+        return _arr6(v) if a.ndim == 0 or a.size == 6 else np.concatenate([a, np.ones(6 - a.size) * a.flat[0]])
+
+    imax, imin = _lim(arm["input_max"]), _lim(arm["input_min"])
+    omax, omin = _lim(arm["output_max"]), _lim(arm["output_min"])
     for k in range(6):
         c.kp[k], c.damping_ratio[k] = kp[k], dr[k]
         c.input_max[k], c.input_min[k], c.output_max[k], c.output_min[k] = imax[k], imin[k], omax[k], omin[k]

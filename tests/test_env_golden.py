@@ -22,13 +22,13 @@ def _golden():
 
 
 def _model(task, G):
-    m = load(task + "_Panda" if "_" not in task else ("Lift_Panda" if "JOINT" in task else task))
+    m = load(task + "_Panda" if "_" not in task else ("Lift_Panda" if ("JOINT" in task or "OSC_" in task) else task))
     m.body_pos[:] = G[task + "/body_pos"]   # the reference writes sampled placements into the model (Door, visual objects)
     m.body_quat[:] = G[task + "/body_quat"]
     return m
 
 
-@pytest.mark.parametrize("task", TASKS + ["Lift_Sawyer", "Stack_Sawyer", "Lift_JOINT_POSITION", "Lift_JOINT_TORQUE"])
+@pytest.mark.parametrize("task", TASKS + ["Lift_Sawyer", "Stack_Sawyer", "Lift_JOINT_POSITION", "Lift_JOINT_TORQUE", "Lift_OSC_POSITION"])
 def test_oracle_env_step_matches_reference_stack(task):
     """150 substeps of {step1, reference controllers, step2} vs the oracle's C controller + loop: <= 1e-6 on qpos
     (the residual is the reference's float32 round trip in transform_utils.quat2mat)"""
@@ -42,7 +42,7 @@ def test_oracle_env_step_matches_reference_stack(task):
     o = Oracle(pack_model(m))
     sawyer = task.endswith("Sawyer")
     cfg = cc.load_composite_controller_config(None, "Sawyer") if sawyer else cc.default_composite_config()
-    if "JOINT" in task:  # part controller selected like demos/demo_control.py:99-103
+    if "JOINT" in task or "OSC_POSITION" in task:  # part controller selected like demos/demo_control.py:99-103
         cfg = cc.refactor_composite_controller_config(cc.load_part_controller_config(task.split("_", 1)[1]), "Panda", ["right"])
     o.ctrl_setup(cc.resolve(m, cfg, OCfg, gripper="rethink" if sawyer else "panda"))
     o.qpos[:] = G[task + "/qpos0"]

@@ -66,7 +66,7 @@ if __name__ == "__main__":
         for k, v in rec.items():
             out[f"{task}/{k}" if robot == "Panda" else f"{task}_{robot}/{k}"] = np.array(v)
         print(task, "object-state", rec["obs_object"].shape, "proprio", rec["obs_proprio"].shape, "reward", np.round(rec["reward"], 4))
-    for ctrl in ("JOINT_POSITION", "JOINT_TORQUE"):
+    for ctrl in ("JOINT_POSITION", "JOINT_TORQUE", "OSC_POSITION"):
         rec = run("Lift", "Panda", controller=ctrl)
         for k, v in rec.items():
             out[f"Lift_{ctrl}/{k}"] = np.array(v)
