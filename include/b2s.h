@@ -87,8 +87,12 @@ int b2s_ctrl_reset(b2s_sim* sim, const uint8_t* env_mask);
 int b2s_env_step(b2s_sim* sim, const void* action, int n_substeps);
 
 /* Observation program = MujocoEnv._get_observations flattened (environments/base.py:429-465): one (op, a, b) entry
- * per output scalar (ops: enum OB_* in csrc/b2s_types.cuh).  Creates the device array "obs" [n_env, obs_dim], written by
- * b2s_env_step after the FIRST substep (Observable sampling rule, utils/observables.py:230-240) and by b2s_forward. */
+ * per output scalar (ops: enum OB_* in csrc/b2s_types.cuh; OB_REL_*_LAG entries read the previous sample, as the reference's
+ * sensor ordering does: manipulation_env.py:268-329).  Creates the device arrays "obs" [n_env, obs_dim] and "obs_fresh" [n_env]
+ * (1 = observation cache empty; set it when an environment is reset).  "obs" is written by b2s_env_step after the LAST
+ * substep - reset()'s forced update advances the observables' period timer by one model step, so every later sample falls on
+ * the last substep of a control step (utils/observables.py:214-259, environments/base.py:418-427) - and by b2s_forward for
+ * environments whose obs_fresh flag is set. obs_dim <= 128. */
 int b2s_obs_config(b2s_sim* sim, int obs_dim, const int* op_host, const int* a_host, const int* b_host);
 /* Task outputs "task_out" [n_env,8] = (target body height, |site - body|, grasp flag, horizontal |body - body2|,
  * obj-obj2 contact flag, 0, 0, 0) from the poses/contacts of the
