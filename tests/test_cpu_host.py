@@ -292,3 +292,27 @@ def test_shard_range_partitions():
     for n, w in ((65536, 8), (10, 3), (7, 8)):
         spans = [shard_range(n, r, w) for r in range(w)]
         assert spans[0][0] == 0 and spans[-1][1] == n and all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+
+
+def test_state_io_formats_roundtrip(tmp_path):
+    """MjSimState.flatten layout and DataCollectionWrapper episode folders (binding_utils.py:221-249,
+    wrappers/data_collection_wrapper.py:100-147)"""
+    from robosuite_b200 import state_io as sio
+
+    rng = np.random.default_rng(0)
+    T, N, nq, nv, A = 5, 3, 16, 15, 7
+    qpos, qvel, time = rng.normal(size=(T + 1, N, nq)), rng.normal(size=(T + 1, N, nv)), np.arange(T + 1) * 0.05
+    states = np.stack([sio.flatten_state(time[t], qpos[t], qvel[t]) for t in range(T + 1)])
+    assert states.shape == (T + 1, N, 1 + nq + nv) and np.all(states[2, :, 0] == 0.1)
+    t2, q2, v2 = sio.unflatten_state(states[3], nq, nv)
+    assert np.array_equal(q2, qpos[3]) and np.array_equal(v2, qvel[3]) and np.allclose(t2, 0.15)
+    with pytest.raises(ValueError):
+        sio.unflatten_state(states[0][:, :-1], nq, nv)
+    actions = rng.uniform(-1, 1, size=(T, N, A))
+    eps = sio.save_episodes(str(tmp_path), "Lift", "<mujoco/>", states, actions, successful=[True, False, False])
+    assert len(eps) == N and sorted(os.listdir(eps[0])) == ["ep_meta.json", "model.xml", "state_0_0.npz"]
+    raw = np.load(os.path.join(eps[1], "state_0_0.npz"), allow_pickle=True)  # the keys the reference writes
+    assert set(raw.files) == {"states", "action_infos", "successful", "env"} and raw["states"].shape == (T + 1, 1 + nq + nv)
+    ep = sio.load_episode(eps[0])
+    assert ep["env"] == "Lift" and ep["successful"] and ep["model_xml"] == "<mujoco/>"
+    assert np.array_equal(ep["states"], states[:, 0]) and np.array_equal(ep["actions"], actions[:, 0])
