@@ -78,7 +78,9 @@ class MjModel:
     def from_xml_string(cls, xml, assets=None):
         from robosuite_b200.mjcf.compiler import compile_mjcf
 
-        return cls._wrap(compile_mjcf(xml))
+        self = cls._wrap(compile_mjcf(xml))
+        self._xml = xml
+        return self
 
     @classmethod
     def from_xml_path(cls, path, assets=None):
@@ -252,8 +254,12 @@ def mju_mat2Quat(quat, mat):
     quat[...] = [q[3], q[0], q[1], q[2]]
 
 
-def mj_saveLastXML(*a, **k):
-    raise NotImplementedError
+def mj_saveLastXML(filename, m, *a):
+    """writes the MJCF the model was compiled from (the engine would re-serialise its compiled model)"""
+    path = filename.decode() if isinstance(filename, bytes) else filename
+    with open(path, "w") as f:
+        f.write(getattr(m, "_xml", "") or "")
+    return 1
 
 
 def __getattr__(name):  # anything else of the rendering / visualisation API
