@@ -17,8 +17,11 @@ _LIB = None
 B2S_F32, B2S_F64, B2S_I32 = 0, 1, 2
 
 
-class B2SError(RuntimeError):
-    pass
+from .errors import SimulationError
+
+
+class B2SError(SimulationError, RuntimeError):
+    """non-zero return code of the C library (message from b2s_last_error)"""
 
 
 class CtrlCfg(C.Structure):

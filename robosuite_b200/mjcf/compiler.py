@@ -161,7 +161,14 @@ class Model:
 
 # ----------------------------------------------------------------------------------------------- compile
 def compile_mjcf(xml_string: str, mesh_root: str = None) -> Model:
-    root = ET.fromstring(xml_string)
+    from ..errors import XMLError
+
+    try:
+        root = ET.fromstring(xml_string)
+    except ET.ParseError as e:  # the reference surfaces the engine's XML errors to the caller
+        raise XMLError("MJCF parse error: %s" % e) from e
+    if root.tag != "mujoco":
+        raise XMLError("root element is <%s>, expected <mujoco>" % root.tag)
     comp = root.find("compiler")
     comp = comp.attrib if comp is not None else {}
     use_degree = comp.get("angle", "degree") == "degree"

@@ -316,3 +316,17 @@ def test_state_io_formats_roundtrip(tmp_path):
     ep = sio.load_episode(eps[0])
     assert ep["env"] == "Lift" and ep["successful"] and ep["model_xml"] == "<mujoco/>"
     assert np.array_equal(ep["states"], states[:, 0]) and np.array_equal(ep["actions"], actions[:, 0])
+
+
+def test_error_classes_follow_the_reference_names():
+    """utils/errors.py names; malformed MJCF -> XMLError; library failures -> SimulationError subclasses"""
+    from robosuite_b200.engine import B2SError
+    from robosuite_b200.errors import RandomizationError, SimulationError, XMLError, robosuiteError
+    from robosuite_b200.mjcf.compiler import compile_mjcf
+
+    assert issubclass(XMLError, robosuiteError) and issubclass(RandomizationError, robosuiteError)
+    assert issubclass(B2SError, SimulationError) and issubclass(B2SError, RuntimeError)
+    with pytest.raises(XMLError):
+        compile_mjcf("<mujoco><worldbody>")
+    with pytest.raises(XMLError):
+        compile_mjcf("<robot/>")
