@@ -9,15 +9,13 @@ import os
 
 import numpy as np
 
+from .errors import SimulationError
 from .mjcf.compiler import Model, compile_mjcf, pack_model
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 B2S_F32, B2S_F64, B2S_I32 = 0, 1, 2
-
-
-from .errors import SimulationError
 
 
 class B2SError(SimulationError, RuntimeError):
