@@ -95,6 +95,10 @@ class BatchedPickPlace(BatchedMujocoEnv):
                     break
                 nx, ny = draw(nb)
                 x[bad], y[bad] = nx, ny
+            else:  # placement_samplers.py:304-305
+                from ..errors import RandomizationError
+
+                raise RandomizationError("Cannot place all objects ):")
             yaw = torch.rand((n,), generator=self.rng, device=dev, dtype=torch.float64) * 2 * math.pi
             self._place_free_body(q, self.obj_qadr[name], x, y, torch.full((n,), z, device=dev, dtype=torch.float64), yaw)
             placed.append((x, y, z, meta))

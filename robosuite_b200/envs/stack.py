@@ -72,6 +72,10 @@ class BatchedStack(BatchedMujocoEnv):
                 break
             nx, ny, nyaw = draw(nb)
             bx[bad], by[bad], byaw[bad] = nx, ny, nyaw
+        else:  # placement_samplers.py:304-305
+            from ..errors import RandomizationError
+
+            raise RandomizationError("Cannot place all objects ):")
         for adr, x, y, yaw, hz in ((self.cubeA_qadr, ax, ay, ayaw, self.half["A"][2]), (self.cubeB_qadr, bx, by, byaw, self.half["B"][2])):
             q[:, adr] = self.table_offset[0] + x
             q[:, adr + 1] = self.table_offset[1] + y
