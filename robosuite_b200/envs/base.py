@@ -102,7 +102,7 @@ class BatchedMujocoEnv:
                  ignore_done=False, reward_scale=1.0, reward_shaping=False, use_object_obs=True, seed=None,
                  initialization_noise="default", precision="f32", xml=None, has_renderer=False,
                  has_offscreen_renderer=False, use_camera_obs=False, hard_reset=False, lite_physics=True, model=None,
-                 kernel_mode="pipeline", **kwargs):
+                 kernel_mode="pipeline", sim_cls=None, **kwargs):
         import torch
 
         if has_renderer or has_offscreen_renderer or use_camera_obs:
@@ -126,7 +126,8 @@ class BatchedMujocoEnv:
             raise ValueError("Control frequency {} is invalid".format(control_freq))
         self.n_substeps = int(self.control_timestep / self.model_timestep)
         caps = {k: v for k, v in (("maxcon", kwargs.get("maxcon", self.maxcon)), ("maxefc", kwargs.get("maxefc", self.maxefc))) if v}
-        self.sim = BatchedSim(self.model, self.num_envs, device=device, precision=precision, **caps)
+        # sim_cls: test hook (tests/oracle_sim.py drives the same host code on the CPU oracle); the product path is BatchedSim
+        self.sim = (sim_cls or BatchedSim)(self.model, self.num_envs, device=device, precision=precision, **caps)
         self.device = self.sim.torch_device
         self.dtype = self.sim.dtype
         self.composite_controller_config = cc.load_composite_controller_config(controller_configs, self.robot_name)

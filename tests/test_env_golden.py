@@ -174,3 +174,40 @@ def test_reference_datacollection_episode_loads_and_replays_on_the_oracle(tmp_pa
     for k in range(4):
         o.env_step(ep["actions"][k], 25)
         assert np.abs(o.qpos - q[k + 1]).max() < 3e-2, (k, np.abs(o.qpos - q[k + 1]).max())
+
+
+CPU_CASES = TASKS + ["Lift_JOINT_POSITION", "Lift_JOINT_TORQUE", "Lift_OSC_POSITION", "Lift_Sawyer", "Stack_Sawyer"]
+
+
+@pytest.mark.parametrize("task", CPU_CASES)
+def test_env_host_layer_matches_reference_stack_on_cpu(task):
+    """the HOST side of the environment layer (observation tables incl. the lagged entries, reset_to, reward / success code of
+    every task class, action_spec, controller config resolution) driven by tests/oracle_sim.OracleSim instead of the CUDA
+    engine: observations, rewards and states must equal what the reference stack produced on the same physics"""
+    import torch
+
+    import robosuite_b200 as suite
+    from robosuite_b200 import controller_config as cc
+    from tests.oracle_sim import OracleSim
+
+    G = _golden()
+    m = _model(task, G)
+    robot = "Sawyer" if task.endswith("Sawyer") else "Panda"
+    kw = {}
+    if "JOINT" in task or "OSC_POSITION" in task:
+        kw["controller_configs"] = cc.refactor_composite_controller_config(cc.load_part_controller_config(task.split("_", 1)[1]), "Panda", ["right"])
+    env = suite.make(task.split("_")[0], robots=robot, num_envs=2, seed=0, horizon=1000, reward_shaping=True, model=m,
+                     sim_cls=OracleSim, **kw)
+    assert env.action_dim == G[task + "/actions"].shape[1]
+    obs = env.reset_to(G[task + "/qpos0"])
+    assert np.abs(obs["object-state"].numpy() - G[task + "/obs0_object"]).max() < 1e-6
+    assert np.abs(obs["robot0_proprio-state"].numpy() - G[task + "/obs0_proprio"]).max() < 1e-6
+    for t, a in enumerate(G[task + "/actions"]):
+        obs, rew, done, info = env.step(torch.as_tensor(np.tile(a, (2, 1))))
+        eo = np.abs(obs["object-state"].numpy() - G[task + "/obs_object"][t]).max()
+        ep = np.abs(obs["robot0_proprio-state"].numpy() - G[task + "/obs_proprio"][t])
+        ep[:, 28:35] /= max(1.0, np.abs(G[task + "/obs_proprio"][t][28:35]).max())
+        assert eo < 2e-6 and ep.max() < 1e-5, (task, t, eo, ep.max(), int(ep[0].argmax()))
+        assert np.abs(rew.numpy() - G[task + "/reward"][t]).max() < 1e-6, (task, t, rew, G[task + "/reward"][t])
+        assert np.abs(env.sim.qpos.numpy() - G[task + "/qpos"][t]).max() < 1e-6
+    env.close()
