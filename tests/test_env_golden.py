@@ -211,3 +211,29 @@ def test_env_host_layer_matches_reference_stack_on_cpu(task):
         assert np.abs(rew.numpy() - G[task + "/reward"][t]).max() < 1e-6, (task, t, rew, G[task + "/reward"][t])
         assert np.abs(env.sim.qpos.numpy() - G[task + "/qpos"][t]).max() < 1e-6
     env.close()
+
+
+@pytest.mark.parametrize("task", ["Lift", "Stack"])
+def test_staged_rewards_grasp_and_success_match_reference_stack_on_cpu(task):
+    """scripted reach / descend / close / lift episode recorded from the reference stack (tools/gen_reward_golden.py):
+    the task classes' staged rewards, grasp detection (fingerpad-group contacts) and success flags, evaluated on the CPU
+    stand-in sim, must follow the reference step by step (70 control steps, 1750 substeps of contact-rich motion)"""
+    import torch
+
+    import robosuite_b200 as suite
+    from tests.oracle_sim import OracleSim
+
+    G = np.load(os.path.join(ROOT, "tests", "golden", "reward_golden.npz"), allow_pickle=True)
+    env = suite.make(task, robots="Panda", num_envs=1, seed=0, horizon=1000, reward_shaping=True, model=load(task + "_Panda"),
+                     sim_cls=OracleSim)
+    env.reset_to(G[task + "/qpos0"])
+    n_grasp = n_succ = 0
+    for t, a in enumerate(G[task + "/actions"]):
+        obs, rew, done, info = env.step(torch.as_tensor(a[None]))
+        assert np.abs(env.sim.qpos.numpy()[0] - G[task + "/qpos"][t]).max() < 1e-5, (task, t)
+        assert abs(float(rew[0]) - G[task + "/reward"][t]) < 1e-5, (task, t, float(rew[0]), G[task + "/reward"][t])
+        assert bool(env.sim.task_out[0, 2] > 0) == bool(G[task + "/grasp"][t]), (task, t)
+        assert bool(env._check_success()[0]) == bool(G[task + "/success"][t]), (task, t)
+        n_grasp += bool(G[task + "/grasp"][t]); n_succ += bool(G[task + "/success"][t])
+    assert n_grasp > 20 and (task != "Lift" or n_succ > 10)
+    env.close()

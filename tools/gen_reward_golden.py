@@ -1,0 +1,55 @@
+"""Scripted pick-and-lift episodes on the UNMODIFIED reference stack (running on oracle/mujoco_shim) to pin the staged
+reward / grasp / success logic: tests/golden/reward_golden.npz holds reset state, actions and per control step the
+reference's reward (shaped), _check_success() and _check_grasp() of the manipulated object.
+Build container only (needs /root/reference).  Usage: python tools/gen_reward_golden.py"""
+import os, sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import gen_env_golden as g  # noqa: E402
+
+ROOT = g.ROOT
+
+
+def scripted(task, obj_body, obj_geoms_attr, steps=70, seed=0):  # seed 0: the composed model then equals the committed fixture (cube size is drawn at model creation)
+    import robosuite as suite
+
+    env = suite.make(task, robots="Panda", has_renderer=False, has_offscreen_renderer=False, use_camera_obs=False,
+                     hard_reset=False, reward_shaping=True, control_freq=20, seed=seed)
+    env.reset()
+    sim = env.sim
+    bid = sim.model.body_name2id(obj_body)
+    eef = env.robots[0].eef_site_id["right"]
+    rec = {"qpos0": np.array(sim.data.qpos)}
+    acts, rews, succ, grasp, qs = [], [], [], [], []
+    for t in range(steps):
+        p_obj, p_eef = np.array(sim.data.body_xpos[bid]), np.array(sim.data.site_xpos[eef])
+        a = np.zeros(7)
+        if t < 18:      # above the object, gripper open
+            tgt = p_obj + np.array([0, 0, 0.08]); a[6] = -1
+        elif t < 32:    # descend
+            tgt = p_obj + np.array([0, 0, 0.0]); a[6] = -1
+        elif t < 44:    # close
+            tgt = p_eef; a[6] = 1
+        else:           # lift
+            tgt = p_eef + np.array([0, 0, 0.05]); a[6] = 1
+        a[:3] = np.clip((tgt - p_eef) / 0.05 * 0.8, -1, 1)
+        obs, r, done, info = env.step(a)
+        acts.append(a); rews.append(r); succ.append(bool(env._check_success()))
+        grasp.append(bool(env._check_grasp(gripper=env.robots[0].gripper, object_geoms=getattr(env, obj_geoms_attr))))
+        qs.append(np.array(sim.data.qpos))
+    rec.update(actions=np.array(acts), reward=np.array(rews), success=np.array(succ), grasp=np.array(grasp), qpos=np.array(qs))
+    return rec
+
+
+if __name__ == "__main__":
+    g.install()
+    out = {}
+    for task, body, geoms in (("Lift", "cube_main", "cube"), ("Stack", "cubeA_main", "cubeA")):
+        rec = scripted(task, body, geoms)
+        for k, v in rec.items():
+            out[f"{task}/{k}"] = np.array(v)
+        print(task, "max reward %.3f" % rec["reward"].max(), "grasp steps", int(rec["grasp"].sum()), "success steps", int(rec["success"].sum()),
+              "lift", float(rec["qpos"][-1][-5] if task == "Lift" else 0))
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "reward_golden.npz"), **out)
