@@ -244,3 +244,31 @@ def test_staged_rewards_grasp_and_success_match_reference_stack_on_cpu(task):
         n_grasp += bool(G[task + "/grasp"][t]); n_succ += bool(G[task + "/success"][t])
     assert (n_grasp > 20 or task in ("NutAssemblyRound", "PickPlace")) and (task != "Lift" or n_succ > 10)
     env.close()
+
+
+def test_batched_gym_wrapper_autoreset_on_cpu():
+    """BatchedGymWrapper (wrappers/gym_wrapper.py:26-180 semantics) on the CPU stand-in sim: key order, 5-tuple, reset inside
+    step, per-environment episode counters"""
+    import torch
+
+    import robosuite_b200 as suite
+    from robosuite_b200.wrappers import BatchedGymWrapper
+    from tests.oracle_sim import OracleSim
+
+    n = 3
+    env = BatchedGymWrapper(suite.make("Lift", robots="Panda", num_envs=n, seed=2, horizon=2, sim_cls=OracleSim))
+    obs, info = env.reset(seed=7)
+    assert obs.shape == (n, 60) and info == {} and env.obs_dim == 60
+    d = env.env._get_observations()
+    assert torch.equal(obs[:, :10], d["object-state"]) and torch.equal(obs[:, 10:], d["robot0_proprio-state"])
+    low, high = env.action_low, env.action_high
+    assert low.shape == (7,) and np.all(low == -1) and np.all(high == 1)
+    obs, rew, term, trunc, info = env.step(torch.zeros((n, 7)))
+    assert not bool(term.any()) and "final_observation" not in info
+    obs, rew, term, trunc, info = env.step(torch.zeros((n, 7)))
+    assert bool(term.all()) and not bool(trunc.any()) and info["final_observation"].shape == (n, 60)
+    assert int(env.env.timestep.max()) == 0 and not bool(env.env.done.any())
+    assert torch.allclose(obs[:, 2], torch.full((n,), 0.83, dtype=obs.dtype), atol=5e-3)  # cube back on the table
+    obs, rew, term, trunc, info = env.step(torch.zeros((n, 7)))
+    assert not bool(term.any())
+    env.close()
