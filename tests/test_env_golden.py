@@ -272,3 +272,35 @@ def test_batched_gym_wrapper_autoreset_on_cpu():
     obs, rew, term, trunc, info = env.step(torch.zeros((n, 7)))
     assert not bool(term.any())
     env.close()
+
+
+@pytest.mark.parametrize("task", ["Lift", "Stack", "NutAssemblyRound", "PickPlace", "Door"])
+def test_reset_distribution_matches_reference_stack(task):
+    """qpos after reset: the batched samplers (torch, one draw per environment) against 250 resets of the reference stack
+    (tools/gen_reset_golden.py): coordinates the reference never varies are reproduced exactly, varying ones stay inside the
+    reference's observed range (plus a sampling margin) and have matching mean / spread"""
+    import robosuite_b200 as suite
+    from tests.oracle_sim import OracleSim
+
+    G = np.load(os.path.join(ROOT, "tests", "golden", "reset_golden.npz"), allow_pickle=True)
+    lo, hi, mean, std = (G[task + "/" + k] for k in ("min", "max", "mean", "std"))
+    n = 400
+    env = suite.make(task, robots="Panda", num_envs=n, seed=123, sim_cls=OracleSim)
+    q = env._sample_reset_state(n).cpu().numpy()
+    env.close()
+    if task == "NutAssemblyRound":  # the unused square nut: the reference parks it at (10, 10, 10) after sampling it
+        a = env.obj_qadr["SquareNut"]
+        assert np.allclose(q[:, a:a + 3], 10.0) and np.allclose(lo[a:a + 3], 10.0)
+    fixed = std < 1e-9
+    assert np.abs(q[:, fixed] - mean[fixed]).max() < 1e-9, (task, np.nonzero(fixed)[0][np.abs(q[:, fixed] - mean[fixed]).max(0) > 1e-9])
+    var = ~fixed
+    span = hi - lo
+    gauss = np.zeros_like(var)
+    gauss[env._ref_joint_pos_indexes] = True  # arm joints: N(init, 0.02^2) - unbounded, compare moments only
+    rng_like = var & ~gauss
+    margin = 0.08 * span + 1e-6                 # 250 reference draws do not reach the ends of a uniform range exactly
+    assert np.all(q[:, rng_like] >= (lo - margin)[rng_like]) and np.all(q[:, rng_like] <= (hi + margin)[rng_like]), task
+    # same centre and spread (quaternion components of a uniform yaw included)
+    assert np.abs(q[:, var].mean(0) - mean[var]).max() < 0.25 * std[var].max() + 0.15 * span[var].max(), task
+    ratio = q[:, var].std(0) / std[var]
+    assert np.all(ratio > 0.7) and np.all(ratio < 1.4), (task, ratio)
