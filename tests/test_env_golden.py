@@ -213,7 +213,7 @@ def test_env_host_layer_matches_reference_stack_on_cpu(task):
     env.close()
 
 
-@pytest.mark.parametrize("task", ["Lift", "Stack", "NutAssemblyRound", "PickPlace"])
+@pytest.mark.parametrize("task", ["Lift", "Stack", "NutAssemblyRound", "PickPlace", "Door"])
 def test_staged_rewards_grasp_and_success_match_reference_stack_on_cpu(task):
     """scripted reach / descend / close / lift episode recorded from the reference stack (tools/gen_reward_golden.py):
     the task classes' staged rewards, grasp detection (fingerpad-group contacts) and success flags, evaluated on the CPU
@@ -224,25 +224,29 @@ def test_staged_rewards_grasp_and_success_match_reference_stack_on_cpu(task):
     from tests.oracle_sim import OracleSim
 
     G = np.load(os.path.join(ROOT, "tests", "golden", "reward_golden.npz"), allow_pickle=True)
-    env = suite.make(task, robots="Panda", num_envs=1, seed=0, horizon=1000, reward_shaping=True, model=load(task + "_Panda"),
-                     sim_cls=OracleSim)
+    m = load(task + "_Panda")
+    if task + "/body_pos" in G.files:  # Door: the placement the reference drew for this episode
+        m.body_pos[:] = G[task + "/body_pos"]; m.body_quat[:] = G[task + "/body_quat"]
+    env = suite.make(task, robots="Panda", num_envs=1, seed=0, horizon=1000, reward_shaping=True, model=m, sim_cls=OracleSim)
     env.reset_to(G[task + "/qpos0"])
     n_grasp = n_succ = 0
     for t, a in enumerate(G[task + "/actions"]):
         obs, rew, done, info = env.step(torch.as_tensor(a[None]))
         dq = np.abs(env.sim.qpos.numpy()[0] - G[task + "/qpos"][t]).max()
-        if task == "PickPlace" and dq >= 1e-5:
-            # the gripper ploughs through four loose objects: the 1e-7 residual of the reference's float32 round trip is
-            # amplified to O(1) within ~20 control steps; the comparison covers the steps before that
-            assert t >= 15, (t, dq)
+        tol = 1e-4 if task == "Door" else 1e-5
+        if task in ("PickPlace", "Door") and dq >= tol:
+            # PickPlace: the gripper ploughs through four loose objects; Door: the open gripper slides along the handle.  The
+            # 1e-7 residual of the reference's float32 round trip is amplified step by step; the comparison covers the steps
+            # before the two trajectories separate (Door: the whole latch rotation)
+            assert t >= (15 if task == "PickPlace" else 55), (t, dq)
             break
-        assert dq < 1e-5, (task, t)
-        assert abs(float(rew[0]) - G[task + "/reward"][t]) < 1e-5, (task, t, float(rew[0]), G[task + "/reward"][t])
+        assert dq < tol, (task, t, dq)
+        assert abs(float(rew[0]) - G[task + "/reward"][t]) < tol, (task, t, float(rew[0]), G[task + "/reward"][t])
         grasped = bool(int(env.sim.task_out[0, 5]) >> 3 & 1) if task == "PickPlace" else bool(env.sim.task_out[0, 2] > 0)  # Can = object 3
-        assert grasped == bool(G[task + "/grasp"][t]), (task, t)
+        assert task == "Door" or grasped == bool(G[task + "/grasp"][t]), (task, t)
         assert bool(env._check_success()[0]) == bool(G[task + "/success"][t]), (task, t)
         n_grasp += bool(G[task + "/grasp"][t]); n_succ += bool(G[task + "/success"][t])
-    assert (n_grasp > 20 or task in ("NutAssemblyRound", "PickPlace")) and (task != "Lift" or n_succ > 10)
+    assert (n_grasp > 20 or task in ("NutAssemblyRound", "PickPlace", "Door")) and (task != "Lift" or n_succ > 10)
     env.close()
 
 

@@ -48,6 +48,34 @@ def scripted(task, obj_body, obj_geoms_attr, steps=70, seed=0, site=None, zoff=0
     return rec
 
 
+def scripted_door(steps=110, seed=0):
+    """press the handle down (rotates the latch to its stop), then drag it sideways: exercises the reaching and latch terms of
+    the shaped Door reward over their whole range (the door itself only opens to ~0.13 rad with this open-gripper script)"""
+    import robosuite as suite
+
+    env = suite.make("Door", robots="Panda", has_renderer=False, has_offscreen_renderer=False, use_camera_obs=False,
+                     hard_reset=False, reward_shaping=True, control_freq=20, seed=seed)
+    env.reset()
+    sim = env.sim
+    eef, hs = env.robots[0].eef_site_id["right"], env.door_handle_site_id
+    rec = {"qpos0": np.array(sim.data.qpos), "body_pos": np.array(sim.model.body_pos), "body_quat": np.array(sim.model.body_quat)}
+    acts, rews, succ, qs = [], [], [], []
+    for t in range(steps):
+        ph, pe = np.array(sim.data.site_xpos[hs]), np.array(sim.data.site_xpos[eef])
+        a = np.zeros(7); a[6] = -1
+        if t < 25:
+            tgt = ph + np.array([0.0, 0.0, 0.08])
+        elif t < 50:
+            tgt = ph + np.array([0.0, 0.0, -0.03])
+        else:
+            tgt = pe + np.array([0.04, 0.04, -0.01])
+        a[:3] = np.clip((tgt - pe) / 0.05 * 0.8, -1, 1)
+        obs, r, done, info = env.step(a)
+        acts.append(a); rews.append(r); succ.append(bool(env._check_success())); qs.append(np.array(sim.data.qpos))
+    rec.update(actions=np.array(acts), reward=np.array(rews), success=np.array(succ), grasp=np.zeros(steps, dtype=bool), qpos=np.array(qs))
+    return rec
+
+
 if __name__ == "__main__":
     g.install()
     out = {}
@@ -60,4 +88,8 @@ if __name__ == "__main__":
             out[f"{task}/{k}"] = np.array(v)
         print(task, "max reward %.3f" % rec["reward"].max(), "grasp steps", int(rec["grasp"].sum()), "success steps", int(rec["success"].sum()),
               "lift", float(rec["qpos"][-1][-5] if task == "Lift" else 0))
+    rec = scripted_door()
+    for k, v in rec.items():
+        out[f"Door/{k}"] = np.array(v)
+    print("Door max reward %.3f" % rec["reward"].max(), "max hinge %.3f" % rec["qpos"][:, -2].max(), "max latch %.3f" % rec["qpos"][:, -1].max())
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "reward_golden.npz"), **out)
