@@ -25,5 +25,19 @@ for f in funcs:
                     print("same stack offset %d passed as params %s and %s in %s" % (k, seen[k][0], p, name[:80]))
                     sus += 1
                 seen[k] = (p, r)
-print("functions: %d, suspicious call sites: %d" % (len(funcs), sus))
+print("functions: %d, call sites passing one stack offset as two pointer arguments: %d" % (len(funcs), sus))
+# Review aid for the round-1 case itself (the two arrays went to two CONSECUTIVE calls, which no per-call check can see):
+# functions in which one stack offset is materialised under several registers.  Legitimate slot sharing looks the same, so
+# these are the functions whose device-vs-oracle parity tests deserve a second look after a compiler upgrade.
+shared = 0
+for f in funcs:
+    m = re.match(r"\.(?:visible |weak )?(?:func|entry)\s*(?:\([^)]*\)\s*)?(\S+?)\(", f)
+    by = {}
+    for r, k in re.findall(r"add\.u64\s+(%rd\d+), %SPL, (\d+);", f):
+        by.setdefault(int(k), set()).add(r)
+    multi = {k: len(v) for k, v in by.items() if len(v) > 1}
+    if multi:
+        shared += 1
+        print("  shared-offset registers in %s: %s" % ((m.group(1) if m else "?")[:70], multi))
+print("functions with shared-offset registers: %d" % shared)
 sys.exit(1 if sus else 0)
