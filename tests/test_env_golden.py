@@ -213,7 +213,7 @@ def test_env_host_layer_matches_reference_stack_on_cpu(task):
     env.close()
 
 
-@pytest.mark.parametrize("task", ["Lift", "Stack", "NutAssemblyRound", "PickPlace", "Door"])
+@pytest.mark.parametrize("task", ["Lift", "Stack", "NutAssemblyRound", "PickPlace", "Door", "Lift_sparse"])
 def test_staged_rewards_grasp_and_success_match_reference_stack_on_cpu(task):
     """scripted reach / descend / close / lift episode recorded from the reference stack (tools/gen_reward_golden.py):
     the task classes' staged rewards, grasp detection (fingerpad-group contacts) and success flags, evaluated on the CPU
@@ -224,10 +224,18 @@ def test_staged_rewards_grasp_and_success_match_reference_stack_on_cpu(task):
     from tests.oracle_sim import OracleSim
 
     G = np.load(os.path.join(ROOT, "tests", "golden", "reward_golden.npz"), allow_pickle=True)
+    key = task
+    kw = {}
+    if task == "Lift_sparse":  # reward_shaping=False, reward_scale=3.0
+        task, kw = "Lift", dict(reward_shaping=False, reward_scale=3.0)
     m = load(task + "_Panda")
-    if task + "/body_pos" in G.files:  # Door: the placement the reference drew for this episode
+    if task + "/body_pos" in G.files and key == task:  # Door: the placement the reference drew for this episode
         m.body_pos[:] = G[task + "/body_pos"]; m.body_quat[:] = G[task + "/body_quat"]
-    env = suite.make(task, robots="Panda", num_envs=1, seed=0, horizon=1000, reward_shaping=True, model=m, sim_cls=OracleSim)
+    mk = dict(reward_shaping=True)
+    mk.update(kw)
+    env = suite.make(task, robots="Panda", num_envs=1, seed=0, horizon=1000, model=m, sim_cls=OracleSim, **mk)
+    G = {k[len(key) + 1:]: G[k] for k in G.files if k.startswith(key + "/")}
+    G = {task + "/" + k: v for k, v in G.items()}
     env.reset_to(G[task + "/qpos0"])
     n_grasp = n_succ = 0
     for t, a in enumerate(G[task + "/actions"]):

@@ -12,11 +12,13 @@ import gen_env_golden as g  # noqa: E402
 ROOT = g.ROOT
 
 
-def scripted(task, obj_body, obj_geoms_attr, steps=70, seed=0, site=None, zoff=0.0):  # seed 0: the composed model then equals the committed fixture (cube size is drawn at model creation)
+def scripted(task, obj_body, obj_geoms_attr, steps=70, seed=0, site=None, zoff=0.0, **make_kw):  # seed 0: the composed model then equals the committed fixture (cube size is drawn at model creation)
     import robosuite as suite
 
+    kw = dict(reward_shaping=True)
+    kw.update(make_kw)
     env = suite.make(task, robots="Panda", has_renderer=False, has_offscreen_renderer=False, use_camera_obs=False,
-                     hard_reset=False, reward_shaping=True, control_freq=20, seed=seed)
+                     hard_reset=False, control_freq=20, seed=seed, **kw)
     env.reset()
     sim = env.sim
     bid = sim.model.body_name2id(obj_body)
@@ -88,6 +90,10 @@ if __name__ == "__main__":
             out[f"{task}/{k}"] = np.array(v)
         print(task, "max reward %.3f" % rec["reward"].max(), "grasp steps", int(rec["grasp"].sum()), "success steps", int(rec["success"].sum()),
               "lift", float(rec["qpos"][-1][-5] if task == "Lift" else 0))
+    rec = scripted("Lift", "cube_main", "cube", reward_shaping=False, reward_scale=3.0)  # sparse reward, non-default scale
+    for k, v in rec.items():
+        out[f"Lift_sparse/{k}"] = np.array(v)
+    print("Lift sparse rewards", sorted(set(np.round(rec["reward"], 6))))
     rec = scripted_door()
     for k, v in rec.items():
         out[f"Door/{k}"] = np.array(v)
