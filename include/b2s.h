@@ -19,7 +19,7 @@ extern "C" {
 typedef struct b2s_sim b2s_sim;
 
 enum { B2S_OK = 0, B2S_ERR_ARG = -1, B2S_ERR_CUDA = -2, B2S_ERR_MODEL = -3, B2S_ERR_UNSUPPORTED = -4 };
-enum { B2S_F32 = 0, B2S_F64 = 1, B2S_I32 = 2 };
+enum { B2S_F32 = 0, B2S_F64 = 1, B2S_I32 = 2, B2S_I64 = 3 };
 /* controller kinds for the fused control step (controller_config "type", controllers/parts/controller_factory.py:145) */
 /* arm part controllers: controllers/parts/arm/osc.py, parts/generic/joint_vel.py, joint_pos.py, joint_tor.py.  The two joint-space
  * kinds 3 / 4 keep their per-joint scaling in jv_in/out_*, their gains in jv_kp / jv_kd (kd = 2 sqrt(kp) damping_ratio). */

@@ -616,7 +616,7 @@ template <typename R> static int enqueue_pipeline(b2s_sim* s, DState<R>& st, int
     cudaStream_t q = G == 1 ? q0 : s->gstreams[gi];
     if (G > 1) CUDA_TRY(cudaStreamWaitEvent(q, s->fork_event, 0));
     int e0 = (int)((long long)s->n_env * gi / G), e1 = (int)((long long)s->n_env * (gi + 1) / G);
-    Grp g{e0, e1 - e0, gi};
+    Grp g{e0, e1 - e0, gi, 0};
     int blocks = (g.nenv + s->wpb - 1) / s->wpb;
     int nA = g.nenv * st.cl_maxa, nG = g.nenv * st.cl_maxg;
     const int cvx_blocks = 148 * 24;
@@ -627,6 +627,7 @@ template <typename R> static int enqueue_pipeline(b2s_sim* s, DState<R>& st, int
       s->tl_events.push_back({gi, type, ev});
     };
     for (int sub = 0; sub < nsub; sub++) {
+      g.sub = sub;
       mark(0);
       CUDA_TRY(cudaMemsetAsync(st.cl_cnt + 4 * gi, 0, 4 * sizeof(int), q));
       mark(1);
@@ -678,8 +679,20 @@ template <typename R> static int launch_pipeline_t(b2s_sim* s, DState<R>& st, in
     st.cl_env = dev_zeros<int>(s, ne * CL_ENVW(st));
     st.gjk_cache = getenv("B2S_NO_GJK_CACHE") ? nullptr : dev_zeros<R>(s, ne * (size_t)(s->precision == B2S_F32 ? s->mf.npair : s->md.npair) * 3);
     s->action_buf = dev_zeros<R>(s, ne * 16);
+#ifdef B2S_INSTR
+    st.st_begin = dev_zeros<unsigned long long>(s, 64 * 32 * 4); st.st_end = dev_zeros<unsigned long long>(s, 64 * 32 * 4);
+    st.stats = dev_zeros<int>(s, 256); st.cyc = dev_zeros<float>(s, ne * 64);
+    s->arrays["st_begin"] = ArrayInfo{st.st_begin, B2S_I64, 1, {64 * 32 * 4, 0, 0, 0}};
+    s->arrays["st_end"] = ArrayInfo{st.st_end, B2S_I64, 1, {64 * 32 * 4, 0, 0, 0}};
+    s->arrays["stats"] = ArrayInfo{st.stats, B2S_I32, 1, {256, 0, 0, 0}};
+    s->arrays["cyc"] = ArrayInfo{st.cyc, B2S_F32, 3, {(int64_t)ne, 32, 2, 0}};
+#endif
     s->dirty = 1;
   }
+#ifdef B2S_INSTR
+  cudaMemsetAsync(st.st_begin, 0xff, sizeof(unsigned long long) * 64 * 32 * 4, s->stream);
+  cudaMemsetAsync(st.st_end, 0, sizeof(unsigned long long) * 64 * 32 * 4, s->stream);
+#endif
   int rc = bind_constants(s);
   if (rc != B2S_OK) return rc;
   phases |= PH_WORKLIST;
@@ -774,11 +787,23 @@ int b2s_set_mode(b2s_sim* s, int mode) {
   return B2S_OK;
 }
 
+static void clear_warm_start(b2s_sim* s, const uint8_t* mask) {
+  int npair = s->precision == B2S_F32 ? s->mf.npair : s->md.npair;
+  bool have = s->precision == B2S_F32 ? s->sf.gjk_cache != nullptr : s->sd.gjk_cache != nullptr;
+  if (!have || npair == 0) return;
+  size_t total = (size_t)s->n_env * npair * 3;
+  int blocks = (int)((total + 255) / 256);
+  if (s->precision == B2S_F32) cache_reset_kernel<float><<<blocks, 256, 0, s->stream>>>(mask);
+  else cache_reset_kernel<double><<<blocks, 256, 0, s->stream>>>(mask);
+  s->launches++;
+}
+
 int b2s_reset(b2s_sim* s, const uint8_t* mask) {
   if (!s) return fail(B2S_ERR_ARG, "null handle");
   { int rc = bind_constants(s); if (rc != B2S_OK) return rc; }
   if (s->precision == B2S_F32) reset_kernel<float><<<(s->n_env + 127) / 128, 128, 0, s->stream>>>(mask);
   else reset_kernel<double><<<(s->n_env + 127) / 128, 128, 0, s->stream>>>(mask);
+  clear_warm_start(s, mask);
   s->launches++;
   CUDA_TRY(cudaGetLastError());
   return B2S_OK;
@@ -837,6 +862,7 @@ int b2s_ctrl_reset(b2s_sim* s, const uint8_t* mask) {
   int threads = 128, blocks = (s->n_env + threads - 1) / threads;
   if (s->precision == B2S_F32) ctrl_reset_kernel<float><<<blocks, threads, 0, s->stream>>>(mask);
   else ctrl_reset_kernel<double><<<blocks, threads, 0, s->stream>>>(mask);
+  clear_warm_start(s, mask);  // an environment whose controller is rebuilt starts a new episode
   s->launches++;
   CUDA_TRY(cudaGetLastError());
   return B2S_OK;

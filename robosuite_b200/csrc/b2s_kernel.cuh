@@ -197,6 +197,19 @@ __global__ void reset_kernel(const uint8_t* mask) {
   s.warn[env] = 0;
 }
 
+// per-episode hidden state of the collision pipeline: the GJK warm-start directions of the environments being reset
+// (a replay from a restored state must not depend on what ran before: tests/test_environments/test_action_playback.py)
+template <typename R>
+__global__ void cache_reset_kernel(const uint8_t* mask) {
+  const DModel<R>& m = cmodel<R>();
+  const DState<R>& s = cstate<R>();
+  if (!s.gjk_cache) return;
+  size_t per = (size_t)m.npair * 3, idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= per * (size_t)s.n_env) return;
+  if (mask && !mask[idx / per]) return;
+  s.gjk_cache[idx] = 0;
+}
+
 // translational / rotational Jacobian of a site from the exported cdof and site_xpos (valid after forward/step1)
 template <typename R>
 __global__ void jac_site_kernel(int site, R* jacp, R* jacr) {

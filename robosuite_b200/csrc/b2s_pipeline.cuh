@@ -91,7 +91,19 @@ template <typename R> DEV void ws_store(const Eng<R>& e, R* row, const PhaseIO& 
 
 // A launch covers one group of environments [env0, env0 + nenv); groups run on separate streams so that the tail of one
 // group's kernel (its slowest environment) overlaps with other groups' work.
-struct Grp { int env0, nenv, gid; };
+struct Grp { int env0, nenv, gid, sub; };
+
+// -DB2S_INSTR: every launch stamps its first / last %globaltimer into st_begin / st_end (device timeline of the CUDA-graph
+// replay, which events cannot subdivide), warps record their clock64 cost per environment-substep.  Empty in product builds.
+#ifdef B2S_INSTR
+DEV unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define INSTR_SLOT(g, kind) ((((g).gid & 63) * 32 + ((g).sub & 31)) * 4 + (kind))
+#define INSTR_BEGIN(st, g, kind) if (threadIdx.x == 0 && (st).st_begin) atomicMin((st).st_begin + INSTR_SLOT(g, kind), gtimer());
+#define INSTR_END(st, g, kind) if ((threadIdx.x & 31) == 0 && (st).st_end) atomicMax((st).st_end + INSTR_SLOT(g, kind), gtimer());
+#else
+#define INSTR_BEGIN(st, g, kind)
+#define INSTR_END(st, g, kind)
+#endif
 #define EPA_PIPE_MAXV EPA_MAXV
 #define EPA_PIPE_MAXF EPA_MAXF
 
@@ -103,7 +115,8 @@ __global__ void __launch_bounds__(128) narrow_analytic_kernel(Grp g) {
   const DState<R>& s = cstate<R>();
   const WSLayout& L = c_L;
   int tid = blockIdx.x * blockDim.x + threadIdx.x;
-  if (tid >= s.cl_cnt[4 * g.gid]) return;
+  INSTR_BEGIN(s, g, 1)
+  if (tid >= s.cl_cnt[4 * g.gid]) { INSTR_END(s, g, 1) return; }
   tid += g.env0 * s.cl_maxa;  // this group's slice of the candidate list / output slots
   int code = s.cl_listA[tid];
   int env = code >> 12, pidx = code & 4095;
@@ -118,6 +131,7 @@ __global__ void __launch_bounds__(128) narrow_analytic_kernel(Grp g) {
   R* out = s.cl_outA + (size_t)tid * CL_RECA;
   out[0] = R(n);
   for (int k = 0; k < n * CREC; k++) out[1 + k] = buf[k];
+  INSTR_END(s, g, 1)
 }
 
 // convex pairs: ONE WARP per candidate pair (mesh support scans split over the lanes).  A block is one warp and owns one EPA
@@ -132,6 +146,7 @@ __global__ void __launch_bounds__(32) narrow_convex_kernel(Grp g) {
   int lane = threadIdx.x & 31;
   R* scratch = reinterpret_cast<R*>(smem_raw);
   const int cnt = s.cl_cnt[4 * g.gid + 1];
+  INSTR_BEGIN(s, g, 2)
   while (true) {
     int item = 0;
     if (lane == 0) item = atomicAdd(s.cl_cnt + 4 * g.gid + 3, 1);
@@ -156,6 +171,7 @@ __global__ void __launch_bounds__(32) narrow_convex_kernel(Grp g) {
     }
     __syncwarp();
   }
+  INSTR_END(s, g, 2)
 }
 
 // collect this environment's contacts from the work-list outputs, in static-pair order (what the fused collide produces)
@@ -231,6 +247,10 @@ __global__ void __launch_bounds__(512, 1) phase_kernel(int phases, int sub, int 
   R* smem = reinterpret_cast<R*>(smem_raw);
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   int env = blockIdx.x * wpb + warp;
+  INSTR_BEGIN(s, g, PH == 0 ? 0 : 3)
+#ifdef B2S_INSTR
+  long long instr_t0 = clock64();
+#endif
 #ifndef B2S_TAIL_BARRIERS
 #define B2S_TAIL_BARRIERS 0  // block barriers between the sub-phases of the merged tail kernel (instruction-cache locality)
 #endif
@@ -335,4 +355,9 @@ __global__ void __launch_bounds__(512, 1) phase_kernel(int phases, int sub, int 
   if (PH == 1 || PH == 2) {
     if (lane < 8) reinterpret_cast<int*>(row + L.hdr)[lane] = hdr[lane];
   }
+#ifdef B2S_INSTR
+  if (lane == 0 && s.cyc && (PH == 0 || PH == 5)) s.cyc[(E * 32 + (sub & 31)) * 2 + (PH == 0 ? 0 : 1)] = (float)(clock64() - instr_t0);
+  if (PH == 5 && lane == 0 && s.stats) { atomicAdd(s.stats + 16 + min(ncon, 32), 1); atomicAdd(s.stats + 64 + min(nefc, 64), 1); }
+#endif
+  INSTR_END(s, g, PH == 0 ? 0 : 3)
 }

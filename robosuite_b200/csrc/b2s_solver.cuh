@@ -479,6 +479,12 @@ template <typename R> DEVN int solve(Eng<R> e, int nefc, int ncon, int& warn) {
   __syncwarp();
   R prev_cost = 0;
   int niter = 0;
+#ifdef B2S_INSTR
+  int instr_ls = 0;
+#define INSTR_SOLVE_DONE { const DState<R>& st_ = cstate<R>(); if (lane == 0 && st_.stats) { atomicAdd(st_.stats + min(niter, 15), 1); atomicAdd(st_.stats + 129, instr_ls); atomicAdd(st_.stats + 130, 1); } }
+#else
+#define INSTR_SOLVE_DONE
+#endif
   // Ma = M qacc and jar = J qacc - aref are formed once and then moved along the search direction with the step
   // (Ma += alpha Mv, jar += alpha jv), as the reference engine does
   B2S_LOOP
@@ -621,6 +627,9 @@ template <typename R> DEVN int solve(Eng<R> e, int nefc, int ncon, int& warn) {
     B2S_LOOP
     for (int ls = 0; ls < (sizeof(R) == 4 ? 20 : 100); ls++) {
       ls_eval(e, nefc, ncon, first_contact_row, alpha, quad1, quad2, d1, d2);
+#ifdef B2S_INSTR
+      instr_ls++;
+#endif
       if (r_abs(d1) <= gtol) break;
       if (d1 < 0) lo = alpha; else hi = alpha;
       R next = alpha - d1 / d2;
@@ -647,5 +656,6 @@ template <typename R> DEVN int solve(Eng<R> e, int nefc, int ncon, int& warn) {
     qcon[i] = s;
   }
   __syncwarp();
+  INSTR_SOLVE_DONE
   return niter;
 }

@@ -91,6 +91,12 @@ struct DState {
   int* obs_fresh;  // [n_env] 1 = observation cache empty (set at reset, cleared by the first sample)
   R* task_vec;     // [n_env, task_dim] task table values after the last substep
   R* task_out;     // [n_env, 8]: body height, |grip site - body|, grasp flag, horizontal |body - body2|, obj-obj2 contact flag
+  // -DB2S_INSTR builds only (measurement aid, see b2s_instr in b2s_pipeline.cuh): device timeline of the graph replay and
+  // solver statistics.  Null in product builds.
+  unsigned long long* st_begin;  // [64 groups][32 substeps][4 kernels] first %globaltimer of the launch
+  unsigned long long* st_end;    //                                     last %globaltimer of the launch
+  int* stats;      // [256] histograms: 0..15 Newton iterations, 16..48 ncon, 64..128 nefc, 129 line-search evaluations, 130 solves
+  float* cyc;      // [n_env][32 substeps][2] clock64 cycles of this environment's warp in P0 / the tail kernel
 };
 
 // offsets (in units of R) of the per-warp shared-memory workspace

@@ -15,7 +15,7 @@ from .mjcf.compiler import Model, compile_mjcf, pack_model
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
-B2S_F32, B2S_F64, B2S_I32 = 0, 1, 2
+B2S_F32, B2S_F64, B2S_I32, B2S_I64 = 0, 1, 2, 3
 
 
 class B2SError(SimulationError, RuntimeError):
@@ -82,7 +82,7 @@ class _DevArray:
         self._owner = owner
 
 
-_TYPESTR = {B2S_F32: "<f4", B2S_F64: "<f8", B2S_I32: "<i4"}
+_TYPESTR = {B2S_F32: "<f4", B2S_F64: "<f8", B2S_I32: "<i4", B2S_I64: "<i8"}
 
 
 class BatchedSim:

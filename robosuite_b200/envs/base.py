@@ -288,12 +288,15 @@ class BatchedMujocoEnv:
         qpos: [nq] or [N, nq]"""
         import torch
 
-        q = torch.as_tensor(np.asarray(qpos), dtype=self.dtype, device=self.device)
+        def dev(x):
+            return x.to(device=self.device, dtype=self.dtype) if torch.is_tensor(x) else torch.as_tensor(np.asarray(x), dtype=self.dtype, device=self.device)
+
+        q = dev(qpos)
         self.sim.qpos[:] = q if q.ndim == 2 else q.unsqueeze(0).expand(self.num_envs, -1)
         if qvel is None:
             self.sim.qvel[:] = 0
         else:
-            v = torch.as_tensor(np.asarray(qvel), dtype=self.dtype, device=self.device)
+            v = dev(qvel)
             self.sim.qvel[:] = v if v.ndim == 2 else v.unsqueeze(0).expand(self.num_envs, -1)
         self.sim.qacc[:] = 0
         self.sim.qacc_warmstart[:] = 0

@@ -163,3 +163,12 @@ class OracleSim:
 
     def get_state(self):
         return torch.cat([self.time[:, None], self.qpos, self.qvel], dim=1)
+
+    # controller state arrays of BatchedSim (read-only views of the oracles' CtrlState)
+    def _cs(self, field, n):
+        return torch.as_tensor([[getattr(o.ctrl_state, field)[k] for k in range(n)] for o in self.o], dtype=torch.float64)
+
+    ctrl_goal_pos = property(lambda self: self._cs("goal_pos", 3))
+    ctrl_goal_ori = property(lambda self: self._cs("goal_ori", 9))
+    ctrl_initial_joint = property(lambda self: self._cs("initial_joint", 8))
+    ctrl_grip_state = property(lambda self: self._cs("grip_action", 4))
