@@ -23,7 +23,8 @@ enum { B2S_F32 = 0, B2S_F64 = 1, B2S_I32 = 2, B2S_I64 = 3 };
 /* controller kinds for the fused control step (controller_config "type", controllers/parts/controller_factory.py:145) */
 /* arm part controllers: controllers/parts/arm/osc.py, parts/generic/joint_vel.py, joint_pos.py, joint_tor.py.  The two joint-space
  * kinds 3 / 4 keep their per-joint scaling in jv_in/out_*, their gains in jv_kp / jv_kd (kd = 2 sqrt(kp) damping_ratio). */
-enum { B2S_CTRL_NONE = 0, B2S_CTRL_OSC_POSE = 1, B2S_CTRL_JOINT_VELOCITY = 2, B2S_CTRL_JOINT_POSITION = 3, B2S_CTRL_JOINT_TORQUE = 4 };
+enum { B2S_CTRL_NONE = 0, B2S_CTRL_OSC_POSE = 1, B2S_CTRL_JOINT_VELOCITY = 2, B2S_CTRL_JOINT_POSITION = 3, B2S_CTRL_JOINT_TORQUE = 4,
+       B2S_CTRL_OSC_POSITION = 5 /* controllers/parts/arm/osc.py:152-166: 3-dim arm action, orientation held */ };
 
 /* MjSim.from_xml_string (binding_utils.py:1074-1087): `model_blob` is the flat compiled model produced by
  * robosuite_b200.mjcf.compiler.pack_model (host memory).  precision: B2S_F32 (production) or B2S_F64 (debug). */

@@ -103,11 +103,18 @@ def resolve(model, composite_cfg, cfg_struct_cls, robot_prefix="robot0_", grippe
         raise NotImplementedError("fused OSC path implements fixed impedance, delta inputs in the base frame")
     if arm.get("interpolation") is not None:
         raise NotImplementedError("interpolators are not implemented")
+    if arm["type"] in ("OSC_POSE", "OSC_POSITION"):
+        # the reference itself raises NotImplementedError when a goal would have to be clipped (osc.py:345-347 `position_limits`,
+        # :398-400 `orientation_limits`): same behaviour, at configuration time instead of at the first set_goal
+        if arm.get("position_limits") is not None:
+            raise NotImplementedError("OSC position_limits: not implemented (the reference raises in compute_goal_pos, osc.py:345-347)")
+        if arm.get("orientation_limits") is not None and np.array(arm.get("orientation_limits")).any():
+            raise NotImplementedError("OSC orientation_limits: not implemented (the reference raises in compute_goal_ori, osc.py:398-400)")
     jn, an, sn = model.names["joint"], model.names["actuator"], model.names["site"]
     # arm joints: the robot's own hinge joints (robots/robot.py:302-332 collects them through the robot model)
     arm_j = [i for i, n in enumerate(jn) if n and n.startswith(robot_prefix) and int(model.jnt_type[i]) == 3]
     c = cfg_struct_cls()
-    # kind 5 (OSC_POSITION) exists in the CPU oracle only so far: b2s_ctrl_config rejects it on the device
+    # kind 5 = OSC_POSITION (3-dim arm action; the orientation goal is re-anchored at every policy step)
     c.kind = {"OSC_POSE": 1, "JOINT_VELOCITY": 2, "JOINT_POSITION": 3, "JOINT_TORQUE": 4, "OSC_POSITION": 5}[arm["type"]]
     c.n_arm = len(arm_j)
     for k, j in enumerate(arm_j):

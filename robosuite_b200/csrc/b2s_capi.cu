@@ -71,6 +71,10 @@ struct b2s_sim {
   std::vector<TlEv> tl_events;
   double tl_mean_us[8] = {0}; int tl_count[8] = {0};
   int merge_tail = 1;  // pipeline: constraint rows + controller + solve in ONE launch (B2S_MERGE_TAIL)
+  int ctrl_split = 1;  // pipeline: OSC controller as its own thread-per-environment kernel (B2S_CTRL_SPLIT=0: inside the tail kernel)
+  int ctrl_fork = 1;   // ... on a side stream, beside the collision narrow phase (B2S_CTRL_FORK=0: in line after phase 0)
+  std::vector<cudaStream_t> cstreams;
+  std::vector<cudaEvent_t> cev_fork, cev_join;
   std::vector<cudaStream_t> gstreams;
   std::vector<cudaEvent_t> gevents;
   cudaEvent_t fork_event = nullptr, in_event = nullptr, out_event = nullptr;
@@ -493,10 +497,12 @@ int b2s_create(const void* blob_host, size_t nbytes, int n_env, int device, int 
   s->wpb_fused = wpbf;
   s->smem_fused = per_warp_fused * wpbf;
   cudaError_t e1 = precision == B2S_F32
-                       ? cudaFuncSetAttribute(step_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_fused)
-                       : cudaFuncSetAttribute(step_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_fused);
+                       ? cudaFuncSetAttribute(step_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
+                       : cudaFuncSetAttribute(step_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e1 == cudaSuccess) {
-    int sb = (int)s->smem_bytes;
+    // the attribute belongs to the FUNCTION, not to the handle: always opt in to the device maximum (a later handle with a
+    // smaller workspace must not lower the limit of an earlier one - that broke mixed-task batches in round 1)
+    int sb = 227 * 1024;
     if (precision == B2S_F32) {
       cudaFuncSetAttribute(phase_kernel<float, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
       cudaFuncSetAttribute(phase_kernel<float, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
@@ -528,6 +534,9 @@ void b2s_destroy(b2s_sim* s) {
   cudaSetDevice(s->device);
   for (void* p : s->allocs) cudaFree(p);
   for (auto q : s->gstreams) cudaStreamDestroy(q);
+  for (auto q : s->cstreams) cudaStreamDestroy(q);
+  for (auto ev : s->cev_fork) cudaEventDestroy(ev);
+  for (auto ev : s->cev_join) cudaEventDestroy(ev);
   for (auto ev : s->gevents) cudaEventDestroy(ev);
   if (s->fork_event) cudaEventDestroy(s->fork_event);
   if (s->in_event) cudaEventDestroy(s->in_event);
@@ -620,6 +629,8 @@ template <typename R> static int enqueue_pipeline(b2s_sim* s, DState<R>& st, int
     int blocks = (g.nenv + s->wpb - 1) / s->wpb;
     int nA = g.nenv * st.cl_maxa, nG = g.nenv * st.cl_maxg;
     const int cvx_blocks = 148 * 24;
+    const bool ctrl_ext = (phases & PH_CTRL_EXT) != 0;
+    cudaStream_t cq = (ctrl_ext && s->ctrl_fork) ? s->cstreams[gi] : q;
     // B2S_TIMELINE=1 (with B2S_NO_GRAPH=1): timing events between the launches, per-kernel means on stderr (debug aid)
     auto mark = [&](int type) {
       if (!s->timeline) return;
@@ -633,12 +644,18 @@ template <typename R> static int enqueue_pipeline(b2s_sim* s, DState<R>& st, int
       mark(1);
       phase_kernel<R, 0><<<blocks, threads, s->smem_bytes, q>>>(phases, sub, nsub, action, g);
       mark(2);
+      if (ctrl_ext) {  // controller: one thread per environment, needs only phase 0's outputs -> runs beside the narrow phase
+        if (cq != q) { CUDA_TRY(cudaEventRecord(s->cev_fork[gi], q)); CUDA_TRY(cudaStreamWaitEvent(cq, s->cev_fork[gi], 0)); }
+        ctrl_osc_kernel<R><<<(g.nenv + OSC_TPB - 1) / OSC_TPB, OSC_TPB, osc_smem_bytes<R>(), cq>>>(sub, action, g.env0, g.nenv, g.gid);
+        if (cq != q) CUDA_TRY(cudaEventRecord(s->cev_join[gi], cq));
+      }
       // upper bounds of the candidate counts size the grids; threads / warps beyond the device-side count exit at once
       if (!(s->debug_skip & 1)) narrow_analytic_kernel<R><<<(nA + 127) / 128, 128, 0, q>>>(g);
       mark(3);
       // one warp per block (its EPA polytope is the block's shared memory), work items claimed through an atomic counter
       if (!(s->debug_skip & 2)) narrow_convex_kernel<R><<<nG < cvx_blocks ? nG : cvx_blocks, 32, epaw, q>>>(g);
       mark(4);
+      if (ctrl_ext && cq != q) CUDA_TRY(cudaStreamWaitEvent(q, s->cev_join[gi], 0));
       if (s->merge_tail) {
         phase_kernel<R, 5><<<blocks, threads, s->smem_bytes, q>>>(phases, sub, nsub, action, g);
         mark(5);
@@ -680,22 +697,24 @@ template <typename R> static int launch_pipeline_t(b2s_sim* s, DState<R>& st, in
     st.gjk_cache = getenv("B2S_NO_GJK_CACHE") ? nullptr : dev_zeros<R>(s, ne * (size_t)(s->precision == B2S_F32 ? s->mf.npair : s->md.npair) * 3);
     s->action_buf = dev_zeros<R>(s, ne * 16);
 #ifdef B2S_INSTR
-    st.st_begin = dev_zeros<unsigned long long>(s, 64 * 32 * 4); st.st_end = dev_zeros<unsigned long long>(s, 64 * 32 * 4);
+    st.st_begin = dev_zeros<unsigned long long>(s, 64 * 32 * 8); st.st_end = dev_zeros<unsigned long long>(s, 64 * 32 * 8);
     st.stats = dev_zeros<int>(s, 256); st.cyc = dev_zeros<float>(s, ne * 64);
-    s->arrays["st_begin"] = ArrayInfo{st.st_begin, B2S_I64, 1, {64 * 32 * 4, 0, 0, 0}};
-    s->arrays["st_end"] = ArrayInfo{st.st_end, B2S_I64, 1, {64 * 32 * 4, 0, 0, 0}};
+    s->arrays["st_begin"] = ArrayInfo{st.st_begin, B2S_I64, 1, {64 * 32 * 8, 0, 0, 0}};
+    s->arrays["st_end"] = ArrayInfo{st.st_end, B2S_I64, 1, {64 * 32 * 8, 0, 0, 0}};
     s->arrays["stats"] = ArrayInfo{st.stats, B2S_I32, 1, {256, 0, 0, 0}};
     s->arrays["cyc"] = ArrayInfo{st.cyc, B2S_F32, 3, {(int64_t)ne, 32, 2, 0}};
 #endif
     s->dirty = 1;
   }
 #ifdef B2S_INSTR
-  cudaMemsetAsync(st.st_begin, 0xff, sizeof(unsigned long long) * 64 * 32 * 4, s->stream);
-  cudaMemsetAsync(st.st_end, 0, sizeof(unsigned long long) * 64 * 32 * 4, s->stream);
+  cudaMemsetAsync(st.st_begin, 0xff, sizeof(unsigned long long) * 64 * 32 * 8, s->stream);
+  cudaMemsetAsync(st.st_end, 0, sizeof(unsigned long long) * 64 * 32 * 8, s->stream);
 #endif
   int rc = bind_constants(s);
   if (rc != B2S_OK) return rc;
   phases |= PH_WORKLIST;
+  const bool osc = s->ctrl.kind == B2S_CTRL_OSC_POSE || s->ctrl.kind == B2S_CTRL_OSC_POSITION;
+  if ((phases & PH_CTRL) && osc && s->ctrl_split && s->merge_tail) phases |= PH_CTRL_EXT;
   int G = s->ngroups;
   if (G > s->n_env) G = s->n_env;
   while ((int)s->gstreams.size() < G) {
@@ -704,6 +723,13 @@ template <typename R> static int launch_pipeline_t(b2s_sim* s, DState<R>& st, in
     CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     s->gstreams.push_back(st2); s->gevents.push_back(ev);
   }
+  while ((int)s->cstreams.size() < G) {
+    cudaStream_t st2; cudaEvent_t e1, e2;
+    CUDA_TRY(cudaStreamCreateWithFlags(&st2, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+    s->cstreams.push_back(st2); s->cev_fork.push_back(e1); s->cev_join.push_back(e2);
+  }
   if (!s->fork_event) {
     CUDA_TRY(cudaEventCreateWithFlags(&s->fork_event, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&s->in_event, cudaEventDisableTiming));
@@ -711,7 +737,7 @@ template <typename R> static int launch_pipeline_t(b2s_sim* s, DState<R>& st, in
     CUDA_TRY(cudaStreamCreateWithFlags(&s->pstream, cudaStreamNonBlocking));
   }
   // kernels per group-substep: phase 0, analytic + convex narrow phase, then the merged tail (or phases 2, [3], 4)
-  int launches_per_call = G * nsub * (3 + (s->merge_tail ? 1 : ((phases & PH_CTRL) ? 3 : 2)));
+  int launches_per_call = G * nsub * (3 + (s->merge_tail ? 1 : ((phases & PH_CTRL) ? 3 : 2)) + ((phases & PH_CTRL_EXT) ? 1 : 0));
   if (!s->use_graph) {
     rc = enqueue_pipeline<R>(s, st, phases, nsub, action, s->stream);
     s->launches += launches_per_call;
@@ -784,6 +810,8 @@ int b2s_set_mode(b2s_sim* s, int mode) {
   if (const char* ds = getenv("B2S_DEBUG_SKIP")) s->debug_skip = atoi(ds);
   if (getenv("B2S_TIMELINE")) { s->timeline = 2; s->use_graph = 0; }
   if (const char* mt = getenv("B2S_MERGE_TAIL")) s->merge_tail = atoi(mt) != 0;
+  if (const char* v = getenv("B2S_CTRL_SPLIT")) s->ctrl_split = atoi(v) != 0;
+  if (const char* v = getenv("B2S_CTRL_FORK")) s->ctrl_fork = atoi(v) != 0;
   return B2S_OK;
 }
 
@@ -832,7 +860,7 @@ int b2s_jac_site(b2s_sim* s, int site_id, void* jacp, void* jacr) {
 int b2s_ctrl_config(b2s_sim* s, const b2s_ctrl_cfg* c) {
   if (!s || !c) return fail(B2S_ERR_ARG, "b2s_ctrl_config: bad argument");
   if (c->kind != B2S_CTRL_OSC_POSE && c->kind != B2S_CTRL_JOINT_VELOCITY && c->kind != B2S_CTRL_JOINT_POSITION &&
-      c->kind != B2S_CTRL_JOINT_TORQUE && c->kind != B2S_CTRL_NONE)
+      c->kind != B2S_CTRL_JOINT_TORQUE && c->kind != B2S_CTRL_OSC_POSITION && c->kind != B2S_CTRL_NONE)
     return fail(B2S_ERR_UNSUPPORTED, "controller kind not implemented");
   if (c->n_arm > 8 || c->n_grip > 4) return fail(B2S_ERR_ARG, "b2s_ctrl_config: too many joints");
   CtrlCfgDev& d = s->ctrl;

@@ -178,8 +178,9 @@ DEVN void ctrl_run(Eng<R> e, CtrlState<R>& cs, int env, const R* action) {
   const R* org_pos = e.p(L.spos) + 3 * cc.base_site; const R* org_ori = e.p(L.smat) + 9 * cc.base_site;
   if (policy_step) {
     const R* act = action + (size_t)env * cc.action_dim;
-    R sd[6];
-    for (int k = 0; k < 6; k++) {
+    const int od = cc.kind == 5 ? 3 : 6;  // OSC_POSITION (osc.py:152-166, 259-270): 3-dim arm action, zero orientation delta
+    R sd[6] = {0, 0, 0, 0, 0, 0};
+    for (int k = 0; k < od; k++) {
       R a = r_clamp(act[k], (R)cc.input_min[k], (R)cc.input_max[k]);
       R scale = (R)(fabs(cc.output_max[k] - cc.output_min[k]) / fabs(cc.input_max[k] - cc.input_min[k]));
       sd[k] = (a - (R)(0.5 * (cc.input_max[k] + cc.input_min[k]))) * scale + (R)(0.5 * (cc.output_max[k] + cc.output_min[k]));
@@ -193,7 +194,7 @@ DEVN void ctrl_run(Eng<R> e, CtrlState<R>& cs, int env, const R* action) {
     delta_rotmat(Rd, sd + 3);
     for (int i = 0; i < 3; i++)
       for (int j = 0; j < 3; j++) cs.goal_ori[3 * i + j] = Rd[3 * i] * cur[j] + Rd[3 * i + 1] * cur[3 + j] + Rd[3 * i + 2] * cur[6 + j];
-    R ga = act[6];
+    R ga = act[od];
     R sg = ga > 0 ? R(1) : (ga < 0 ? R(-1) : R(0));
     for (int g = 0; g < cc.n_grip; g++) cs.grip[g] = r_clamp(cs.grip[g] + (R)(cc.grip_sign[g] * cc.grip_speed) * sg, R(-1), R(1));
   }

@@ -97,13 +97,15 @@ struct Grp { int env0, nenv, gid, sub; };
 // replay, which events cannot subdivide), warps record their clock64 cost per environment-substep.  Empty in product builds.
 #ifdef B2S_INSTR
 DEV unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
-#define INSTR_SLOT(g, kind) ((((g).gid & 63) * 32 + ((g).sub & 31)) * 4 + (kind))
+#define INSTR_SLOT(g, kind) ((((g).gid & 63) * 32 + ((g).sub & 31)) * 8 + (kind))
 #define INSTR_BEGIN(st, g, kind) if (threadIdx.x == 0 && (st).st_begin) atomicMin((st).st_begin + INSTR_SLOT(g, kind), gtimer());
 #define INSTR_END(st, g, kind) if ((threadIdx.x & 31) == 0 && (st).st_end) atomicMax((st).st_end + INSTR_SLOT(g, kind), gtimer());
 #else
 #define INSTR_BEGIN(st, g, kind)
 #define INSTR_END(st, g, kind)
 #endif
+#include "b2s_ctrlkernel.cuh"
+
 #define EPA_PIPE_MAXV EPA_MAXV
 #define EPA_PIPE_MAXF EPA_MAXF
 
@@ -237,8 +239,12 @@ template <typename R> DEVN int gather_contacts(Eng<R> e, int env, int& warn) {
 
 // PH: 0 kinematics+velocity+crb, 1 collision, 2 constraint rows, 3 controller, 4 actuation+solve+integrate(+obs),
 //     5 = 2 + 3 + 4 in one launch (constraint rows, Jacobian and controller output never leave shared memory)
+#ifndef B2S_LB_THREADS
+#define B2S_LB_THREADS 512  // phase kernels: threads per block / resident blocks per SM the register allocation is sized for
+#define B2S_LB_BLOCKS 1
+#endif
 template <typename R, int PH>
-__global__ void __launch_bounds__(512, 1) phase_kernel(int phases, int sub, int nsub, const R* action, Grp g) {
+__global__ void __launch_bounds__(B2S_LB_THREADS, B2S_LB_BLOCKS) phase_kernel(int phases, int sub, int nsub, const R* action, Grp g) {
   const DModel<R>& m = cmodel<R>();
   const DState<R>& s = cstate<R>();
   const WSLayout& L = c_L;
@@ -317,7 +323,7 @@ __global__ void __launch_bounds__(512, 1) phase_kernel(int phases, int sub, int 
     __syncwarp();
   }
   TAIL_BAR(1)
-  if (PH == 3 || (PH == 5 && (phases & PH_CTRL))) {
+  if ((PH == 3 || (PH == 5 && (phases & PH_CTRL))) && !(phases & PH_CTRL_EXT)) {
     CtrlState<R> cs;
     ctrl_load(e, cs, env);
     ctrl_run(e, cs, env, sub == 0 ? action : (const R*)nullptr);

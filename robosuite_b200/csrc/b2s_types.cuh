@@ -23,6 +23,7 @@ enum {
   PH_POLICY = 32,    // first substep of a control step: consume `action` (set_goal)
   PH_PROFILE = 128,  // accumulate per-phase clock() cycles per environment into `prof`
   PH_WORKLIST = 256, // pipeline mode: collision narrow phase runs as global work-list kernels
+  PH_CTRL_EXT = 512, // pipeline mode: the controller ran as its own kernel (ctrl_osc_kernel), `ctrl` is already in HBM
   PH_OBS = 64        // write the observation row and the task outputs (after the last substep)
 };
 
@@ -93,7 +94,7 @@ struct DState {
   R* task_out;     // [n_env, 8]: body height, |grip site - body|, grasp flag, horizontal |body - body2|, obj-obj2 contact flag
   // -DB2S_INSTR builds only (measurement aid, see b2s_instr in b2s_pipeline.cuh): device timeline of the graph replay and
   // solver statistics.  Null in product builds.
-  unsigned long long* st_begin;  // [64 groups][32 substeps][4 kernels] first %globaltimer of the launch
+  unsigned long long* st_begin;  // [64 groups][32 substeps][8 kernel kinds] first %globaltimer of the launch
   unsigned long long* st_end;    //                                     last %globaltimer of the launch
   int* stats;      // [256] histograms: 0..15 Newton iterations, 16..48 ncon, 64..128 nefc, 129 line-search evaluations, 130 solves
   float* cyc;      // [n_env][32 substeps][2] clock64 cycles of this environment's warp in P0 / the tail kernel

@@ -140,7 +140,7 @@ def test_split_equals_fused_f32():
     assert abs(a[0] - b[0]) < 1e-6
 
 
-def _env_rollout(prec, n_steps, n=8, nsub=25, seed=11):
+def _env_rollout(prec, n_steps, n=8, nsub=25, seed=11, mode=0):
     """Fused control steps (25 x {step1, OSC_POSE + GRIP, step2} per launch) vs the oracle's env step."""
     import torch
     from oracle.pyoracle import CtrlCfg as OCfg
@@ -152,6 +152,9 @@ def _env_rollout(prec, n_steps, n=8, nsub=25, seed=11):
     sim = BatchedSim(model, n, precision=prec)
     dt = sim.dtype
     sim.ctrl_config(cc.resolve(model, cc.default_composite_config(), CtrlCfg))
+    if mode == 1:  # phase-kernel pipeline: the controller runs as ctrl_osc_kernel (one thread per environment)
+        sim.set_export(False)
+        sim.set_mode(1)
     sim.qpos.copy_(torch.as_tensor(q, dtype=dt))
     sim.forward()
     sim.ctrl_reset()
@@ -189,6 +192,19 @@ def test_env_step_f64():
     assert eq < 1e-7 and ev < 1e-5 and et < 1e-6
 
 
+def test_env_step_pipeline_f64():
+    """same rollout through the phase-kernel pipeline: P0 / work-list narrow phase / thread-per-environment OSC kernel / tail"""
+    eq, ev, et = _env_rollout("f64", 4, mode=1)
+    print("f64 env 4 control steps, pipeline + controller kernel: qpos %.3g qvel %.3g tau %.3g" % (eq, ev, et))
+    assert eq < 1e-7 and ev < 1e-5 and et < 1e-6
+
+
+def test_env_step_pipeline_f32():
+    eq, ev, et = _env_rollout("f32", 4, mode=1)
+    print("f32 env 4 control steps, pipeline + controller kernel: qpos %.3g qvel %.3g tau %.3g" % (eq, ev, et))
+    assert eq < 1e-4 and ev < 1e-3
+
+
 def test_env_step_f32_100_substeps():
     eq, ev, et = _env_rollout("f32", 4)
     print("f32 env 4 control steps (100 substeps): qpos %.3g qvel %.3g tau %.3g" % (eq, ev, et))
@@ -202,7 +218,7 @@ def test_env_step_f32_100_control_steps():
     assert eq < 5e-2
 
 
-def _scripted_rollout(mode, steps, no_cache):
+def _scripted_rollout(mode, steps, no_cache, ctrl_split=False):
     import os
     import torch
     from robosuite_b200 import controller_config as cc
@@ -219,6 +235,9 @@ def _scripted_rollout(mode, steps, no_cache):
         os.environ["B2S_NO_GJK_CACHE"] = "1"
     else:
         os.environ.pop("B2S_NO_GJK_CACHE", None)
+    # the thread-per-environment controller kernel orders its fp64 sums differently from the in-kernel controller (last-bit
+    # differences in the torques): bit-exactness of the two SCHEDULES is tested with the controller inside the tail kernel
+    os.environ["B2S_CTRL_SPLIT"] = "1" if ctrl_split else "0"
     sim = BatchedSim(model, n, precision="f32")
     sim.ctrl_config(cc.resolve(model, cc.default_composite_config(), CtrlCfg))
     sim.set_export(False)
@@ -233,6 +252,7 @@ def _scripted_rollout(mode, steps, no_cache):
     out = (sim.qpos.cpu().numpy().copy(), sim.qvel.cpu().numpy().copy())
     sim.close()
     os.environ.pop("B2S_NO_GJK_CACHE", None)
+    os.environ.pop("B2S_CTRL_SPLIT", None)
     return out
 
 
@@ -253,6 +273,17 @@ def test_pipeline_gjk_warm_start_changes_paths_not_results():
     dq = np.abs(a[0] - b[0]).max()
     print("pipeline(warm start) vs fused after 300 substeps: max |dqpos| %.3g" % dq)
     assert dq < 1e-4
+
+
+def test_split_controller_kernel_matches_in_kernel_controller():
+    """the OSC controller as its own thread-per-environment kernel (ctrl_osc_kernel, default in pipeline mode) vs the same
+    controller evaluated inside the tail kernel: same inputs, fp64 algebra in both, different summation order -> torques agree to
+    fp32 rounding; over 100 substeps of free-space motion the states stay within 1e-6"""
+    a = _scripted_rollout(1, 4, True, ctrl_split=False)
+    b = _scripted_rollout(1, 4, True, ctrl_split=True)
+    dq = np.abs(a[0] - b[0]).max()
+    print("split controller kernel vs in-kernel controller after 100 substeps: max |dqpos| %.3g" % dq)
+    assert np.isfinite(b[0]).all() and dq < 1e-5
 
 
 @pytest.mark.parametrize("name", ["Stack_Panda", "NutAssemblyRound_Panda", "Door_Panda", "PickPlace_Panda", "Lift_Sawyer"])

@@ -38,17 +38,19 @@ sim.env_step(act, 25)
 e1.record()
 torch.cuda.synchronize()
 step_ms = e0.elapsed_time(e1)
-b = sim.st_begin.cpu().numpy().astype(np.uint64).reshape(64, 32, 4)
-e = sim.st_end.cpu().numpy().astype(np.uint64).reshape(64, 32, 4)
+b = sim.st_begin.cpu().numpy().astype(np.uint64).reshape(64, 32, 8)
+e = sim.st_end.cpu().numpy().astype(np.uint64).reshape(64, 32, 8)
 G = int(os.environ.get("B2S_GROUPS", "4"))
 valid = e[:G, :25] > 0
 t0 = b[:G, :25][valid].min()
 B = (b[:G, :25].astype(np.float64) - float(t0)) / 1e3  # us
 E = (e[:G, :25].astype(np.float64) - float(t0)) / 1e3
-names = ["P0", "narrowA", "narrowG", "tail"]
+names = ["P0", "narrowA", "narrowG", "tail", "ctrl"]
 out = {"task": task, "robot": robot, "n_env": n, "controller": ctrl, "groups": G, "step_ms_events": step_ms,
        "span_us": float(E.max()), "kernels": {}, "gaps_us": {}}
 for k, nm in enumerate(names):
+    if not (e[:G, :25, k] > 0).any():
+        continue
     d = E[:, :, k] - B[:, :, k]
     out["kernels"][nm] = {"mean_us": float(d.mean()), "p50": float(np.median(d)), "max": float(d.max()), "sum_per_group_us": float(d.sum(1).mean())}
 # gaps between dependent launches of one group: end(prev) -> begin(next)
@@ -56,6 +58,9 @@ out["gaps_us"]["P0->narrowA"] = float((B[:, :, 1] - E[:, :, 0]).mean())
 out["gaps_us"]["narrowA->narrowG"] = float((B[:, :, 2] - E[:, :, 1]).mean())
 out["gaps_us"]["narrowG->tail"] = float((B[:, :, 3] - E[:, :, 2]).mean())
 out["gaps_us"]["tail->next P0"] = float((B[:, 1:, 0] - E[:, :-1, 3]).mean())
+if "ctrl" in out["kernels"]:
+    out["gaps_us"]["P0->ctrl"] = float((B[:, :, 4] - E[:, :, 0]).mean())
+    out["gaps_us"]["ctrl->tail"] = float((B[:, :, 3] - E[:, :, 4]).mean())
 per_group_busy = sum((E[:, :, k] - B[:, :, k]).sum(1) for k in range(4))
 out["per_group_kernel_time_us"] = [float(x) for x in per_group_busy]
 out["per_group_span_us"] = [float(E[g].max() - B[g].min()) for g in range(G)]
