@@ -134,6 +134,12 @@ int64_t b2s_launch_count(const b2s_sim* sim);
  * [4] convex narrow phase, [5] merged tail phase (or phase 2), [6] phase 3, [7] phase 4. */
 int b2s_timeline(b2s_sim* sim, int enable, double mean_us[8], int count[8]);
 
+/* Host-only diagnostic (no device needed): words per warp of the shared-memory layouts and of the global workspace row that a model
+ * of these dimensions gets - out_words[5] = fused kernel, phase 0, tail small tier, tail large tier, row.  out_layouts / out_pio may
+ * be NULL; see csrc/b2s_capi.cu for their packing (tests/test_cpu_layouts.py checks the layout invariants with them). */
+int b2s_debug_layouts(int nq, int nv, int nu, int nbody, int ncg, int nsite, int hc_stride, int maxcon, int maxefc, int mc_small,
+                      int me_small, int osc_in_tail, int* out_words, int* out_layouts, int* out_pio);
+
 #ifdef __cplusplus
 }
 #endif

@@ -50,19 +50,22 @@ struct b2s_sim {
   cudaStream_t stream = 0;
   std::vector<void*> allocs;
   std::map<std::string, ArrayInfo> arrays;
-  WSLayout L{};
+  WSLayout lay[B2S_NLAY]{};  // LAY_FULL (fused kernel), LAY_P0, LAY_TS / LAY_TL (tail tiers), LAY_ROW (global workspace row)
+  int slot = -1;             // constant-memory descriptor slot (per device)
+  int mc_small = 0, me_small = 0;  // capacities of the small tail tier (== maxcon / maxefc: no tiering)
+  int osc_in_tail = 0;       // layouts built for the in-kernel OSC controller (B2S_CTRL_SPLIT=0)
+  int wpb0 = 8, wpb5s = 8, wpb5l = 4;
+  size_t smem0 = 0, smem5s = 0, smem5l = 0;
   DModel<float> mf{};
   DModel<double> md{};
   DState<float> sf{};
   DState<double> sd{};
   CtrlCfgDev ctrl{};
   int has_ctrl = 0;
-  int wpb = 4;          // warps (environments) per block (pipeline phase kernels)
-  size_t smem_bytes = 0;
   int wpb_fused = 4;    // fused kernel: workspace + EPA polytope area per warp
   size_t smem_fused = 0;
   int64_t launches = 0;
-  int nq = 0, nv = 0, nu = 0, nbody = 0, ngeom = 0, nsite = 0, maxcon = 0, maxefc = 0;
+  int nq = 0, nv = 0, nu = 0, nbody = 0, ngeom = 0, nsite = 0, maxcon = 0, maxefc = 0, ncg = 0, hc_stride = 0;
   std::vector<double> qpos0;
   std::vector<int> site_bodyid, cgid;
   int has_obs = 0, export_env_step = 1, dirty = 1, profile = 0, mode = 0, worklist = 1, ngroups = 4;
@@ -70,7 +73,6 @@ struct b2s_sim {
   struct TlEv { int group, type; cudaEvent_t ev; };
   std::vector<TlEv> tl_events;
   double tl_mean_us[8] = {0}; int tl_count[8] = {0};
-  int merge_tail = 1;  // pipeline: constraint rows + controller + solve in ONE launch (B2S_MERGE_TAIL)
   int ctrl_split = 1;  // pipeline: OSC controller as its own thread-per-environment kernel (B2S_CTRL_SPLIT=0: inside the tail kernel)
   int ctrl_fork = 1;   // ... on a side stream, beside the collision narrow phase (B2S_CTRL_FORK=0: in line after phase 0)
   std::vector<cudaStream_t> cstreams;
@@ -82,7 +84,7 @@ struct b2s_sim {
   void* action_buf = nullptr;
   int use_graph = 1;
   std::map<long long, cudaGraphExec_t> graphs;
-  PhaseIO pio[B2S_NPHASE];
+  PhaseIO pio[B2S_NPIO];
   std::map<std::string, Region> reg;
 };
 
@@ -344,81 +346,202 @@ template <typename R> static void build_state(b2s_sim* s, const DModel<R>& m, DS
   }
 }
 
-static void build_layout(b2s_sim* s, int nq, int nv, int nu, int nb, int ncg, int ns, int mc, int me, int hc_stride) {
-  WSLayout& L = s->L;
+// ---- workspace layouts.  Every region is 16-byte aligned in offset and length (TMA bulk copies).
+struct LayB {
   int o = 0;
-  auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };  // every region 16-byte aligned (TMA bulk copies)
-  auto rec = [&](const char* name, int off, int n) { s->reg[name] = Region{off, (n + 3) & ~3, 0}; };
-  // persistent across substeps
-  L.qpos = take(nq); L.qvel = take(nv); L.qacc = take(nv); L.qacc_ws = take(nv); L.ctrl = take(nu);
-  // live from step1 to the end of the substep (controller, solver, observations read them)
-  L.xpos = take(3 * nb); L.xquat = take(4 * nb); L.xmat = take(9 * nb);
-  L.cdof = take(6 * nv); L.cvel = take(6 * nb);
-  L.M = take(nv * nv); L.H = take(nv * nv);
-  L.bias = take(nv); L.passive = take(nv); L.qact = take(nv); L.qsmooth = take(nv); L.qaccs = take(nv); L.qcon = take(nv);
-  L.spos = take(3 * ns); L.smat = take(9 * ns);
-  L.c_pos = take(3 * mc); L.c_frame = take(3 * mc); L.c_dist = take(mc); L.c_fric = take(3 * mc);
-  L.c_solref = 0; L.c_solimp = 0;
-  L.c_mu = 0; L.c_int = take(5 * mc);
-  L.e_D = take(me); L.e_R = take(me); L.e_aref = take(me); L.e_jar = take(me); L.e_jv = take(me);
-  L.e_force = take(me); L.e_floss = take(me); L.e_int = take(me);
-  L.Ma = take(nv); L.grad = take(nv); L.search = take(nv); L.Mv = take(nv);
+  int take(int n) { int r = o; o += (n + 3) & ~3; return r; }
+};
+struct Dims { int nq, nv, nu, nb, ncg, ns, hc; };
+
+// the one-size-fits-all layout of the fused kernel (every phase's regions at once)
+static void layout_full(const Dims& d, int mc, int me, WSLayout& L) {
+  LayB B;
+  int nq = d.nq, nv = d.nv, nu = d.nu, nb = d.nb, ncg = d.ncg, ns = d.ns;
+  L = WSLayout{};
+  L.mc = mc; L.me = me;
+  L.qpos = B.take(nq); L.qvel = B.take(nv); L.qacc = B.take(nv); L.qacc_ws = B.take(nv); L.ctrl = B.take(nu);
+  L.xpos = B.take(3 * nb); L.xquat = B.take(4 * nb); L.xmat = B.take(9 * nb);
+  L.cdof = B.take(6 * nv); L.cvel = B.take(6 * nb);
+  L.M = B.take(nv * nv); L.H = B.take(nv * nv);
+  L.bias = B.take(nv); L.passive = B.take(nv); L.qact = B.take(nv); L.qsmooth = B.take(nv); L.qaccs = B.take(nv); L.qcon = B.take(nv);
+  L.spos = B.take(3 * ns); L.smat = B.take(9 * ns);
+  L.c_pos = B.take(3 * mc); L.c_frame = B.take(3 * mc); L.c_dist = B.take(mc); L.c_fric = B.take(3 * mc); L.c_int = B.take(5 * mc);
+  L.e_D = B.take(me); L.e_R = B.take(me); L.e_aref = B.take(me); L.e_jar = B.take(me); L.e_jv = B.take(me);
+  L.e_force = B.take(me); L.e_floss = B.take(me); L.e_int = B.take(me);
+  L.Ma = B.take(nv); L.grad = B.take(nv); L.search = B.take(nv); L.Mv = B.take(nv);
   // union: kinematics intermediates that are dead once collision is done  |  the constraint Jacobian
-  int ubase = o;
-  L.xipos = take(3 * nb); L.cdofdot = take(6 * nv); L.cinert = take(10 * nb); L.frne = take(6 * nb); L.ffl = take(6 * nb);
-  L.gpos = take(3 * ncg); L.gmat = take(9 * ncg);
-  int uend = o;
+  int ubase = B.o;
+  L.xipos = B.take(3 * nb); L.cdofdot = B.take(6 * nv); L.cinert = B.take(10 * nb); L.frne = B.take(6 * nb); L.ffl = B.take(6 * nb);
+  L.gpos = B.take(3 * ncg); L.gmat = B.take(9 * ncg);
   L.J = ubase;
-  if (ubase + me * nv > uend) uend = ubase + ((me * nv + 3) & ~3);
-  o = uend;
-  int sc = 10 * nb;
-  if (200 > sc) sc = 200;  // candidate lists of the fused collision
-  int hs = me + hc_stride * mc + 64;  // + support dof list of the Hessian assembly
-  if (hs > sc) sc = hs;
-  if (9 * mc > sc) sc = 9 * mc;
+  if (ubase + me * nv > B.o) B.o = ubase + ((me * nv + 3) & ~3);
+  int sc = std::max(std::max(10 * nb, 200), std::max(me + d.hc * mc + 64, 9 * mc));
   if (sc < 672) sc = 672;  // controller work area (336 doubles)
-  L.scratch_size = sc;
-  L.scratch = take(sc);
-  L.hdr = take(8);
-  L.total = (o + 3) & ~3;  // rows stay 16-byte aligned (TMA bulk copies of workspace regions)
+  L.scratch_size = sc; L.scratch = B.take(sc);
+  L.hdr = B.take(8);
+  L.total = B.o;
   L.fused_stride = L.total + ((9 * EPA_MAXV + 4 * EPA_MAXF + EPA_MAXF + 8 + 3) & ~3);
-  rec("xpos", L.xpos, 3 * nb); rec("xquat", L.xquat, 4 * nb); rec("xmat", L.xmat, 9 * nb); rec("cdof", L.cdof, 6 * nv);
-  rec("cvel", L.cvel, 6 * nb); rec("M", L.M, nv * nv); rec("bias", L.bias, nv); rec("passive", L.passive, nv);
-  rec("spos", L.spos, 3 * ns); rec("smat", L.smat, 9 * ns); rec("gpos", L.gpos, 3 * ncg); rec("gmat", L.gmat, 9 * ncg);
-  rec("c_pos", L.c_pos, 3 * mc); rec("c_frame", L.c_frame, 3 * mc); rec("c_dist", L.c_dist, mc); rec("c_fric", L.c_fric, 3 * mc);
-  rec("c_int", L.c_int, 5 * mc); rec("e_D", L.e_D, me); rec("e_R", L.e_R, me); rec("e_aref", L.e_aref, me);
-  rec("e_floss", L.e_floss, me); rec("e_int", L.e_int, me);
-  s->reg["J"] = Region{L.J, (me * nv + 3) & ~3, 1};
-  // adjacent regions merge into one span (one bulk copy); the dynamic Jacobian span stays on its own
-  auto spans = [&](std::initializer_list<const char*> names, Region* out, int& n, int* words, int* dyn) {
-    std::vector<Region> v;
-    for (const char* nm : names) v.push_back(s->reg[nm]);
-    std::sort(v.begin(), v.end(), [](const Region& a, const Region& b) { return a.off < b.off; });
-    n = 0;
-    if (words) *words = 0;
-    if (dyn) *dyn = 0;
-    for (const Region& r : v) {
-      if (n > 0 && !r.dyn && !out[n - 1].dyn && out[n - 1].off + out[n - 1].len == r.off) out[n - 1].len += r.len;
-      else out[n++] = r;
-    }
-    for (int k = 0; k < n; k++) {
-      if (out[k].dyn) { if (dyn) *dyn = 1; }
-      else if (words) *words += out[k].len;
-    }
-  };
-  auto mk = [&](PhaseIO& io, std::initializer_list<const char*> ld, std::initializer_list<const char*> st) {
-    spans(ld, io.load, io.nload, &io.load_words, &io.load_dyn);
-    spans(st, io.store, io.nstore, nullptr, nullptr);
-  };
-  mk(s->pio[0], {}, {"xpos", "xquat", "xmat", "cdof", "cvel", "M", "bias", "passive", "spos", "smat", "gpos", "gmat"});
-  mk(s->pio[1], {"gpos", "gmat"}, {"c_pos", "c_frame", "c_dist", "c_fric", "c_int"});
-  mk(s->pio[2], {"cdof"}, {"J", "e_D", "e_R", "e_aref", "e_floss", "e_int", "c_int", "c_fric", "c_dist"});
-  mk(s->pio[3], {"cdof", "cvel", "M", "bias", "spos", "smat"}, {});
-  mk(s->pio[5], {"cdof", "cvel", "M", "bias", "passive", "xpos", "xquat", "spos", "smat"}, {});
-  mk(s->pio[4], {"M", "bias", "passive", "J", "e_D", "e_R", "e_aref", "e_floss", "e_int", "c_fric", "c_int", "c_dist", "xpos", "xquat", "spos", "smat"}, {});
 }
 
-static b2s_sim* g_owner[64] = {nullptr};
+// phase 0: kinematics, velocity stage, CRB, broad phase.  The regions it hands to the other kernels come first, in row order.
+static void layout_p0(const Dims& d, WSLayout& L) {
+  LayB B;
+  int nq = d.nq, nv = d.nv, nb = d.nb, ncg = d.ncg, ns = d.ns;
+  L = WSLayout{};
+  L.qpos = B.take(nq); L.qvel = B.take(nv);
+  L.xpos = B.take(3 * nb); L.xquat = B.take(4 * nb); L.cdof = B.take(6 * nv); L.cvel = B.take(6 * nb);
+  bool m_own = 12 * nb < nv * nv;  // otherwise M (written by crb) lives over frne + ffl (dead after velocity)
+  if (m_own) L.M = B.take(nv * nv);
+  L.bias = B.take(nv); L.passive = B.take(nv); L.spos = B.take(3 * ns); L.smat = B.take(9 * ns);
+  L.gpos = B.take(3 * ncg); L.gmat = B.take(9 * ncg);
+  L.xmat = B.take(9 * nb); L.xipos = B.take(3 * nb); L.cdofdot = B.take(6 * nv); L.cinert = B.take(10 * nb);
+  L.frne = B.take(6 * nb); L.ffl = B.take(6 * nb);
+  if (!m_own) L.M = L.frne;
+  int sc = std::max(10 * nb, 200);  // kinematics locals (8 nb), composite inertias (10 nb), candidate lists (96 + 32 + ...)
+  L.scratch_size = sc; L.scratch = B.take(sc);
+  L.hdr = B.take(8);
+  L.total = B.o;
+}
+
+// tail kernel with capacities (mc, me).  osc_in_tail: the OSC controller runs inside (needs body velocities and site poses from
+// the start); otherwise the poses the observation / task tables read arrive late, over the dead constraint Jacobian.
+static void layout_tail(const Dims& d, int mc, int me, bool osc_in_tail, WSLayout& L) {
+  LayB B;
+  int nq = d.nq, nv = d.nv, nu = d.nu, nb = d.nb, ns = d.ns;
+  L = WSLayout{};
+  L.mc = mc; L.me = me;
+  L.qpos = B.take(nq); L.qvel = B.take(nv); L.qacc = B.take(nv); L.qacc_ws = B.take(nv); L.ctrl = B.take(nu);
+  L.cdof = B.take(6 * nv);
+  L.M = B.take(nv * nv); L.H = B.take(nv * nv);
+  L.bias = B.take(nv); L.passive = B.take(nv); L.qact = B.take(nv); L.qsmooth = B.take(nv); L.qaccs = B.take(nv); L.qcon = B.take(nv);
+  L.c_pos = B.take(3 * mc); L.c_frame = B.take(3 * mc); L.c_dist = B.take(mc); L.c_fric = B.take(3 * mc); L.c_int = B.take(5 * mc);
+  L.e_D = B.take(me); L.e_R = B.take(me); L.e_aref = B.take(me); L.e_jar = B.take(me); L.e_jv = B.take(me);
+  L.e_force = B.take(me); L.e_floss = B.take(me); L.e_int = B.take(me);
+  L.Ma = B.take(nv); L.grad = B.take(nv); L.search = B.take(nv); L.Mv = B.take(nv);
+  L.J = B.o;
+  int jwords = (me * nv + 3) & ~3;
+  if (osc_in_tail) {
+    B.o += jwords;
+    L.xpos = B.take(3 * nb); L.xquat = B.take(4 * nb); L.spos = B.take(3 * ns); L.smat = B.take(9 * ns); L.cvel = B.take(6 * nb);
+  } else {
+    LayB O; O.o = B.o;  // overlay on J: loaded after the solve, before the observation sample
+    L.xpos = O.take(3 * nb); L.xquat = O.take(4 * nb); L.spos = O.take(3 * ns); L.smat = O.take(9 * ns);
+    B.o = std::max(B.o + jwords, O.o);
+  }
+  int sc = std::max(me + d.hc * mc + 64, 9 * mc);
+  if (osc_in_tail && sc < 672) sc = 672;  // in-kernel OSC work area (336 doubles)
+  L.scratch_size = sc; L.scratch = B.take(sc);
+  L.hdr = B.take(8);
+  L.total = B.o;
+}
+
+// global workspace row: what phase 0 hands to the narrow phase, the controller kernel and the tail
+static void layout_row(const Dims& d, WSLayout& L) {
+  LayB B;
+  int nv = d.nv, nb = d.nb, ncg = d.ncg, ns = d.ns;
+  L = WSLayout{};
+  L.xpos = B.take(3 * nb); L.xquat = B.take(4 * nb); L.cdof = B.take(6 * nv); L.cvel = B.take(6 * nb);
+  L.M = B.take(nv * nv); L.bias = B.take(nv); L.passive = B.take(nv); L.spos = B.take(3 * ns); L.smat = B.take(9 * ns);
+  L.gpos = B.take(3 * ncg); L.gmat = B.take(9 * ncg);
+  L.hdr = B.take(8);
+  L.total = B.o;
+}
+
+// load / store list of one phase: (shared-memory offset, row offset, words) per named region, adjacent regions merged into spans
+static void make_io(const Dims& d, const WSLayout& S, const WSLayout& ROW, std::initializer_list<const char*> names, Region* out, int& n, int* words) {
+  int nv = d.nv, nb = d.nb, ncg = d.ncg, ns = d.ns;
+  auto a4 = [](int x) { return (x + 3) & ~3; };
+  std::vector<Region> v;
+  for (const char* nm : names) {
+    std::string k = nm;
+    Region r{0, 0, 0, 0};
+#define REG(name, field, len_) if (k == name) { r.off = S.field; r.goff = ROW.field; r.len = a4(len_); }
+    REG("xpos", xpos, 3 * nb) REG("xquat", xquat, 4 * nb) REG("cdof", cdof, 6 * nv) REG("cvel", cvel, 6 * nb) REG("M", M, nv * nv)
+    REG("bias", bias, nv) REG("passive", passive, nv) REG("spos", spos, 3 * ns) REG("smat", smat, 9 * ns)
+    REG("gpos", gpos, 3 * ncg) REG("gmat", gmat, 9 * ncg)
+#undef REG
+    if (r.len > 0) v.push_back(r);
+  }
+  std::sort(v.begin(), v.end(), [](const Region& a, const Region& b) { return a.goff < b.goff; });
+  n = 0;
+  if (words) *words = 0;
+  for (const Region& r : v) {
+    if (n > 0 && out[n - 1].off + out[n - 1].len == r.off && out[n - 1].goff + out[n - 1].len == r.goff) out[n - 1].len += r.len;
+    else { if (n >= B2S_MAXREG) throw std::string("too many workspace spans"); out[n++] = r; }
+  }
+  if (words) for (int k = 0; k < n; k++) *words += out[k].len;
+}
+
+static void build_layouts(b2s_sim* s, int ncg, int hc_stride) {
+  Dims d{s->nq, s->nv, s->nu, s->nbody, ncg, s->nsite, hc_stride};
+  layout_full(d, s->maxcon, s->maxefc, s->lay[LAY_FULL]);
+  layout_p0(d, s->lay[LAY_P0]);
+  layout_tail(d, s->mc_small, s->me_small, s->osc_in_tail != 0, s->lay[LAY_TS]);
+  layout_tail(d, s->maxcon, s->maxefc, s->osc_in_tail != 0, s->lay[LAY_TL]);
+  layout_row(d, s->lay[LAY_ROW]);
+  for (int k = 0; k < B2S_NPIO; k++) s->pio[k] = PhaseIO{};
+  const WSLayout& ROW = s->lay[LAY_ROW];
+  make_io(d, s->lay[LAY_P0], ROW, {"xpos", "xquat", "cdof", "cvel", "M", "bias", "passive", "spos", "smat", "gpos", "gmat"},
+          s->pio[PIO_P0].store, s->pio[PIO_P0].nstore, nullptr);
+  for (int t = 0; t < 2; t++) {
+    const WSLayout& T = s->lay[t ? LAY_TL : LAY_TS];
+    PhaseIO& early = s->pio[t ? PIO_TL : PIO_TS];
+    PhaseIO& late = s->pio[t ? PIO_TL_LATE : PIO_TS_LATE];
+    if (s->osc_in_tail) make_io(d, T, ROW, {"cdof", "cvel", "M", "bias", "passive", "xpos", "xquat", "spos", "smat"}, early.load, early.nload, &early.load_words);
+    else {
+      make_io(d, T, ROW, {"cdof", "M", "bias", "passive"}, early.load, early.nload, &early.load_words);
+      make_io(d, T, ROW, {"xpos", "xquat", "spos", "smat"}, late.load, late.nload, &late.load_words);
+    }
+  }
+}
+
+// opt a kernel in to the device's maximum dynamic shared memory (the limit is the opt-in maximum MINUS the kernel's static shared
+// memory: asking for the full 227 KB on a kernel with a static mbarrier array is an invalid argument)
+template <typename F> static cudaError_t optin_max_smem(F fn, int device, int* limit_out = nullptr) {
+  cudaFuncAttributes a;
+  cudaError_t e = cudaFuncGetAttributes(&a, fn);
+  if (e != cudaSuccess) return e;
+  int optin = 0;
+  e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  if (e != cudaSuccess) return e;
+  int lim = optin - (int)a.sharedSizeBytes;
+  if (limit_out) *limit_out = lim;
+  return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+}
+
+// block shapes: warps per block bounded by the kernels' launch bounds and by 227 KB of shared memory per block
+static int fit_wpb(size_t per_warp, int cap) {
+  int w = cap;
+  while (w > 1 && per_warp * w > 226 * 1024) w--;
+  return w;
+}
+static int choose_blocks(b2s_sim* s) {
+  size_t rsz = s->precision == B2S_F32 ? 4 : 8;
+  size_t pw0 = s->lay[LAY_P0].total * rsz, pws = s->lay[LAY_TS].total * rsz, pwl = s->lay[LAY_TL].total * rsz, pwf = s->lay[LAY_FULL].fused_stride * rsz;
+  if (std::max(std::max(pw0, pws), std::max(pwl, pwf)) > 226 * 1024) return fail(B2S_ERR_UNSUPPORTED, "model workspace exceeds shared memory");
+  // warps per block: as many as the launch bounds allow while B2S_LBx_BLOCKS blocks still fit one SM's shared memory
+  auto pick = [&](size_t pw, int lb_threads, int lb_blocks) {
+    int cap = lb_threads / 32, w = cap;
+    while (w > 1 && (pw * w + 1024) * lb_blocks > 228 * 1024) w--;  // 1 KB per block is reserved by the system
+    if ((pw * w + 1024) * lb_blocks > 228 * 1024) w = fit_wpb(pw, cap);  // cannot reach the block count: largest block that fits
+    return w;
+  };
+  s->wpb0 = pick(pw0, B2S_LB0_THREADS, B2S_LB0_BLOCKS);
+  s->wpb5s = pick(pws, B2S_LB5_THREADS, B2S_LB5_BLOCKS);
+  s->wpb5l = fit_wpb(pwl, B2S_LB5_THREADS / 32);
+  if (const char* v = getenv("B2S_WPB0")) { int x = atoi(v); if (x >= 1 && x <= B2S_LB0_THREADS / 32 && pw0 * x <= 226 * 1024) s->wpb0 = x; }
+  if (const char* v = getenv("B2S_WPB5")) { int x = atoi(v); if (x >= 1 && x <= B2S_LB5_THREADS / 32 && pws * x <= 226 * 1024) s->wpb5s = x; }
+  s->smem0 = pw0 * s->wpb0; s->smem5s = pws * s->wpb5s; s->smem5l = pwl * s->wpb5l;
+  int wf = fit_wpb(pwf, 16);
+  s->wpb_fused = wf; s->smem_fused = pwf * wf;
+  if (getenv("B2S_VERBOSE"))
+    fprintf(stderr, "[b2s] slot %d words/warp: fused %d, P0 %d (%d warps/block), tail small %d [mc %d me %d] (%d warps/block), tail large %d [mc %d me %d] (%d), row %d\n",
+            s->slot, s->lay[LAY_FULL].fused_stride, s->lay[LAY_P0].total, s->wpb0, s->lay[LAY_TS].total, s->mc_small, s->me_small, s->wpb5s,
+            s->lay[LAY_TL].total, s->maxcon, s->maxefc, s->wpb5l, s->lay[LAY_ROW].total);
+  return B2S_OK;
+}
+
+static b2s_sim* g_slots[64][B2S_NSLOT] = {{nullptr}};  // live handles per device: descriptor slot owners
 
 // The phase / narrow-phase kernels need different amounts of per-thread local memory (stack).  By default the driver shrinks the
 // local-memory pool after a launch and grows it again for the next kernel that needs more - a device-wide reallocation worth
@@ -476,52 +599,41 @@ int b2s_create(const void* blob_host, size_t nbytes, int n_env, int device, int 
     int ncg, hcs;
     if (precision == B2S_F32) { build_model(s, b, s->mf); build_state(s, s->mf, s->sf); ncg = s->mf.ncg; hcs = s->mf.hc_stride; }
     else { build_model(s, b, s->md); build_state(s, s->md, s->sd); ncg = s->md.ncg; hcs = s->md.hc_stride; }
-    build_layout(s, s->nq, s->nv, s->nu, s->nbody, ncg, s->nsite, s->maxcon, s->maxefc, hcs);
+    s->ncg = ncg; s->hc_stride = hcs;
+    // small tail tier: capacities almost every environment of this task stays within (compiled into the model blob by the task
+    // class, B2S_TIER_SMALL="mc,me" overrides); environments that need more are re-run by the large tier
+    int nfl = precision == B2S_F32 ? s->mf.nfl : s->md.nfl;
+    s->mc_small = b.has("opt_maxcon_small") ? b.scalar_i("opt_maxcon_small") : s->maxcon;
+    s->me_small = b.has("opt_maxefc_small") ? b.scalar_i("opt_maxefc_small") : s->maxefc;
+    if (const char* v = getenv("B2S_TIER_SMALL")) { int a_ = 0, b_ = 0; if (sscanf(v, "%d,%d", &a_, &b_) == 2 && a_ > 0 && b_ > 0) { s->mc_small = a_; s->me_small = b_; } }
+    s->mc_small = std::min(std::max(s->mc_small, 4), s->maxcon);
+    s->me_small = std::min(std::max(s->me_small, nfl + 8), s->maxefc);  // friction-loss rows are always present
+    if (s->maxefc < nfl + 8) throw std::string("opt_maxefc too small for the model's friction-loss rows");
+    // descriptor slot
+    for (int k = 0; k < B2S_NSLOT && s->slot < 0; k++)
+      if (!g_slots[device & 63][k]) { g_slots[device & 63][k] = s; s->slot = k; }
+    if (s->slot < 0) throw std::string("more than 8 live handles on one device");
+    build_layouts(s, ncg, hcs);
   } catch (const std::string& e) {
     b2s_destroy(s);
     return fail(B2S_ERR_MODEL, "b2s_create: " + e);
   }
-  size_t rsz = precision == B2S_F32 ? 4 : 8;
-  size_t per_warp = (size_t)s->L.total * rsz;
-  size_t per_warp_fused = (size_t)s->L.fused_stride * rsz;
-  int wpb = 16;
-  while (wpb > 1 && per_warp * wpb > 227 * 1024) wpb--;
-  if (per_warp > 227 * 1024) { b2s_destroy(s); return fail(B2S_ERR_UNSUPPORTED, "model workspace exceeds shared memory"); }
-  const char* env_wpb = getenv("B2S_WARPS_PER_BLOCK");
-  if (env_wpb) { int v = atoi(env_wpb); if (v >= 1 && v <= 16 && per_warp * v <= 227 * 1024) wpb = v; }
-  s->wpb = wpb;
-  s->smem_bytes = per_warp * wpb;
-  int wpbf = 16;
-  while (wpbf > 1 && per_warp_fused * wpbf > 227 * 1024) wpbf--;
-  if (per_warp_fused > 227 * 1024) { b2s_destroy(s); return fail(B2S_ERR_UNSUPPORTED, "model workspace exceeds shared memory"); }
-  s->wpb_fused = wpbf;
-  s->smem_fused = per_warp_fused * wpbf;
-  cudaError_t e1 = precision == B2S_F32
-                       ? cudaFuncSetAttribute(step_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
-                       : cudaFuncSetAttribute(step_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  if (e1 == cudaSuccess) {
+  if (choose_blocks(s) != B2S_OK) { b2s_destroy(s); return B2S_ERR_UNSUPPORTED; }
+  {
     // the attribute belongs to the FUNCTION, not to the handle: always opt in to the device maximum (a later handle with a
     // smaller workspace must not lower the limit of an earlier one - that broke mixed-task batches in round 1)
-    int sb = 227 * 1024;
+    cudaError_t e1;
     if (precision == B2S_F32) {
-      cudaFuncSetAttribute(phase_kernel<float, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
-      cudaFuncSetAttribute(phase_kernel<float, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
-      cudaFuncSetAttribute(phase_kernel<float, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
-      cudaFuncSetAttribute(phase_kernel<float, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
-      cudaFuncSetAttribute(phase_kernel<float, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
-      e1 = cudaFuncSetAttribute(phase_kernel<float, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
-      cudaFuncSetAttribute(narrow_convex_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (9 * EPA_PIPE_MAXV + 4 * EPA_PIPE_MAXF + EPA_PIPE_MAXF + 8) * 4);
+      e1 = optin_max_smem(step_kernel<float>, device);
+      if (e1 == cudaSuccess) e1 = optin_max_smem(phase0_kernel<float>, device);
+      if (e1 == cudaSuccess) e1 = optin_max_smem(tail_kernel<float>, device);
     } else {
-      cudaFuncSetAttribute(phase_kernel<double, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
-      cudaFuncSetAttribute(phase_kernel<double, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
-      cudaFuncSetAttribute(phase_kernel<double, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
-      cudaFuncSetAttribute(phase_kernel<double, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
-      cudaFuncSetAttribute(phase_kernel<double, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
-      e1 = cudaFuncSetAttribute(phase_kernel<double, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
-      cudaFuncSetAttribute(narrow_convex_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (9 * EPA_PIPE_MAXV + 4 * EPA_PIPE_MAXF + EPA_PIPE_MAXF + 8) * 8);
+      e1 = optin_max_smem(step_kernel<double>, device);
+      if (e1 == cudaSuccess) e1 = optin_max_smem(phase0_kernel<double>, device);
+      if (e1 == cudaSuccess) e1 = optin_max_smem(tail_kernel<double>, device);
     }
+    if (e1 != cudaSuccess) { std::string msg = cudaGetErrorString(e1); b2s_destroy(s); return fail(B2S_ERR_CUDA, "cudaFuncSetAttribute: " + msg); }
   }
-  if (e1 != cudaSuccess) { std::string msg = cudaGetErrorString(e1); b2s_destroy(s); return fail(B2S_ERR_CUDA, "cudaFuncSetAttribute: " + msg); }
   *out = s;
   int rc = b2s_reset(s, nullptr);
   if (rc != 0) { b2s_destroy(s); *out = nullptr; return rc; }
@@ -530,8 +642,9 @@ int b2s_create(const void* blob_host, size_t nbytes, int n_env, int device, int 
 
 void b2s_destroy(b2s_sim* s) {
   if (!s) return;
-  if (g_owner[s->device & 63] == s) g_owner[s->device & 63] = nullptr;
+  if (s->slot >= 0 && g_slots[s->device & 63][s->slot] == s) g_slots[s->device & 63][s->slot] = nullptr;
   cudaSetDevice(s->device);
+  cudaDeviceSynchronize();  // kernels of this handle may still be reading its buffers
   for (void* p : s->allocs) cudaFree(p);
   for (auto q : s->gstreams) cudaStreamDestroy(q);
   for (auto q : s->cstreams) cudaStreamDestroy(q);
@@ -580,22 +693,40 @@ int b2s_array(b2s_sim* s, const char* name, void** dev_ptr, int* dtype, int* ndi
   return B2S_OK;
 }
 
-// constant-memory descriptors belong to one handle at a time (per device); re-upload when the owner changes or is dirty
+// upload this handle's descriptors into its constant-memory slot (only after a configuration change)
 static int bind_constants(b2s_sim* s) {
   CUDA_TRY(cudaSetDevice(s->device));
-  if (g_owner[s->device & 63] == s && !s->dirty) return B2S_OK;
+  if (!s->dirty) return B2S_OK;
+  const size_t k = (size_t)s->slot;
   if (s->precision == B2S_F32) {
-    CUDA_TRY(cudaMemcpyToSymbolAsync(c_model_f, &s->mf, sizeof(s->mf), 0, cudaMemcpyHostToDevice, s->stream));
-    CUDA_TRY(cudaMemcpyToSymbolAsync(c_state_f, &s->sf, sizeof(s->sf), 0, cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaMemcpyToSymbolAsync(c_model_f, &s->mf, sizeof(s->mf), k * sizeof(s->mf), cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaMemcpyToSymbolAsync(c_state_f, &s->sf, sizeof(s->sf), k * sizeof(s->sf), cudaMemcpyHostToDevice, s->stream));
   } else {
-    CUDA_TRY(cudaMemcpyToSymbolAsync(c_model_d, &s->md, sizeof(s->md), 0, cudaMemcpyHostToDevice, s->stream));
-    CUDA_TRY(cudaMemcpyToSymbolAsync(c_state_d, &s->sd, sizeof(s->sd), 0, cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaMemcpyToSymbolAsync(c_model_d, &s->md, sizeof(s->md), k * sizeof(s->md), cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaMemcpyToSymbolAsync(c_state_d, &s->sd, sizeof(s->sd), k * sizeof(s->sd), cudaMemcpyHostToDevice, s->stream));
   }
-  CUDA_TRY(cudaMemcpyToSymbolAsync(c_L, &s->L, sizeof(s->L), 0, cudaMemcpyHostToDevice, s->stream));
-  CUDA_TRY(cudaMemcpyToSymbolAsync(c_cc, &s->ctrl, sizeof(s->ctrl), 0, cudaMemcpyHostToDevice, s->stream));
-  CUDA_TRY(cudaMemcpyToSymbolAsync(c_pio, s->pio, sizeof(s->pio), 0, cudaMemcpyHostToDevice, s->stream));
-  g_owner[s->device & 63] = s;
+  CUDA_TRY(cudaMemcpyToSymbolAsync(c_lay, s->lay, sizeof(s->lay), k * sizeof(s->lay), cudaMemcpyHostToDevice, s->stream));
+  CUDA_TRY(cudaMemcpyToSymbolAsync(c_cc, &s->ctrl, sizeof(s->ctrl), k * sizeof(s->ctrl), cudaMemcpyHostToDevice, s->stream));
+  CUDA_TRY(cudaMemcpyToSymbolAsync(c_pio, s->pio, sizeof(s->pio), k * sizeof(s->pio), cudaMemcpyHostToDevice, s->stream));
+  // the host structs must outlive the asynchronous copies only until they are enqueued: pageable-memory sources are staged
   s->dirty = 0;
+  return B2S_OK;
+}
+
+// layouts depend on where the OSC controller runs; a change invalidates the captured graphs (they carry block shapes)
+static int rebuild_layouts(b2s_sim* s) {
+  const bool osc = s->ctrl.kind == B2S_CTRL_OSC_POSE || s->ctrl.kind == B2S_CTRL_OSC_POSITION;
+  int want = (osc && !s->ctrl_split) ? 1 : 0;
+  if (want == s->osc_in_tail && s->smem0 != 0) return B2S_OK;
+  s->osc_in_tail = want;
+  try { build_layouts(s, s->ncg, s->hc_stride); } catch (const std::string& e) { return fail(B2S_ERR_MODEL, e); }
+  int rc = choose_blocks(s);
+  if (rc != B2S_OK) return rc;
+  bool have_ws = s->precision == B2S_F32 ? s->sf.wsg != nullptr : s->sd.wsg != nullptr;
+  if (have_ws) { cudaSetDevice(s->device); cudaDeviceSynchronize(); }
+  for (auto& kv : s->graphs) cudaGraphExecDestroy(kv.second);
+  s->graphs.clear();
+  s->dirty = 1;
   return B2S_OK;
 }
 
@@ -604,9 +735,9 @@ static int launch(b2s_sim* s, int phases, int nsub, const void* action = nullptr
   if (rc != B2S_OK) return rc;
   int blocks = (s->n_env + s->wpb_fused - 1) / s->wpb_fused;
   if (s->precision == B2S_F32)
-    step_kernel<float><<<blocks, s->wpb_fused * 32, s->smem_fused, s->stream>>>(phases, nsub, (const float*)action);
+    step_kernel<float><<<blocks, s->wpb_fused * 32, s->smem_fused, s->stream>>>(phases, nsub, (const float*)action, s->slot);
   else
-    step_kernel<double><<<blocks, s->wpb_fused * 32, s->smem_fused, s->stream>>>(phases, nsub, (const double*)action);
+    step_kernel<double><<<blocks, s->wpb_fused * 32, s->smem_fused, s->stream>>>(phases, nsub, (const double*)action, s->slot);
   s->launches++;
   CUDA_TRY(cudaGetLastError());
   return B2S_OK;
@@ -616,17 +747,18 @@ static int launch(b2s_sim* s, int phases, int nsub, const void* action = nullptr
 
 // enqueue the launches of `nsub` substeps for every environment group; `q0` is the stream the caller forks from / joins to
 template <typename R> static int enqueue_pipeline(b2s_sim* s, DState<R>& st, int phases, int nsub, const R* action, cudaStream_t q0) {
-  const int threads = s->wpb * 32;
   const int epaw = (9 * EPA_PIPE_MAXV + 4 * EPA_PIPE_MAXF + EPA_PIPE_MAXF + 8) * (int)sizeof(R);
   int G = s->ngroups;
   if (G > s->n_env) G = s->n_env;
+  const bool tiered = s->mc_small < s->maxcon || s->me_small < s->maxefc;
   CUDA_TRY(cudaEventRecord(s->fork_event, q0));
   for (int gi = 0; gi < G; gi++) {
     cudaStream_t q = G == 1 ? q0 : s->gstreams[gi];
     if (G > 1) CUDA_TRY(cudaStreamWaitEvent(q, s->fork_event, 0));
     int e0 = (int)((long long)s->n_env * gi / G), e1 = (int)((long long)s->n_env * (gi + 1) / G);
-    Grp g{e0, e1 - e0, gi, 0};
-    int blocks = (g.nenv + s->wpb - 1) / s->wpb;
+    Grp g{e0, e1 - e0, gi, 0, s->slot};
+    int blocks0 = (g.nenv + s->wpb0 - 1) / s->wpb0, blocks5 = (g.nenv + s->wpb5s - 1) / s->wpb5s;
+    int blocksL = std::min((g.nenv + s->wpb5l - 1) / s->wpb5l, 2 * 148);  // large tier: warps claim overflowed environments
     int nA = g.nenv * st.cl_maxa, nG = g.nenv * st.cl_maxg;
     const int cvx_blocks = 148 * 24;
     const bool ctrl_ext = (phases & PH_CTRL_EXT) != 0;
@@ -640,13 +772,13 @@ template <typename R> static int enqueue_pipeline(b2s_sim* s, DState<R>& st, int
     for (int sub = 0; sub < nsub; sub++) {
       g.sub = sub;
       mark(0);
-      CUDA_TRY(cudaMemsetAsync(st.cl_cnt + 4 * gi, 0, 4 * sizeof(int), q));
+      CUDA_TRY(cudaMemsetAsync(st.cl_cnt + 8 * gi, 0, 8 * sizeof(int), q));
       mark(1);
-      phase_kernel<R, 0><<<blocks, threads, s->smem_bytes, q>>>(phases, sub, nsub, action, g);
+      phase0_kernel<R><<<blocks0, s->wpb0 * 32, s->smem0, q>>>(phases, g);
       mark(2);
       if (ctrl_ext) {  // controller: one thread per environment, needs only phase 0's outputs -> runs beside the narrow phase
         if (cq != q) { CUDA_TRY(cudaEventRecord(s->cev_fork[gi], q)); CUDA_TRY(cudaStreamWaitEvent(cq, s->cev_fork[gi], 0)); }
-        ctrl_osc_kernel<R><<<(g.nenv + OSC_TPB - 1) / OSC_TPB, OSC_TPB, osc_smem_bytes<R>(), cq>>>(sub, action, g.env0, g.nenv, g.gid);
+        ctrl_osc_kernel<R><<<(g.nenv + OSC_TPB - 1) / OSC_TPB, OSC_TPB, osc_smem_bytes<R>(), cq>>>(sub, action, g.env0, g.nenv, g.gid, s->slot);
         if (cq != q) CUDA_TRY(cudaEventRecord(s->cev_join[gi], cq));
       }
       // upper bounds of the candidate counts size the grids; threads / warps beyond the device-side count exit at once
@@ -656,16 +788,11 @@ template <typename R> static int enqueue_pipeline(b2s_sim* s, DState<R>& st, int
       if (!(s->debug_skip & 2)) narrow_convex_kernel<R><<<nG < cvx_blocks ? nG : cvx_blocks, 32, epaw, q>>>(g);
       mark(4);
       if (ctrl_ext && cq != q) CUDA_TRY(cudaStreamWaitEvent(q, s->cev_join[gi], 0));
-      if (s->merge_tail) {
-        phase_kernel<R, 5><<<blocks, threads, s->smem_bytes, q>>>(phases, sub, nsub, action, g);
-        mark(5);
-      } else {
-        phase_kernel<R, 2><<<blocks, threads, s->smem_bytes, q>>>(phases, sub, nsub, action, g);
-        mark(5);
-        if (phases & PH_CTRL) phase_kernel<R, 3><<<blocks, threads, s->smem_bytes, q>>>(phases, sub, nsub, action, g);
+      tail_kernel<R><<<blocks5, s->wpb5s * 32, s->smem5s, q>>>(phases, nsub, action, g, 0);
+      mark(5);
+      if (tiered) {
+        tail_kernel<R><<<blocksL, s->wpb5l * 32, s->smem5l, q>>>(phases, nsub, action, g, 1);
         mark(6);
-        phase_kernel<R, 4><<<blocks, threads, s->smem_bytes, q>>>(phases, sub, nsub, action, g);
-        mark(7);
       }
     }
     if (G > 1) {
@@ -680,12 +807,13 @@ template <typename R> static int enqueue_pipeline(b2s_sim* s, DState<R>& st, int
 template <typename R> static int launch_pipeline_t(b2s_sim* s, DState<R>& st, int phases, int nsub, const R* action) {
   if (!st.wsg) {
     R* p = nullptr;
-    if (cudaMalloc(&p, (size_t)s->n_env * s->L.total * sizeof(R)) != cudaSuccess) return fail(B2S_ERR_CUDA, "cudaMalloc(pipeline workspace) failed");
-    cudaMemsetAsync(p, 0, (size_t)s->n_env * s->L.total * sizeof(R), s->stream);
+    if (cudaMalloc(&p, (size_t)s->n_env * s->lay[LAY_ROW].total * sizeof(R)) != cudaSuccess) return fail(B2S_ERR_CUDA, "cudaMalloc(pipeline workspace) failed");
+    cudaMemsetAsync(p, 0, (size_t)s->n_env * s->lay[LAY_ROW].total * sizeof(R), s->stream);
     s->allocs.push_back(p);
     st.wsg = p;
     size_t ne = (size_t)s->n_env;
-    st.cl_cnt = dev_zeros<int>(s, 4 * 64);
+    st.cl_cnt = dev_zeros<int>(s, 8 * 64);
+    st.ovf_list = dev_zeros<int>(s, ne);
     // candidate capacity per environment: small models keep small grids (the narrow-phase grids are sized by these bounds)
     st.cl_maxa = s->maxcon <= 32 ? 8 : (s->maxcon <= 48 ? 16 : CL_MAXA);
     st.cl_maxg = s->maxcon <= 32 ? 16 : CL_MAXG;
@@ -698,10 +826,10 @@ template <typename R> static int launch_pipeline_t(b2s_sim* s, DState<R>& st, in
     s->action_buf = dev_zeros<R>(s, ne * 16);
 #ifdef B2S_INSTR
     st.st_begin = dev_zeros<unsigned long long>(s, 64 * 32 * 8); st.st_end = dev_zeros<unsigned long long>(s, 64 * 32 * 8);
-    st.stats = dev_zeros<int>(s, 256); st.cyc = dev_zeros<float>(s, ne * 64);
+    st.stats = dev_zeros<int>(s, 512); st.cyc = dev_zeros<float>(s, ne * 64);
     s->arrays["st_begin"] = ArrayInfo{st.st_begin, B2S_I64, 1, {64 * 32 * 8, 0, 0, 0}};
     s->arrays["st_end"] = ArrayInfo{st.st_end, B2S_I64, 1, {64 * 32 * 8, 0, 0, 0}};
-    s->arrays["stats"] = ArrayInfo{st.stats, B2S_I32, 1, {256, 0, 0, 0}};
+    s->arrays["stats"] = ArrayInfo{st.stats, B2S_I32, 1, {512, 0, 0, 0}};
     s->arrays["cyc"] = ArrayInfo{st.cyc, B2S_F32, 3, {(int64_t)ne, 32, 2, 0}};
 #endif
     s->dirty = 1;
@@ -710,11 +838,12 @@ template <typename R> static int launch_pipeline_t(b2s_sim* s, DState<R>& st, in
   cudaMemsetAsync(st.st_begin, 0xff, sizeof(unsigned long long) * 64 * 32 * 8, s->stream);
   cudaMemsetAsync(st.st_end, 0, sizeof(unsigned long long) * 64 * 32 * 8, s->stream);
 #endif
-  int rc = bind_constants(s);
-  if (rc != B2S_OK) return rc;
   phases |= PH_WORKLIST;
   const bool osc = s->ctrl.kind == B2S_CTRL_OSC_POSE || s->ctrl.kind == B2S_CTRL_OSC_POSITION;
-  if ((phases & PH_CTRL) && osc && s->ctrl_split && s->merge_tail) phases |= PH_CTRL_EXT;
+  if ((phases & PH_CTRL) && osc && s->ctrl_split) phases |= PH_CTRL_EXT;
+  { int rc2 = rebuild_layouts(s); if (rc2 != B2S_OK) return rc2; }  // before the descriptors are (re)uploaded
+  int rc = bind_constants(s);
+  if (rc != B2S_OK) return rc;
   int G = s->ngroups;
   if (G > s->n_env) G = s->n_env;
   while ((int)s->gstreams.size() < G) {
@@ -737,13 +866,14 @@ template <typename R> static int launch_pipeline_t(b2s_sim* s, DState<R>& st, in
     CUDA_TRY(cudaStreamCreateWithFlags(&s->pstream, cudaStreamNonBlocking));
   }
   // kernels per group-substep: phase 0, analytic + convex narrow phase, then the merged tail (or phases 2, [3], 4)
-  int launches_per_call = G * nsub * (3 + (s->merge_tail ? 1 : ((phases & PH_CTRL) ? 3 : 2)) + ((phases & PH_CTRL_EXT) ? 1 : 0));
+  const bool tiered = s->mc_small < s->maxcon || s->me_small < s->maxefc;
+  int launches_per_call = G * nsub * (4 + (tiered ? 1 : 0) + ((phases & PH_CTRL_EXT) ? 1 : 0));
   if (!s->use_graph) {
     rc = enqueue_pipeline<R>(s, st, phases, nsub, action, s->stream);
     s->launches += launches_per_call;
     if (s->timeline && rc == B2S_OK) {
       cudaStreamSynchronize(s->stream);
-      static const char* names[8] = {"(prev->memset)", "memset", "P0", "narrowA", "narrowG", "P2|P5", "P3", "P4"};
+      static const char* names[8] = {"(prev->memset)", "memset", "P0", "narrowA", "narrowG", "tail", "tail(large tier)", "-"};
       double sum[8] = {0}; int cnt[8] = {0};
       for (size_t i = 1; i < s->tl_events.size(); i++) {
         auto &a = s->tl_events[i - 1], &b = s->tl_events[i];
@@ -801,6 +931,31 @@ static int launch_pipeline(b2s_sim* s, int phases, int nsub, const void* action)
 
 extern "C" {
 
+/* Host-only: the workspace layouts libb2s would build for a model of the given dimensions (no device needed).  out_words[5] receives
+ * words per warp / row of LAY_FULL (incl. the EPA area), LAY_P0, LAY_TS, LAY_TL, LAY_ROW; out_layouts (may be NULL) receives the five
+ * WSLayout structs as ints, out_pio (may be NULL) B2S_NPIO x (nload, nstore, load_words, then 12 + 12 regions x 4 ints). */
+int b2s_debug_layouts(int nq, int nv, int nu, int nbody, int ncg, int nsite, int hc_stride, int maxcon, int maxefc, int mc_small,
+                      int me_small, int osc_in_tail, int* out_words, int* out_layouts, int* out_pio) {
+  b2s_sim tmp;
+  tmp.nq = nq; tmp.nv = nv; tmp.nu = nu; tmp.nbody = nbody; tmp.nsite = nsite; tmp.maxcon = maxcon; tmp.maxefc = maxefc;
+  tmp.mc_small = mc_small; tmp.me_small = me_small; tmp.osc_in_tail = osc_in_tail;
+  try { build_layouts(&tmp, ncg, hc_stride); } catch (const std::string& e) { return fail(B2S_ERR_MODEL, e); }
+  if (out_words) {
+    out_words[0] = tmp.lay[LAY_FULL].fused_stride;
+    for (int k = 1; k < B2S_NLAY; k++) out_words[k] = tmp.lay[k].total;
+  }
+  if (out_layouts) memcpy(out_layouts, tmp.lay, sizeof(tmp.lay));
+  if (out_pio) {
+    for (int k = 0; k < B2S_NPIO; k++) {
+      int* o = out_pio + k * (3 + 2 * B2S_MAXREG * 4);
+      o[0] = tmp.pio[k].nload; o[1] = tmp.pio[k].nstore; o[2] = tmp.pio[k].load_words;
+      memcpy(o + 3, tmp.pio[k].load, sizeof(Region) * B2S_MAXREG);
+      memcpy(o + 3 + 4 * B2S_MAXREG, tmp.pio[k].store, sizeof(Region) * B2S_MAXREG);
+    }
+  }
+  return B2S_OK;
+}
+
 int b2s_set_mode(b2s_sim* s, int mode) {
   if (!s || (mode != 0 && mode != 1)) return fail(B2S_ERR_ARG, "b2s_set_mode: mode must be 0 (fused) or 1 (pipeline)");
   s->mode = mode;
@@ -809,7 +964,6 @@ int b2s_set_mode(b2s_sim* s, int mode) {
   if (getenv("B2S_NO_GRAPH")) s->use_graph = 0;
   if (const char* ds = getenv("B2S_DEBUG_SKIP")) s->debug_skip = atoi(ds);
   if (getenv("B2S_TIMELINE")) { s->timeline = 2; s->use_graph = 0; }
-  if (const char* mt = getenv("B2S_MERGE_TAIL")) s->merge_tail = atoi(mt) != 0;
   if (const char* v = getenv("B2S_CTRL_SPLIT")) s->ctrl_split = atoi(v) != 0;
   if (const char* v = getenv("B2S_CTRL_FORK")) s->ctrl_fork = atoi(v) != 0;
   return B2S_OK;
@@ -821,16 +975,16 @@ static void clear_warm_start(b2s_sim* s, const uint8_t* mask) {
   if (!have || npair == 0) return;
   size_t total = (size_t)s->n_env * npair * 3;
   int blocks = (int)((total + 255) / 256);
-  if (s->precision == B2S_F32) cache_reset_kernel<float><<<blocks, 256, 0, s->stream>>>(mask);
-  else cache_reset_kernel<double><<<blocks, 256, 0, s->stream>>>(mask);
+  if (s->precision == B2S_F32) cache_reset_kernel<float><<<blocks, 256, 0, s->stream>>>(mask, s->slot);
+  else cache_reset_kernel<double><<<blocks, 256, 0, s->stream>>>(mask, s->slot);
   s->launches++;
 }
 
 int b2s_reset(b2s_sim* s, const uint8_t* mask) {
   if (!s) return fail(B2S_ERR_ARG, "null handle");
   { int rc = bind_constants(s); if (rc != B2S_OK) return rc; }
-  if (s->precision == B2S_F32) reset_kernel<float><<<(s->n_env + 127) / 128, 128, 0, s->stream>>>(mask);
-  else reset_kernel<double><<<(s->n_env + 127) / 128, 128, 0, s->stream>>>(mask);
+  if (s->precision == B2S_F32) reset_kernel<float><<<(s->n_env + 127) / 128, 128, 0, s->stream>>>(mask, s->slot);
+  else reset_kernel<double><<<(s->n_env + 127) / 128, 128, 0, s->stream>>>(mask, s->slot);
   clear_warm_start(s, mask);
   s->launches++;
   CUDA_TRY(cudaGetLastError());
@@ -850,8 +1004,8 @@ int b2s_jac_site(b2s_sim* s, int site_id, void* jacp, void* jacr) {
   if (!s || site_id < 0 || site_id >= s->nsite) return fail(B2S_ERR_ARG, "b2s_jac_site: bad argument");
   { int rc = bind_constants(s); if (rc != B2S_OK) return rc; }
   int threads = 128, blocks = (s->n_env * s->nv + threads - 1) / threads;
-  if (s->precision == B2S_F32) jac_site_kernel<float><<<blocks, threads, 0, s->stream>>>(site_id, (float*)jacp, (float*)jacr);
-  else jac_site_kernel<double><<<blocks, threads, 0, s->stream>>>(site_id, (double*)jacp, (double*)jacr);
+  if (s->precision == B2S_F32) jac_site_kernel<float><<<blocks, threads, 0, s->stream>>>(site_id, (float*)jacp, (float*)jacr, s->slot);
+  else jac_site_kernel<double><<<blocks, threads, 0, s->stream>>>(site_id, (double*)jacp, (double*)jacr, s->slot);
   s->launches++;
   CUDA_TRY(cudaGetLastError());
   return B2S_OK;
@@ -888,8 +1042,8 @@ int b2s_ctrl_reset(b2s_sim* s, const uint8_t* mask) {
   if (!s || !s->has_ctrl) return fail(B2S_ERR_ARG, "b2s_ctrl_reset: controller not configured");
   { int rc = bind_constants(s); if (rc != B2S_OK) return rc; }
   int threads = 128, blocks = (s->n_env + threads - 1) / threads;
-  if (s->precision == B2S_F32) ctrl_reset_kernel<float><<<blocks, threads, 0, s->stream>>>(mask);
-  else ctrl_reset_kernel<double><<<blocks, threads, 0, s->stream>>>(mask);
+  if (s->precision == B2S_F32) ctrl_reset_kernel<float><<<blocks, threads, 0, s->stream>>>(mask, s->slot);
+  else ctrl_reset_kernel<double><<<blocks, threads, 0, s->stream>>>(mask, s->slot);
   clear_warm_start(s, mask);  // an environment whose controller is rebuilt starts a new episode
   s->launches++;
   CUDA_TRY(cudaGetLastError());

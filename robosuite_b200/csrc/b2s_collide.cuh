@@ -18,11 +18,11 @@ struct Shape {
 
 template <typename R>
 DEV void shape_get(const Eng<R>& e, int g, Shape<R>& s) {
-  const DModel<R>& m = cmodel<R>();
+  const DModel<R>& m = e.model();
   int k = m.geom_cgid[g];
   s.type = m.geom_type[g];
-  s.pos = e.p(c_L.gpos) + 3 * k;
-  s.mat = e.p(c_L.gmat) + 9 * k;
+  s.pos = e.p(e.lay().gpos) + 3 * k;
+  s.mat = e.p(e.lay().gmat) + 9 * k;
   s.size[0] = m.geom_size[3 * g]; s.size[1] = m.geom_size[3 * g + 1]; s.size[2] = m.geom_size[3 * g + 2];
   s.vert = nullptr; s.nvert = 0;
   if (s.type == G_MESH) {
@@ -33,8 +33,7 @@ DEV void shape_get(const Eng<R>& e, int g, Shape<R>& s) {
 }
 
 template <typename R>
-DEV void shape_from(int g, const R* gpos, const R* gmat, Shape<R>& s) {
-  const DModel<R>& m = cmodel<R>();
+DEV void shape_from(const DModel<R>& m, int g, const R* gpos, const R* gmat, Shape<R>& s) {
   int k = m.geom_cgid[g];
   s.type = m.geom_type[g];
   s.pos = gpos + 3 * k;
@@ -775,19 +774,19 @@ DEVN int convex_convex(const Shape<R>& A, const Shape<R>& B, R* out, int maxn, R
 // ---------------------------------------------------------------------------------------------- driver
 // oriented-box overlap of the two geoms' local AABBs (15-axis separating test); planes use the box/plane distance
 template <typename R> DEVN bool obb_overlap(const Eng<R> e, int g1, int g2) {
-  const DModel<R>& m = cmodel<R>();
+  const DModel<R>& m = e.model();
   int k1 = m.geom_cgid[g1], k2 = m.geom_cgid[g2];
-  const R* M1 = e.p(c_L.gmat) + 9 * k1; const R* M2 = e.p(c_L.gmat) + 9 * k2;
+  const R* M1 = e.p(e.lay().gmat) + 9 * k1; const R* M2 = e.p(e.lay().gmat) + 9 * k2;
   const R* a1 = m.geom_aabb + 6 * g1; const R* a2 = m.geom_aabb + 6 * g2;
   R c1[3], c2[3], t[3];
   R o1[3] = {a1[0], a1[1], a1[2]}, o2[3] = {a2[0], a2[1], a2[2]};
-  m3mulv(t, M1, o1); v3add(c1, t, e.p(c_L.gpos) + 3 * k1);
-  m3mulv(t, M2, o2); v3add(c2, t, e.p(c_L.gpos) + 3 * k2);
+  m3mulv(t, M1, o1); v3add(c1, t, e.p(e.lay().gpos) + 3 * k1);
+  m3mulv(t, M2, o2); v3add(c2, t, e.p(e.lay().gpos) + 3 * k2);
   R ha[3] = {a1[3], a1[4], a1[5]}, hb[3] = {a2[3], a2[4], a2[5]};
   int t1 = m.geom_type[g1], t2 = m.geom_type[g2];
   if (t1 == G_PLANE || t2 == G_PLANE) {
     const R* Mp = t1 == G_PLANE ? M1 : M2; const R* Mo = t1 == G_PLANE ? M2 : M1;
-    const R* pp = e.p(c_L.gpos) + 3 * (t1 == G_PLANE ? k1 : k2);
+    const R* pp = e.p(e.lay().gpos) + 3 * (t1 == G_PLANE ? k1 : k2);
     const R* co = t1 == G_PLANE ? c2 : c1; const R* ho = t1 == G_PLANE ? hb : ha;
     R n[3] = COLV(Mp, 2), df[3];
     v3sub(df, co, pp);
@@ -858,8 +857,8 @@ template <typename R> DEV int narrow_analytic(const Shape<R>& A, const Shape<R>&
 
 // Cull the static pair list (bounding spheres, then oriented boxes); candidate pair indices in pair order.
 template <typename R> DEVN void cull_pairs(Eng<R> e, int* cand, int* cand_g, int maxa, int maxg, int& na_out, int& ng_out) {
-  const DModel<R>& m = cmodel<R>();
-  const WSLayout& L = c_L;
+  const DModel<R>& m = e.model();
+  const WSLayout& L = e.lay();
   int lane = e.lane, na = 0, ng = 0;
   const R* gpos = e.p(L.gpos); const R* gmat = e.p(L.gmat);
   for (int base = 0; base < m.npair; base += 32) {
@@ -896,8 +895,8 @@ template <typename R> DEVN void cull_pairs(Eng<R> e, int* cand, int* cand_g, int
 
 // per contact: condim + friction mixing (shared by the fused and the pipelined collision paths)
 template <typename R> DEV void finish_contacts(const Eng<R>& e, int ncon) {
-  const DModel<R>& m = cmodel<R>();
-  const WSLayout& L = c_L;
+  const DModel<R>& m = e.model();
+  const WSLayout& L = e.lay();
   R* cfric = e.p(L.c_fric);
   int* cint = e.pi(L.c_int);
   for (int c = e.lane; c < ncon; c += 32) {
@@ -915,8 +914,8 @@ template <typename R> DEV void finish_contacts(const Eng<R>& e, int ncon) {
 template <typename R> DEVN int collide(Eng<R> e, int& warn, int* dbg3, float* pc = nullptr) {
   long long tp0 = pc ? clock64() : 0;
 #define CTICK(slot) if (pc) { __syncwarp(); long long tp1 = clock64(); pc[slot] += (float)(tp1 - tp0); tp0 = tp1; }
-  const DModel<R>& m = cmodel<R>();
-  const WSLayout& L = c_L;
+  const DModel<R>& m = e.model();
+  const WSLayout& L = e.lay();
   int lane = e.lane;
   int* cand = reinterpret_cast<int*>(e.p(L.scratch));  // candidate pair indices, analytic first then gjk
   int* cand_g = cand + 96;
@@ -990,7 +989,7 @@ template <typename R> DEVN int collide(Eng<R> e, int& warn, int* dbg3, float* pc
     off = ncon + off - n;
     for (int k = 0; k < n; k++) {
       int c = off + k;
-      if (c >= m.maxcon) break;
+      if (c >= L.mc) break;
       const R* b = buf + CREC * k;
       cpos[3 * c] = b[0]; cpos[3 * c + 1] = b[1]; cpos[3 * c + 2] = b[2];
       cfr[3 * c] = b[3]; cfr[3 * c + 1] = b[4]; cfr[3 * c + 2] = b[5];
@@ -999,7 +998,7 @@ template <typename R> DEVN int collide(Eng<R> e, int& warn, int* dbg3, float* pc
     }
     ncon += total;
   }
-  if (ncon > m.maxcon) { ncon = m.maxcon; warn |= 4; }
+  if (ncon > L.mc) { ncon = L.mc; warn |= 4; }
   __syncwarp();
   CTICK(9)
   // --- convex candidates: the whole warp per pair (scratch beyond the candidate lists holds the EPA polytope)
@@ -1015,7 +1014,7 @@ template <typename R> DEVN int collide(Eng<R> e, int& warn, int* dbg3, float* pc
     int n = convex_convex(A, B, buf, 1, epa_scratch, lane);
     if (n > 0) {
       dbg3[2]++;
-      if (ncon < m.maxcon) {
+      if (ncon < L.mc) {
         int c = ncon;
         if (lane == 0) {
           cpos[3 * c] = buf[0]; cpos[3 * c + 1] = buf[1]; cpos[3 * c + 2] = buf[2];

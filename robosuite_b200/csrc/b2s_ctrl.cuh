@@ -18,14 +18,14 @@ template <typename R> struct CtrlState {
 };
 
 template <typename R> DEV void ctrl_load(Eng<R> e, CtrlState<R>& cs, int env) {
-  const DState<R>& s = cstate<R>();
+  const DState<R>& s = e.state();
   size_t E = env;
   for (int k = 0; k < 3; k++) cs.goal_pos[k] = s.goal_pos[E * 3 + k];
   for (int k = 0; k < 9; k++) cs.goal_ori[k] = s.goal_ori[E * 9 + k];
   for (int k = 0; k < 4; k++) cs.grip[k] = s.grip_state[E * 4 + k];
 }
 template <typename R> DEV void ctrl_store(Eng<R> e, CtrlState<R>& cs, int env) {
-  const DState<R>& s = cstate<R>();
+  const DState<R>& s = e.state();
   size_t E = env;
   if (e.lane == 0) {
     for (int k = 0; k < 3; k++) s.goal_pos[E * 3 + k] = cs.goal_pos[k];
@@ -64,10 +64,10 @@ template <typename R> DEV void delta_rotmat(R* Rm, const R* aa) {
 // action, torque = goal + qfrc_bias).  One lane per joint; the goal lives in the first 8 words of the jv_state row.
 template <typename R>
 DEVN void ctrl_run_joint(Eng<R> e, CtrlState<R>& cs, int env, const R* action) {
-  const DModel<R>& m = cmodel<R>();
-  const WSLayout& L = c_L;
-  const DState<R>& s = cstate<R>();
-  const CtrlCfgDev& cc = c_cc;
+  const DModel<R>& m = e.model();
+  const WSLayout& L = e.lay();
+  const DState<R>& s = e.state();
+  const CtrlCfgDev& cc = e.ccfg();
   int lane = e.lane, na = cc.n_arm, nv = m.nv;
   R* st = s.jv_state + (size_t)env * 72;
   R* ctrl = e.p(L.ctrl);
@@ -111,10 +111,10 @@ DEVN void ctrl_run_joint(Eng<R> e, CtrlState<R>& cs, int env, const R* action) {
 
 template <typename R>
 DEVN void ctrl_run_jv(Eng<R> e, CtrlState<R>& cs, int env, const R* action) {
-  const DModel<R>& m = cmodel<R>();
-  const WSLayout& L = c_L;
-  const DState<R>& s = cstate<R>();
-  const CtrlCfgDev& cc = c_cc;
+  const DModel<R>& m = e.model();
+  const WSLayout& L = e.lay();
+  const DState<R>& s = e.state();
+  const CtrlCfgDev& cc = e.ccfg();
   int lane = e.lane, na = cc.n_arm;
   R* st = s.jv_state + (size_t)env * 72;
   R* ctrl = e.p(L.ctrl);
@@ -166,10 +166,10 @@ DEVN void ctrl_run_jv(Eng<R> e, CtrlState<R>& cs, int env, const R* action) {
 
 template <typename R>
 DEVN void ctrl_run(Eng<R> e, CtrlState<R>& cs, int env, const R* action) {
-  const DModel<R>& m = cmodel<R>();
-  const WSLayout& L = c_L;
-  const DState<R>& s = cstate<R>();
-  const CtrlCfgDev& cc = c_cc;
+  const DModel<R>& m = e.model();
+  const WSLayout& L = e.lay();
+  const DState<R>& s = e.state();
+  const CtrlCfgDev& cc = e.ccfg();
   if (cc.kind == 2) { ctrl_run_jv(e, cs, env, action); return; }
   if (cc.kind == 3 || cc.kind == 4) { ctrl_run_joint(e, cs, env, action); return; }
   bool policy_step = action != nullptr;
@@ -420,7 +420,7 @@ template <typename R> DEV void mat2quat_wpos(const R* M, R* q) {
 // qpos/qvel/qacc are the freshly integrated values, poses are those of the last step1 (reference staleness).
 // one scalar of the observation / task tables; `prev` = this environment's previous observation row (lagged entries)
 template <typename R> DEV R table_value(const Eng<R>& e, int op, int a, int b, const R* prev, int fresh) {
-  const WSLayout& L = c_L;
+  const WSLayout& L = e.lay();
   R v = 0;
   switch (op) {
     case OB_QPOS: v = e.p(L.qpos)[a]; break;
@@ -462,8 +462,8 @@ template <typename R> DEV R table_value(const Eng<R>& e, int op, int a, int b, c
 
 // `only_fresh`: called from forward() - sample only environments whose observation cache is empty (just reset)
 template <typename R> DEVN void write_obs(const Eng<R> e, int env, bool only_fresh = false) {
-  const DState<R>& s = cstate<R>();
-  const CtrlCfgDev& cc = c_cc;
+  const DState<R>& s = e.state();
+  const CtrlCfgDev& cc = e.ccfg();
   R* out = s.obs + (size_t)env * cc.obs_dim;
   int fresh = s.obs_fresh[env];
   if (only_fresh && !fresh) return;
@@ -485,10 +485,10 @@ template <typename R> DEVN void write_obs(const Eng<R> e, int env, bool only_fre
 // Task outputs after the last substep (poses / contacts of the last step1, as the reference's reward() sees them:
 // manipulation/lift.py:224-273,433-444; manipulation_env.py:331-376 _check_grasp; utils/sim_utils.py:8-40)
 template <typename R> DEVN void write_task(const Eng<R> e, int env, int ncon) {
-  const DModel<R>& m = cmodel<R>();
-  const WSLayout& L = c_L;
-  const DState<R>& s = cstate<R>();
-  const CtrlCfgDev& cc = c_cc;
+  const DModel<R>& m = e.model();
+  const WSLayout& L = e.lay();
+  const DState<R>& s = e.state();
+  const CtrlCfgDev& cc = e.ccfg();
   const int* cint = e.pi(L.c_int);
   int hitl = 0, hitr = 0, hit2 = 0, hl4 = 0, hr4 = 0;
   for (int c = e.lane; c < ncon; c += 32) {
@@ -523,10 +523,10 @@ template <typename R> DEVN void write_task(const Eng<R> e, int env, int ncon) {
 // controller.reset_goal + initial joints (osc.py:520-544, controller.py:126-132): goal <- current eef pose (world),
 // initial_joint <- current arm qpos, gripper integrator <- 0.  Uses the exported site arrays of a prior forward.
 template <typename R>
-__global__ void ctrl_reset_kernel(const uint8_t* mask) {
-  const DModel<R>& m = cmodel<R>();
-  const DState<R>& s = cstate<R>();
-  const CtrlCfgDev& cc = c_cc;
+__global__ void ctrl_reset_kernel(const uint8_t* mask, int slot) {
+  const DModel<R>& m = cmodel<R>(slot);
+  const DState<R>& s = cstate<R>(slot);
+  const CtrlCfgDev& cc = c_cc[slot];
   int env = blockIdx.x * blockDim.x + threadIdx.x;
   if (env >= s.n_env) return;
   if (mask && !mask[env]) return;

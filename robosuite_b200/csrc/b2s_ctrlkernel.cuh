@@ -17,11 +17,11 @@ template <typename R> constexpr size_t osc_smem_bytes() { return (size_t)OSC_TPB
 
 struct Grp;
 template <typename R>
-__global__ void __launch_bounds__(OSC_TPB) ctrl_osc_kernel(int sub, const R* action, int env0, int nenv, int gid) {
-  const DModel<R>& m = cmodel<R>();
-  const DState<R>& s = cstate<R>();
-  const WSLayout& L = c_L;
-  const CtrlCfgDev& cc = c_cc;
+__global__ void __launch_bounds__(OSC_TPB) ctrl_osc_kernel(int sub, const R* action, int env0, int nenv, int gid, int slot) {
+  const DModel<R>& m = cmodel<R>(slot);
+  const DState<R>& s = cstate<R>(slot);
+  const WSLayout& L = c_lay[slot][LAY_ROW];  // inputs come from phase 0's global workspace row
+  const CtrlCfgDev& cc = c_cc[slot];
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* wd = reinterpret_cast<double*>(smem_raw);                          // [OSC_WORK_DOUBLES][OSC_TPB]
   R* jt = reinterpret_cast<R*>(wd + (size_t)OSC_WORK_DOUBLES * OSC_TPB);      // [6 * OSC_NA_MAX][OSC_TPB]

@@ -71,11 +71,10 @@ DEVN int spd_solve_reg(const R* A, int n, const R* dadd, R dscale, R* x, int lan
 // time by its own lanes: lane i keeps row i restricted to its tree's columns (NVB = padded size of the largest tree).
 // Lanes whose tree is smaller than the current column see d = 1, l = 0 and shuffle from themselves: no-ops without selects.
 template <typename R, int NVB>
-DEVN int spd_solve_blk(const R* A, int n, const R* dadd, R dscale, R* x, int lane) {
-  const DModel<R>& m = cmodel<R>();
+DEVN int spd_solve_blk(const R* A, int n, const R* dadd, R dscale, R* x, int lane, const int* dof_treebase, const int* dof_treesize) {
   R a[NVB];
   int row = lane < n ? lane : 0;
-  int base = m.dof_treebase[row], size = m.dof_treesize[row];
+  int base = dof_treebase[row], size = dof_treesize[row];
   int li = row - base;  // local index of this lane's row inside its tree
   if (lane >= n) size = 0;
   R dl = (dadd != nullptr && lane < n) ? dscale * dadd[row] : R(0);
@@ -127,14 +126,19 @@ template <typename R>
 struct Eng {
   R* ws;  // this warp's workspace
   int lane;
+  int slot, lid;  // descriptor slot of the owning handle, workspace layout of the running kernel (LAY_*)
 
-  DEV Eng(R* ws_, int lane_) : ws(ws_), lane(lane_) {}
+  DEV Eng(R* ws_, int lane_, int slot_, int lid_) : ws(ws_), lane(lane_), slot(slot_), lid(lid_) {}
+  DEV const DModel<R>& model() const { return cmodel<R>(slot); }
+  DEV const DState<R>& state() const { return cstate<R>(slot); }
+  DEV const WSLayout& lay() const { return c_lay[slot][lid]; }
+  DEV const CtrlCfgDev& ccfg() const { return c_cc[slot]; }
   DEV R* p(int off) const { return ws + off; }
   DEV int* pi(int off) const { return reinterpret_cast<int*>(ws + off); }
 
   // ------------------------------------------------------------------------------------------- kinematics
   DEVN void kinematics() {
-    const DModel<R>& m = cmodel<R>(); const WSLayout& L = c_L;
+    const DModel<R>& m = model(); const WSLayout& L = lay();
     R* xpos = p(L.xpos); R* xquat = p(L.xquat); R* xmat = p(L.xmat);
     const R* qpos = p(L.qpos);
     // bodies welded to the world: constant pose
@@ -283,7 +287,7 @@ struct Eng {
 
   // last dof on the kinematic chain ending at body b (-1 if none)
   DEV int chain_end(int b) const {
-    const DModel<R>& m = cmodel<R>();
+    const DModel<R>& m = model();
     while (b > 0 && m.body_dofnum[b] == 0) b = m.body_parentid[b];
     return b > 0 ? m.body_dofadr[b] + m.body_dofnum[b] - 1 : -1;
   }
@@ -291,7 +295,7 @@ struct Eng {
   // ------------------------------------------------------------------------------------------- velocity stage
   // cvel, cdof_dot, RNE bias forces, passive (damping + fluid) forces
   DEVN void velocity() {
-    const DModel<R>& m = cmodel<R>(); const WSLayout& L = c_L;
+    const DModel<R>& m = model(); const WSLayout& L = lay();
     const R* cdof = p(L.cdof); const R* qvel = p(L.qvel);
     R* cvel = p(L.cvel); R* cdd = p(L.cdofdot);
     for (int b = lane; b < m.nbody; b += 32) {
@@ -401,7 +405,7 @@ struct Eng {
 
   // ------------------------------------------------------------------------------------------- CRB -> dense M
   DEVN void crb() {
-    const DModel<R>& m = cmodel<R>(); const WSLayout& L = c_L;
+    const DModel<R>& m = model(); const WSLayout& L = lay();
     R* cinert = p(L.cinert);
     // composite inertia = sum over the (contiguous, DFS-ordered) subtree, written to scratch
     int nb = m.nbody;
@@ -482,9 +486,11 @@ struct Eng {
   // blockdiag: the caller guarantees that A has no entries between different kinematic trees
   DEV int spd_solve(R* A, int n, const R* dadd, R dscale, R* x, R* work, bool blockdiag = false) {
     if (blockdiag && n <= 32) {
-      int ts = cmodel<R>().max_treesize;
-      if (ts <= 8) return spd_solve_blk<R, 8>(A, n, dadd, dscale, x, lane);
-      if (ts <= 12) return spd_solve_blk<R, 12>(A, n, dadd, dscale, x, lane);
+      const DModel<R>& m = model();
+      int ts = m.max_treesize;
+      if (ts <= 8) return spd_solve_blk<R, 8>(A, n, dadd, dscale, x, lane, m.dof_treebase, m.dof_treesize);
+      if (ts <= 9) return spd_solve_blk<R, 9>(A, n, dadd, dscale, x, lane, m.dof_treebase, m.dof_treesize);
+      if (ts <= 12) return spd_solve_blk<R, 12>(A, n, dadd, dscale, x, lane, m.dof_treebase, m.dof_treesize);
     }
     if (n <= 16) return spd_solve_reg<R, 16>(A, n, dadd, dscale, x, lane);
     if (n <= 24) return spd_solve_reg<R, 24>(A, n, dadd, dscale, x, lane);
@@ -500,7 +506,7 @@ struct Eng {
 
   // ------------------------------------------------------------------------------------------- actuation
   DEVN void actuation(R* act_force_out) {
-    const DModel<R>& m = cmodel<R>(); const WSLayout& L = c_L;
+    const DModel<R>& m = model(); const WSLayout& L = lay();
     R* qact = p(L.qact);
     const R* ctrl = p(L.ctrl); const R* qpos = p(L.qpos); const R* qvel = p(L.qvel);
     for (int i = lane; i < m.nv; i += 32) qact[i] = 0;
@@ -522,7 +528,7 @@ struct Eng {
 
   // qfrc_smooth, qacc_smooth = M^-1 qfrc_smooth (factor of M left in H)
   DEVN int acceleration() {
-    const DModel<R>& m = cmodel<R>(); const WSLayout& L = c_L;
+    const DModel<R>& m = model(); const WSLayout& L = lay();
     int nv = m.nv;
     R* qs = p(L.qsmooth); R* qa = p(L.qaccs);
     for (int i = lane; i < nv; i += 32) {
@@ -537,7 +543,7 @@ struct Eng {
   // ------------------------------------------------------------------------------------------- Euler
   // semi-implicit Euler with implicit joint damping: (M + h D) a = qfrc_smooth + qfrc_constraint
   DEVN int euler(R* time) {
-    const DModel<R>& m = cmodel<R>(); const WSLayout& L = c_L;
+    const DModel<R>& m = model(); const WSLayout& L = lay();
     int nv = m.nv;
     R h = m.timestep;
     R* a = p(L.grad);  // reuse solver vector as the integration acceleration

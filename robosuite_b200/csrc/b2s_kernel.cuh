@@ -13,9 +13,9 @@ template <typename R> DEV void load_row(R* dst, const R* src, int n, int lane) {
 
 template <typename R>
 DEVN void export_step1(const Eng<R> e, int env, int ncon) {
-  const DModel<R>& m = cmodel<R>();
-  const WSLayout& L = c_L;
-  const DState<R>& s = cstate<R>();
+  const DModel<R>& m = e.model();
+  const WSLayout& L = e.lay();
+  const DState<R>& s = e.state();
   int lane = e.lane;
   size_t E = env;
   load_row(s.xpos + E * 3 * m.nbody, e.p(L.xpos), 3 * m.nbody, lane);
@@ -53,9 +53,9 @@ DEVN void export_step1(const Eng<R> e, int env, int ncon) {
 // constraint rows (the Jacobian overlays kinematics scratch, so this runs after make_constraint)
 template <typename R>
 DEVN void export_efc(const Eng<R> e, int env, int nefc) {
-  const DModel<R>& m = cmodel<R>();
-  const WSLayout& L = c_L;
-  const DState<R>& s = cstate<R>();
+  const DModel<R>& m = e.model();
+  const WSLayout& L = e.lay();
+  const DState<R>& s = e.state();
   int lane = e.lane;
   size_t E = env;
   for (int r = lane; r < m.maxefc; r += 32) {
@@ -71,9 +71,9 @@ DEVN void export_efc(const Eng<R> e, int env, int nefc) {
 
 template <typename R>
 DEVN void export_step2(const Eng<R> e, int env, int nefc, int niter) {
-  const DModel<R>& m = cmodel<R>();
-  const WSLayout& L = c_L;
-  const DState<R>& s = cstate<R>();
+  const DModel<R>& m = e.model();
+  const WSLayout& L = e.lay();
+  const DState<R>& s = e.state();
   int lane = e.lane;
   size_t E = env;
   load_row(s.qfrc_actuator + E * m.nv, e.p(L.qact), m.nv, lane);
@@ -85,10 +85,10 @@ DEVN void export_step2(const Eng<R> e, int env, int nefc, int niter) {
 }
 
 template <typename R>
-__global__ void __launch_bounds__(512, 1) step_kernel(int phases, int nsub, const R* action) {
-  const DModel<R>& m = cmodel<R>();
-  const DState<R>& s = cstate<R>();
-  const WSLayout& L = c_L;
+__global__ void __launch_bounds__(512, 1) step_kernel(int phases, int nsub, const R* action, int slot) {
+  const DModel<R>& m = cmodel<R>(slot);
+  const DState<R>& s = cstate<R>(slot);
+  const WSLayout& L = c_lay[slot][LAY_FULL];
   extern __shared__ __align__(16) unsigned char smem_raw[];
   R* smem = reinterpret_cast<R*>(smem_raw);
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(512, 1) step_kernel(int phases, int nsub, cons
   // region, which is what bounds the instruction-cache working set); warps beyond n_env shadow the last env
   bool live = env < s.n_env;
   if (!live) env = s.n_env - 1;
-  Eng<R> e(smem + (size_t)warp * L.fused_stride, lane);
+  Eng<R> e(smem + (size_t)warp * L.fused_stride, lane, slot, LAY_FULL);
   size_t E = env;
   load_row(e.p(L.qpos), s.qpos + E * m.nq, m.nq, lane);
   load_row(e.p(L.qvel), s.qvel + E * m.nv, m.nv, lane);
@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(512, 1) step_kernel(int phases, int nsub, cons
       }
       TICK(7)
     }
-    if (live && (phases & PH_OBS) && c_cc.obs_dim > 0) {
+    if (live && (phases & PH_OBS) && c_cc[slot].obs_dim > 0) {
       // The reference's observables sample on the LAST substep of a control step: reset()'s forced update already
       // advances their period timer by one model timestep (utils/observables.py:214-259, environments/base.py:418-427),
       // so the period closes after substep 24 and the next update - substep 25 - takes the sample.
@@ -183,9 +183,9 @@ __global__ void __launch_bounds__(512, 1) step_kernel(int phases, int nsub, cons
 }
 
 template <typename R>
-__global__ void reset_kernel(const uint8_t* mask) {
-  const DModel<R>& m = cmodel<R>();
-  const DState<R>& s = cstate<R>();
+__global__ void reset_kernel(const uint8_t* mask, int slot) {
+  const DModel<R>& m = cmodel<R>(slot);
+  const DState<R>& s = cstate<R>(slot);
   int env = blockIdx.x * blockDim.x + threadIdx.x;
   if (env >= s.n_env) return;
   if (mask && !mask[env]) return;
@@ -200,9 +200,9 @@ __global__ void reset_kernel(const uint8_t* mask) {
 // per-episode hidden state of the collision pipeline: the GJK warm-start directions of the environments being reset
 // (a replay from a restored state must not depend on what ran before: tests/test_environments/test_action_playback.py)
 template <typename R>
-__global__ void cache_reset_kernel(const uint8_t* mask) {
-  const DModel<R>& m = cmodel<R>();
-  const DState<R>& s = cstate<R>();
+__global__ void cache_reset_kernel(const uint8_t* mask, int slot) {
+  const DModel<R>& m = cmodel<R>(slot);
+  const DState<R>& s = cstate<R>(slot);
   if (!s.gjk_cache) return;
   size_t per = (size_t)m.npair * 3, idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= per * (size_t)s.n_env) return;
@@ -212,9 +212,9 @@ __global__ void cache_reset_kernel(const uint8_t* mask) {
 
 // translational / rotational Jacobian of a site from the exported cdof and site_xpos (valid after forward/step1)
 template <typename R>
-__global__ void jac_site_kernel(int site, R* jacp, R* jacr) {
-  const DModel<R>& m = cmodel<R>();
-  const DState<R>& s = cstate<R>();
+__global__ void jac_site_kernel(int site, R* jacp, R* jacr, int slot) {
+  const DModel<R>& m = cmodel<R>(slot);
+  const DState<R>& s = cstate<R>(slot);
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= s.n_env * m.nv) return;
   int env = idx / m.nv, i = idx % m.nv;

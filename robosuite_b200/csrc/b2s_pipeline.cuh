@@ -1,8 +1,9 @@
-// Pipeline mode: one substep = five small phase kernels (kinematics+dynamics | collision | constraint rows |
-// controller | solve+integrate) that exchange a per-environment workspace row through L2.  Same device functions as
-// the fused kernel; what changes is scheduling: every launch runs ONE phase's code on all environments, so the
-// instruction working set fits the I-cache without block barriers and environments with expensive collision or many
-// solver iterations no longer stall their neighbours (hardware block scheduling balances the tail).
+// Pipeline mode: one substep = phase 0 (kinematics + dynamics + broad phase) | work-list narrow phase (analytic, convex) beside the
+// thread-per-environment controller kernel | tail (contact gather, constraint rows, solve, integrate, observations), exchanging a
+// per-environment workspace row through L2.  Same device functions as the fused kernel; what changes is scheduling and MEMORY:
+// every kernel has its own compact shared-memory layout (LAY_P0 / LAY_TS / LAY_TL), so 24-28 warps are resident per SM instead of
+// the 14 the one-size-fits-all layout allowed, and the tail kernel runs in two capacity tiers: the small tier holds the contact /
+// row counts almost every environment has, the few that need more are re-run by the large tier (same results, no truncation).
 #pragma once
 #include "b2s_kernel.cuh"
 
@@ -52,46 +53,47 @@ DEV void tma_store_1d(void* gdst, const void* smem_src, unsigned bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
 }
 
-// Every region of a phase's load / store list is 16-byte aligned in offset and length (build_layout) and adjacent regions
-// are merged into spans on the host, so a phase moves its workspace with a handful of bulk copies: lane k issues span k.
-template <typename R> DEV void ws_load(const Eng<R>& e, const R* row, const PhaseIO& io, int nefc_nv, unsigned long long* bar) {
-  const int W = 16 / (int)sizeof(R);
-  int dynlen = (nefc_nv + W - 1) / W * W;
+// Every region of a phase's load / store list is 16-byte aligned in both its shared-memory and its global-row offset and in its
+// length (build_layouts); regions adjacent on both sides are merged into spans on the host, so a phase moves its workspace with
+// a handful of bulk copies: lane k issues span k.
+template <typename R> DEV void ws_load(const Eng<R>& e, const R* row, const PhaseIO& io, unsigned long long* bar, unsigned& parity) {
+  if (io.nload == 0) return;
 #if B2S_TMA
-  if (e.lane == 0) mbar_expect_tx(bar, (unsigned)(io.load_words + (io.load_dyn ? dynlen : 0)) * (unsigned)sizeof(R));
+  if (e.lane == 0) mbar_expect_tx(bar, (unsigned)io.load_words * (unsigned)sizeof(R));
   __syncwarp();
   if (e.lane < io.nload) {
     Region r = io.load[e.lane];
-    int len = r.dyn == 1 ? dynlen : r.len;
-    if (len > 0) tma_load_1d(e.ws + r.off, row + r.off, (unsigned)len * sizeof(R), bar);
+    tma_load_1d(e.ws + r.off, row + r.goff, (unsigned)r.len * sizeof(R), bar);
   }
-  mbar_wait(bar, 0);
+  mbar_wait(bar, parity);
+  parity ^= 1u;
 #else
-  for (int k = 0; k < io.nload; k++) row_copy(e.ws + io.load[k].off, row + io.load[k].off, io.load[k].dyn == 1 ? dynlen : io.load[k].len, e.lane);
+  for (int k = 0; k < io.nload; k++) row_copy(e.ws + io.load[k].off, row + io.load[k].goff, io.load[k].len, e.lane);
+  __syncwarp();
 #endif
 }
-template <typename R> DEV void ws_store(const Eng<R>& e, R* row, const PhaseIO& io, int nefc_nv) {
-  const int W = 16 / (int)sizeof(R);
-  int dynlen = (nefc_nv + W - 1) / W * W;
+template <typename R> DEV void ws_store(const Eng<R>& e, R* row, const PhaseIO& io) {
 #if B2S_TMA
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // this lane's generic-proxy writes -> visible to the async proxy
   __syncwarp();
   if (e.lane < io.nstore) {
     Region r = io.store[e.lane];
-    int len = r.dyn == 1 ? dynlen : r.len;
-    if (len > 0) tma_store_1d(row + r.off, e.ws + r.off, (unsigned)len * sizeof(R));
+    tma_store_1d(row + r.goff, e.ws + r.off, (unsigned)r.len * sizeof(R));
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   __syncwarp();
 #else
-  for (int k = 0; k < io.nstore; k++) row_copy(row + io.store[k].off, e.ws + io.store[k].off, io.store[k].dyn == 1 ? dynlen : io.store[k].len, e.lane);
+  for (int k = 0; k < io.nstore; k++) row_copy(row + io.store[k].goff, e.ws + io.store[k].off, io.store[k].len, e.lane);
 #endif
 }
 
 // A launch covers one group of environments [env0, env0 + nenv); groups run on separate streams so that the tail of one
-// group's kernel (its slowest environment) overlaps with other groups' work.
-struct Grp { int env0, nenv, gid, sub; };
+// group's kernel (its slowest environment) overlaps with other groups' work.  slot = descriptor slot of the owning handle.
+struct Grp { int env0, nenv, gid, sub, slot; };
+#define EPA_PIPE_MAXV EPA_MAXV
+#define EPA_PIPE_MAXF EPA_MAXF
+#define CLC(s, g) ((s).cl_cnt + 8 * (g).gid)  // this group's counters: nA, nG, overflowed envs, next convex item, next overflow item
 
 // -DB2S_INSTR: every launch stamps its first / last %globaltimer into st_begin / st_end (device timeline of the CUDA-graph
 // replay, which events cannot subdivide), warps record their clock64 cost per environment-substep.  Empty in product builds.
@@ -106,28 +108,25 @@ DEV unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0
 #endif
 #include "b2s_ctrlkernel.cuh"
 
-#define EPA_PIPE_MAXV EPA_MAXV
-#define EPA_PIPE_MAXF EPA_MAXF
-
 // ---- work-list narrow phase --------------------------------------------------------------------------------------
 // analytic pairs: ONE THREAD per candidate pair of any environment (32 different pairs per warp)
 template <typename R>
 __global__ void __launch_bounds__(128) narrow_analytic_kernel(Grp g) {
-  const DModel<R>& m = cmodel<R>();
-  const DState<R>& s = cstate<R>();
-  const WSLayout& L = c_L;
+  const DModel<R>& m = cmodel<R>(g.slot);
+  const DState<R>& s = cstate<R>(g.slot);
+  const WSLayout& RL = c_lay[g.slot][LAY_ROW];
   int tid = blockIdx.x * blockDim.x + threadIdx.x;
   INSTR_BEGIN(s, g, 1)
-  if (tid >= s.cl_cnt[4 * g.gid]) { INSTR_END(s, g, 1) return; }
+  if (tid >= CLC(s, g)[0]) { INSTR_END(s, g, 1) return; }
   tid += g.env0 * s.cl_maxa;  // this group's slice of the candidate list / output slots
   int code = s.cl_listA[tid];
   int env = code >> 12, pidx = code & 4095;
-  const R* row = s.wsg + (size_t)env * L.total;
+  const R* row = s.wsg + (size_t)env * RL.total;
   int g1 = m.pair_geom[2 * pidx], g2 = m.pair_geom[2 * pidx + 1];
   if (m.geom_type[g1] > m.geom_type[g2]) { int t = g1; g1 = g2; g2 = t; }
   Shape<R> A, B;
-  shape_from(g1, row + L.gpos, row + L.gmat, A);
-  shape_from(g2, row + L.gpos, row + L.gmat, B);
+  shape_from(m, g1, row + RL.gpos, row + RL.gmat, A);
+  shape_from(m, g2, row + RL.gpos, row + RL.gmat, B);
   R buf[8 * CREC];
   int n = narrow_analytic(A, B, buf);
   R* out = s.cl_outA + (size_t)tid * CL_RECA;
@@ -137,32 +136,32 @@ __global__ void __launch_bounds__(128) narrow_analytic_kernel(Grp g) {
 }
 
 // convex pairs: ONE WARP per candidate pair (mesh support scans split over the lanes).  A block is one warp and owns one EPA
-// polytope in shared memory (7.3 KB fp32 -> ~30 resident warps per SM); warps claim work items through an atomic counter, so
-// the few expensive pairs (penetrating meshes: tens of EPA expansions) never hold idle neighbours resident.
+// polytope in shared memory; warps claim work items through an atomic counter, so the few expensive pairs (penetrating meshes:
+// tens of EPA expansions) never hold idle neighbours resident.
 template <typename R>
 __global__ void __launch_bounds__(32) narrow_convex_kernel(Grp g) {
-  const DModel<R>& m = cmodel<R>();
-  const DState<R>& s = cstate<R>();
-  const WSLayout& L = c_L;
+  const DModel<R>& m = cmodel<R>(g.slot);
+  const DState<R>& s = cstate<R>(g.slot);
+  const WSLayout& RL = c_lay[g.slot][LAY_ROW];
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int lane = threadIdx.x & 31;
   R* scratch = reinterpret_cast<R*>(smem_raw);
-  const int cnt = s.cl_cnt[4 * g.gid + 1];
+  const int cnt = CLC(s, g)[1];
   INSTR_BEGIN(s, g, 2)
   while (true) {
     int item = 0;
-    if (lane == 0) item = atomicAdd(s.cl_cnt + 4 * g.gid + 3, 1);
+    if (lane == 0) item = atomicAdd(CLC(s, g) + 3, 1);
     item = __shfl_sync(B2S_FULL, item, 0);
     if (item >= cnt) break;
     int wid = item + g.env0 * s.cl_maxg;
     int code = s.cl_listG[wid];
     int env = code >> 12, pidx = code & 4095;
-    const R* row = s.wsg + (size_t)env * L.total;
+    const R* row = s.wsg + (size_t)env * RL.total;
     int g1 = m.pair_geom[2 * pidx], g2 = m.pair_geom[2 * pidx + 1];
     if (m.geom_type[g1] > m.geom_type[g2]) { int t = g1; g1 = g2; g2 = t; }
     Shape<R> A, B;
-    shape_from(g1, row + L.gpos, row + L.gmat, A);
-    shape_from(g2, row + L.gpos, row + L.gmat, B);
+    shape_from(m, g1, row + RL.gpos, row + RL.gmat, A);
+    shape_from(m, g2, row + RL.gpos, row + RL.gmat, B);
     R buf[CREC];
     int n = convex_convex(A, B, buf, 1, scratch, lane, s.gjk_cache ? s.gjk_cache + ((size_t)env * m.npair + pidx) * 3 : (R*)nullptr,
                           EPA_PIPE_MAXV, EPA_PIPE_MAXF);
@@ -178,9 +177,9 @@ __global__ void __launch_bounds__(32) narrow_convex_kernel(Grp g) {
 
 // collect this environment's contacts from the work-list outputs, in static-pair order (what the fused collide produces)
 template <typename R> DEVN int gather_contacts(Eng<R> e, int env, int& warn) {
-  const DModel<R>& m = cmodel<R>();
-  const DState<R>& s = cstate<R>();
-  const WSLayout& L = c_L;
+  const DModel<R>& m = e.model();
+  const DState<R>& s = e.state();
+  const WSLayout& L = e.lay();
   int lane = e.lane;
   const int* tab = s.cl_env + (size_t)env * CL_ENVW(s);
   int na = tab[0], ng = tab[1], nc = na + ng;  // nc <= CL_MAXA + CL_MAXG = 96: up to IT candidates per lane
@@ -212,6 +211,7 @@ template <typename R> DEVN int gather_contacts(Eng<R> e, int env, int& warn) {
         if (op < pairv[it]) offv[it] += on;
     }
   }
+  if (total > L.mc) { warn |= 4; if (L.mc < m.maxcon) return L.mc; }  // small tier: the caller hands the environment to the large tier
   R* cpos = e.p(L.c_pos); R* cfr = e.p(L.c_frame); R* cdist = e.p(L.c_dist);
   int* cint = e.pi(L.c_int);
 #pragma unroll
@@ -223,7 +223,7 @@ template <typename R> DEVN int gather_contacts(Eng<R> e, int env, int& warn) {
     if (m.geom_type[g1] > m.geom_type[g2]) { int t = g1; g1 = g2; g2 = t; }
     for (int k = 0; k < n; k++) {
       int c = off + k;
-      if (c >= m.maxcon) break;
+      if (c >= L.mc) break;
       const R* b = rec + CREC * k;
       cpos[3 * c] = b[0]; cpos[3 * c + 1] = b[1]; cpos[3 * c + 2] = b[2];
       cfr[3 * c] = b[3]; cfr[3 * c + 1] = b[4]; cfr[3 * c + 2] = b[5];
@@ -231,122 +231,156 @@ template <typename R> DEVN int gather_contacts(Eng<R> e, int env, int& warn) {
       cint[5 * c] = g1; cint[5 * c + 1] = g2; cint[5 * c + 4] = pair;
     }
   }
-  if (total > m.maxcon) { total = m.maxcon; warn |= 4; }
+  if (total > L.mc) total = L.mc;
   __syncwarp();
   finish_contacts(e, total);
   return total;
 }
 
-// PH: 0 kinematics+velocity+crb, 1 collision, 2 constraint rows, 3 controller, 4 actuation+solve+integrate(+obs),
-//     5 = 2 + 3 + 4 in one launch (constraint rows, Jacobian and controller output never leave shared memory)
-#ifndef B2S_LB_THREADS
-#define B2S_LB_THREADS 512  // phase kernels: threads per block / resident blocks per SM the register allocation is sized for
-#define B2S_LB_BLOCKS 1
+#ifndef B2S_LB0_THREADS
+#define B2S_LB0_THREADS 256  // phase 0: threads per block / resident blocks per SM the register allocation is sized for
+#define B2S_LB0_BLOCKS 3
 #endif
-template <typename R, int PH>
-__global__ void __launch_bounds__(B2S_LB_THREADS, B2S_LB_BLOCKS) phase_kernel(int phases, int sub, int nsub, const R* action, Grp g) {
-  const DModel<R>& m = cmodel<R>();
-  const DState<R>& s = cstate<R>();
-  const WSLayout& L = c_L;
-  const PhaseIO& io = c_pio[PH];
+#ifndef B2S_LB5_THREADS
+#define B2S_LB5_THREADS 256  // tail kernel
+#define B2S_LB5_BLOCKS 3
+#endif
+
+// ---- phase 0: kinematics, velocity stage + RNE bias, CRB -> M, broad phase -> global candidate work lists
+template <typename R>
+__global__ void __launch_bounds__(B2S_LB0_THREADS, B2S_LB0_BLOCKS) phase0_kernel(int phases, Grp g) {
+  const DModel<R>& m = cmodel<R>(g.slot);
+  const DState<R>& s = cstate<R>(g.slot);
+  const WSLayout& L = c_lay[g.slot][LAY_P0];
+  const WSLayout& RL = c_lay[g.slot][LAY_ROW];
   extern __shared__ __align__(16) unsigned char smem_raw[];
   R* smem = reinterpret_cast<R*>(smem_raw);
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   int env = blockIdx.x * wpb + warp;
-  INSTR_BEGIN(s, g, PH == 0 ? 0 : 3)
+  INSTR_BEGIN(s, g, 0)
 #ifdef B2S_INSTR
   long long instr_t0 = clock64();
 #endif
-#ifndef B2S_TAIL_BARRIERS
-#define B2S_TAIL_BARRIERS 0  // block barriers between the sub-phases of the merged tail kernel (instruction-cache locality)
-#endif
-#define TAIL_BAR(level) if (PH == 5 && B2S_TAIL_BARRIERS >= level) __syncthreads();
-  if (env >= g.nenv) {  // warps past the end of the group still take part in the block barriers
-    TAIL_BAR(1) TAIL_BAR(2) TAIL_BAR(3) TAIL_BAR(4)
-    return;
-  }
+  if (env >= g.nenv) return;
   env += g.env0;
-  __shared__ unsigned long long mbar[16];  // one transaction barrier per warp (TMA loads of its workspace regions)
+  Eng<R> e(smem + (size_t)warp * L.total, lane, g.slot, LAY_P0);
+  size_t E = env;
+  R* row = s.wsg + E * RL.total;
+  load_row(e.p(L.qpos), s.qpos + E * m.nq, m.nq, lane);
+  load_row(e.p(L.qvel), s.qvel + E * m.nv, m.nv, lane);
+  __syncwarp();
+  e.kinematics();
+  e.velocity();
+  e.crb();
+  // collision candidates of this environment -> global work lists (slots by warp-aggregated atomics)
+  int* cand = reinterpret_cast<int*>(e.p(L.scratch));
+  int* cand_g = cand + 96;
+  int na, ng, warn = 0;
+  cull_pairs(e, cand, cand_g, s.cl_maxa, s.cl_maxg, na, ng);
+  if (na > s.cl_maxa) { na = s.cl_maxa; warn |= 4; }
+  if (ng > s.cl_maxg) { ng = s.cl_maxg; warn |= 4; }
+  int baseA = 0, baseG = 0;
+  if (lane == 0) {
+    if (na) baseA = g.env0 * s.cl_maxa + atomicAdd(CLC(s, g), na);
+    if (ng) baseG = g.env0 * s.cl_maxg + atomicAdd(CLC(s, g) + 1, ng);
+  }
+  baseA = __shfl_sync(B2S_FULL, baseA, 0);
+  baseG = __shfl_sync(B2S_FULL, baseG, 0);
+  int* tab = s.cl_env + E * CL_ENVW(s);
+  if (lane == 0) { tab[0] = na; tab[1] = ng; }
+  for (int i = lane; i < na; i += 32) { s.cl_listA[baseA + i] = (env << 12) | cand[i]; tab[2 + 2 * i] = cand[i]; tab[3 + 2 * i] = baseA + i; }
+  for (int i = lane; i < ng; i += 32) { s.cl_listG[baseG + i] = (env << 12) | cand_g[i]; tab[2 + 2 * (s.cl_maxa + i)] = cand_g[i]; tab[3 + 2 * (s.cl_maxa + i)] = baseG + i; }
+  if (lane == 0) reinterpret_cast<int*>(row + RL.hdr)[2] = warn;
+  __syncwarp();
+  ws_store(e, row, c_pio[g.slot][PIO_P0]);
+#ifdef B2S_INSTR
+  if (lane == 0 && s.cyc) s.cyc[(E * 32 + (g.sub & 31)) * 2] = (float)(clock64() - instr_t0);
+#endif
+  INSTR_END(s, g, 0)
+}
+
+// ---- tail: gather contacts, constraint rows + Jacobian, (in-kernel controller), actuation, Newton solve, Euler, observations.
+// tier 0: warp per environment of the group, small-capacity layout; an environment whose contacts / rows do not fit is appended to
+// the group's overflow list untouched.  tier 1: warps claim the overflowed environments and run them with the full-capacity layout.
+template <typename R>
+__global__ void __launch_bounds__(B2S_LB5_THREADS, B2S_LB5_BLOCKS) tail_kernel(int phases, int nsub, const R* action, Grp g, int tier) {
+  const DModel<R>& m = cmodel<R>(g.slot);
+  const DState<R>& s = cstate<R>(g.slot);
+  const int lid = tier ? LAY_TL : LAY_TS;
+  const WSLayout& L = c_lay[g.slot][lid];
+  const WSLayout& RL = c_lay[g.slot][LAY_ROW];
+  const PhaseIO& io = c_pio[g.slot][tier ? PIO_TL : PIO_TS];
+  const PhaseIO& io_late = c_pio[g.slot][tier ? PIO_TL_LATE : PIO_TS_LATE];
+  const CtrlCfgDev& cc = c_cc[g.slot];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  R* smem = reinterpret_cast<R*>(smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5, sub = g.sub;
+  INSTR_BEGIN(s, g, tier ? 5 : 3)
+  __shared__ unsigned long long mbar[32];  // one transaction barrier per warp (TMA loads of its workspace regions)
   if (lane == 0) mbar_init(&mbar[warp]);
   __syncwarp();
-  Eng<R> e(smem + (size_t)warp * L.total, lane);
-  size_t E = env;
-  R* row = s.wsg + E * L.total;
-  int* hdr = e.pi(L.hdr);
-  if (PH >= 2) {  // ncon / nefc / warn travel in the header
-    if (lane < 8) hdr[lane] = reinterpret_cast<const int*>(row + L.hdr)[lane];
-    __syncwarp();
-  }
-  int ncon = PH >= 2 ? hdr[0] : 0, nefc = (PH == 3 || PH == 4) ? hdr[1] : 0, warn = PH >= 2 ? hdr[2] : 0;
-  ws_load(e, row, io, nefc * m.nv, &mbar[warp]);
-  if (PH == 0 || PH >= 2) {
+  unsigned parity = 0;
+  Eng<R> e(smem + (size_t)warp * L.total, lane, g.slot, lid);
+  int* clc = CLC(s, g);
+  const bool tiered = L.mc < m.maxcon || L.me < m.maxefc;
+  for (int iter = 0;; iter++) {
+    int env;
+    if (tier == 0) {
+      if (iter > 0) break;
+      env = blockIdx.x * wpb + warp;
+      if (env >= g.nenv) break;
+      env += g.env0;
+    } else {
+      int item = 0;
+      if (lane == 0) item = atomicAdd(clc + 4, 1);
+      item = __shfl_sync(B2S_FULL, item, 0);
+      if (item >= clc[2]) break;
+      env = s.ovf_list[g.env0 + item];
+    }
+#ifdef B2S_INSTR
+    long long instr_t0 = clock64();
+#endif
+    const size_t E = env;
+    const R* row = s.wsg + E * RL.total;
+    int warn = reinterpret_cast<const int*>(row + RL.hdr)[2];  // phase 0: candidate-list overflow
+    ws_load(e, row, io, &mbar[warp], parity);
     load_row(e.p(L.qpos), s.qpos + E * m.nq, m.nq, lane);
     load_row(e.p(L.qvel), s.qvel + E * m.nv, m.nv, lane);
-  }
-  if (PH >= 3) load_row(e.p(L.ctrl), s.ctrl + E * m.nu, m.nu, lane);
-  if (PH >= 4) load_row(e.p(L.qacc_ws), s.qacc_ws + E * m.nv, m.nv, lane);
-  __syncwarp();
-  if (PH == 0) {
-    e.kinematics();
-    e.velocity();
-    e.crb();
-    // collision candidates of this environment -> global work lists (slots by warp-aggregated atomics)
-    int* cand = reinterpret_cast<int*>(e.p(L.scratch));
-    int* cand_g = cand + 96;
-    int na, ng;
-    cull_pairs(e, cand, cand_g, s.cl_maxa, s.cl_maxg, na, ng);
-    if (na > s.cl_maxa) { na = s.cl_maxa; warn |= 4; }
-    if (ng > s.cl_maxg) { ng = s.cl_maxg; warn |= 4; }
-    int baseA = 0, baseG = 0;
-    if (lane == 0) {
-      if (na) baseA = g.env0 * s.cl_maxa + atomicAdd(s.cl_cnt + 4 * g.gid, na);
-      if (ng) baseG = g.env0 * s.cl_maxg + atomicAdd(s.cl_cnt + 4 * g.gid + 1, ng);
+    load_row(e.p(L.ctrl), s.ctrl + E * m.nu, m.nu, lane);
+    load_row(e.p(L.qacc_ws), s.qacc_ws + E * m.nv, m.nv, lane);
+    __syncwarp();
+    int wl = 0;
+    int ncon = gather_contacts(e, env, wl);
+    int nefc = (tiered && (wl & 4)) ? 0 : make_constraint(e, ncon, wl);
+    if (tiered && (wl & 12)) {  // does not fit this tier: nothing of the environment's state has been touched yet
+      if (lane == 0) s.ovf_list[g.env0 + atomicAdd(clc + 2, 1)] = env;
+      __syncwarp();
+      continue;
     }
-    baseA = __shfl_sync(B2S_FULL, baseA, 0);
-    baseG = __shfl_sync(B2S_FULL, baseG, 0);
-    int* tab = s.cl_env + E * CL_ENVW(s);
-    if (lane == 0) { tab[0] = na; tab[1] = ng; }
-    for (int i = lane; i < na; i += 32) { s.cl_listA[baseA + i] = (env << 12) | cand[i]; tab[2 + 2 * i] = cand[i]; tab[3 + 2 * i] = baseA + i; }
-    for (int i = lane; i < ng; i += 32) { s.cl_listG[baseG + i] = (env << 12) | cand_g[i]; tab[2 + 2 * (s.cl_maxa + i)] = cand_g[i]; tab[3 + 2 * (s.cl_maxa + i)] = baseG + i; }
-    hdr[0] = 0; hdr[1] = 0;
-    if (lane == 0) { hdr[2] = warn; reinterpret_cast<int*>(row + L.hdr)[2] = warn; }
-  } else if (PH == 1) {
-    int dbgc[3] = {0, 0, 0};
-    ncon = collide(e, warn, dbgc);
-    if (lane == 0) { hdr[0] = ncon; hdr[1] = 0; hdr[2] = warn; hdr[3] = 0; }
-    __syncwarp();
-  }
-  if (PH == 2 || PH == 5) {
-    if (phases & PH_WORKLIST) ncon = gather_contacts(e, env, warn);
-    nefc = make_constraint(e, ncon, warn);
-    if (lane == 0) { hdr[0] = ncon; hdr[1] = nefc; hdr[2] = warn; }
-    __syncwarp();
-  }
-  TAIL_BAR(1)
-  if ((PH == 3 || (PH == 5 && (phases & PH_CTRL))) && !(phases & PH_CTRL_EXT)) {
-    CtrlState<R> cs;
-    ctrl_load(e, cs, env);
-    ctrl_run(e, cs, env, sub == 0 ? action : (const R*)nullptr);
-    for (int i = lane; i < m.nu; i += 32) s.ctrl[E * m.nu + i] = e.p(L.ctrl)[i];
-    if (sub == 0) ctrl_store(e, cs, env);
-    __syncwarp();
-  }
-  TAIL_BAR(2)
-  if (PH == 4 || PH == 5) {
+    warn |= wl;
+    if ((phases & PH_CTRL) && !(phases & PH_CTRL_EXT)) {
+      CtrlState<R> cs;
+      ctrl_load(e, cs, env);
+      ctrl_run(e, cs, env, sub == 0 ? action : (const R*)nullptr);
+      for (int i = lane; i < m.nu; i += 32) s.ctrl[E * m.nu + i] = e.p(L.ctrl)[i];
+      if (sub == 0) ctrl_store(e, cs, env);
+      __syncwarp();
+    }
     R time = s.time[env];
     e.actuation((R*)nullptr);
     if (e.acceleration()) warn |= 1;
-    TAIL_BAR(3)
     solve(e, nefc, ncon, warn);
-    TAIL_BAR(4)
     if (!(phases & PH_NOINTEGRATE)) {
       if (e.euler(&time)) warn |= 2;
     }
-    if ((phases & PH_OBS) && c_cc.obs_dim > 0) {
+    if ((phases & PH_OBS) && cc.obs_dim > 0 && sub == nsub - 1) {
       // The reference's observables sample on the LAST substep of a control step: reset()'s forced update already
       // advances their period timer by one model timestep (utils/observables.py:214-259, environments/base.py:418-427),
       // so the period closes after substep 24 and the next update - substep 25 - takes the sample.
-      if (sub == nsub - 1) { write_obs(e, env, (phases & PH_NOINTEGRATE) != 0); write_task(e, env, ncon); }
+      // Body / site poses of this substep's step1 arrive now, over the (dead) constraint Jacobian.
+      ws_load(e, row, io_late, &mbar[warp], parity);
+      write_obs(e, env, (phases & PH_NOINTEGRATE) != 0);
+      write_task(e, env, ncon);
     }
     for (int i = lane; i < m.nq; i += 32) s.qpos[E * m.nq + i] = e.p(L.qpos)[i];
     for (int i = lane; i < m.nv; i += 32) {
@@ -355,15 +389,11 @@ __global__ void __launch_bounds__(B2S_LB_THREADS, B2S_LB_BLOCKS) phase_kernel(in
       s.qacc_ws[E * m.nv + i] = e.p(L.qacc_ws)[i];
     }
     if (lane == 0) { s.time[env] = time; s.warn[env] |= warn; }
-  }
-  __syncwarp();
-  ws_store(e, row, io, nefc * m.nv);
-  if (PH == 1 || PH == 2) {
-    if (lane < 8) reinterpret_cast<int*>(row + L.hdr)[lane] = hdr[lane];
-  }
+    __syncwarp();
 #ifdef B2S_INSTR
-  if (lane == 0 && s.cyc && (PH == 0 || PH == 5)) s.cyc[(E * 32 + (sub & 31)) * 2 + (PH == 0 ? 0 : 1)] = (float)(clock64() - instr_t0);
-  if (PH == 5 && lane == 0 && s.stats) { atomicAdd(s.stats + 16 + min(ncon, 32), 1); atomicAdd(s.stats + 64 + min(nefc, 64), 1); }
+    if (lane == 0 && s.cyc) s.cyc[(E * 32 + (sub & 31)) * 2 + 1] = (float)(clock64() - instr_t0);
+    if (lane == 0 && s.stats) { atomicAdd(s.stats + 32 + min(ncon, 128), 1); atomicAdd(s.stats + 176 + min(nefc, 320), 1); if (tier) atomicAdd(s.stats + 19, 1); }
 #endif
-  INSTR_END(s, g, PH == 0 ? 0 : 3)
+  }
+  INSTR_END(s, g, tier ? 5 : 3)
 }

@@ -48,8 +48,8 @@ template <typename R> DEV R row_friction(const R* f3, int k) { return k <= 2 ? f
 // Builds all constraint rows in the workspace.  Returns nefc (warp-uniform).
 template <typename R> DEVN int make_constraint(Eng<R> e, int ncon, int& warn, float* pc = nullptr) {
 #define MTICK(slot)
-  const DModel<R>& m = cmodel<R>();
-  const WSLayout& L = c_L;
+  const DModel<R>& m = e.model();
+  const WSLayout& L = e.lay();
   int lane = e.lane, nv = m.nv;
   R* J = e.p(L.J);
   R* eD = e.p(L.e_D); R* eR = e.p(L.e_R); R* earef = e.p(L.e_aref); R* efl = e.p(L.e_floss);
@@ -83,7 +83,7 @@ template <typename R> DEVN int make_constraint(Eng<R> e, int ncon, int& warn, fl
     unsigned mask = __ballot_sync(B2S_FULL, act);
     if (act) {
       int r = nefc + __popc(mask & ((1u << lane) - 1));
-      if (r < m.maxefc) {
+      if (r < L.me) {
         int dof = m.jnt_dofadr[j];
         B2S_LOOP
         for (int i = 0; i < nv; i++) J[r * nv + i] = i == dof ? R(-side) : R(0);
@@ -94,7 +94,7 @@ template <typename R> DEVN int make_constraint(Eng<R> e, int ncon, int& warn, fl
     }
     nefc += __popc(mask);
   }
-  if (nefc > m.maxefc) { nefc = m.maxefc; warn |= 8; }
+  if (nefc > L.me) { nefc = L.me; warn |= 8; }
   // --- contacts: row addresses by ordered prefix sum over active contacts
   int* cint = e.pi(L.c_int);
   const R* cdist = e.p(L.c_dist);
@@ -109,12 +109,12 @@ template <typename R> DEVN int make_constraint(Eng<R> e, int ncon, int& warn, fl
     int total = __shfl_sync(B2S_FULL, off, 31);
     int adr = nefc + off - dim;
     if (c < ncon) {
-      if (dim > 0 && adr + dim <= m.maxefc) cint[5 * c + 3] = adr;
+      if (dim > 0 && adr + dim <= L.me) cint[5 * c + 3] = adr;
       else { cint[5 * c + 3] = -1; if (dim > 0) warn |= 8; }
     }
     nefc += total;
   }
-  if (nefc > m.maxefc) nefc = m.maxefc;  // rows of dropped contacts are simply absent (flagged in warn)
+  if (nefc > L.me) nefc = L.me;  // rows of dropped contacts are simply absent (flagged in warn)
   __syncwarp();
   // recompute exact nefc as end of the last placed contact
   {
@@ -260,13 +260,13 @@ template <typename R> DEVN int make_constraint(Eng<R> e, int ncon, int& warn, fl
 // Hessian blocks (scratch), returns total constraint cost (warp-uniform).  If hess==0 only cost/forces.
 template <typename R>
 DEVN R constraint_update(Eng<R> e, int nefc, int ncon, bool hess) {
-  const DModel<R>& m = cmodel<R>();
-  const WSLayout& L = c_L;
+  const DModel<R>& m = e.model();
+  const WSLayout& L = e.lay();
   int lane = e.lane;
   const R* jar = e.p(L.e_jar); const R* eD = e.p(L.e_D); const R* eR = e.p(L.e_R); const R* efl = e.p(L.e_floss);
   R* force = e.p(L.e_force);
   R* act = e.p(L.scratch);             // per-row curvature (D or 0); cone rows 0
-  R* Hc = e.p(L.scratch) + m.maxefc;   // per-contact cone Hessian blocks, 36 each
+  R* Hc = e.p(L.scratch) + L.me;   // per-contact cone Hessian blocks, 36 each
   const int* eint = e.pi(L.e_int);
   const int* cint = e.pi(L.c_int);
   R cost = 0;
@@ -359,8 +359,8 @@ DEVN R constraint_update(Eng<R> e, int nefc, int ncon, bool hess) {
 // first / second derivative of the cost along the search direction at step alpha (warp-uniform result)
 template <typename R>
 DEVN void ls_eval(Eng<R> e, int nefc, int ncon, int first_contact_row, R alpha, R quad1, R quad2, R& d1, R& d2) {
-  const DModel<R>& m = cmodel<R>();
-  const WSLayout& L = c_L;
+  const DModel<R>& m = e.model();
+  const WSLayout& L = e.lay();
   int lane = e.lane;
   const R* jar = e.p(L.e_jar); const R* jv = e.p(L.e_jv); const R* eD = e.p(L.e_D); const R* eR = e.p(L.e_R);
   const R* efl = e.p(L.e_floss);
@@ -415,8 +415,8 @@ DEVN void ls_eval(Eng<R> e, int nefc, int ncon, int first_contact_row, R alpha, 
 
 // Newton solve: qacc (workspace) <- argmin; efc_force, qfrc_constraint filled.  Returns iterations used.
 template <typename R> DEVN int solve(Eng<R> e, int nefc, int ncon, int& warn) {
-  const DModel<R>& m = cmodel<R>();
-  const WSLayout& L = c_L;
+  const DModel<R>& m = e.model();
+  const WSLayout& L = e.lay();
   int lane = e.lane, nv = m.nv;
   R* qacc = e.p(L.qacc); R* qcon = e.p(L.qcon);
   const R* qs = e.p(L.qsmooth); const R* qas = e.p(L.qaccs);
@@ -431,7 +431,7 @@ template <typename R> DEVN int solve(Eng<R> e, int nefc, int ncon, int& warn) {
   R* Ma = e.p(L.Ma); R* grad = e.p(L.grad); R* search = e.p(L.search); R* Mv = e.p(L.Mv);
   const int* cint = e.pi(L.c_int);
   const int* eint = e.pi(L.e_int);
-  R* act = e.p(L.scratch); R* Hcb = e.p(L.scratch) + m.maxefc;
+  R* act = e.p(L.scratch); R* Hcb = e.p(L.scratch) + L.me;
   R scale = R(1) / (m.meaninertia * R(nv > 1 ? nv : 1));
   int first_contact_row = nefc;
   B2S_LOOP
@@ -481,7 +481,7 @@ template <typename R> DEVN int solve(Eng<R> e, int nefc, int ncon, int& warn) {
   int niter = 0;
 #ifdef B2S_INSTR
   int instr_ls = 0;
-#define INSTR_SOLVE_DONE { const DState<R>& st_ = cstate<R>(); if (lane == 0 && st_.stats) { atomicAdd(st_.stats + min(niter, 15), 1); atomicAdd(st_.stats + 129, instr_ls); atomicAdd(st_.stats + 130, 1); } }
+#define INSTR_SOLVE_DONE { const DState<R>& st_ = e.state(); if (lane == 0 && st_.stats) { atomicAdd(st_.stats + min(niter, 15), 1); atomicAdd(st_.stats + 16, instr_ls); atomicAdd(st_.stats + 17, 1); } }
 #else
 #define INSTR_SOLVE_DONE
 #endif
@@ -547,7 +547,7 @@ template <typename R> DEVN int solve(Eng<R> e, int nefc, int ncon, int& warn) {
     }
     __syncwarp();
     {
-      int* dofs = reinterpret_cast<int*>(Hcb + m.hc_stride * m.maxcon);
+      int* dofs = reinterpret_cast<int*>(Hcb + m.hc_stride * L.mc);
       B2S_LOOP
       for (int c = 0; c < ncon; c++) {
         int adr = cint[5 * c + 3];

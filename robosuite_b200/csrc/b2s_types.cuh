@@ -81,7 +81,9 @@ struct DState {
   int* dbg;        // [n_env, 4] analytic candidates, convex candidates, EPA calls, reserved
   R* wsg;          // [n_env, L.total] global workspace rows (pipeline mode)
   // pipeline-mode collision work lists (candidate pairs of ALL environments, compacted with atomics)
-  int* cl_cnt;     // per group [4]: number of analytic / convex candidates this substep, (spare), next convex work item
+  int* cl_cnt;     // per group [8]: number of analytic / convex candidates this substep, overflowed environments (small tail tier),
+                   // next convex work item, next overflow item, (spare x3)
+  int* ovf_list;   // [n_env] environments whose contacts / rows did not fit the small tier (group g's slice starts at its env0)
   int cl_maxa, cl_maxg;  // per-environment candidate capacity of the two work lists
   int* cl_listA;   // [n_env * cl_maxa] env << 12 | pair
   int* cl_listG;   // [n_env * cl_maxg]
@@ -96,7 +98,8 @@ struct DState {
   // solver statistics.  Null in product builds.
   unsigned long long* st_begin;  // [64 groups][32 substeps][8 kernel kinds] first %globaltimer of the launch
   unsigned long long* st_end;    //                                     last %globaltimer of the launch
-  int* stats;      // [256] histograms: 0..15 Newton iterations, 16..48 ncon, 64..128 nefc, 129 line-search evaluations, 130 solves
+  int* stats;      // [512]: 0..15 Newton-iteration histogram, 16 line-search evaluations, 17 solves, 19 large-tier environments,
+                   // 32..160 ncon histogram, 176..496 nefc histogram
   float* cyc;      // [n_env][32 substeps][2] clock64 cycles of this environment's warp in P0 / the tail kernel
 };
 
@@ -115,17 +118,25 @@ struct WSLayout {
   int fused_stride;  // words per warp in the fused kernel = total + EPA polytope area
   int hdr;  // 8 words of per-env integers passed between pipeline phases: ncon, nefc, warn, niter
   int total;
+  int mc, me;  // contact / constraint-row capacity of THIS layout (the small tier of the tail kernel holds fewer than the model's
+               // maxcon / maxefc; environments that need more are re-run with the large tier)
 };
+
+// A handle owns one slot of every descriptor array below; a kernel is told its slot and which of the slot's layouts its warps use:
+// the full layout (fused kernel), phase 0's, the tail kernel's small / large tier, and the layout of the global workspace row.
+#define B2S_NSLOT 8
+enum { LAY_FULL = 0, LAY_P0 = 1, LAY_TS = 2, LAY_TL = 3, LAY_ROW = 4, B2S_NLAY = 5 };
 
 // Pipeline mode: the substep is split into phase kernels; each phase loads / stores these workspace regions
 // from / to the per-environment global workspace row (L2 resident).
-struct Region { int off, len, dyn; };  // dyn: 0 fixed, 1 = nefc*nv words (constraint Jacobian)
-#define B2S_NPHASE 6
+struct Region { int off, goff, len, dyn; };  // shared-memory offset, offset in the global row, words; dyn: 1 = nefc*nv words
+// PhaseIO slots: what phase 0 stores, what the tail kernel loads at its start / before the observation sample, per tier
+enum { PIO_P0 = 0, PIO_TS = 1, PIO_TS_LATE = 2, PIO_TL = 3, PIO_TL_LATE = 4, B2S_NPIO = 5 };
 #define CL_MAXA 64  // hard upper bounds of the per-environment candidate counts (analytic / convex pairs);
 #define CL_MAXG 32  // the run-time caps DState::cl_maxa / cl_maxg are chosen per model (b2s_capi.cu)
 #define CL_RECA 58
 #define CL_ENVW(s) (2 + 2 * ((s).cl_maxa + (s).cl_maxg))
-#define B2S_MAXREG 20
+#define B2S_MAXREG 12
 // load / store lists hold merged 16-byte aligned spans; load_words = sum of the fixed spans, load_dyn = list has the Jacobian
 struct PhaseIO { int nload, nstore, load_words, load_dyn; Region load[B2S_MAXREG], store[B2S_MAXREG]; };
 
@@ -151,19 +162,19 @@ struct CtrlCfgDev {
   double grip_sign[4], grip_speed, kp[6], kd[6], input_max[6], input_min[6], output_max[6], output_min[6], null_kp;
 };
 
-// ---- per-process constant-memory copies of the descriptors (uploaded by the host before a launch whenever the
-// owning handle changes).  Device code reads them through the constant bank, so non-inlined phase functions need no
-// descriptor arguments and the kernel's instruction footprint stays small.
-__constant__ DModel<float> c_model_f;
-__constant__ DModel<double> c_model_d;
-__constant__ DState<float> c_state_f;
-__constant__ DState<double> c_state_d;
-__constant__ WSLayout c_L;
-__constant__ CtrlCfgDev c_cc;
-__constant__ PhaseIO c_pio[B2S_NPHASE];
-template <typename R> __device__ __forceinline__ const DModel<R>& cmodel();
-template <> __device__ __forceinline__ const DModel<float>& cmodel<float>() { return c_model_f; }
-template <> __device__ __forceinline__ const DModel<double>& cmodel<double>() { return c_model_d; }
-template <typename R> __device__ __forceinline__ const DState<R>& cstate();
-template <> __device__ __forceinline__ const DState<float>& cstate<float>() { return c_state_f; }
-template <> __device__ __forceinline__ const DState<double>& cstate<double>() { return c_state_d; }
+// ---- constant-memory descriptors, one slot per live handle (b2s_create takes a free slot, b2s_destroy returns it).  Device code
+// reads them through the constant bank with a warp-uniform slot index, so non-inlined phase functions need no descriptor
+// arguments beyond the (slot, layout) pair carried by Eng, and handles of different tasks run concurrently on one GPU.
+__constant__ DModel<float> c_model_f[B2S_NSLOT];
+__constant__ DModel<double> c_model_d[B2S_NSLOT];
+__constant__ DState<float> c_state_f[B2S_NSLOT];
+__constant__ DState<double> c_state_d[B2S_NSLOT];
+__constant__ WSLayout c_lay[B2S_NSLOT][B2S_NLAY];
+__constant__ CtrlCfgDev c_cc[B2S_NSLOT];
+__constant__ PhaseIO c_pio[B2S_NSLOT][B2S_NPIO];
+template <typename R> __device__ __forceinline__ const DModel<R>& cmodel(int slot);
+template <> __device__ __forceinline__ const DModel<float>& cmodel<float>(int slot) { return c_model_f[slot]; }
+template <> __device__ __forceinline__ const DModel<double>& cmodel<double>(int slot) { return c_model_d[slot]; }
+template <typename R> __device__ __forceinline__ const DState<R>& cstate(int slot);
+template <> __device__ __forceinline__ const DState<float>& cstate<float>(int slot) { return c_state_f[slot]; }
+template <> __device__ __forceinline__ const DState<double>& cstate<double>(int slot) { return c_state_d[slot]; }

@@ -88,17 +88,25 @@ _TYPESTR = {B2S_F32: "<f4", B2S_F64: "<f8", B2S_I32: "<i4", B2S_I64: "<i8"}
 class BatchedSim:
     """n_env independent copies of one compiled model, stepped by the per-warp CUDA engine."""
 
-    def __init__(self, model, n_env, device=0, precision="f32", maxcon=None, maxefc=None):
+    def __init__(self, model, n_env, device=0, precision="f32", maxcon=None, maxefc=None, tier_small=None):
+        import copy
+
         import torch
 
         if isinstance(model, str):
             model = compile_mjcf(model)
         assert isinstance(model, Model)
+        if maxcon is not None or maxefc is not None or tier_small is not None:
+            model = copy.copy(model)  # capacities travel inside the model blob: never write them into the caller's (shared) Model
+            if maxcon is not None:
+                model.opt_maxcon = int(maxcon)
+            if maxefc is not None:
+                model.opt_maxefc = int(maxefc)
+            if tier_small is not None:
+                # small tier of the tail kernel: capacities (contacts, constraint rows) almost every environment stays within; the
+                # rest is re-run with (maxcon, maxefc) - results are the same, shared memory per warp is 2-3x smaller
+                model.opt_maxcon_small, model.opt_maxefc_small = int(tier_small[0]), int(tier_small[1])
         self.model = model
-        if maxcon is not None:
-            model.opt_maxcon = int(maxcon)
-        if maxefc is not None:
-            model.opt_maxefc = int(maxefc)
         self.n_env = int(n_env)
         self.device = int(device)
         self.torch_device = torch.device("cuda", self.device)

@@ -97,6 +97,9 @@ class BatchedMujocoEnv:
 
     maxcon = None  # per-environment contact / constraint-row capacity (None: engine defaults 32 / 64); overflow sets warn bit 4
     maxefc = None
+    # capacities of the tail kernel's small tier (contacts, rows): what all but ~0.1 % of this task's environment-substeps stay within
+    # under random actions (measured: tools/probe_instr.py); None = no tiering
+    tier_small = None
 
     def __init__(self, robots="Panda", num_envs=1, device=0, controller_configs=None, control_freq=20, horizon=500,
                  ignore_done=False, reward_scale=1.0, reward_shaping=False, use_object_obs=True, seed=None,
@@ -125,7 +128,8 @@ class BatchedMujocoEnv:
         if control_freq <= 0:
             raise ValueError("Control frequency {} is invalid".format(control_freq))
         self.n_substeps = int(self.control_timestep / self.model_timestep)
-        caps = {k: v for k, v in (("maxcon", kwargs.get("maxcon", self.maxcon)), ("maxefc", kwargs.get("maxefc", self.maxefc))) if v}
+        caps = {k: v for k, v in (("maxcon", kwargs.get("maxcon", self.maxcon)), ("maxefc", kwargs.get("maxefc", self.maxefc)),
+                                  ("tier_small", kwargs.get("tier_small", self.tier_small))) if v}
         # sim_cls: test hook (tests/oracle_sim.py drives the same host code on the CPU oracle); the product path is BatchedSim
         self.sim = (sim_cls or BatchedSim)(self.model, self.num_envs, device=device, precision=precision, **caps)
         self.device = self.sim.torch_device

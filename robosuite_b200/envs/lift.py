@@ -15,6 +15,8 @@ GRIPPER_INIT_QPOS = {"Panda": [0.020833, -0.020833], "Sawyer": [0.020833, -0.020
 class BatchedLift(BatchedMujocoEnv):
     """suite.make("Lift", robots="Panda", num_envs=N): table arena + one cube, sparse/shaped lifting reward."""
 
+    tier_small = (8, 32)  # small tail tier: see BatchedMujocoEnv.tier_small
+
     table_offset = (0.0, 0.0, 0.8)  # lift.py:146
 
     def _load_model(self, xml):

@@ -12,6 +12,8 @@ from .lift import GRIPPER_INIT_QPOS, PANDA_INIT_QPOS, SAWYER_INIT_QPOS
 class BatchedStack(BatchedMujocoEnv):
     """suite.make("Stack", robots="Sawyer", num_envs=N): red cube A (2 cm) to be stacked on green cube B (2.5 cm)"""
 
+    tier_small = (12, 40)  # small tail tier: see BatchedMujocoEnv.tier_small
+
     table_offset = (0.0, 0.0, 0.8)  # stack.py:154
 
     def _load_model(self, xml):

@@ -29,7 +29,7 @@ def _m2q_xyzw_wpos(M):
 
 
 class OracleSim:
-    def __init__(self, model, n_env, device=0, precision="f64", maxcon=None, maxefc=None):
+    def __init__(self, model, n_env, device=0, precision="f64", maxcon=None, maxefc=None, tier_small=None):
         self.model, self.n_env = model, int(n_env)
         self.torch_device, self.dtype = torch.device("cpu"), torch.float64
         blob = pack_model(model)

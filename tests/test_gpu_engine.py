@@ -218,7 +218,7 @@ def test_env_step_f32_100_control_steps():
     assert eq < 5e-2
 
 
-def _scripted_rollout(mode, steps, no_cache, ctrl_split=False):
+def _scripted_rollout(mode, steps, no_cache, ctrl_split=False, tier_small=None):
     import os
     import torch
     from robosuite_b200 import controller_config as cc
@@ -238,7 +238,7 @@ def _scripted_rollout(mode, steps, no_cache, ctrl_split=False):
     # the thread-per-environment controller kernel orders its fp64 sums differently from the in-kernel controller (last-bit
     # differences in the torques): bit-exactness of the two SCHEDULES is tested with the controller inside the tail kernel
     os.environ["B2S_CTRL_SPLIT"] = "1" if ctrl_split else "0"
-    sim = BatchedSim(model, n, precision="f32")
+    sim = BatchedSim(model, n, precision="f32", tier_small=tier_small)
     sim.ctrl_config(cc.resolve(model, cc.default_composite_config(), CtrlCfg))
     sim.set_export(False)
     sim.set_mode(mode)
@@ -273,6 +273,17 @@ def test_pipeline_gjk_warm_start_changes_paths_not_results():
     dq = np.abs(a[0] - b[0]).max()
     print("pipeline(warm start) vs fused after 300 substeps: max |dqpos| %.3g" % dq)
     assert dq < 1e-4
+
+
+@pytest.mark.parametrize("tier", [(4, 24), (8, 32)])
+def test_small_tail_tier_is_exact(tier):
+    """the tail kernel's small capacity tier + large-tier re-run of the environments that do not fit must be BIT-IDENTICAL to running
+    every environment with the full capacities: the arithmetic is the same, only the shared-memory layout differs.  (4, 24) is
+    small enough that most environments of this contact-rich rollout overflow; (8, 32) is Lift's production setting."""
+    a = _scripted_rollout(1, 24, True, ctrl_split=True)
+    b = _scripted_rollout(1, 24, True, ctrl_split=True, tier_small=tier)
+    assert np.isfinite(b[0]).all()
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
 
 
 def test_split_controller_kernel_matches_in_kernel_controller():

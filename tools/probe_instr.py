@@ -45,7 +45,7 @@ valid = e[:G, :25] > 0
 t0 = b[:G, :25][valid].min()
 B = (b[:G, :25].astype(np.float64) - float(t0)) / 1e3  # us
 E = (e[:G, :25].astype(np.float64) - float(t0)) / 1e3
-names = ["P0", "narrowA", "narrowG", "tail", "ctrl"]
+names = ["P0", "narrowA", "narrowG", "tail", "ctrl", "tailL"]
 out = {"task": task, "robot": robot, "n_env": n, "controller": ctrl, "groups": G, "step_ms_events": step_ms,
        "span_us": float(E.max()), "kernels": {}, "gaps_us": {}}
 for k, nm in enumerate(names):
@@ -73,11 +73,22 @@ for g in range(G):
             run += (ts >= B[g, s, k]) & (ts < E[g, s, k])
 out["phase_kernels_running_hist"] = {str(i): float((run == i).mean()) for i in range(G + 1)}
 st = sim.stats.cpu().numpy()
-nsolve = max(int(st[130]), 1)
-out["solver"] = {"solves": int(st[130]), "niter_hist": st[:16].tolist(), "mean_niter": float((st[:16] * np.arange(16)).sum() / max(st[:16].sum(), 1)),
-                 "ls_evals_per_solve": float(st[129]) / nsolve, "ncon_hist": st[16:49].tolist(), "nefc_hist": st[64:129].tolist()}
+nsolve = max(int(st[17]), 1)
+nc, ne = st[32:161], st[176:497]
+
+
+def pct(h, q):
+    c = np.cumsum(h) / max(h.sum(), 1)
+    return int(np.searchsorted(c, q))
+
+
+out["solver"] = {"solves": int(st[17]), "niter_hist": st[:16].tolist(), "mean_niter": float((st[:16] * np.arange(16)).sum() / max(st[:16].sum(), 1)),
+                 "ls_evals_per_solve": float(st[16]) / nsolve, "large_tier_env_substeps": int(st[19]),
+                 "ncon": {"mean": float((nc * np.arange(len(nc))).sum() / max(nc.sum(), 1)), "p99": pct(nc, 0.99), "p999": pct(nc, 0.999), "max": int(np.nonzero(nc)[0].max())},
+                 "nefc": {"mean": float((ne * np.arange(len(ne))).sum() / max(ne.sum(), 1)), "p99": pct(ne, 0.99), "p999": pct(ne, 0.999), "max": int(np.nonzero(ne)[0].max())},
+                 "ncon_hist": nc.tolist(), "nefc_hist": ne.tolist()}
 cy = sim.cyc.cpu().numpy()[:, :25]  # [n, 25, 2]
-wpb = int(os.environ.get("B2S_WARPS_PER_BLOCK", "14"))
+wpb = int(os.environ.get("B2S_WPB5", "8"))
 for k, nm in ((0, "P0"), (1, "tail")):
     c = cy[:, :, k]
     ge = n // G
