@@ -74,9 +74,6 @@ struct b2s_sim {
   std::vector<TlEv> tl_events;
   double tl_mean_us[8] = {0}; int tl_count[8] = {0};
   int ctrl_split = 1;  // pipeline: OSC controller as its own thread-per-environment kernel (B2S_CTRL_SPLIT=0: inside the tail kernel)
-  int ctrl_fork = 1;   // ... on a side stream, beside the collision narrow phase (B2S_CTRL_FORK=0: in line after phase 0)
-  std::vector<cudaStream_t> cstreams;
-  std::vector<cudaEvent_t> cev_fork, cev_join;
   std::vector<cudaStream_t> gstreams;
   std::vector<cudaEvent_t> gevents;
   cudaEvent_t fork_event = nullptr, in_event = nullptr, out_event = nullptr;
@@ -270,6 +267,14 @@ template <typename R> static void build_model(b2s_sim* s, const Blob& b, DModel<
   m.geom_rbound = up_f<R>(s, b, "geom_rbound"); m.geom_aabb = up_f<R>(s, b, "geom_aabb");
   m.pair_geom = up_i(s, b, "pair_geom");
   m.mesh_vertadr = up_i(s, b, "mesh_vertadr"); m.mesh_vertnum = up_i(s, b, "mesh_vertnum"); m.mesh_vert = up_f<R>(s, b, "mesh_vert");
+  {  // staging area of the convex narrow-phase kernel: room for the two largest hulls (at most 56 KB), see convex_convex
+    int64_t nm = 0; const int* vn = b.i32("mesh_vertnum", &nm);
+    int n1 = 0, n2 = 0;
+    for (int64_t i = 0; i < nm; i++) { int v = vn[i]; if (v > n1) { n2 = n1; n1 = v; } else if (v > n2) n2 = v; }
+    int need = ((3 * n1 + 3) & ~3) + ((3 * n2 + 3) & ~3);
+    int cap = (int)(56 * 1024 / sizeof(R));
+    m.stage_cap = getenv("B2S_NO_STAGE") ? 0 : std::min(need, cap);
+  }
   m.site_bodyid = up_i(s, b, "site_bodyid"); m.site_pos = up_f<R>(s, b, "site_pos"); m.site_quat = up_f<R>(s, b, "site_quat");
   m.act_trnid = up_i(s, b, "actuator_trnid"); m.act_ctrllimited = up_i(s, b, "actuator_ctrllimited");
   m.act_forcelimited = up_i(s, b, "actuator_forcelimited"); m.act_biastype = up_i(s, b, "actuator_biastype");
@@ -627,10 +632,12 @@ int b2s_create(const void* blob_host, size_t nbytes, int n_env, int device, int 
       e1 = optin_max_smem(step_kernel<float>, device);
       if (e1 == cudaSuccess) e1 = optin_max_smem(phase0_kernel<float>, device);
       if (e1 == cudaSuccess) e1 = optin_max_smem(tail_kernel<float>, device);
+      if (e1 == cudaSuccess) e1 = optin_max_smem(phase1_kernel<float>, device);
     } else {
       e1 = optin_max_smem(step_kernel<double>, device);
       if (e1 == cudaSuccess) e1 = optin_max_smem(phase0_kernel<double>, device);
       if (e1 == cudaSuccess) e1 = optin_max_smem(tail_kernel<double>, device);
+      if (e1 == cudaSuccess) e1 = optin_max_smem(phase1_kernel<double>, device);
     }
     if (e1 != cudaSuccess) { std::string msg = cudaGetErrorString(e1); b2s_destroy(s); return fail(B2S_ERR_CUDA, "cudaFuncSetAttribute: " + msg); }
   }
@@ -647,9 +654,6 @@ void b2s_destroy(b2s_sim* s) {
   cudaDeviceSynchronize();  // kernels of this handle may still be reading its buffers
   for (void* p : s->allocs) cudaFree(p);
   for (auto q : s->gstreams) cudaStreamDestroy(q);
-  for (auto q : s->cstreams) cudaStreamDestroy(q);
-  for (auto ev : s->cev_fork) cudaEventDestroy(ev);
-  for (auto ev : s->cev_join) cudaEventDestroy(ev);
   for (auto ev : s->gevents) cudaEventDestroy(ev);
   if (s->fork_event) cudaEventDestroy(s->fork_event);
   if (s->in_event) cudaEventDestroy(s->in_event);
@@ -747,7 +751,8 @@ static int launch(b2s_sim* s, int phases, int nsub, const void* action = nullptr
 
 // enqueue the launches of `nsub` substeps for every environment group; `q0` is the stream the caller forks from / joins to
 template <typename R> static int enqueue_pipeline(b2s_sim* s, DState<R>& st, int phases, int nsub, const R* action, cudaStream_t q0) {
-  const int epaw = (9 * EPA_PIPE_MAXV + 4 * EPA_PIPE_MAXF + EPA_PIPE_MAXF + 8) * (int)sizeof(R);
+  const int epaw = (EPA_PIPE_WORDS + (s->precision == B2S_F32 ? s->mf.stage_cap : s->md.stage_cap)) * (int)sizeof(R);
+  const int p1smem = std::max(epaw, (int)osc_smem_bytes<R>());  // one block shape for the three roles of phase 1
   int G = s->ngroups;
   if (G > s->n_env) G = s->n_env;
   const bool tiered = s->mc_small < s->maxcon || s->me_small < s->maxefc;
@@ -762,7 +767,6 @@ template <typename R> static int enqueue_pipeline(b2s_sim* s, DState<R>& st, int
     int nA = g.nenv * st.cl_maxa, nG = g.nenv * st.cl_maxg;
     const int cvx_blocks = 148 * 24;
     const bool ctrl_ext = (phases & PH_CTRL_EXT) != 0;
-    cudaStream_t cq = (ctrl_ext && s->ctrl_fork) ? s->cstreams[gi] : q;
     // B2S_TIMELINE=1 (with B2S_NO_GRAPH=1): timing events between the launches, per-kernel means on stderr (debug aid)
     auto mark = [&](int type) {
       if (!s->timeline) return;
@@ -776,18 +780,14 @@ template <typename R> static int enqueue_pipeline(b2s_sim* s, DState<R>& st, int
       mark(1);
       phase0_kernel<R><<<blocks0, s->wpb0 * 32, s->smem0, q>>>(phases, g);
       mark(2);
-      if (ctrl_ext) {  // controller: one thread per environment, needs only phase 0's outputs -> runs beside the narrow phase
-        if (cq != q) { CUDA_TRY(cudaEventRecord(s->cev_fork[gi], q)); CUDA_TRY(cudaStreamWaitEvent(cq, s->cev_fork[gi], 0)); }
-        ctrl_osc_kernel<R><<<(g.nenv + OSC_TPB - 1) / OSC_TPB, OSC_TPB, osc_smem_bytes<R>(), cq>>>(sub, action, g.env0, g.nenv, g.gid, s->slot);
-        if (cq != q) CUDA_TRY(cudaEventRecord(s->cev_join[gi], cq));
+      // phase 1: convex narrow phase | controller | analytic narrow phase as block roles of ONE launch (no forks in the graph).
+      // Upper bounds of the candidate counts size the grid; warps / threads beyond the device-side counts exit at once.
+      {
+        P1Cfg c{(s->debug_skip & 2) ? 0 : std::min(nG, cvx_blocks), ctrl_ext ? (g.nenv + OSC_TPB - 1) / OSC_TPB : 0, sub};
+        int nAb = (s->debug_skip & 1) ? 0 : (nA + 31) / 32;
+        if (c.nG + c.nC + nAb > 0) phase1_kernel<R><<<c.nG + c.nC + nAb, 32, p1smem, q>>>(action, g, c);
       }
-      // upper bounds of the candidate counts size the grids; threads / warps beyond the device-side count exit at once
-      if (!(s->debug_skip & 1)) narrow_analytic_kernel<R><<<(nA + 127) / 128, 128, 0, q>>>(g);
-      mark(3);
-      // one warp per block (its EPA polytope is the block's shared memory), work items claimed through an atomic counter
-      if (!(s->debug_skip & 2)) narrow_convex_kernel<R><<<nG < cvx_blocks ? nG : cvx_blocks, 32, epaw, q>>>(g);
       mark(4);
-      if (ctrl_ext && cq != q) CUDA_TRY(cudaStreamWaitEvent(q, s->cev_join[gi], 0));
       tail_kernel<R><<<blocks5, s->wpb5s * 32, s->smem5s, q>>>(phases, nsub, action, g, 0);
       mark(5);
       if (tiered) {
@@ -852,13 +852,6 @@ template <typename R> static int launch_pipeline_t(b2s_sim* s, DState<R>& st, in
     CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     s->gstreams.push_back(st2); s->gevents.push_back(ev);
   }
-  while ((int)s->cstreams.size() < G) {
-    cudaStream_t st2; cudaEvent_t e1, e2;
-    CUDA_TRY(cudaStreamCreateWithFlags(&st2, cudaStreamNonBlocking));
-    CUDA_TRY(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
-    CUDA_TRY(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
-    s->cstreams.push_back(st2); s->cev_fork.push_back(e1); s->cev_join.push_back(e2);
-  }
   if (!s->fork_event) {
     CUDA_TRY(cudaEventCreateWithFlags(&s->fork_event, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&s->in_event, cudaEventDisableTiming));
@@ -867,7 +860,7 @@ template <typename R> static int launch_pipeline_t(b2s_sim* s, DState<R>& st, in
   }
   // kernels per group-substep: phase 0, analytic + convex narrow phase, then the merged tail (or phases 2, [3], 4)
   const bool tiered = s->mc_small < s->maxcon || s->me_small < s->maxefc;
-  int launches_per_call = G * nsub * (4 + (tiered ? 1 : 0) + ((phases & PH_CTRL_EXT) ? 1 : 0));
+  int launches_per_call = G * nsub * (3 + (tiered ? 1 : 0));  // phase 0, phase 1 (narrow phase + controller), tail, [tail large tier]
   if (!s->use_graph) {
     rc = enqueue_pipeline<R>(s, st, phases, nsub, action, s->stream);
     s->launches += launches_per_call;
@@ -965,7 +958,6 @@ int b2s_set_mode(b2s_sim* s, int mode) {
   if (const char* ds = getenv("B2S_DEBUG_SKIP")) s->debug_skip = atoi(ds);
   if (getenv("B2S_TIMELINE")) { s->timeline = 2; s->use_graph = 0; }
   if (const char* v = getenv("B2S_CTRL_SPLIT")) s->ctrl_split = atoi(v) != 0;
-  if (const char* v = getenv("B2S_CTRL_FORK")) s->ctrl_fork = atoi(v) != 0;
   return B2S_OK;
 }
 

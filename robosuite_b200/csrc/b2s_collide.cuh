@@ -418,12 +418,14 @@ template <typename R> DEVN void support_w(const Shape<R>& s, R dx, R dy, R dz, R
     case G_MESH: {
       R best = -Lim<R>::big();
       int bi = 0x7fffffff;
+      // generic loads: the work-list convex kernel stages the hull vertices of a pair that needs real GJK / EPA work in shared memory
+      const R* vt = s.vert;
       for (int i = lane; i < s.nvert; i += 32) {
-        R v = __ldg(s.vert + 3 * i) * l[0] + __ldg(s.vert + 3 * i + 1) * l[1] + __ldg(s.vert + 3 * i + 2) * l[2];
+        R v = vt[3 * i] * l[0] + vt[3 * i + 1] * l[1] + vt[3 * i + 2] * l[2];
         if (v > best) { best = v; bi = i; }
       }
       warp_argmax(best, bi);
-      pnt[0] = __ldg(s.vert + 3 * bi); pnt[1] = __ldg(s.vert + 3 * bi + 1); pnt[2] = __ldg(s.vert + 3 * bi + 2);
+      pnt[0] = vt[3 * bi]; pnt[1] = vt[3 * bi + 1]; pnt[2] = vt[3 * bi + 2];
       break;
     }
     default: break;  // sphere: core = centre
@@ -744,13 +746,41 @@ DEVN int epa(const Shape<R>& A, const Shape<R>& B, SV<R>* simplex, int ns, R& de
   return 0;
 }
 
+// `stage` (work-list convex kernel only): shared-memory area of `stage_cap` reals for the hull vertices of the pair.  The mesh support
+// scans are L2-latency bound when they read the model's vertex array (L1 is a few KB beside 200+ KB of shared memory): a pair
+// that the remembered separating direction does not dismiss at once gets its vertices copied in first (one coalesced pass, the
+// cost of a single support scan) and all later scans - tens in GJK, up to ~190 in a deep EPA - run from shared memory.  Same
+// vertex values, same arithmetic, same results.
 template <typename R>
-DEVN int convex_convex(const Shape<R>& A, const Shape<R>& B, R* out, int maxn, R* scratch, int lane, R* cache = nullptr,
-                       int maxv = EPA_MAXV, int maxf = EPA_MAXF) {
+DEVN int convex_convex(const Shape<R>& A0, const Shape<R>& B0, R* out, int maxn, R* scratch, int lane, R* cache = nullptr,
+                       int maxv = EPA_MAXV, int maxf = EPA_MAXF, R* stage = nullptr, int stage_cap = 0) {
   SV<R> simplex[4];
   int ns = 0;
   R dist = 0, wa[3], wb[3], n[3], pos[3], pa[3], pb[3];
+  Shape<R> A = A0, B = B0;
   R ra = shape_radius(A), rb = shape_radius(B);
+  if (stage != nullptr && (A.nvert > 0 || B.nvert > 0)) {
+    if (cache != nullptr) {  // gjk()'s own first test, made here so that dismissed pairs (the common case) never pay for staging
+      R cv[3] = {cache[0], cache[1], cache[2]};
+      if (v3dot(cv, cv) > R(1e-12)) {
+        R nv[3] = {-cv[0], -cv[1], -cv[2]};
+        SV<R> w0;
+        sv_support(A, B, nv, w0, lane);
+        R vv0 = v3dot(cv, cv), vw0 = v3dot(cv, w0.w), cut = ra + rb;
+        if (vw0 > 0 && vw0 * vw0 > cut * cut * vv0) return 0;
+      }
+    }
+    int used = 0;
+    if (A.nvert > 0 && 3 * A.nvert <= stage_cap) {
+      for (int i = lane; i < 3 * A.nvert; i += 32) stage[i] = A.vert[i];
+      A.vert = stage; used = (3 * A.nvert + 3) & ~3;
+    }
+    if (B.nvert > 0 && used + 3 * B.nvert <= stage_cap) {
+      if (B.vert == A0.vert && A.vert == stage) B.vert = stage;  // the same hull twice (two instances of one mesh)
+      else { for (int i = lane; i < 3 * B.nvert; i += 32) stage[used + i] = B.vert[i]; B.vert = stage + used; }
+    }
+    __syncwarp();
+  }
   int hit = gjk(A, B, simplex, ns, dist, wa, wb, ra + rb, lane, cache);
   if (!hit) {
     if (ra + rb <= 0 || dist > ra + rb) return 0;

@@ -1,10 +1,10 @@
-// Operational-space controller as its own kernel: ONE THREAD per environment.
+// Operational-space controller outside the per-warp tail kernel: ONE THREAD per environment.
 //
 // Inside the per-warp tail kernel the controller was 25 % of the time: serial 7x7 / 6x6 fp64 algebra on <= 8 of 32 lanes, ~4100 warp
 // instructions per environment-substep.  The same arithmetic with one environment per LANE keeps all 32 lanes busy (~90 warp
 // instructions per environment-substep), has no divergence (the controller is branch-free except for the singular-pose path) and
 // depends only on phase 0's outputs (site poses, motion axes, M, bias, body velocities), so it runs beside the collision narrow
-// phase.  Work arrays are columns of a shared-memory tile ([k][lane]: conflict-free), the arithmetic is b2s_oscmath.h - the very
+// phase: as one of the three block roles of the phase-1 kernel (b2s_pipeline.cuh).  Work arrays are columns of a shared-memory tile ([k][lane]: conflict-free), the arithmetic is b2s_oscmath.h - the very
 // source the host test compiles and checks against the oracle / the reference's OperationalSpaceController.
 // Reference: OperationalSpaceController.set_goal / run_controller (controllers/parts/arm/osc.py:225-283, 403-495),
 // SimpleGripController (parts/gripper/simple_grip.py:150-186), FixedBaseRobot.control clipping (robots/fixed_base_robot.py:149-153).
@@ -15,22 +15,16 @@
 #define OSC_TPB 32
 template <typename R> constexpr size_t osc_smem_bytes() { return (size_t)OSC_TPB * (OSC_WORK_DOUBLES * sizeof(double) + 6 * OSC_NA_MAX * sizeof(R)); }
 
-struct Grp;
+// body of one 32-thread block (role block `rb` of the phase-1 kernel, b2s_pipeline.cuh): environments rb * 32 .. rb * 32 + 31 of the group
 template <typename R>
-__global__ void __launch_bounds__(OSC_TPB) ctrl_osc_kernel(int sub, const R* action, int env0, int nenv, int gid, int slot) {
+DEV void ctrl_osc_block(int sub, const R* action, int env0, int nenv, int gid, int slot, unsigned char* smem_raw, int rb) {
   const DModel<R>& m = cmodel<R>(slot);
   const DState<R>& s = cstate<R>(slot);
   const WSLayout& L = c_lay[slot][LAY_ROW];  // inputs come from phase 0's global workspace row
   const CtrlCfgDev& cc = c_cc[slot];
-  extern __shared__ __align__(16) unsigned char smem_raw[];
   double* wd = reinterpret_cast<double*>(smem_raw);                          // [OSC_WORK_DOUBLES][OSC_TPB]
   R* jt = reinterpret_cast<R*>(wd + (size_t)OSC_WORK_DOUBLES * OSC_TPB);      // [6 * OSC_NA_MAX][OSC_TPB]
-  const int t = threadIdx.x, idx = blockIdx.x * OSC_TPB + t;
-#ifdef B2S_INSTR
-  unsigned long long* ib = s.st_begin ? s.st_begin + (((gid & 63) * 32 + (sub & 31)) * 8 + 4) : nullptr;
-  unsigned long long* ie = s.st_end ? s.st_end + (((gid & 63) * 32 + (sub & 31)) * 8 + 4) : nullptr;
-  if (t == 0 && ib) atomicMin(ib, gtimer());
-#endif
+  const int t = threadIdx.x, idx = rb * OSC_TPB + t;
   if (idx >= nenv) return;
   const int env = env0 + idx, na = cc.n_arm, nv = m.nv;
   const size_t E = env;
@@ -125,7 +119,5 @@ __global__ void __launch_bounds__(OSC_TPB) ctrl_osc_kernel(int sub, const R* act
     R lo = m.act_ctrlrange[2 * u], hi = m.act_ctrlrange[2 * u + 1];
     ctrl[u] = r_clamp(R(0.5) * (hi + lo) + R(0.5) * (hi - lo) * grip[gI], lo, hi);
   }
-#ifdef B2S_INSTR
-  if (ie) atomicMax(ie, gtimer());
-#endif
+  (void)gid;
 }

@@ -179,6 +179,7 @@ __global__ void __launch_bounds__(512, 1) step_kernel(int phases, int nsub, cons
     for (int i = lane; i < m.nu; i += 32) s.ctrl[E * m.nu + i] = e.p(L.ctrl)[i];
     ctrl_store(e, cs, env);
   }
+  warn = warp_or_i(warn);  // some flags (a dropped contact's rows) are raised on the lane that owns the item
   if (lane == 0) { s.time[env] = time; s.warn[env] |= warn; }
 }
 

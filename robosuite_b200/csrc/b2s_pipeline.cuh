@@ -93,6 +93,7 @@ template <typename R> DEV void ws_store(const Eng<R>& e, R* row, const PhaseIO& 
 struct Grp { int env0, nenv, gid, sub, slot; };
 #define EPA_PIPE_MAXV EPA_MAXV
 #define EPA_PIPE_MAXF EPA_MAXF
+#define EPA_PIPE_WORDS ((9 * EPA_PIPE_MAXV + 4 * EPA_PIPE_MAXF + EPA_PIPE_MAXF + 8 + 3) & ~3)  // polytope area, then the vertex staging area
 #define CLC(s, g) ((s).cl_cnt + 8 * (g).gid)  // this group's counters: nA, nG, overflowed envs, next convex item, next overflow item
 
 // -DB2S_INSTR: every launch stamps its first / last %globaltimer into st_begin / st_end (device timeline of the CUDA-graph
@@ -108,16 +109,20 @@ DEV unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0
 #endif
 #include "b2s_ctrlkernel.cuh"
 
-// ---- work-list narrow phase --------------------------------------------------------------------------------------
+// ---- phase 1: the three consumers of phase 0's outputs in ONE launch (block roles) -----------------------------------------------
+// Controller, convex and analytic narrow phase are independent of each other.  As separate graph nodes on forked streams they
+// serialised the environment groups (measured: any fork inside the captured graph halves the throughput); as roles of one kernel
+// node they overlap with no fork: blocks [0, nG) convex narrow phase, [nG, nG + nC) controller, the rest analytic narrow phase -
+// the role with the longest single work item (a deep EPA) is scheduled first.  Every block is one warp.
+struct P1Cfg { int nG, nC, sub; };
+
 // analytic pairs: ONE THREAD per candidate pair of any environment (32 different pairs per warp)
-template <typename R>
-__global__ void __launch_bounds__(128) narrow_analytic_kernel(Grp g) {
+template <typename R> DEV void narrow_analytic_block(const Grp& g, int rb) {
   const DModel<R>& m = cmodel<R>(g.slot);
   const DState<R>& s = cstate<R>(g.slot);
   const WSLayout& RL = c_lay[g.slot][LAY_ROW];
-  int tid = blockIdx.x * blockDim.x + threadIdx.x;
-  INSTR_BEGIN(s, g, 1)
-  if (tid >= CLC(s, g)[0]) { INSTR_END(s, g, 1) return; }
+  int tid = rb * 32 + threadIdx.x;
+  if (tid >= CLC(s, g)[0]) return;
   tid += g.env0 * s.cl_maxa;  // this group's slice of the candidate list / output slots
   int code = s.cl_listA[tid];
   int env = code >> 12, pidx = code & 4095;
@@ -132,22 +137,18 @@ __global__ void __launch_bounds__(128) narrow_analytic_kernel(Grp g) {
   R* out = s.cl_outA + (size_t)tid * CL_RECA;
   out[0] = R(n);
   for (int k = 0; k < n * CREC; k++) out[1 + k] = buf[k];
-  INSTR_END(s, g, 1)
 }
 
-// convex pairs: ONE WARP per candidate pair (mesh support scans split over the lanes).  A block is one warp and owns one EPA
-// polytope in shared memory; warps claim work items through an atomic counter, so the few expensive pairs (penetrating meshes:
-// tens of EPA expansions) never hold idle neighbours resident.
-template <typename R>
-__global__ void __launch_bounds__(32) narrow_convex_kernel(Grp g) {
+// convex pairs: ONE WARP per candidate pair (mesh support scans split over the lanes).  The block owns one EPA polytope and the
+// vertex staging area in shared memory; warps claim work items through an atomic counter, so the few expensive pairs (penetrating
+// meshes: tens of EPA expansions) never hold idle neighbours resident.
+template <typename R> DEV void narrow_convex_block(const Grp& g, unsigned char* smem_raw) {
   const DModel<R>& m = cmodel<R>(g.slot);
   const DState<R>& s = cstate<R>(g.slot);
   const WSLayout& RL = c_lay[g.slot][LAY_ROW];
-  extern __shared__ __align__(16) unsigned char smem_raw[];
   int lane = threadIdx.x & 31;
   R* scratch = reinterpret_cast<R*>(smem_raw);
   const int cnt = CLC(s, g)[1];
-  INSTR_BEGIN(s, g, 2)
   while (true) {
     int item = 0;
     if (lane == 0) item = atomicAdd(CLC(s, g) + 3, 1);
@@ -164,7 +165,7 @@ __global__ void __launch_bounds__(32) narrow_convex_kernel(Grp g) {
     shape_from(m, g2, row + RL.gpos, row + RL.gmat, B);
     R buf[CREC];
     int n = convex_convex(A, B, buf, 1, scratch, lane, s.gjk_cache ? s.gjk_cache + ((size_t)env * m.npair + pidx) * 3 : (R*)nullptr,
-                          EPA_PIPE_MAXV, EPA_PIPE_MAXF);
+                          EPA_PIPE_MAXV, EPA_PIPE_MAXF, m.stage_cap > 0 ? scratch + EPA_PIPE_WORDS : (R*)nullptr, m.stage_cap);
     R* out = s.cl_outG + (size_t)wid * 8;
     if (lane == 0) {
       out[0] = R(n);
@@ -172,7 +173,23 @@ __global__ void __launch_bounds__(32) narrow_convex_kernel(Grp g) {
     }
     __syncwarp();
   }
-  INSTR_END(s, g, 2)
+}
+
+template <typename R>
+__global__ void __launch_bounds__(32) phase1_kernel(const R* action, Grp g, P1Cfg c) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int b = blockIdx.x;
+#ifdef B2S_INSTR
+  const DState<R>& s = cstate<R>(g.slot);
+  const int kind = b < c.nG ? 2 : (b < c.nG + c.nC ? 4 : 1);
+  INSTR_BEGIN(s, g, kind)
+#endif
+  if (b < c.nG) narrow_convex_block<R>(g, smem_raw);
+  else if (b < c.nG + c.nC) ctrl_osc_block<R>(g.sub, action, g.env0, g.nenv, g.gid, g.slot, smem_raw, b - c.nG);
+  else narrow_analytic_block<R>(g, b - c.nG - c.nC);
+#ifdef B2S_INSTR
+  INSTR_END(s, g, kind)
+#endif
 }
 
 // collect this environment's contacts from the work-list outputs, in static-pair order (what the fused collide produces)
@@ -352,6 +369,7 @@ __global__ void __launch_bounds__(B2S_LB5_THREADS, B2S_LB5_BLOCKS) tail_kernel(i
     int wl = 0;
     int ncon = gather_contacts(e, env, wl);
     int nefc = (tiered && (wl & 4)) ? 0 : make_constraint(e, ncon, wl);
+    wl = warp_or_i(wl);  // make_constraint flags a dropped contact on the lane that owns it: the decision below must be warp-uniform
     if (tiered && (wl & 12)) {  // does not fit this tier: nothing of the environment's state has been touched yet
       if (lane == 0) s.ovf_list[g.env0 + atomicAdd(clc + 2, 1)] = env;
       __syncwarp();
@@ -388,6 +406,7 @@ __global__ void __launch_bounds__(B2S_LB5_THREADS, B2S_LB5_BLOCKS) tail_kernel(i
       s.qacc[E * m.nv + i] = e.p(L.qacc)[i];
       s.qacc_ws[E * m.nv + i] = e.p(L.qacc_ws)[i];
     }
+    warn = warp_or_i(warn);
     if (lane == 0) { s.time[env] = time; s.warn[env] |= warn; }
     __syncwarp();
 #ifdef B2S_INSTR

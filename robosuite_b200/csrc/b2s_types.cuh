@@ -30,6 +30,7 @@ enum {
 template <typename R>
 struct DModel {
   int nq, nv, nu, nbody, njnt, ngeom, nsite, npair, ncg, nment, maxdepth, maxcon, maxefc, nmocap, nfl, nlim, hc_stride, max_treesize;
+  int stage_cap;  // reals of shared memory the convex narrow-phase kernel has for staging the hull vertices of a pair
   R timestep, impratio, density, viscosity, tolerance, meaninertia;
   int iterations, ls_iterations;
   R gravity[3];

@@ -16,6 +16,7 @@ class BatchedDoor(BatchedMujocoEnv):
 
     table_offset = (-0.2, -0.35, 0.8)  # door.py:177
     maxcon, maxefc = 48, 160
+    tier_small = (8, 32)  # small tail tier: see BatchedMujocoEnv.tier_small
 
     def __init__(self, *args, door_placement=None, **kwargs):
         # (x, y, yaw) relative to table_offset; sampler ranges x [0.07, 0.09], y [-0.01, 0.01], yaw [-pi/2 - 0.25, -pi/2]

@@ -103,6 +103,8 @@ for k, nm in ((0, "P0"), (1, "tail")):
                            "p99": float(np.percentile(c, 99)), "max": float(c.max()),
                            "block_max_over_mean": float(np.mean(ratios)), "launch_max_over_mean": float(np.mean(lratios))}
 out["warn"] = int(sim.warn.abs().max())
+out["raw_begin_us"] = np.where(e[:G, :25] > 0, B, -1).round(1).tolist()  # [group][substep][kind]
+out["raw_end_us"] = np.where(e[:G, :25] > 0, E, -1).round(1).tolist()
 print(json.dumps(out))
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 with open(os.path.join(ROOT, "gpurun_out", f"instr_{task}_{robot}_{n}.json"), "w") as f:
