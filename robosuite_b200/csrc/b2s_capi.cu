@@ -80,6 +80,7 @@ struct b2s_sim {
   cudaStream_t pstream = nullptr;
   void* action_buf = nullptr;
   int use_graph = 1;
+  int graph_per_group = 1;  // one CUDA graph per environment group on its own stream (B2S_GRAPH_PER_GROUP=0: one graph for all)
   std::map<long long, cudaGraphExec_t> graphs;
   PhaseIO pio[B2S_NPIO];
   std::map<std::string, Region> reg;
@@ -385,7 +386,7 @@ static void layout_full(const Dims& d, int mc, int me, WSLayout& L) {
   L.scratch_size = sc; L.scratch = B.take(sc);
   L.hdr = B.take(8);
   L.total = B.o;
-  L.fused_stride = L.total + ((9 * EPA_MAXV + 4 * EPA_MAXF + EPA_MAXF + 8 + 3) & ~3);
+  L.fused_stride = L.total + EPA_AREA_WORDS(EPA_MAXV, EPA_MAXF);
 }
 
 // phase 0: kinematics, velocity stage, CRB, broad phase.  The regions it hands to the other kernels come first, in row order.
@@ -750,16 +751,12 @@ static int launch(b2s_sim* s, int phases, int nsub, const void* action = nullptr
 }  // extern "C"
 
 // enqueue the launches of `nsub` substeps for every environment group; `q0` is the stream the caller forks from / joins to
-template <typename R> static int enqueue_pipeline(b2s_sim* s, DState<R>& st, int phases, int nsub, const R* action, cudaStream_t q0) {
+// the launches of `nsub` substeps of ONE environment group on stream q
+template <typename R> static int enqueue_group(b2s_sim* s, DState<R>& st, int phases, int nsub, const R* action, int gi, int G, cudaStream_t q) {
   const int epaw = (EPA_PIPE_WORDS + (s->precision == B2S_F32 ? s->mf.stage_cap : s->md.stage_cap)) * (int)sizeof(R);
   const int p1smem = std::max(epaw, (int)osc_smem_bytes<R>());  // one block shape for the three roles of phase 1
-  int G = s->ngroups;
-  if (G > s->n_env) G = s->n_env;
   const bool tiered = s->mc_small < s->maxcon || s->me_small < s->maxefc;
-  CUDA_TRY(cudaEventRecord(s->fork_event, q0));
-  for (int gi = 0; gi < G; gi++) {
-    cudaStream_t q = G == 1 ? q0 : s->gstreams[gi];
-    if (G > 1) CUDA_TRY(cudaStreamWaitEvent(q, s->fork_event, 0));
+  {
     int e0 = (int)((long long)s->n_env * gi / G), e1 = (int)((long long)s->n_env * (gi + 1) / G);
     Grp g{e0, e1 - e0, gi, 0, s->slot};
     int blocks0 = (g.nenv + s->wpb0 - 1) / s->wpb0, blocks5 = (g.nenv + s->wpb5s - 1) / s->wpb5s;
@@ -795,12 +792,26 @@ template <typename R> static int enqueue_pipeline(b2s_sim* s, DState<R>& st, int
         mark(6);
       }
     }
+  }
+  CUDA_TRY(cudaGetLastError());
+  return B2S_OK;
+}
+
+// all groups, forked from / joined to q0 (eager mode and the single-graph capture)
+template <typename R> static int enqueue_pipeline(b2s_sim* s, DState<R>& st, int phases, int nsub, const R* action, cudaStream_t q0) {
+  int G = s->ngroups;
+  if (G > s->n_env) G = s->n_env;
+  CUDA_TRY(cudaEventRecord(s->fork_event, q0));
+  for (int gi = 0; gi < G; gi++) {
+    cudaStream_t q = G == 1 ? q0 : s->gstreams[gi];
+    if (G > 1) CUDA_TRY(cudaStreamWaitEvent(q, s->fork_event, 0));
+    int rc = enqueue_group<R>(s, st, phases, nsub, action, gi, G, q);
+    if (rc != B2S_OK) return rc;
     if (G > 1) {
       CUDA_TRY(cudaEventRecord(s->gevents[gi], q));
       CUDA_TRY(cudaStreamWaitEvent(q0, s->gevents[gi], 0));
     }
   }
-  CUDA_TRY(cudaGetLastError());
   return B2S_OK;
 }
 
@@ -896,8 +907,35 @@ template <typename R> static int launch_pipeline_t(b2s_sim* s, DState<R>& st, in
     act_in = (const R*)s->action_buf;
   }
   CUDA_TRY(cudaEventRecord(s->in_event, s->stream));
+  if (s->graph_per_group && G > 1) {
+    // one graph per environment group, each a plain chain replayed on its own stream: the groups' chains then overlap freely
+    // (inside ONE graph, parallel branches were observed to share a limited number of execution lanes)
+    for (int gi = 0; gi < G; gi++) {
+      long long key = ((long long)phases << 28) | ((long long)(gi + 1) << 20) | (long long)nsub << 4 | (action ? 1 : 0);
+      cudaStream_t q = s->gstreams[gi];
+      auto it = s->graphs.find(key);
+      if (it == s->graphs.end()) {
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        CUDA_TRY(cudaStreamBeginCapture(q, cudaStreamCaptureModeRelaxed));
+        rc = enqueue_group<R>(s, st, phases, nsub, act_in, gi, G, q);
+        cudaError_t ce = cudaStreamEndCapture(q, &graph);
+        if (rc != B2S_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (ce != cudaSuccess) return fail(B2S_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
+        CUDA_TRY(cudaGraphInstantiate(&exec, graph, 0));
+        cudaGraphDestroy(graph);
+        it = s->graphs.emplace(key, exec).first;
+      }
+      CUDA_TRY(cudaStreamWaitEvent(q, s->in_event, 0));
+      CUDA_TRY(cudaGraphLaunch(it->second, q));
+      CUDA_TRY(cudaEventRecord(s->gevents[gi], q));
+      CUDA_TRY(cudaStreamWaitEvent(s->stream, s->gevents[gi], 0));
+    }
+    s->launches += launches_per_call;
+    return B2S_OK;
+  }
   CUDA_TRY(cudaStreamWaitEvent(s->pstream, s->in_event, 0));
-  long long key = ((long long)phases << 20) | (long long)nsub << 4 | (action ? 1 : 0);
+  long long key = ((long long)phases << 28) | (long long)nsub << 4 | (action ? 1 : 0);
   auto it = s->graphs.find(key);
   if (it == s->graphs.end()) {
     cudaGraph_t graph = nullptr;
@@ -958,6 +996,7 @@ int b2s_set_mode(b2s_sim* s, int mode) {
   if (const char* ds = getenv("B2S_DEBUG_SKIP")) s->debug_skip = atoi(ds);
   if (getenv("B2S_TIMELINE")) { s->timeline = 2; s->use_graph = 0; }
   if (const char* v = getenv("B2S_CTRL_SPLIT")) s->ctrl_split = atoi(v) != 0;
+  if (const char* v = getenv("B2S_GRAPH_PER_GROUP")) s->graph_per_group = atoi(v) != 0;
   return B2S_OK;
 }
 

@@ -571,6 +571,8 @@ DEVN int gjk(const Shape<R>& A, const Shape<R>& B, SV<R>* simplex, int& ns, R& d
 
 #define EPA_MAXV 96   // polytope capacity (same numbers in the oracle: oracle/o_collide.c)
 #define EPA_MAXF 192
+// words of the EPA work area: vertices 9 x maxv, face planes 4 x maxf, packed face ids maxf, horizon edge list 64, spare 8
+#define EPA_AREA_WORDS(maxv, maxf) ((9 * (maxv) + 5 * (maxf) + 64 + 8 + 3) & ~3)
 // EPA polytope lives in this warp's scratch: V[EPA_MAXV][9], Fn[EPA_MAXF][4] (normal, dist), Fi[EPA_MAXF] packed ids
 template <typename R>
 DEVN int epa(const Shape<R>& A, const Shape<R>& B, SV<R>* simplex, int ns, R& depth, R* normal, R* wa, R* wb, R* scratch, int lane,
@@ -579,6 +581,8 @@ DEVN int epa(const Shape<R>& A, const Shape<R>& B, SV<R>* simplex, int ns, R& de
   R* V = scratch;
   R* Fn = V + 9 * maxv;
   int* Fi = reinterpret_cast<int*>(Fn + 4 * maxf);
+  int* edges = Fi + maxf;  // horizon edge list (64 entries) - in the work area, NOT a per-thread array: a dynamically indexed local
+                           // array lives in local memory, and the serial edge search on it was most of a deep EPA's 300 us
   int nV = 0, nF = 0;
   SV<R> S[4];
   for (int k = 0; k < ns; k++) S[k] = simplex[k];
@@ -668,7 +672,6 @@ DEVN int epa(const Shape<R>& A, const Shape<R>& B, SV<R>* simplex, int ns, R& de
     if (dw - bd < epa_tol || nV >= maxv - 1 || nF >= maxf - 16) break;
     // remove the faces visible from w and build the horizon.  Visibility is tested lane-parallel (32 faces at a time);
     // the few visible faces are then processed in increasing face order by the whole warp (same order as a serial scan).
-    int edges[64];
     int ne = 0;
     for (int base = 0; base < nF; base += 32) {
       int f = base + lane, fi = 0;
@@ -687,11 +690,23 @@ DEVN int epa(const Shape<R>& A, const Shape<R>& B, SV<R>* simplex, int ns, R& de
         int fv = __shfl_sync(B2S_FULL, fi, l);
         if (lane == 0) Fi[base + l] = fv & 0xffffff;
         int vs[3] = {fv & 255, (fv >> 8) & 255, (fv >> 16) & 255};
+#pragma unroll
         for (int k = 0; k < 3; k++) {
-          int a = vs[k], b = vs[(k + 1) % 3], found = 0;
-          for (int q = 0; q < ne; q++)
-            if (edges[q] == (b | (a << 8))) { edges[q] = edges[ne - 1]; ne--; found = 1; break; }
-          if (!found && ne < 64) edges[ne++] = a | (b << 8);
+          // toggle the directed edge (a, b): it cancels against its reverse if that is in the list (swap-remove, same list order as
+          // the serial search of the oracle), otherwise it is appended.  The search is lane-parallel; at most one entry matches.
+          int a = vs[k], b = vs[(k + 1) % 3], key = b | (a << 8), hit = -1;
+          for (int q = lane; q < ne; q += 32)
+            if (edges[q] == key) hit = q;
+          unsigned hm = __ballot_sync(B2S_FULL, hit >= 0);
+          if (hm) {
+            int idx = __shfl_sync(B2S_FULL, hit, __ffs(hm) - 1);
+            if (lane == 0) edges[idx] = edges[ne - 1];
+            ne--;
+          } else if (ne < 64) {
+            if (lane == 0) edges[ne] = a | (b << 8);
+            ne++;
+          }
+          __syncwarp();
         }
       }
     }

@@ -93,7 +93,7 @@ template <typename R> DEV void ws_store(const Eng<R>& e, R* row, const PhaseIO& 
 struct Grp { int env0, nenv, gid, sub, slot; };
 #define EPA_PIPE_MAXV EPA_MAXV
 #define EPA_PIPE_MAXF EPA_MAXF
-#define EPA_PIPE_WORDS ((9 * EPA_PIPE_MAXV + 4 * EPA_PIPE_MAXF + EPA_PIPE_MAXF + 8 + 3) & ~3)  // polytope area, then the vertex staging area
+#define EPA_PIPE_WORDS EPA_AREA_WORDS(EPA_PIPE_MAXV, EPA_PIPE_MAXF)  // polytope area, then the vertex staging area
 #define CLC(s, g) ((s).cl_cnt + 8 * (g).gid)  // this group's counters: nA, nG, overflowed envs, next convex item, next overflow item
 
 // -DB2S_INSTR: every launch stamps its first / last %globaltimer into st_begin / st_end (device timeline of the CUDA-graph

@@ -12,7 +12,8 @@ from .lift import GRIPPER_INIT_QPOS, PANDA_INIT_QPOS, SAWYER_INIT_QPOS
 class BatchedStack(BatchedMujocoEnv):
     """suite.make("Stack", robots="Sawyer", num_envs=N): red cube A (2 cm) to be stacked on green cube B (2.5 cm)"""
 
-    tier_small = (12, 40)  # small tail tier: see BatchedMujocoEnv.tier_small
+    maxcon, maxefc = 48, 128
+    tier_small = (12, 48)  # small tail tier: see BatchedMujocoEnv.tier_small (two cubes at rest: 8 contacts, 33-37 rows)
 
     table_offset = (0.0, 0.0, 0.8)  # stack.py:154
 
