@@ -164,8 +164,20 @@ template <typename R> DEV void narrow_convex_block(const Grp& g, unsigned char* 
     shape_from(m, g1, row + RL.gpos, row + RL.gmat, A);
     shape_from(m, g2, row + RL.gpos, row + RL.gmat, B);
     R buf[CREC];
+#ifdef B2S_INSTR
+    long long it0 = clock64();
+#endif
     int n = convex_convex(A, B, buf, 1, scratch, lane, s.gjk_cache ? s.gjk_cache + ((size_t)env * m.npair + pidx) * 3 : (R*)nullptr,
                           EPA_PIPE_MAXV, EPA_PIPE_MAXF, m.stage_cap > 0 ? scratch + EPA_PIPE_WORDS : (R*)nullptr, m.stage_cap);
+#ifdef B2S_INSTR
+    if (lane == 0 && s.stats) {  // per-item cost histogram: bucket k = cycles in [2^(k+8), 2^(k+9)), by shape types (mesh-mesh / other)
+      long long dt = clock64() - it0;
+      int k = 0;
+      while (k < 11 && (dt >> (k + 9)) > 0) k++;
+      atomicAdd(s.stats + 500 - 12 * ((A.type == G_MESH && B.type == G_MESH) ? 2 : 1) + k, 1);
+      if (n > 0) atomicAdd(s.stats + 18, 1);
+    }
+#endif
     R* out = s.cl_outG + (size_t)wid * 8;
     if (lane == 0) {
       out[0] = R(n);
@@ -254,13 +266,18 @@ template <typename R> DEVN int gather_contacts(Eng<R> e, int env, int& warn) {
   return total;
 }
 
+// Launch bounds (threads per block, resident blocks per SM the register allocation is sized for).  (256, 2) = 128 registers per
+// thread: with (256, 3) = 80 registers the heavily spilling build mis-executed solve() on 21-dof models (a corrupted workspace
+// pointer; compute-sanitizer: tools/run8.sh) - the same family of nvcc 12.9 stack-slot problems as DESIGN.md section 3 records.
+// The kernels are latency bound at 4096 environments (every environment's warp is resident either way), so the lost occupancy
+// costs nothing measurable (lb256x2 was the fastest variant of tools/run7.sh).
 #ifndef B2S_LB0_THREADS
-#define B2S_LB0_THREADS 256  // phase 0: threads per block / resident blocks per SM the register allocation is sized for
-#define B2S_LB0_BLOCKS 3
+#define B2S_LB0_THREADS 256  // phase 0
+#define B2S_LB0_BLOCKS 2
 #endif
 #ifndef B2S_LB5_THREADS
 #define B2S_LB5_THREADS 256  // tail kernel
-#define B2S_LB5_BLOCKS 3
+#define B2S_LB5_BLOCKS 2
 #endif
 
 // ---- phase 0: kinematics, velocity stage + RNE bias, CRB -> M, broad phase -> global candidate work lists

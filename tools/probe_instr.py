@@ -87,6 +87,7 @@ out["solver"] = {"solves": int(st[17]), "niter_hist": st[:16].tolist(), "mean_ni
                  "ncon": {"mean": float((nc * np.arange(len(nc))).sum() / max(nc.sum(), 1)), "p99": pct(nc, 0.99), "p999": pct(nc, 0.999), "max": int(np.nonzero(nc)[0].max())},
                  "nefc": {"mean": float((ne * np.arange(len(ne))).sum() / max(ne.sum(), 1)), "p99": pct(ne, 0.99), "p999": pct(ne, 0.999), "max": int(np.nonzero(ne)[0].max())},
                  "ncon_hist": nc.tolist(), "nefc_hist": ne.tolist()}
+out["convex_items"] = {"hits": int(st[18]), "cycles_log2_bucket0_is_256": {"other": st[488:500].tolist(), "mesh_mesh": st[476:488].tolist()}}
 cy = sim.cyc.cpu().numpy()[:, :25]  # [n, 25, 2]
 wpb = int(os.environ.get("B2S_WPB5", "8"))
 for k, nm in ((0, "P0"), (1, "tail")):
