@@ -762,7 +762,11 @@ template <typename R> static int enqueue_group(b2s_sim* s, DState<R>& st, int ph
     int blocks0 = (g.nenv + s->wpb0 - 1) / s->wpb0, blocks5 = (g.nenv + s->wpb5s - 1) / s->wpb5s;
     int blocksL = std::min((g.nenv + s->wpb5l - 1) / s->wpb5l, 2 * 148);  // large tier: warps claim overflowed environments
     int nA = g.nenv * st.cl_maxa, nG = g.nenv * st.cl_maxg;
-    const int cvx_blocks = 148 * 24;
+    // convex role: one warp per block, items claimed through a counter.  ~1.6 items per environment are queued per substep (Lift), most of
+    // them dismissed in a few microseconds: half a block per environment keeps every slow item on its own warp without flooding the
+    // block scheduler with thousands of empty blocks per launch (B2S_CVX_BLOCKS overrides)
+    int cvx_blocks = std::max(148, g.nenv / 2);
+    if (const char* v = getenv("B2S_CVX_BLOCKS")) { int x = atoi(v); if (x > 0) cvx_blocks = x; }
     const bool ctrl_ext = (phases & PH_CTRL_EXT) != 0;
     // B2S_TIMELINE=1 (with B2S_NO_GRAPH=1): timing events between the launches, per-kernel means on stderr (debug aid)
     auto mark = [&](int type) {
@@ -842,6 +846,8 @@ template <typename R> static int launch_pipeline_t(b2s_sim* s, DState<R>& st, in
     s->arrays["st_end"] = ArrayInfo{st.st_end, B2S_I64, 1, {64 * 32 * 8, 0, 0, 0}};
     s->arrays["stats"] = ArrayInfo{st.stats, B2S_I32, 1, {512, 0, 0, 0}};
     s->arrays["cyc"] = ArrayInfo{st.cyc, B2S_F32, 3, {(int64_t)ne, 32, 2, 0}};
+    st.slowlog = dev_zeros<int>(s, 64 * 12);
+    s->arrays["slowlog"] = ArrayInfo{st.slowlog, B2S_I32, 2, {64, 12, 0, 0}};
 #endif
     s->dirty = 1;
   }

@@ -737,6 +737,9 @@ DEVN int epa(const Shape<R>& A, const Shape<R>& B, SV<R>* simplex, int ns, R& de
     nF += nnew;
     __syncwarp();
   }
+#ifdef B2S_INSTR
+  if (lane == 0) { edges[64] = nV; edges[65] = nF; }
+#endif
 #ifdef B2S_CVX_STATS
   if (lane == 0 && (nF >= maxf - 16 || nV >= maxv - 1)) printf("EPA cap: nV %d nF %d types %d %d depth %.6g\n", nV, nF, A.type, B.type, (double)(bestf >= 0 ? Fn[4 * bestf + 3] : -1));
 #endif
@@ -796,7 +799,16 @@ DEVN int convex_convex(const Shape<R>& A0, const Shape<R>& B0, R* out, int maxn,
     }
     __syncwarp();
   }
+#ifdef B2S_INSTR
+  long long tg0 = clock64();
+#endif
   int hit = gjk(A, B, simplex, ns, dist, wa, wb, ra + rb, lane, cache);
+#ifdef B2S_INSTR
+  if (stage != nullptr && lane == 0) {
+    int* sp = reinterpret_cast<int*>(scratch + 9 * maxv + 4 * maxf) + maxf + 64;
+    sp[2] = (int)(clock64() - tg0); sp[3] = hit; sp[0] = 0; sp[1] = 0; sp[4] = (A.vert == stage) | ((B.vert != B0.vert) << 1);
+  }
+#endif
   if (!hit) {
     if (ra + rb <= 0 || dist > ra + rb) return 0;
     v3sub(n, wb, wa);

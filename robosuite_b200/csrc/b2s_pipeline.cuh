@@ -176,6 +176,15 @@ template <typename R> DEV void narrow_convex_block(const Grp& g, unsigned char* 
       while (k < 11 && (dt >> (k + 9)) > 0) k++;
       atomicAdd(s.stats + 500 - 12 * ((A.type == G_MESH && B.type == G_MESH) ? 2 : 1) + k, 1);
       if (n > 0) atomicAdd(s.stats + 18, 1);
+      if (dt > (1 << 19) && s.slowlog) {  // items above 524 k cycles (~270 us): what are they?
+        int slot = atomicAdd(s.stats + 20, 1);
+        if (slot < 64) {
+          const int* sp = reinterpret_cast<const int*>(scratch + 9 * EPA_PIPE_MAXV + 4 * EPA_PIPE_MAXF) + EPA_PIPE_MAXF + 64;
+          int* o = s.slowlog + 12 * slot;
+          o[0] = (int)dt; o[1] = A.type; o[2] = B.type; o[3] = A.nvert; o[4] = B.nvert; o[5] = sp[0]; o[6] = sp[1]; o[7] = sp[2]; o[8] = sp[3];
+          o[9] = sp[4]; o[10] = g1; o[11] = g2;
+        }
+      }
     }
 #endif
     R* out = s.cl_outG + (size_t)wid * 8;

@@ -102,6 +102,7 @@ struct DState {
   int* stats;      // [512]: 0..15 Newton-iteration histogram, 16 line-search evaluations, 17 solves, 19 large-tier environments,
                    // 32..160 ncon histogram, 176..496 nefc histogram
   float* cyc;      // [n_env][32 substeps][2] clock64 cycles of this environment's warp in P0 / the tail kernel
+  int* slowlog;    // [64][12] convex work items above 131 k cycles: cycles, shape types, hull sizes, EPA nV nF, GJK cycles, hit, staged, geoms
 };
 
 // offsets (in units of R) of the per-warp shared-memory workspace

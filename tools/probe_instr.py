@@ -88,6 +88,11 @@ out["solver"] = {"solves": int(st[17]), "niter_hist": st[:16].tolist(), "mean_ni
                  "nefc": {"mean": float((ne * np.arange(len(ne))).sum() / max(ne.sum(), 1)), "p99": pct(ne, 0.99), "p999": pct(ne, 0.999), "max": int(np.nonzero(ne)[0].max())},
                  "ncon_hist": nc.tolist(), "nefc_hist": ne.tolist()}
 out["convex_items"] = {"hits": int(st[18]), "cycles_log2_bucket0_is_256": {"other": st[488:500].tolist(), "mesh_mesh": st[476:488].tolist()}}
+sl = sim.slowlog.cpu().numpy()
+gn = env.model.names["geom"]
+out["slow_items"] = [dict(cycles=int(r[0]), types=(int(r[1]), int(r[2])), nvert=(int(r[3]), int(r[4])), epa_nV=int(r[5]), epa_nF=int(r[6]), gjk_cycles=int(r[7]),
+                          hit=int(r[8]), staged=int(r[9]), geoms=(gn[int(r[10])], gn[int(r[11])])) for r in sl if r[0] > 0][:40]
+out["slow_items_total"] = int(st[20])
 cy = sim.cyc.cpu().numpy()[:, :25]  # [n, 25, 2]
 wpb = int(os.environ.get("B2S_WPB5", "8"))
 for k, nm in ((0, "P0"), (1, "tail")):
