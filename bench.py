@@ -23,6 +23,9 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# The engine replays one CUDA graph per environment group on its own stream; with the default of 8 hardware work queues per process
+# streams beyond the eighth share a queue and serialise falsely.  Must be set before CUDA initialises.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 N_SUBSTEPS = 25
 _SCALE = float(os.environ.get("B2S_BENCH_SCALE", "1"))  # scaling experiments only: multiplies every batch size
@@ -420,7 +423,7 @@ def run_gpu(args):
     peak, how = _peaks()
     step_bytes = sum(e.num_envs for e in envs) * (per_env_in + per_env_out)
     achieved_step = step_bytes / (ms / K * 1e-3) / 1e9
-    groups = int(os.environ.get("B2S_GROUPS", "4"))
+    groups = int(os.environ.get("B2S_GROUPS", "8"))
     kernel, launch_us, envs_per_launch, launch_src = "step_kernel", ms / K * 1e3, env0.num_envs, "whole step (CUDA events)"
     alg_bytes = step_bytes
     tl = None

@@ -51,6 +51,24 @@ int b2s_step(b2s_sim* sim, int n_substeps);
  * (the attributes the reference touches).  dtype is B2S_F32/F64/I32. */
 int b2s_array(b2s_sim* sim, const char* name, void** dev_ptr, int* dtype, int* ndim, int64_t shape[4]);
 
+/* MjSim.get_state().flatten() / set_state_from_flattened (binding_utils.py:1155-1184, MjSimState.flatten :56-70): device buffers
+ * [n_env, 1 + nq + nv] holding time, qpos, qvel per environment.  b2s_set_state does what the reference does after it: nothing else
+ * (call b2s_forward next, as callers of set_state_from_flattened do). */
+int b2s_get_state(b2s_sim* sim, void* out_dev);
+int b2s_set_state(b2s_sim* sim, const void* in_dev);
+/* MjModel.{body,joint,geom,site,actuator,...}_name2id / id2name (binding_utils.py:362-492).  type: "body" "joint" "geom" "site"
+ * "actuator" "mesh" "camera" "light".  name2id returns the id or -1 (unknown name / type); id2name returns a pointer that stays valid
+ * for the life of the handle, NULL when out of range ("" for unnamed objects). */
+int b2s_name2id(const b2s_sim* sim, const char* type, const char* name);
+const char* b2s_id2name(const b2s_sim* sim, const char* type, int id);
+/* mj_fullM (controllers/parts/controller.py:226-229 builds the dense mass matrix from qM): out_dev [n_env, nv, nv], valid after
+ * b2s_forward / b2s_step1 */
+int b2s_full_m(b2s_sim* sim, void* out_dev);
+/* MjData.get_body_jacp/jacr, get_geom_jacp/jacr (binding_utils.py:853-878 and the geom variants): Jacobian of the body frame origin /
+ * geom centre, [n_env, 3, nv] device buffers (either may be NULL), valid after b2s_forward / b2s_step1 */
+int b2s_jac_body(b2s_sim* sim, int body_id, void* jacp, void* jacr);
+int b2s_jac_geom(b2s_sim* sim, int geom_id, void* jacp, void* jacr);
+
 /* MjData.get_site_jacp/jacr (binding_utils.py:826-852): jacp/jacr are [n_env,3,nv] device buffers (either may be NULL);
  * valid after b2s_forward/b2s_step1. */
 int b2s_jac_site(b2s_sim* sim, int site_id, void* jacp, void* jacr);

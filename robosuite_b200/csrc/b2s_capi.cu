@@ -68,7 +68,8 @@ struct b2s_sim {
   int nq = 0, nv = 0, nu = 0, nbody = 0, ngeom = 0, nsite = 0, maxcon = 0, maxefc = 0, ncg = 0, hc_stride = 0;
   std::vector<double> qpos0;
   std::vector<int> site_bodyid, cgid;
-  int has_obs = 0, export_env_step = 1, dirty = 1, profile = 0, mode = 0, worklist = 1, ngroups = 4;
+  std::map<std::string, std::vector<std::string>> names;  // object type -> names by id (MjModel name tables)
+  int has_obs = 0, export_env_step = 1, dirty = 1, profile = 0, mode = 0, worklist = 1, ngroups = 8;
   int timeline = 0, debug_skip = 0;  // B2S_DEBUG_SKIP: bit 0 / 1 = leave out the analytic / convex narrow-phase launch (timing experiments)
   struct TlEv { int group, type; cudaEvent_t ev; };
   std::vector<TlEv> tl_events;
@@ -602,6 +603,15 @@ int b2s_create(const void* blob_host, size_t nbytes, int n_env, int device, int 
     s->qpos0.assign(q0, q0 + s->nq);
     const int* sb = b.i32("site_bodyid");
     s->site_bodyid.assign(sb, sb + s->nsite);
+    for (const char* ty : {"body", "joint", "geom", "site", "actuator", "mesh", "camera", "light"}) {
+      std::string key = std::string("names_") + ty;
+      if (!b.has(key.c_str())) continue;
+      int64_t nc = 0; const int* cp = b.i32(key.c_str(), &nc);
+      std::vector<std::string>& v = s->names[ty];
+      std::string cur;
+      for (int64_t i = 0; i < nc; i++) { if (cp[i] == '\n') { v.push_back(cur); cur.clear(); } else cur.push_back((char)cp[i]); }
+      if (nc > 0) v.push_back(cur);
+    }
     int ncg, hcs;
     if (precision == B2S_F32) { build_model(s, b, s->mf); build_state(s, s->mf, s->sf); ncg = s->mf.ncg; hcs = s->mf.hc_stride; }
     else { build_model(s, b, s->md); build_state(s, s->md, s->sd); ncg = s->md.ncg; hcs = s->md.hc_stride; }
@@ -1046,6 +1056,66 @@ int b2s_jac_site(b2s_sim* s, int site_id, void* jacp, void* jacr) {
   s->launches++;
   CUDA_TRY(cudaGetLastError());
   return B2S_OK;
+}
+
+int b2s_get_state(b2s_sim* s, void* out) {
+  if (!s || !out) return fail(B2S_ERR_ARG, "b2s_get_state: bad argument");
+  { int rc = bind_constants(s); if (rc != B2S_OK) return rc; }
+  size_t total = (size_t)s->n_env * (1 + s->nq + s->nv);
+  int blocks = (int)((total + 255) / 256);
+  if (s->precision == B2S_F32) state_io_kernel<float><<<blocks, 256, 0, s->stream>>>((float*)out, 0, s->slot);
+  else state_io_kernel<double><<<blocks, 256, 0, s->stream>>>((double*)out, 0, s->slot);
+  s->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return B2S_OK;
+}
+int b2s_set_state(b2s_sim* s, const void* in) {
+  if (!s || !in) return fail(B2S_ERR_ARG, "b2s_set_state: bad argument");
+  { int rc = bind_constants(s); if (rc != B2S_OK) return rc; }
+  size_t total = (size_t)s->n_env * (1 + s->nq + s->nv);
+  int blocks = (int)((total + 255) / 256);
+  if (s->precision == B2S_F32) state_io_kernel<float><<<blocks, 256, 0, s->stream>>>((float*)in, 1, s->slot);
+  else state_io_kernel<double><<<blocks, 256, 0, s->stream>>>((double*)in, 1, s->slot);
+  s->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return B2S_OK;
+}
+int b2s_name2id(const b2s_sim* s, const char* type, const char* name) {
+  if (!s || !type || !name) return -1;
+  auto it = s->names.find(type);
+  if (it == s->names.end()) return -1;
+  for (size_t i = 0; i < it->second.size(); i++) if (it->second[i] == name) return (int)i;
+  return -1;
+}
+const char* b2s_id2name(const b2s_sim* s, const char* type, int id) {
+  if (!s || !type) return nullptr;
+  auto it = s->names.find(type);
+  if (it == s->names.end() || id < 0 || id >= (int)it->second.size()) return nullptr;
+  return it->second[id].c_str();
+}
+int b2s_full_m(b2s_sim* s, void* out) {
+  if (!s || !out) return fail(B2S_ERR_ARG, "b2s_full_m: bad argument");
+  size_t rsz = s->precision == B2S_F32 ? 4 : 8;
+  const void* src = s->precision == B2S_F32 ? (const void*)s->sf.qM : (const void*)s->sd.qM;
+  CUDA_TRY(cudaMemcpyAsync(out, src, (size_t)s->n_env * s->nv * s->nv * rsz, cudaMemcpyDeviceToDevice, s->stream));
+  return B2S_OK;
+}
+static int jac_point(b2s_sim* s, int kind, int id, void* jacp, void* jacr) {
+  { int rc = bind_constants(s); if (rc != B2S_OK) return rc; }
+  int threads = 128, blocks = (s->n_env * s->nv + threads - 1) / threads;
+  if (s->precision == B2S_F32) jac_point_kernel<float><<<blocks, threads, 0, s->stream>>>(kind, id, (float*)jacp, (float*)jacr, s->slot);
+  else jac_point_kernel<double><<<blocks, threads, 0, s->stream>>>(kind, id, (double*)jacp, (double*)jacr, s->slot);
+  s->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return B2S_OK;
+}
+int b2s_jac_body(b2s_sim* s, int body_id, void* jacp, void* jacr) {
+  if (!s || body_id < 0 || body_id >= s->nbody) return fail(B2S_ERR_ARG, "b2s_jac_body: bad argument");
+  return jac_point(s, 0, body_id, jacp, jacr);
+}
+int b2s_jac_geom(b2s_sim* s, int geom_id, void* jacp, void* jacr) {
+  if (!s || geom_id < 0 || geom_id >= s->ngeom) return fail(B2S_ERR_ARG, "b2s_jac_geom: bad argument");
+  return jac_point(s, 1, geom_id, jacp, jacr);
 }
 
 int b2s_ctrl_config(b2s_sim* s, const b2s_ctrl_cfg* c) {

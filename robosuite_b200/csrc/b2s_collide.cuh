@@ -444,36 +444,78 @@ template <typename R> DEV void sv_support(const Shape<R>& A, const Shape<R>& B, 
   v3sub(o.w, o.a, o.b);
 }
 
-template <typename R> DEV void closest_seg(SV<R>* s, int& n, R* lam) {
-  R ab[3];
-  v3sub(ab, s[1].w, s[0].w);
-  R den = v3dot(ab, ab);
-  R t = den > 0 ? -v3dot(s[0].w, ab) / den : R(0);
-  if (t <= 0) { n = 1; lam[0] = 1; }
-  else if (t >= 1) { s[0] = s[1]; n = 1; lam[0] = 1; }
-  else { lam[0] = 1 - t; lam[1] = t; }
+// ---- GJK simplex in SHARED memory ----------------------------------------------------------------------------------------------
+// 4 entries x 9 reals (w = a - b, a, b).  Every lane of the warp runs the same scalar code on the same values; as per-thread arrays
+// the simplex (dynamically indexed) lived in local memory - 32 redundant copies behind an L1 that is a few KB beside the phase
+// kernels' shared memory - and a 64-iteration GJK on a curved shape took up to 0.9 ms (tools/probe_instr.py "slow_items").  One copy
+// per warp in shared memory: loads are broadcasts, stores go through lane 0.
+template <typename R> DEV void sx_load(const R* sx, int k, SV<R>& o) {
+  const R* p = sx + 9 * k;
+#pragma unroll
+  for (int e = 0; e < 3; e++) { o.w[e] = p[e]; o.a[e] = p[3 + e]; o.b[e] = p[6 + e]; }
 }
-template <typename R> DEVN void closest_tri(SV<R>* s, int& n, R* lam) {
-  const R *a = s[0].w, *b = s[1].w, *c = s[2].w;
+template <typename R> DEV void sx_store(R* sx, int k, const SV<R>& v, int lane) {
+  __syncwarp();
+  if (lane == 0) {
+    R* p = sx + 9 * k;
+#pragma unroll
+    for (int e = 0; e < 3; e++) { p[e] = v.w[e]; p[3 + e] = v.a[e]; p[6 + e] = v.b[e]; }
+  }
+  __syncwarp();
+}
+// keep entries i0, i1, i2 (the first n of them) as the new entries 0..n-1
+template <typename R> DEV void sx_select(R* sx, int n, int i0, int i1, int i2, int lane) {
+  SV<R> t0, t1, t2;
+  sx_load(sx, i0, t0);
+  if (n > 1) sx_load(sx, i1, t1);
+  if (n > 2) sx_load(sx, i2, t2);
+  if (i0 != 0) sx_store(sx, 0, t0, lane);
+  if (n > 1 && i1 != 1) sx_store(sx, 1, t1, lane);
+  if (n > 2 && i2 != 2) sx_store(sx, 2, t2, lane);
+}
+
+// closest point of the triangle (a, b, c) to the origin: which of the three vertices support it (idx, n of them) and their weights
+template <typename R> DEV void tri_closest(const R* a, const R* b, const R* c, int& n, int* idx, R* lam) {
   R ab[3], ac[3];
   v3sub(ab, b, a); v3sub(ac, c, a);
+  idx[0] = 0; idx[1] = 1; idx[2] = 2; lam[0] = 1; lam[1] = 0; lam[2] = 0;
   R d1 = -v3dot(ab, a), d2 = -v3dot(ac, a);
-  if (d1 <= 0 && d2 <= 0) { n = 1; lam[0] = 1; return; }
+  if (d1 <= 0 && d2 <= 0) { n = 1; return; }
   R d3 = -v3dot(ab, b), d4 = -v3dot(ac, b);
-  if (d3 >= 0 && d4 <= d3) { s[0] = s[1]; n = 1; lam[0] = 1; return; }
+  if (d3 >= 0 && d4 <= d3) { idx[0] = 1; n = 1; return; }
   R vc = d1 * d4 - d3 * d2;
   if (vc <= 0 && d1 >= 0 && d3 <= 0) { R v = d1 / (d1 - d3); n = 2; lam[0] = 1 - v; lam[1] = v; return; }
   R d5 = -v3dot(ab, c), d6 = -v3dot(ac, c);
-  if (d6 >= 0 && d5 <= d6) { s[0] = s[2]; n = 1; lam[0] = 1; return; }
+  if (d6 >= 0 && d5 <= d6) { idx[0] = 2; n = 1; return; }
   R vb = d5 * d2 - d1 * d6;
-  if (vb <= 0 && d2 >= 0 && d6 <= 0) { R w = d2 / (d2 - d6); s[1] = s[2]; n = 2; lam[0] = 1 - w; lam[1] = w; return; }
+  if (vb <= 0 && d2 >= 0 && d6 <= 0) { R w = d2 / (d2 - d6); idx[1] = 2; n = 2; lam[0] = 1 - w; lam[1] = w; return; }
   R va = d3 * d6 - d5 * d4;
   if (va <= 0 && (d4 - d3) >= 0 && (d5 - d6) >= 0) {
     R w = (d4 - d3) / ((d4 - d3) + (d5 - d6));
-    s[0] = s[1]; s[1] = s[2]; n = 2; lam[0] = 1 - w; lam[1] = w; return;
+    idx[0] = 1; idx[1] = 2; n = 2; lam[0] = 1 - w; lam[1] = w; return;
   }
   R den = R(1) / (va + vb + vc);
+  n = 3;
   lam[1] = vb * den; lam[2] = vc * den; lam[0] = 1 - lam[1] - lam[2];
+}
+
+template <typename R> DEV void closest_seg(R* sx, int& n, R* lam, int lane) {
+  R ab[3];
+  const R *s0 = sx, *s1 = sx + 9;
+  v3sub(ab, s1, s0);
+  R den = v3dot(ab, ab);
+  R t = den > 0 ? -v3dot(s0, ab) / den : R(0);
+  if (t <= 0) { n = 1; lam[0] = 1; }
+  else if (t >= 1) { sx_select(sx, 1, 1, 0, 0, lane); n = 1; lam[0] = 1; }
+  else { lam[0] = 1 - t; lam[1] = t; }
+}
+template <typename R> DEV void closest_tri(R* sx, int& n, R* lam, int lane) {
+  R a[3] = {sx[0], sx[1], sx[2]}, b[3] = {sx[9], sx[10], sx[11]}, c[3] = {sx[18], sx[19], sx[20]};
+  int idx[3];
+  R l3[3];
+  tri_closest(a, b, c, n, idx, l3);
+  sx_select(sx, n, idx[0], idx[1], idx[2], lane);
+  for (int k = 0; k < n; k++) lam[k] = l3[k];
 }
 template <typename R> DEV R orient3(const R* a, const R* b, const R* c, const R* d) {
   R ab[3], ac[3], ad[3], cr[3];
@@ -481,39 +523,56 @@ template <typename R> DEV R orient3(const R* a, const R* b, const R* c, const R*
   v3cross(cr, ab, ac);
   return v3dot(cr, ad);
 }
-template <typename R> DEVN int closest_tet(SV<R>* s, int& n, R* lam) {
-  const int F[4][3] = {{0, 1, 2}, {0, 1, 3}, {0, 2, 3}, {1, 2, 3}};
-  const int O[4] = {3, 2, 1, 0};
+template <typename R> DEVN int closest_tet(R* sx, int& n, R* lam, int lane) {
+  R w4[4][3];
+#pragma unroll
+  for (int k = 0; k < 4; k++) { w4[k][0] = sx[9 * k]; w4[k][1] = sx[9 * k + 1]; w4[k][2] = sx[9 * k + 2]; }
   R zero[3] = {0, 0, 0};
   R bestd = Lim<R>::big();
-  SV<R> bests[3];
   R bestlam[3] = {0, 0, 0};
-  int bestn = 0, outside = 0;
-  R tiny = sizeof(R) == 4 ? R(1e-30) : R(1e-30);
+  int bestn = 0, outside = 0, bi0 = 0, bi1 = 0, bi2 = 0;
+  const R tiny = R(1e-30);
+#pragma unroll
   for (int f = 0; f < 4; f++) {
-    R so = orient3(s[F[f][0]].w, s[F[f][1]].w, s[F[f][2]].w, zero);
-    R sd = orient3(s[F[f][0]].w, s[F[f][1]].w, s[F[f][2]].w, s[O[f]].w);
+    // faces (0,1,2) (0,1,3) (0,2,3) (1,2,3), opposite vertices 3 2 1 0
+    const int f0 = f == 3 ? 1 : 0, f1 = f < 2 ? 1 : 2, f2 = f == 0 ? 2 : 3, op = 3 - f;
+    R so = orient3(w4[f0], w4[f1], w4[f2], zero);
+    R sd = orient3(w4[f0], w4[f1], w4[f2], w4[op]);
     if (r_abs(sd) < tiny) outside = 1;
     if (r_abs(sd) >= tiny && so * sd > 0) continue;
     outside = 1;
-    SV<R> t[3] = {s[F[f][0]], s[F[f][1]], s[F[f][2]]};
-    int tn = 3;
-    R tl[3] = {0, 0, 0};
-    closest_tri(t, tn, tl);
+    int tn, idx[3];
+    R tl[3];
+    tri_closest(w4[f0], w4[f1], w4[f2], tn, idx, tl);
+    // (selects instead of indexing by idx[]: the vertex array stays in registers)
     R pp[3] = {0, 0, 0};
-    for (int k = 0; k < tn; k++) v3addscl(pp, pp, t[k].w, tl[k]);
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+      if (k < tn) {
+        const int j = idx[k];
+#pragma unroll
+        for (int e = 0; e < 3; e++) pp[e] += (j == 0 ? w4[f0][e] : (j == 1 ? w4[f1][e] : w4[f2][e])) * tl[k];
+      }
     R dd = v3dot(pp, pp);
-    if (dd < bestd) { bestd = dd; bestn = tn; for (int k = 0; k < tn; k++) { bests[k] = t[k]; bestlam[k] = tl[k]; } }
+    if (dd < bestd) {
+      bestd = dd; bestn = tn;
+      bi0 = idx[0] == 0 ? f0 : (idx[0] == 1 ? f1 : f2);
+      bi1 = tn > 1 ? (idx[1] == 0 ? f0 : (idx[1] == 1 ? f1 : f2)) : 0;
+      bi2 = tn > 2 ? (idx[2] == 0 ? f0 : (idx[2] == 1 ? f1 : f2)) : 0;
+#pragma unroll
+      for (int k = 0; k < 3; k++) bestlam[k] = tl[k];
+    }
   }
   if (!outside) return 1;
   n = bestn;
-  for (int k = 0; k < bestn; k++) { s[k] = bests[k]; lam[k] = bestlam[k]; }
+  sx_select(sx, bestn, bi0, bi1, bi2, lane);
+  for (int k = 0; k < bestn; k++) lam[k] = bestlam[k];
   return 0;
 }
 
-// returns 1 if the cores overlap (simplex valid), else 0 with dist / witnesses
+// returns 1 if the cores overlap (simplex valid), else 0 with dist / witnesses.  sx: the warp's simplex area in shared memory (36 reals)
 template <typename R>
-DEVN int gjk(const Shape<R>& A, const Shape<R>& B, SV<R>* simplex, int& ns, R& dist, R* wa, R* wb, R cutoff, int lane, R* cache = nullptr) {
+DEVN int gjk(const Shape<R>& A, const Shape<R>& B, R* sx, int& ns, R& dist, R* wa, R* wb, R cutoff, int lane, R* cache = nullptr) {
   const R tol_vv = sizeof(R) == 4 ? R(1e-16) : R(1e-24);
   const R tol_rel = sizeof(R) == 4 ? R(1e-6) : R(1e-12);
   R v[3], nv[3];
@@ -526,17 +585,18 @@ DEVN int gjk(const Shape<R>& A, const Shape<R>& B, SV<R>* simplex, int& ns, R& d
   int n = 0;
   R lam[4] = {1, 0, 0, 0};
   v3scl(nv, v, R(-1));
-  sv_support(A, B, nv, simplex[0], lane);
+  SV<R> w;
+  sv_support(A, B, nv, w, lane);
+  sx_store(sx, 0, w, lane);
   n = 1;
   if (cache && cutoff >= 0) {  // does the remembered direction still separate the pair?  (one support pair, no iteration)
-    R vv0 = v3dot(v, v), vw0 = v3dot(v, simplex[0].w);
+    R vv0 = v3dot(v, v), vw0 = v3dot(v, w.w);
     if (vw0 > 0 && vw0 * vw0 > cutoff * cutoff * vv0) { dist = cutoff + 1; ns = 1; return 0; }
   }
-  v3copy(v, simplex[0].w);
+  v3copy(v, w.w);
   for (int it = 0; it < 64; it++) {
     R vv = v3dot(v, v);
     if (vv < tol_vv) { ns = n; if (cache && lane == 0) { cache[0] = 0; cache[1] = 0; cache[2] = 0; } return 1; }
-    SV<R> w;
     v3scl(nv, v, R(-1));
     sv_support(A, B, nv, w, lane);
     R vw = v3dot(v, w.w);
@@ -549,33 +609,36 @@ DEVN int gjk(const Shape<R>& A, const Shape<R>& B, SV<R>* simplex, int& ns, R& d
     int dup = 0;
     for (int k = 0; k < n; k++) {
       R e3[3];
-      v3sub(e3, simplex[k].w, w.w);
+      v3sub(e3, sx + 9 * k, w.w);
       if (v3dot(e3, e3) < tol_vv) dup = 1;
     }
     if (dup) break;
-    simplex[n++] = w;
-    if (n == 2) closest_seg(simplex, n, lam);
-    else if (n == 3) closest_tri(simplex, n, lam);
-    else if (closest_tet(simplex, n, lam)) { ns = 4; if (cache && lane == 0) { cache[0] = 0; cache[1] = 0; cache[2] = 0; } return 1; }
+    sx_store(sx, n, w, lane);
+    n++;
+    if (n == 2) closest_seg(sx, n, lam, lane);
+    else if (n == 3) closest_tri(sx, n, lam, lane);
+    else if (closest_tet(sx, n, lam, lane)) { ns = 4; if (cache && lane == 0) { cache[0] = 0; cache[1] = 0; cache[2] = 0; } return 1; }
     v3set(v, R(0), R(0), R(0));
-    for (int k = 0; k < n; k++) v3addscl(v, v, simplex[k].w, lam[k]);
+    for (int k = 0; k < n; k++) v3addscl(v, v, sx + 9 * k, lam[k]);
   }
   ns = n;
   dist = v3norm(v);
   if (cache && lane == 0) { cache[0] = v[0]; cache[1] = v[1]; cache[2] = v[2]; }
   v3set(wa, R(0), R(0), R(0));
   v3set(wb, R(0), R(0), R(0));
-  for (int k = 0; k < n; k++) { v3addscl(wa, wa, simplex[k].a, lam[k]); v3addscl(wb, wb, simplex[k].b, lam[k]); }
+  for (int k = 0; k < n; k++) { v3addscl(wa, wa, sx + 9 * k + 3, lam[k]); v3addscl(wb, wb, sx + 9 * k + 6, lam[k]); }
   return 0;
 }
 
 #define EPA_MAXV 96   // polytope capacity (same numbers in the oracle: oracle/o_collide.c)
 #define EPA_MAXF 192
-// words of the EPA work area: vertices 9 x maxv, face planes 4 x maxf, packed face ids maxf, horizon edge list 64, spare 8
-#define EPA_AREA_WORDS(maxv, maxf) ((9 * (maxv) + 5 * (maxf) + 64 + 8 + 3) & ~3)
+// words of the EPA work area: vertices 9 x maxv, face planes 4 x maxf, packed face ids maxf, horizon edge list 64, spare 8, and - its
+// last 40 words - the GJK simplex (4 x 9)
+#define EPA_AREA_WORDS(maxv, maxf) ((9 * (maxv) + 5 * (maxf) + 64 + 8 + 40 + 3) & ~3)
+#define EPA_SIMPLEX(scratch, maxv, maxf) ((scratch) + EPA_AREA_WORDS(maxv, maxf) - 40)
 // EPA polytope lives in this warp's scratch: V[EPA_MAXV][9], Fn[EPA_MAXF][4] (normal, dist), Fi[EPA_MAXF] packed ids
 template <typename R>
-DEVN int epa(const Shape<R>& A, const Shape<R>& B, SV<R>* simplex, int ns, R& depth, R* normal, R* wa, R* wb, R* scratch, int lane,
+DEVN int epa(const Shape<R>& A, const Shape<R>& B, R* sx, int ns, R& depth, R* normal, R* wa, R* wb, R* scratch, int lane,
              int maxv = EPA_MAXV, int maxf = EPA_MAXF) {
   // polytope capacity: (EPA_MAXV, EPA_MAXF) inside the fused kernel's scratch, larger in the work-list convex kernel
   R* V = scratch;
@@ -584,22 +647,20 @@ DEVN int epa(const Shape<R>& A, const Shape<R>& B, SV<R>* simplex, int ns, R& de
   int* edges = Fi + maxf;  // horizon edge list (64 entries) - in the work area, NOT a per-thread array: a dynamically indexed local
                            // array lives in local memory, and the serial edge search on it was most of a deep EPA's 300 us
   int nV = 0, nF = 0;
-  SV<R> S[4];
-  for (int k = 0; k < ns; k++) S[k] = simplex[k];
-  nV = ns;
+  nV = ns;  // the simplex (shared memory, sx) is completed to a tetrahedron in place
   const R dirs[6][3] = {{1, 0, 0}, {-1, 0, 0}, {0, 1, 0}, {0, -1, 0}, {0, 0, 1}, {0, 0, -1}};
   if (nV == 1) {
     for (int k = 0; k < 6 && nV < 2; k++) {
       SV<R> w;
       sv_support(A, B, dirs[k], w, lane);
       R e3[3];
-      v3sub(e3, w.w, S[0].w);
-      if (v3dot(e3, e3) > R(1e-12)) S[nV++] = w;
+      v3sub(e3, w.w, sx);
+      if (v3dot(e3, e3) > R(1e-12)) { sx_store(sx, nV, w, lane); nV++; }
     }
   }
   if (nV == 2) {
     R ab[3];
-    v3sub(ab, S[1].w, S[0].w);
+    v3sub(ab, sx + 9, sx);
     for (int k = 0; k < 6 && nV < 3; k++) {
       R dir[3];
       v3cross(dir, ab, dirs[k]);
@@ -607,15 +668,15 @@ DEVN int epa(const Shape<R>& A, const Shape<R>& B, SV<R>* simplex, int ns, R& de
       SV<R> w;
       sv_support(A, B, dir, w, lane);
       R e3[3], cr[3];
-      v3sub(e3, w.w, S[0].w);
+      v3sub(e3, w.w, sx);
       v3cross(cr, ab, e3);
-      if (v3dot(cr, cr) > R(1e-12) * v3dot(ab, ab) * v3dot(ab, ab)) S[nV++] = w;
+      if (v3dot(cr, cr) > R(1e-12) * v3dot(ab, ab) * v3dot(ab, ab)) { sx_store(sx, nV, w, lane); nV++; }
     }
   }
   if (nV == 3) {
     R ab[3], ac[3], nrm[3];
-    v3sub(ab, S[1].w, S[0].w);
-    v3sub(ac, S[2].w, S[0].w);
+    v3sub(ab, sx + 9, sx);
+    v3sub(ac, sx + 18, sx);
     v3cross(nrm, ab, ac);
     for (int s = 0; s < 2 && nV < 4; s++) {
       R dir[3];
@@ -623,16 +684,18 @@ DEVN int epa(const Shape<R>& A, const Shape<R>& B, SV<R>* simplex, int ns, R& de
       SV<R> w;
       sv_support(A, B, dir, w, lane);
       R e3[3];
-      v3sub(e3, w.w, S[0].w);
-      if (r_abs(v3dot(e3, nrm)) > R(1e-7) * v3dot(nrm, nrm)) S[nV++] = w;
+      v3sub(e3, w.w, sx);
+      if (r_abs(v3dot(e3, nrm)) > R(1e-7) * v3dot(nrm, nrm)) { sx_store(sx, nV, w, lane); nV++; }
     }
   }
   if (nV < 4) return -1;
-  if (orient3(S[0].w, S[1].w, S[2].w, S[3].w) > 0) { SV<R> t = S[0]; S[0] = S[1]; S[1] = t; }
+  const bool flip = orient3(sx, sx + 9, sx + 18, sx + 27) > 0;  // entries 0 and 1 swap
   __syncwarp();
   if (lane == 0)
-    for (int k = 0; k < 4; k++)
-      for (int e = 0; e < 3; e++) { V[9 * k + e] = S[k].w[e]; V[9 * k + 3 + e] = S[k].a[e]; V[9 * k + 6 + e] = S[k].b[e]; }
+    for (int k = 0; k < 4; k++) {
+      const R* src = sx + 9 * (flip && k < 2 ? 1 - k : k);
+      for (int e = 0; e < 9; e++) V[9 * k + e] = src[e];
+    }
   __syncwarp();
   auto mkface = [&](int f, int a, int b, int c) {
     // all lanes compute the same values; lane 0 stores
@@ -772,7 +835,7 @@ DEVN int epa(const Shape<R>& A, const Shape<R>& B, SV<R>* simplex, int ns, R& de
 template <typename R>
 DEVN int convex_convex(const Shape<R>& A0, const Shape<R>& B0, R* out, int maxn, R* scratch, int lane, R* cache = nullptr,
                        int maxv = EPA_MAXV, int maxf = EPA_MAXF, R* stage = nullptr, int stage_cap = 0) {
-  SV<R> simplex[4];
+  R* simplex = EPA_SIMPLEX(scratch, maxv, maxf);  // shared memory
   int ns = 0;
   R dist = 0, wa[3], wb[3], n[3], pos[3], pa[3], pb[3];
   Shape<R> A = A0, B = B0;

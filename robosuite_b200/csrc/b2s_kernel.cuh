@@ -211,6 +211,44 @@ __global__ void cache_reset_kernel(const uint8_t* mask, int slot) {
   s.gjk_cache[idx] = 0;
 }
 
+// flattened simulator state [time, qpos, qvel] per environment <-> the state arrays (MjSimState.flatten, binding_utils.py:56-70)
+template <typename R>
+__global__ void state_io_kernel(R* flat, int set, int slot) {
+  const DModel<R>& m = cmodel<R>(slot);
+  const DState<R>& s = cstate<R>(slot);
+  const int w = 1 + m.nq + m.nv;
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)s.n_env * w) return;
+  size_t env = idx / w; int k = (int)(idx % w);
+  R* p = k == 0 ? s.time + env : (k <= m.nq ? s.qpos + env * m.nq + (k - 1) : s.qvel + env * m.nv + (k - 1 - m.nq));
+  if (set) *p = flat[idx]; else flat[idx] = *p;
+}
+
+// Jacobian of a point that moves with `body` (body frame origin: kind 0, geom centre: kind 1, site: the dedicated kernel below)
+template <typename R>
+__global__ void jac_point_kernel(int kind, int id, R* jacp, R* jacr, int slot) {
+  const DModel<R>& m = cmodel<R>(slot);
+  const DState<R>& s = cstate<R>(slot);
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= s.n_env * m.nv) return;
+  int env = idx / m.nv, i = idx % m.nv;
+  size_t E = env;
+  int body = kind == 0 ? id : m.geom_bodyid[id];
+  const R* pos = kind == 0 ? s.xpos + (E * m.nbody + id) * 3 : s.geom_xpos + (E * m.ngeom + id) * 3;
+  bool on = (m.body_dofmask[body] >> i) & 1ull;
+  const R* cd = s.cdof + (E * m.nv + i) * 6;
+  R t[3] = {0, 0, 0}, w[3] = {0, 0, 0};
+  if (on) {
+    v3cross(t, cd, pos);
+    t[0] += cd[3]; t[1] += cd[4]; t[2] += cd[5];
+    w[0] = cd[0]; w[1] = cd[1]; w[2] = cd[2];
+  }
+  for (int r = 0; r < 3; r++) {
+    if (jacp) jacp[(E * 3 + r) * m.nv + i] = t[r];
+    if (jacr) jacr[(E * 3 + r) * m.nv + i] = w[r];
+  }
+}
+
 // translational / rotational Jacobian of a site from the exported cdof and site_xpos (valid after forward/step1)
 template <typename R>
 __global__ void jac_site_kernel(int site, R* jacp, R* jacr, int slot) {

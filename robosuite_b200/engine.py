@@ -55,6 +55,14 @@ def lib():
         L.b2s_array.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                 C.POINTER(C.c_int64)]
         L.b2s_jac_site.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.b2s_get_state.argtypes = [C.c_void_p, C.c_void_p]
+        L.b2s_set_state.argtypes = [C.c_void_p, C.c_void_p]
+        L.b2s_name2id.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
+        L.b2s_id2name.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+        L.b2s_id2name.restype = C.c_char_p
+        L.b2s_full_m.argtypes = [C.c_void_p, C.c_void_p]
+        L.b2s_jac_body.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.b2s_jac_geom.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.b2s_ctrl_config.argtypes = [C.c_void_p, C.POINTER(CtrlCfg)]
         L.b2s_ctrl_reset.argtypes = [C.c_void_p, C.c_void_p]
         L.b2s_env_step.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
@@ -246,10 +254,40 @@ class BatchedSim:
     def get_state(self):
         import torch
 
-        return torch.cat([self.array("time")[:, None], self.array("qpos"), self.array("qvel")], dim=1)
+        out = torch.empty((self.n_env, 1 + self.model.nq + self.model.nv), dtype=self.dtype, device=self.torch_device)
+        self._check(self._L.b2s_get_state(self._h, C.c_void_p(out.data_ptr())))
+        return out
 
     def set_state(self, flat):
-        nq, nv = self.model.nq, self.model.nv
-        self.array("time").copy_(flat[:, 0])
-        self.array("qpos").copy_(flat[:, 1:1 + nq])
-        self.array("qvel").copy_(flat[:, 1 + nq:1 + nq + nv])
+        flat = flat.to(device=self.torch_device, dtype=self.dtype).contiguous()
+        assert flat.shape == (self.n_env, 1 + self.model.nq + self.model.nv)
+        self._check(self._L.b2s_set_state(self._h, C.c_void_p(flat.data_ptr())))
+
+    # ---- MjModel name tables / mj_fullM / body and geom Jacobians (binding_utils.py:362-492, 853-878; controller.py:226-229)
+    def name2id(self, objtype, name):
+        return int(self._L.b2s_name2id(self._h, objtype.encode(), name.encode()))
+
+    def id2name(self, objtype, idx):
+        r = self._L.b2s_id2name(self._h, objtype.encode(), int(idx))
+        return None if r is None else r.decode()
+
+    def full_m(self):
+        import torch
+
+        out = torch.empty((self.n_env, self.model.nv, self.model.nv), dtype=self.dtype, device=self.torch_device)
+        self._check(self._L.b2s_full_m(self._h, C.c_void_p(out.data_ptr())))
+        return out
+
+    def _jac(self, fn, idx):
+        import torch
+
+        jp = torch.empty((self.n_env, 3, self.model.nv), dtype=self.dtype, device=self.torch_device)
+        jr = torch.empty_like(jp)
+        self._check(fn(self._h, int(idx), C.c_void_p(jp.data_ptr()), C.c_void_p(jr.data_ptr())))
+        return jp, jr
+
+    def jac_body(self, body_id):
+        return self._jac(self._L.b2s_jac_body, body_id)
+
+    def jac_geom(self, geom_id):
+        return self._jac(self._L.b2s_jac_geom, geom_id)

@@ -841,6 +841,11 @@ def pack_model(m: Model) -> bytes:
     for k, v in sorted(m.scalars().items()):
         a = np.array([v], dtype=np.int32 if isinstance(v, int) else np.float64)
         items.append((k, a))
+    # name tables (MjModel name2id / id2name, binding_utils.py:362-492): per object type one '\n'-joined UTF-8 string as an i32 array of
+    # byte values ("names_body", "names_joint", ...); unnamed objects are empty strings
+    for objtype, lst in sorted(getattr(m, "names", {}).items()):
+        joined = "\n".join("" if x is None else str(x) for x in lst).encode("utf-8")
+        items.append(("names_" + objtype, np.frombuffer(joined, dtype=np.uint8).astype(np.int32) if joined else np.zeros(0, np.int32)))
     for k, v in sorted(m.arrays().items()):
         if v.dtype.kind in "iub":
             a = np.ascontiguousarray(v, dtype=np.int32)

@@ -8,6 +8,8 @@ import json
 import os
 import sys
 
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 import numpy as np
 import torch
 
@@ -40,7 +42,7 @@ torch.cuda.synchronize()
 step_ms = e0.elapsed_time(e1)
 b = sim.st_begin.cpu().numpy().astype(np.uint64).reshape(64, 32, 8)
 e = sim.st_end.cpu().numpy().astype(np.uint64).reshape(64, 32, 8)
-G = int(os.environ.get("B2S_GROUPS", "4"))
+G = int(os.environ.get("B2S_GROUPS", "8"))
 valid = e[:G, :25] > 0
 t0 = b[:G, :25][valid].min()
 B = (b[:G, :25].astype(np.float64) - float(t0)) / 1e3  # us

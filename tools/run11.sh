@@ -12,4 +12,5 @@ run G32 B2S_GROUPS=32
 run G8_cvx3552 B2S_GROUPS=8 B2S_CVX_BLOCKS=3552
 run G8_cvx1024 B2S_GROUPS=8 B2S_CVX_BLOCKS=1024
 run G16_onegraph B2S_GROUPS=16 B2S_GRAPH_PER_GROUP=0
+timeout 600 python -m pytest tests/test_gpu_boundary.py -q -s > gpurun_out/r11_pytest_boundary.log 2>&1; echo "pytest exit $?" >> gpurun_out/r11_pytest_boundary.log
 echo done
