@@ -273,7 +273,7 @@ template <typename R> static void build_model(b2s_sim* s, const Blob& b, DModel<
     int64_t nm = 0; const int* vn = b.i32("mesh_vertnum", &nm);
     int n1 = 0, n2 = 0;
     for (int64_t i = 0; i < nm; i++) { int v = vn[i]; if (v > n1) { n2 = n1; n1 = v; } else if (v > n2) n2 = v; }
-    int need = ((3 * n1 + 3) & ~3) + ((3 * n2 + 3) & ~3);
+    int need = 24 + ((3 * n1 + 3) & ~3) + ((3 * n2 + 3) & ~3);  // two poses, two hulls
     int cap = (int)(56 * 1024 / sizeof(R));
     m.stage_cap = getenv("B2S_NO_STAGE") ? 0 : std::min(need, cap);
   }

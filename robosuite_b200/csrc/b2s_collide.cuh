@@ -840,7 +840,7 @@ DEVN int convex_convex(const Shape<R>& A0, const Shape<R>& B0, R* out, int maxn,
   R dist = 0, wa[3], wb[3], n[3], pos[3], pa[3], pb[3];
   Shape<R> A = A0, B = B0;
   R ra = shape_radius(A), rb = shape_radius(B);
-  if (stage != nullptr && (A.nvert > 0 || B.nvert > 0)) {
+  if (stage != nullptr) {
     if (cache != nullptr) {  // gjk()'s own first test, made here so that dismissed pairs (the common case) never pay for staging
       R cv[3] = {cache[0], cache[1], cache[2]};
       if (v3dot(cv, cv) > R(1e-12)) {
@@ -851,6 +851,12 @@ DEVN int convex_convex(const Shape<R>& A0, const Shape<R>& B0, R* out, int maxn,
         if (vw0 > 0 && vw0 * vw0 > cut * cut * vv0) return 0;
       }
     }
+    // the two poses first (24 reals): support_w reads them on every call, through pointers into the global workspace row otherwise
+    __syncwarp();
+    if (lane < 12) stage[lane] = lane < 3 ? A.pos[lane] : A.mat[lane - 3];
+    else if (lane < 24) stage[lane] = lane < 15 ? B.pos[lane - 12] : B.mat[lane - 15];
+    A.pos = stage; A.mat = stage + 3; B.pos = stage + 12; B.mat = stage + 15;
+    stage += 24; stage_cap -= 24;
     int used = 0;
     if (A.nvert > 0 && 3 * A.nvert <= stage_cap) {
       for (int i = lane; i < 3 * A.nvert; i += 32) stage[i] = A.vert[i];

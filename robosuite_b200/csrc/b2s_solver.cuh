@@ -536,16 +536,21 @@ template <typename R> DEVN int solve(Eng<R> e, int nefc, int ncon, int& warn) {
     B2S_LOOP
     for (int k = lane; k < nv * nv; k += 32) H[k] = M[k];
     __syncwarp();
+    // a dof can carry a friction-loss row AND a joint-limit row: two passes of plain adds (rows of one kind hit distinct dofs) keep the
+    // summation order fixed - a float atomicAdd left it to the hardware, and two handles stepping side by side then drifted apart
     B2S_LOOP
-    for (int r = lane; r < first_contact_row; r += 32) {
-      R d = act[r];
-      if (d != 0) {
+    for (int pass = 0; pass < 2; pass++) {
+      B2S_LOOP
+      for (int r = lane; r < first_contact_row; r += 32) {
         int ty = eint[r] & 255, id = eint[r] >> 8;
-        int dof = ty == C_FRICTION ? id : m.jnt_dofadr[id];
-        atomicAdd(&H[dof * nv + dof], d);
+        R d = act[r];
+        if ((ty == C_FRICTION) == (pass == 0) && d != 0) {
+          int dof = ty == C_FRICTION ? id : m.jnt_dofadr[id];
+          H[dof * nv + dof] += d;
+        }
       }
+      __syncwarp();
     }
-    __syncwarp();
     {
       int* dofs = reinterpret_cast<int*>(Hcb + m.hc_stride * L.mc);
       B2S_LOOP
