@@ -361,8 +361,7 @@ def run_gpu(args):
     wraps = [BatchedGymWrapper(e) for e in envs]
     for e in envs:
         e.ignore_done = False
-        e.timestep[:] = torch.randint(0, e.horizon, (e.num_envs,), generator=gen, device=dev)
-        e._max_steps_since_reset = e.horizon  # the wrapper then checks `done` every step
+        e.set_episode_steps(torch.randint(0, e.horizon, (e.num_envs,), generator=gen, device=dev))
     obs_dim = max(w.obs_dim for w in wraps)
     esz = 4 if dtype == torch.float32 else 8
     h_act = [torch.empty((K, e.num_envs, e.action_dim), dtype=dtype).pin_memory() for e in envs]

@@ -104,6 +104,12 @@ int b2s_ctrl_config(b2s_sim* sim, const b2s_ctrl_cfg* cfg);
 /* controller.reset_goal + update_initial_joints (osc.py:520-544) for masked envs (NULL = all); needs a prior forward */
 int b2s_ctrl_reset(b2s_sim* sim, const uint8_t* env_mask);
 int b2s_env_step(b2s_sim* sim, const void* action, int n_substeps);
+/* MujocoEnv.reset for a device-resident subset (environments/base.py:277-347: _reset_internal -> sim.forward -> controller reset -> observation
+ * cache emptied): masked envs (device bytes, NULL = all) take qpos from `qpos_new` ([n_env, nq] device array of the handle's precision holding a
+ * sampled initial state for every environment; NULL = qpos0), velocities / accelerations / warm start / ctrl / time / warn cleared, forward pass,
+ * controller goals rebuilt, GJK warm starts dropped.  Every launch is asynchronous on the handle's stream: no host round trip, so a horizon-based
+ * auto-reset can be enqueued after every step. */
+int b2s_reset_envs(b2s_sim* sim, const uint8_t* env_mask, const void* qpos_new);
 
 /* Observation program = MujocoEnv._get_observations flattened (environments/base.py:429-465): one (op, a, b) entry
  * per output scalar (ops: enum OB_* in csrc/b2s_types.cuh; OB_REL_*_LAG entries read the previous sample, as the reference's

@@ -745,14 +745,14 @@ static int rebuild_layouts(b2s_sim* s) {
   return B2S_OK;
 }
 
-static int launch(b2s_sim* s, int phases, int nsub, const void* action = nullptr) {
+static int launch(b2s_sim* s, int phases, int nsub, const void* action = nullptr, const uint8_t* mask = nullptr) {
   int rc = bind_constants(s);
   if (rc != B2S_OK) return rc;
   int blocks = (s->n_env + s->wpb_fused - 1) / s->wpb_fused;
   if (s->precision == B2S_F32)
-    step_kernel<float><<<blocks, s->wpb_fused * 32, s->smem_fused, s->stream>>>(phases, nsub, (const float*)action, s->slot);
+    step_kernel<float><<<blocks, s->wpb_fused * 32, s->smem_fused, s->stream>>>(phases, nsub, (const float*)action, s->slot, mask);
   else
-    step_kernel<double><<<blocks, s->wpb_fused * 32, s->smem_fused, s->stream>>>(phases, nsub, (const double*)action, s->slot);
+    step_kernel<double><<<blocks, s->wpb_fused * 32, s->smem_fused, s->stream>>>(phases, nsub, (const double*)action, s->slot, mask);
   s->launches++;
   CUDA_TRY(cudaGetLastError());
   return B2S_OK;
@@ -1154,6 +1154,21 @@ int b2s_ctrl_reset(b2s_sim* s, const uint8_t* mask) {
   clear_warm_start(s, mask);  // an environment whose controller is rebuilt starts a new episode
   s->launches++;
   CUDA_TRY(cudaGetLastError());
+  return B2S_OK;
+}
+
+int b2s_reset_envs(b2s_sim* s, const uint8_t* mask, const void* qpos_new) {
+  if (!s) return fail(B2S_ERR_ARG, "null handle");
+  { int rc = bind_constants(s); if (rc != B2S_OK) return rc; }
+  int threads = 128, blocks = (s->n_env + threads - 1) / threads;
+  if (s->precision == B2S_F32) reset_envs_kernel<float><<<blocks, threads, 0, s->stream>>>(mask, (const float*)qpos_new, s->slot);
+  else reset_envs_kernel<double><<<blocks, threads, 0, s->stream>>>(mask, (const double*)qpos_new, s->slot);
+  s->launches++;
+  CUDA_TRY(cudaGetLastError());
+  int rc = launch(s, PH_STEP1 | PH_STEP2 | PH_NOINTEGRATE | PH_EXPORT | (s->has_obs ? PH_OBS : 0), 1, nullptr, mask);
+  if (rc != B2S_OK) return rc;
+  if (s->has_ctrl) return b2s_ctrl_reset(s, mask);
+  clear_warm_start(s, mask);
   return B2S_OK;
 }
 

@@ -85,7 +85,7 @@ DEVN void export_step2(const Eng<R> e, int env, int nefc, int niter) {
 }
 
 template <typename R>
-__global__ void __launch_bounds__(512, 1) step_kernel(int phases, int nsub, const R* action, int slot) {
+__global__ void __launch_bounds__(512, 1) step_kernel(int phases, int nsub, const R* action, int slot, const uint8_t* mask = nullptr) {
   const DModel<R>& m = cmodel<R>(slot);
   const DState<R>& s = cstate<R>(slot);
   const WSLayout& L = c_lay[slot][LAY_FULL];
@@ -97,6 +97,18 @@ __global__ void __launch_bounds__(512, 1) step_kernel(int phases, int nsub, cons
   // region, which is what bounds the instruction-cache working set); warps beyond n_env shadow the last env
   bool live = env < s.n_env;
   if (!live) env = s.n_env - 1;
+  if (mask) {
+    // masked launch (forward pass of the environments being reset): blocks without a selected environment leave, the other warps of a
+    // block shadow a selected one (they write the same values to the same addresses, like the tail warps above)
+    __shared__ int pick;
+    if (threadIdx.x == 0) pick = -1;
+    __syncthreads();
+    live = live && mask[env];
+    if (live && lane == 0) atomicMax(&pick, env);
+    __syncthreads();
+    if (pick < 0) return;
+    if (!live) env = pick;
+  }
   Eng<R> e(smem + (size_t)warp * L.fused_stride, lane, slot, LAY_FULL);
   size_t E = env;
   load_row(e.p(L.qpos), s.qpos + E * m.nq, m.nq, lane);
@@ -181,6 +193,24 @@ __global__ void __launch_bounds__(512, 1) step_kernel(int phases, int nsub, cons
   }
   warn = warp_or_i(warn);  // some flags (a dropped contact's rows) are raised on the lane that owns the item
   if (lane == 0) { s.time[env] = time; s.warn[env] |= warn; }
+}
+
+// masked episode reset without a host round trip: selected environments take their generalized positions from `qpos_new` (a pool of
+// sampled initial states, [n_env, nq]; nullptr: the model's qpos0), everything else is cleared the way reset_kernel does
+template <typename R>
+__global__ void reset_envs_kernel(const uint8_t* mask, const R* qpos_new, int slot) {
+  const DModel<R>& m = cmodel<R>(slot);
+  const DState<R>& s = cstate<R>(slot);
+  int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= s.n_env) return;
+  if (mask && !mask[env]) return;
+  size_t E = env;
+  for (int i = 0; i < m.nq; i++) s.qpos[E * m.nq + i] = qpos_new ? qpos_new[E * m.nq + i] : m.qpos0[i];
+  for (int i = 0; i < m.nv; i++) { s.qvel[E * m.nv + i] = 0; s.qacc[E * m.nv + i] = 0; s.qacc_ws[E * m.nv + i] = 0; }
+  for (int i = 0; i < m.nu; i++) s.ctrl[E * m.nu + i] = 0;
+  s.time[env] = 0;
+  s.warn[env] = 0;
+  if (s.obs_fresh) s.obs_fresh[env] = 1;
 }
 
 template <typename R>

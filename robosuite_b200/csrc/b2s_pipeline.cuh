@@ -59,6 +59,10 @@ DEV void tma_store_1d(void* gdst, const void* smem_src, unsigned bytes) {
 template <typename R> DEV void ws_load(const Eng<R>& e, const R* row, const PhaseIO& io, unsigned long long* bar, unsigned& parity) {
   if (io.nload == 0) return;
 #if B2S_TMA
+  // the destination may have been read / written through the generic proxy before (the constraint Jacobian under the late poses, the
+  // previous environment of a large-tier warp): order those accesses before the async-proxy writes of the bulk copies
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
   if (e.lane == 0) mbar_expect_tx(bar, (unsigned)io.load_words * (unsigned)sizeof(R));
   __syncwarp();
   if (e.lane < io.nload) {
@@ -200,6 +204,10 @@ template <typename R>
 __global__ void __launch_bounds__(32) phase1_kernel(const R* action, Grp g, P1Cfg c) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int b = blockIdx.x;
+#ifdef B2S_ZERO_SMEM
+  for (int i = threadIdx.x; i < 6000; i += 32) reinterpret_cast<int*>(smem_raw)[i] = 0;
+  __syncwarp();
+#endif
 #ifdef B2S_INSTR
   const DState<R>& s = cstate<R>(g.slot);
   const int kind = b < c.nG ? 2 : (b < c.nG + c.nC ? 4 : 1);
@@ -307,6 +315,10 @@ __global__ void __launch_bounds__(B2S_LB0_THREADS, B2S_LB0_BLOCKS) phase0_kernel
   if (env >= g.nenv) return;
   env += g.env0;
   Eng<R> e(smem + (size_t)warp * L.total, lane, g.slot, LAY_P0);
+#ifdef B2S_ZERO_SMEM
+  for (int i = lane; i < L.total; i += 32) e.ws[i] = 0;
+  __syncwarp();
+#endif
   size_t E = env;
   R* row = s.wsg + E * RL.total;
   load_row(e.p(L.qpos), s.qpos + E * m.nq, m.nq, lane);
@@ -364,6 +376,10 @@ __global__ void __launch_bounds__(B2S_LB5_THREADS, B2S_LB5_BLOCKS) tail_kernel(i
   __syncwarp();
   unsigned parity = 0;
   Eng<R> e(smem + (size_t)warp * L.total, lane, g.slot, lid);
+#ifdef B2S_ZERO_SMEM
+  for (int i = lane; i < L.total; i += 32) e.ws[i] = 0;
+  __syncwarp();
+#endif
   int* clc = CLC(s, g);
   const bool tiered = L.mc < m.maxcon || L.me < m.maxefc;
   for (int iter = 0;; iter++) {

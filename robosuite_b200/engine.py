@@ -66,6 +66,7 @@ def lib():
         L.b2s_ctrl_config.argtypes = [C.c_void_p, C.POINTER(CtrlCfg)]
         L.b2s_ctrl_reset.argtypes = [C.c_void_p, C.c_void_p]
         L.b2s_env_step.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.b2s_reset_envs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.b2s_obs_config.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.b2s_task_config.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.b2s_task_config2.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
@@ -195,6 +196,13 @@ class BatchedSim:
 
     def ctrl_config(self, cfg: CtrlCfg):
         self._check(self._L.b2s_ctrl_config(self._h, C.byref(cfg)))
+
+    def reset_envs(self, mask=None, qpos=None):
+        """masked episode reset entirely on the device (b2s_reset_envs): mask uint8 [n_env] or None, qpos [n_env, nq] or None (qpos0)"""
+        if qpos is not None:
+            assert qpos.is_cuda and qpos.dtype == self.dtype and qpos.is_contiguous() and qpos.shape == (self.n_env, self.model.nq)
+        self._check(self._L.b2s_reset_envs(self._h, None if mask is None else C.c_void_p(mask.data_ptr()),
+                                           None if qpos is None else C.c_void_p(qpos.data_ptr())))
 
     def ctrl_reset(self, mask=None):
         self._check(self._L.b2s_ctrl_reset(self._h, None if mask is None else C.c_void_p(mask.data_ptr())))

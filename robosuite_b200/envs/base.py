@@ -92,6 +92,11 @@ class ObsBuilder:
         return arr[:, 0], arr[:, 1], arr[:, 2], slices, mod_slices
 
 
+# bits of sim.warn / info["sim_warn"] (robosuite_b200/csrc: b2s_kernel.cuh, b2s_collide.cuh, b2s_solver.cuh)
+SIM_WARN_BITS = {1: "singular mass matrix", 2: "non-finite state in the integrator", 4: "contact capacity overflow (maxcon)",
+                 8: "constraint-row capacity overflow (maxefc)", 16: "singular Newton Hessian"}
+
+
 class BatchedMujocoEnv:
     """N copies of one task on one GPU.  All returned arrays are torch.cuda tensors with leading dim N."""
 
@@ -156,6 +161,7 @@ class BatchedMujocoEnv:
         self.done = torch.zeros(self.num_envs, dtype=torch.bool, device=self.device)
         self.cur_time = 0.0
         self._max_steps_since_reset = 0  # host-side upper bound of `timestep` (avoids a device sync per step)
+        self._host_steps = np.zeros(self.num_envs, dtype=np.int64)  # host mirror of `timestep` (None once a caller resets by device mask)
         self.reset()
 
     # ---- to be provided by tasks
@@ -260,31 +266,50 @@ class BatchedMujocoEnv:
             l, r = ["gripper0_right_l_fingerpad_g0"], ["gripper0_right_r_fingerpad_g0"]
         return [gn.index(x) for x in l], [gn.index(x) for x in r]
 
-    def reset(self, mask=None):
+    def reset(self, mask=None, host_mask=None):
         """Re-initialise all (or masked) environments: robot init pose + noise, gripper open, task objects sampled,
-        controllers rebuilt (goal <- current eef pose), observations force-updated (environments/base.py:277-347)."""
+        controllers rebuilt (goal <- current eef pose), observations force-updated (environments/base.py:277-347).
+        Everything runs on the device without a host round trip: an initial state is sampled for every environment (a few small
+        tensor ops) and `b2s_reset_envs` applies it to the masked ones, so a per-step auto-reset costs three short launches.
+        host_mask: the same mask as a numpy bool array when the caller has it (keeps the host mirror of the episode clocks exact)."""
         import torch
 
-        idx = torch.arange(self.num_envs, device=self.device) if mask is None else torch.nonzero(mask).flatten()
-        n = int(idx.numel())
-        if n:
-            q = self._sample_reset_state(n)
-            self.sim.qpos[idx] = q.to(self.dtype)
-            self.sim.qvel[idx] = 0
-            self.sim.qacc[idx] = 0
-            self.sim.qacc_warmstart[idx] = 0
-            self.sim.ctrl[idx] = 0
-            self.sim.time[idx] = 0
-            self.timestep[idx] = 0
-            self.done[idx] = False
-            self.sim.obs_fresh[idx] = 1  # observation cache emptied (environments/base.py:332-335)
+        q = self._sample_reset_state(self.num_envs).to(self.dtype).contiguous()
         if mask is None:
+            self.timestep.zero_()
+            self.done.zero_()
             self._max_steps_since_reset = 0
-        self.sim.forward()
-        m8 = None if mask is None else mask.to(torch.uint8).contiguous()
-        self.sim.ctrl_reset(m8)
+            self._host_steps = np.zeros(self.num_envs, dtype=np.int64)
+            self.sim.reset_envs(None, q)
+        else:
+            mask = mask.to(device=self.device, dtype=torch.bool)
+            self.timestep.masked_fill_(mask, 0)
+            self.done.masked_fill_(mask, False)
+            self._reset_mask8 = mask.to(torch.uint8).contiguous()  # kept alive until the launches that read it have run
+            self.sim.reset_envs(self._reset_mask8, q)
+            if host_mask is not None and self._host_steps is not None:
+                self._host_steps[np.asarray(host_mask, dtype=bool)] = 0
+                self._max_steps_since_reset = int(self._host_steps.max())
+            else:
+                self._host_steps = None  # episode clocks now only known on the device; `_max_steps_since_reset` stays an upper bound
+        self._reset_qpos = q
         self.cur_time = 0.0
         return self._get_observations()
+
+    def set_episode_steps(self, steps):
+        """Set the per-environment episode clocks (e.g. to stagger the episode phases of a long-running vector environment)."""
+        import torch
+
+        h = np.asarray(steps.cpu() if torch.is_tensor(steps) else steps, dtype=np.int64).reshape(self.num_envs)
+        self._host_steps = h.copy()
+        self.timestep[:] = torch.as_tensor(h, device=self.device)
+        self._max_steps_since_reset = int(h.max())
+
+    def host_done(self):
+        """numpy bool [N]: which environments have reached the horizon, from the host mirror of the episode clocks; None if unknown"""
+        if self._host_steps is None or self.ignore_done:
+            return None
+        return self._host_steps >= self.horizon
 
     def reset_to(self, qpos, qvel=None):
         """Put every environment into the given state and do what reset() does afterwards (forward, controllers rebuilt,
@@ -309,7 +334,9 @@ class BatchedMujocoEnv:
         self.timestep[:] = 0
         self.done[:] = False
         self.sim.obs_fresh[:] = 1
+        self.sim.warn[:] = 0
         self._max_steps_since_reset = 0
+        self._host_steps = np.zeros(self.num_envs, dtype=np.int64)
         self.sim.forward()
         self.sim.ctrl_reset(None)
         self.cur_time = 0.0
@@ -320,9 +347,13 @@ class BatchedMujocoEnv:
         import torch
 
         # an env can only be done once the longest-running one has reached the horizon: no device sync before that
-        if not self.ignore_done and self._max_steps_since_reset >= self.horizon and bool(self.done.any()):
-            raise ValueError("executing action in terminated episode")
+        if not self.ignore_done and self._max_steps_since_reset >= self.horizon:
+            hd = self.host_done()
+            if bool(hd.any()) if hd is not None else bool(self.done.any()):
+                raise ValueError("executing action in terminated episode")
         self._max_steps_since_reset += 1
+        if self._host_steps is not None:
+            self._host_steps += 1
         action = torch.as_tensor(action, dtype=self.dtype, device=self.device).contiguous()
         assert action.shape == (self.num_envs, self.action_dim), "environment got invalid action dimension -- expected {}, got {}".format(
             (self.num_envs, self.action_dim), tuple(action.shape))
@@ -331,7 +362,19 @@ class BatchedMujocoEnv:
         self.cur_time += self.control_timestep
         reward = self.reward(action)
         self.done = (self.timestep >= self.horizon) & (not self.ignore_done)
-        return self._get_observations(), reward, self.done, {}
+        # per-environment engine flags since the last reset, as a device tensor (no host sync here; see SIM_WARN_BITS): a non-zero entry means
+        # the episode is no longer a faithful MuJoCo rollout (capacity overflow, singular mass matrix / Hessian, diverged state)
+        return self._get_observations(), reward, self.done, {"sim_warn": self.sim.warn}
+
+    def check_sim_warnings(self):
+        """Host-side check of the engine flags (one device sync): raises SimulationError naming the flags and how many
+        environments carry them.  The reference surfaces the same conditions as mujoco warnings / MujocoException."""
+        from ..errors import SimulationError
+
+        w = self.sim.warn
+        if bool((w != 0).any()):
+            bits = {name: int(((w & bit) != 0).sum()) for bit, name in SIM_WARN_BITS.items()}
+            raise SimulationError("engine flags raised: " + ", ".join(f"{k} in {v} envs" for k, v in bits.items() if v))
 
     def _get_observations(self):
         """OrderedDict of per-observable tensors plus the per-modality concatenations (base.py:429-465)."""

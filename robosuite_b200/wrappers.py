@@ -3,7 +3,9 @@
 Same key selection and flattening rule (`object-state` first, then `robot{i}_proprio-state`), same 5-tuple `step` return,
 but every array carries a leading environment axis and lives on the GPU, and finished episodes are reset inside `step`
 (gymnasium VectorEnv "next-step autoreset is too late for a fused simulator": the observation returned for a finished
-environment is the first observation of its next episode, the final one is in `info["final_observation"]`)."""
+environment is the first observation of its next episode, the final one is in `info["final_observation"]`).  `step` never
+synchronises with the device: which episodes ended is known on the host (horizon-only termination) and the masked reset is a
+device-side launch sequence (`b2s_reset_envs`)."""
 import numpy as np
 
 
@@ -54,12 +56,17 @@ class BatchedGymWrapper:
         ob_dict, reward, done, info = self.env.step(action)
         obs = self._format(ob_dict)
         terminated = done.clone()
-        if self.auto_reset and not self.env.ignore_done and self.env._max_steps_since_reset >= self.env.horizon and bool(done.any()):
-            info = dict(info)
-            info["final_observation"] = obs.clone() if self.flatten_obs else {k: v.clone() for k, v in obs.items()}
-            obs = self._format(self.env.reset(mask=done))
-            # environments that were not reset keep counting from their own timestep
-            self.env._max_steps_since_reset = int(self.env.timestep.max())
+        env = self.env
+        if self.auto_reset and not env.ignore_done and env._max_steps_since_reset >= env.horizon:
+            # the horizon is the only termination rule (environments/base.py:513-514), so the host mirror of the episode clocks says which
+            # environments finished without reading `done` back; the reset itself is a masked device-side launch sequence.  Without the mirror
+            # (a caller reset by device mask) the masked reset is enqueued anyway: it is a no-op for an all-false mask
+            hd = env.host_done()
+            if hd is None or hd.any():
+                info = dict(info)
+                info["final_observation"] = obs.clone() if self.flatten_obs else {k: v.clone() for k, v in obs.items()}
+                info["sim_warn"] = info["sim_warn"].clone()  # the reset clears the flags of the finished episodes
+                obs = self._format(env.reset(mask=done, host_mask=hd))
         return obs, reward, terminated, torch.zeros_like(terminated), info
 
     def compute_reward(self, achieved_goal=None, desired_goal=None, info=None):

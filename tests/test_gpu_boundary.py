@@ -28,7 +28,7 @@ class CtrlCfg(C.Structure):  # b2s_ctrl_cfg, include/b2s.h
 
 
 def _lib():
-    L = C.CDLL(os.path.join(ROOT, "robosuite_b200", "libb2s.so"))
+    L = C.CDLL(os.environ.get("B2S_LIB", os.path.join(ROOT, "robosuite_b200", "libb2s.so")))
     L.b2s_last_error.restype = C.c_char_p
     L.b2s_create.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
     L.b2s_destroy.argtypes = [C.c_void_p]; L.b2s_destroy.restype = None
