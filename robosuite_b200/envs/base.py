@@ -282,10 +282,10 @@ class BatchedMujocoEnv:
             self._host_steps = np.zeros(self.num_envs, dtype=np.int64)
             self.sim.reset_envs(None, q)
         else:
-            mask = mask.to(device=self.device, dtype=torch.bool)
+            self._reset_mask8 = mask.to(device=self.device, dtype=torch.uint8).contiguous()  # a copy (the caller may pass `self.done`), kept alive
+            mask = self._reset_mask8.bool()
             self.timestep.masked_fill_(mask, 0)
             self.done.masked_fill_(mask, False)
-            self._reset_mask8 = mask.to(torch.uint8).contiguous()  # kept alive until the launches that read it have run
             self.sim.reset_envs(self._reset_mask8, q)
             if host_mask is not None and self._host_steps is not None:
                 self._host_steps[np.asarray(host_mask, dtype=bool)] = 0

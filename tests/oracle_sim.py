@@ -147,6 +147,21 @@ class OracleSim:
                 self._sample_obs(e)
             self._sample_task(e)
 
+    def reset_envs(self, mask=None, qpos=None):
+        """b2s_reset_envs: masked environments take the sampled state, are cleared, forwarded, and get their controller rebuilt"""
+        for e in range(self.n_env):
+            if mask is not None and not bool(mask[e]):
+                continue
+            self.qpos[e] = torch.as_tensor(np.asarray(self.model.qpos0)) if qpos is None else qpos[e].to(torch.float64)
+            self.qvel[e] = 0; self.qacc[e] = 0; self.qacc_warmstart[e] = 0; self.ctrl[e] = 0; self.time[e] = 0
+            self.warn[e] = 0; self.obs_fresh[e] = 1
+            self._push(e); self.o[e].forward()
+            self.qacc[e] = torch.as_tensor(self.o[e].qacc.copy())
+            self._sample_obs(e)
+            self._sample_task(e)
+            if self._cfg is not None:
+                self.o[e].ctrl_reset()
+
     def ctrl_reset(self, mask=None):
         for e in range(self.n_env):
             if mask is None or bool(mask[e]):

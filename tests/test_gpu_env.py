@@ -2,7 +2,9 @@
 import numpy as np
 import pytest
 
-from tests.util import load
+import os
+
+from tests.util import ROOT, load
 
 pytestmark = pytest.mark.gpu
 
@@ -265,4 +267,37 @@ def test_batched_gym_wrapper_autoreset():
     assert torch.allclose(obs[:, 2], torch.full((n,), 0.83, device=obs.device), atol=5e-3)
     obs, rew, term, trunc, info = env.step(torch.zeros((n, 7), device=obs.device))  # stepping continues without an explicit reset
     assert not bool(term.any())
+    env.close()
+
+
+@pytest.mark.gpu
+def test_device_joint_velocity_replays_reference_class_golden():
+    """Device (fp64) replay of tests/golden/jv_golden.npz - actions, torques and trajectories recorded from the reference's own
+    JointVelocityController methods (tools/gen_jv_golden.py) on Stack / Sawyer: the arm-torque part of `ctrl` per control step and the
+    state after every control step.  Tolerance: 1e-6 absolute on qpos over 150 substeps of contact-free motion with a saturating PID
+    (the controller is a discontinuous map at the clip, so agreement here means the same branch was taken on every substep)."""
+    import torch
+
+    import robosuite_b200 as suite
+    from robosuite_b200 import controller_config as cc
+    from tests.util import dedegenerate_sawyer
+
+    g = np.load(os.path.join(ROOT, "tests", "golden", "jv_golden.npz"))
+    n, n_steps = g["actions"].shape[:2]
+    nsub = int(g["nsub"])
+    cfg = cc.refactor_composite_controller_config(cc.load_part_controller_config("JOINT_VELOCITY"), "Sawyer", ["right"])
+    env = suite.make("Stack", robots="Sawyer", num_envs=n, seed=1, controller_configs=cfg, horizon=1000,
+                     model=dedegenerate_sawyer(load("Stack_Sawyer")), precision="f64")
+    env.reset_to(torch.as_tensor(g["qpos0"]))
+    worst_q, worst_v, worst_u = 0.0, 0.0, 0.0
+    for t in range(n_steps):
+        env.step(torch.as_tensor(g["actions"][:, t]))
+        q, v = env.sim.qpos.cpu().numpy(), env.sim.qvel.cpu().numpy()
+        u = env.sim.ctrl.cpu().numpy()
+        worst_q = max(worst_q, np.abs(q - g["qpos"][:, t]).max())
+        worst_v = max(worst_v, np.abs(v - g["qvel"][:, t]).max())
+        worst_u = max(worst_u, np.abs(u - g["ctrl"][:, (t + 1) * nsub - 1]).max())
+    print("JV golden replay on the device: |dq| %.3g |dv| %.3g |dctrl| %.3g" % (worst_q, worst_v, worst_u))
+    assert worst_q < 1e-6 and worst_v < 1e-4 and worst_u < 1e-3
+    assert int(env.sim.warn.abs().max()) == 0
     env.close()

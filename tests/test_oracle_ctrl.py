@@ -117,3 +117,45 @@ def test_oracle_joint_velocity_matches_reference_code_body():
     # gripper: rethink sign pattern [+1, -1] integrated at 0.2 per policy step (rethink_gripper.py:43-58)
     assert np.allclose(np.array(o.ctrl_state.grip_action[:2]), np.clip(np.array([1.0, -1.0]) * 0.2 * np.sign(a[7]), -1, 1) +
                        np.array(o.ctrl_state.grip_action[:2]) * 0, atol=2.0)
+
+
+def test_oracle_joint_velocity_matches_reference_class_golden():
+    """tests/golden/jv_golden.npz: torques / goals / saturation flags / trajectories recorded from the reference's own
+    JointVelocityController code (tools/gen_jv_golden.py: the class's unmodified methods, with the one attribute that makes it
+    unconstructible at this commit - joint_vel.py:127 vs controller.py:303-311 - given both of its readings).  The oracle's controller
+    (oracle/o_ctrl.c) replays the same actions on the same physics; everything must agree to rounding."""
+    from oracle.pyoracle import CtrlCfg, Oracle
+    from robosuite_b200 import controller_config as cc
+    from robosuite_b200.mjcf.compiler import pack_model
+
+    from tests.util import dedegenerate_sawyer
+
+    g = np.load(os.path.join(ROOT, "tests", "golden", "jv_golden.npz"))
+    model = dedegenerate_sawyer(load("Stack_Sawyer"))
+    cfg = cc.refactor_composite_controller_config(cc.load_part_controller_config("JOINT_VELOCITY"), "Sawyer", ["right"])
+    c = cc.resolve(model, cfg, CtrlCfg, gripper="rethink")
+    nsub = int(g["nsub"])
+    n_env, n_steps = g["actions"].shape[:2]
+    assert g["saturated"].sum() > 100 and (~g["saturated"]).sum() > 10  # both branches of the anti-windup are in the record
+    for e in range(n_env):
+        o = Oracle(pack_model(model))
+        o.ctrl_setup(c)
+        o.qpos[:] = g["qpos0"][e]
+        o.qvel[:] = 0
+        o.forward()
+        o.ctrl_reset()
+        k = 0
+        for t in range(n_steps):
+            a = g["actions"][e, t]
+            for sub in range(nsub):
+                o.step1()
+                o.ctrl_run(a if sub == 0 else None)
+                # run_controller returns the clipped torques (joint_vel.py:198-209); the oracle keeps the PID output before the clip
+                tau = np.clip(np.array(o.ctrl_state.torques[:7]), model.actuator_ctrlrange[:7, 0], model.actuator_ctrlrange[:7, 1])
+                ref = g["torques"][e, k]
+                assert np.abs(tau - ref).max() <= 1e-10 * max(1.0, np.abs(ref).max()), (e, t, sub)
+                assert np.allclose(o.ctrl, g["ctrl"][e, k], rtol=0, atol=1e-10), (e, t, sub)
+                o.step2()
+                k += 1
+            assert np.allclose(o.qpos, g["qpos"][e, t], rtol=0, atol=1e-9), (e, t)
+            assert np.allclose(o.qvel, g["qvel"][e, t], rtol=0, atol=1e-8), (e, t)

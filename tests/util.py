@@ -30,3 +30,13 @@ def lift_states(model, n, seed=0, vel=0.0):
     q[:, 15] = np.sin(yaw / 2)
     v = rng.normal(0, vel, size=(n, model.nv)) if vel > 0 else np.zeros((n, model.nv))
     return q, v
+
+
+def dedegenerate_sawyer(model):
+    """The composed Sawyer models carry two knife-edge coincidences that make constraint activation depend on the last bit of rounding
+    in ANY engine: the l0 collision sphere exactly touches the rim of the base cylinder (dist = -5.6e-17 in fp64) and the gripper's
+    initial qpos equals its joint limit.  Parity records that are to be replayed by more than one engine move both off the edge."""
+    model.geom_size[model.names["geom"].index("robot0_link0_collision"), 0] -= 1e-5
+    model.jnt_range[[model.names["joint"].index("gripper0_right_l_finger_joint"),
+                     model.names["joint"].index("gripper0_right_r_finger_joint")]] += np.array([-1e-6, 1e-6])
+    return model
