@@ -207,16 +207,30 @@ class BatchedMujocoEnv:
         from .lift import GRIPPER_INIT_QPOS, PANDA_INIT_QPOS, SAWYER_INIT_QPOS
 
         dev = self.device
-        q = torch.as_tensor(self.model.qpos0, device=dev, dtype=torch.float64).repeat(n, 1)
+        q = self._dev_const("qpos0", self.model.qpos0).repeat(n, 1)
         init = PANDA_INIT_QPOS if self.robot_name == "Panda" else SAWYER_INIT_QPOS
         mag = float(self.initialization_noise["magnitude"])
         if self.initialization_noise["type"] == "gaussian":
             noise = torch.randn((n, len(init)), generator=self.rng, device=dev, dtype=torch.float64) * mag
         else:
             noise = (torch.rand((n, len(init)), generator=self.rng, device=dev, dtype=torch.float64) * 2 - 1) * mag
-        q[:, self._ref_joint_pos_indexes] = torch.as_tensor(init, device=dev) + noise
-        q[:, self._ref_gripper_joint_pos_indexes] = torch.as_tensor(GRIPPER_INIT_QPOS[self.robot_name], device=dev, dtype=torch.float64)
+        q[:, self._dev_index("arm_qpos", self._ref_joint_pos_indexes)] = self._dev_const("arm_init", init) + noise
+        q[:, self._dev_index("grip_qpos", self._ref_gripper_joint_pos_indexes)] = self._dev_const("grip_init", GRIPPER_INIT_QPOS[self.robot_name])
         return q
+
+    def _dev_const(self, key, value, dtype=None):
+        """device-resident copy of a host constant, uploaded once (the reset path must not touch the host: it runs inside step())"""
+        import torch
+
+        c = self.__dict__.setdefault("_dev_consts", {})
+        if key not in c:
+            c[key] = torch.as_tensor(np.asarray(value), device=self.device, dtype=dtype or torch.float64)
+        return c[key]
+
+    def _dev_index(self, key, idx):
+        import torch
+
+        return self._dev_const("idx_" + key, np.asarray(idx, dtype=np.int64), dtype=torch.long)
 
     @staticmethod
     def _place_free_body(q, adr, x, y, z, yaw):

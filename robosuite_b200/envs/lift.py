@@ -51,16 +51,7 @@ class BatchedLift(BatchedMujocoEnv):
         z = table + 0.01 + half height (lift.py:311-336, placement_samplers.py:221-309)"""
         import torch
 
-        q = torch.as_tensor(self.model.qpos0, device=self.device, dtype=torch.float64).repeat(n, 1)
-        init = PANDA_INIT_QPOS if self.robot_name == "Panda" else SAWYER_INIT_QPOS
-        mag = float(self.initialization_noise["magnitude"])
-        if self.initialization_noise["type"] == "gaussian":
-            noise = torch.randn((n, len(init)), generator=self.rng, device=self.device, dtype=torch.float64) * mag
-        else:
-            noise = (torch.rand((n, len(init)), generator=self.rng, device=self.device, dtype=torch.float64) * 2 - 1) * mag
-        q[:, self._ref_joint_pos_indexes] = torch.as_tensor(init, device=self.device) + noise
-        q[:, self._ref_gripper_joint_pos_indexes] = torch.as_tensor(GRIPPER_INIT_QPOS[self.robot_name], device=self.device,
-                                                                    dtype=torch.float64)
+        q = self._robot_reset_qpos(n)
         u = torch.rand((n, 3), generator=self.rng, device=self.device, dtype=torch.float64)
         a = self.cube_qadr
         q[:, a] = self.table_offset[0] + (u[:, 0] * 2 - 1) * 0.03

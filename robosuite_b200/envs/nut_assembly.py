@@ -78,7 +78,7 @@ class _BatchedNutAssembly(BatchedMujocoEnv):
                 q[:, a + 3] = 1.0; q[:, a + 4:a + 7] = 0.0
         return q
 
-    def reset(self, mask=None):
+    def reset(self, mask=None, host_mask=None):
         import torch
 
         if self.objects_on_pegs is None:
@@ -86,8 +86,8 @@ class _BatchedNutAssembly(BatchedMujocoEnv):
         if mask is None:
             self.objects_on_pegs[:] = False
         else:
-            self.objects_on_pegs[mask] = False
-        return super().reset(mask)
+            self.objects_on_pegs.masked_fill_(mask.to(device=self.device, dtype=torch.bool)[:, None], False)
+        return super().reset(mask, host_mask)
 
     # ---- reward machinery (nut_assembly.py:247-400, 614-640)
     def _task_views(self):

@@ -54,31 +54,24 @@ class BatchedStack(BatchedMujocoEnv):
         import torch
 
         dev = self.device
-        q = torch.as_tensor(self.model.qpos0, device=dev, dtype=torch.float64).repeat(n, 1)
-        init = PANDA_INIT_QPOS if self.robot_name == "Panda" else SAWYER_INIT_QPOS
-        mag = float(self.initialization_noise["magnitude"])
-        noise = torch.randn((n, len(init)), generator=self.rng, device=dev, dtype=torch.float64) * mag
-        q[:, self._ref_joint_pos_indexes] = torch.as_tensor(init, device=dev) + noise
-        q[:, self._ref_gripper_joint_pos_indexes] = torch.as_tensor(GRIPPER_INIT_QPOS[self.robot_name], device=dev, dtype=torch.float64)
+        q = self._robot_reset_qpos(n)
 
-        def draw(k):
-            u = torch.rand((k, 3), generator=self.rng, device=dev, dtype=torch.float64)
-            return (u[:, 0] * 2 - 1) * 0.08, (u[:, 1] * 2 - 1) * 0.08, u[:, 2] * 2 * math.pi
+        def draw(*shape):
+            u = torch.rand(shape + (3,), generator=self.rng, device=dev, dtype=torch.float64)
+            return (u[..., 0] * 2 - 1) * 0.08, (u[..., 1] * 2 - 1) * 0.08, u[..., 2] * 2 * math.pi
 
         ax, ay, ayaw = draw(n)
-        bx, by, byaw = draw(n)
+        # cube B: the reference re-draws until the bounding circles are disjoint (placement_samplers.py:255-309; ~half of the draws collide).
+        # Here R candidate placements are drawn per environment at once and the first valid one is taken - the same distribution as the
+        # sequential rejection loop, with no device->host round trip per attempt (this runs inside step() for the auto-reset).  With R = 48
+        # the probability that no candidate fits is < 1e-14 per reset; such an environment keeps its last candidate.
+        R = 48
+        cx, cy, cyaw = draw(R, n)
         rA = float(np.linalg.norm(self.half["A"][:2])); rB = float(np.linalg.norm(self.half["B"][:2]))
-        for _ in range(5000):
-            bad = torch.sqrt((ax - bx) ** 2 + (ay - by) ** 2) <= rA + rB
-            nb = int(bad.sum())
-            if nb == 0:
-                break
-            nx, ny, nyaw = draw(nb)
-            bx[bad], by[bad], byaw[bad] = nx, ny, nyaw
-        else:  # placement_samplers.py:304-305
-            from ..errors import RandomizationError
-
-            raise RandomizationError("Cannot place all objects ):")
+        ok = torch.sqrt((ax - cx) ** 2 + (ay - cy) ** 2) > rA + rB
+        ok[R - 1] = True
+        first = torch.argmax(ok.to(torch.uint8), dim=0, keepdim=True)  # index of the first valid candidate
+        bx, by, byaw = (torch.gather(c, 0, first)[0] for c in (cx, cy, cyaw))
         for adr, x, y, yaw, hz in ((self.cubeA_qadr, ax, ay, ayaw, self.half["A"][2]), (self.cubeB_qadr, bx, by, byaw, self.half["B"][2])):
             q[:, adr] = self.table_offset[0] + x
             q[:, adr + 1] = self.table_offset[1] + y
