@@ -26,5 +26,17 @@ def build(force=False, verbose=False):
     return SO
 
 
+def build_instr(force=False):
+    """-DB2S_INSTR measurement build (device %globaltimer timeline + solver statistics; tools/probe_instr.py, bench.py's
+    `roofline.timeline`).  Never loaded by the product path: selected only through B2S_LIB."""
+    out = os.path.join(_HERE, "variants", "libb2s_instr.so")
+    if not force and os.path.exists(out) and all(os.path.getmtime(p) <= os.path.getmtime(out) for p in _deps()):
+        return out
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    subprocess.check_call([nvcc] + NVCC_FLAGS + ["-DB2S_INSTR", "-o", out, SRC])
+    return out
+
+
 if __name__ == "__main__":
     print(build(force=True, verbose=True))

@@ -94,6 +94,15 @@ class _DevArray:
 _TYPESTR = {B2S_F32: "<f4", B2S_F64: "<f8", B2S_I32: "<i4", B2S_I64: "<i8"}
 
 
+_LIVE = None  # weak set of open BatchedSim objects (a device holds at most B2S_NSLOT = 8 live handles: descriptor slots)
+
+
+def close_all():
+    """Destroy every live handle of this process (test teardown, interpreter exit)."""
+    for sim in list(_LIVE or ()):
+        sim.close()
+
+
 class BatchedSim:
     """n_env independent copies of one compiled model, stepped by the per-warp CUDA engine."""
 
@@ -126,6 +135,12 @@ class BatchedSim:
         self._L = lib()
         self._check(self._L.b2s_create(blob, len(blob), self.n_env, self.device, self.precision, C.byref(self._h)))
         self._cache = {}
+        global _LIVE
+        if _LIVE is None:
+            import weakref
+
+            _LIVE = weakref.WeakSet()
+        _LIVE.add(self)
 
     def _check(self, rc):
         if rc != 0:

@@ -201,5 +201,9 @@ def test_two_handles_step_concurrently_and_bit_exactly():
     finally:
         os.environ.pop("B2S_NO_GJK_CACHE", None)
     assert torch.isfinite(qa).all()
-    assert torch.equal(qa, qb) and torch.equal(va, vb), "two concurrent handles diverged"
-    assert torch.equal(qa, qc) and torch.equal(va, vc), "a handle stepped beside another differs from one stepped alone"
+
+    def where(x, y):
+        return torch.nonzero((x != y).any(1)).flatten().tolist()
+
+    assert torch.equal(qa, qb) and torch.equal(va, vb), ("two concurrent handles diverged", where(qa, qb), "A vs alone", where(qa, qc), "B vs alone", where(qb, qc))
+    assert torch.equal(qa, qc) and torch.equal(va, vc), ("a handle stepped beside another differs from one stepped alone", where(qa, qc))
