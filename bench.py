@@ -483,7 +483,7 @@ def run_gpu(args):
         "config": {"workload": cfg["workload"], "baseline_config": args.config, "envs_per_gpu": N,
                    "tasks": [f"{t}/{r}/{c} x{n}" for t, r, c, n in parts], "substeps_per_step": N_SUBSTEPS,
                    "l2": "flushed (256 MiB memset) between timed iterations", "solver_warn_flags": warn,
-                   "preroll_steps": args.preroll, "kernel_mode": "pipeline" if args.mode else "fused",
+                   "preroll_steps": args.preroll, "kernel_mode": ["fused", "pipeline", "unit-queue"][args.mode],
                    "e2e": f"BatchedGymWrapper.step, horizon 500 with staggered episode phases ({n_resets} in-step resets during the "
                           f"{K} timed steps), pinned-host action upload and obs+reward download",
                    "multi_gpu": "env shards independent; NCCL: model broadcast at start" + (", obs all-gather per step (e2e loop)" if args.allgather_obs else "")},
@@ -518,7 +518,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-timeline", action="store_true", help="skip the per-kernel device timeline (child process, INSTR build)")
     ap.add_argument("--preroll", type=int, default=100, help="untimed control steps before the timed region")
-    ap.add_argument("--mode", type=int, default=1, help="0 fused kernel, 1 phase-kernel pipeline (default)")
+    ap.add_argument("--mode", type=int, default=int(os.environ.get("B2S_BENCH_MODE", "1")), help="0 fused kernel, 1 phase-kernel pipeline, 2 unit queue (persistent kernel)")
     ap.add_argument("--allgather-obs", type=int, default=1, help="N>1: all-gather observations over NCCL every e2e step")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl != "reference":

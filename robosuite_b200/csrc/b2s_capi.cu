@@ -1,7 +1,7 @@
 // libb2s: C ABI + host side of the batched engine (model upload, workspace layout, kernel launches).
 // Entry points are declared in include/b2s.h; each cites the reference call it replaces.
 #include "../../include/b2s.h"
-#include "b2s_pipeline.cuh"
+#include "b2s_unit.cuh"
 
 #include <cstdio>
 #include <cstdlib>
@@ -85,6 +85,10 @@ struct b2s_sim {
   std::map<long long, cudaGraphExec_t> graphs;
   PhaseIO pio[B2S_NPIO];
   std::map<std::string, Region> reg;
+  // unit-queue mode (mode 2, b2s_unit.cuh)
+  int* uq_ring = nullptr; int* uq_ovf = nullptr; int* uq_ctr = nullptr; int uq_cap = 0;
+  int uq_wpb = 0, uq_bps = 0, uq_stride = 0, uq_stride_large = 0, uq_wpb_large = 0, uq_nlarge = 0, uq_grid = 0;
+  size_t uq_smem = 0;
 };
 
 template <typename T> static T* dev_upload(b2s_sim* s, const std::vector<T>& h) {
@@ -93,6 +97,9 @@ template <typename T> static T* dev_upload(b2s_sim* s, const std::vector<T>& h) 
   if (cudaMalloc(&d, n * sizeof(T)) != cudaSuccess) throw std::string("cudaMalloc failed");
   s->allocs.push_back(d);
   if (h.size()) cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+  // cudaMemcpy from pageable memory returns once the data is STAGED; the DMA runs on the legacy stream, which non-blocking streams
+  // (the handle's group streams, every torch stream) do not wait for: finish it here
+  cudaStreamSynchronize(cudaStreamLegacy);
   return d;
 }
 template <typename R> static const R* up_f(b2s_sim* s, const Blob& b, const char* name) {
@@ -294,7 +301,10 @@ template <typename T> static T* dev_zeros(b2s_sim* s, size_t n) {
   T* d = nullptr;
   if (n == 0) n = 1;
   if (cudaMalloc(&d, n * sizeof(T)) != cudaSuccess) throw std::string("cudaMalloc failed");
+  // cudaMemset is asynchronous and runs on the legacy stream; the handle's kernels run on non-blocking streams that do not wait for
+  // it (a zero-fill of the action buffer that landed in the middle of the first control step made two concurrent handles diverge)
   cudaMemset(d, 0, n * sizeof(T));
+  cudaStreamSynchronize(cudaStreamLegacy);
   s->allocs.push_back(d);
   return d;
 }
@@ -731,8 +741,9 @@ static int bind_constants(b2s_sim* s) {
 // layouts depend on where the OSC controller runs; a change invalidates the captured graphs (they carry block shapes)
 static int rebuild_layouts(b2s_sim* s) {
   const bool osc = s->ctrl.kind == B2S_CTRL_OSC_POSE || s->ctrl.kind == B2S_CTRL_OSC_POSITION;
-  int want = (osc && !s->ctrl_split) ? 1 : 0;
+  int want = (osc && (!s->ctrl_split || s->mode == 2)) ? 1 : 0;  // unit-queue mode runs the controller inside the unit
   if (want == s->osc_in_tail && s->smem0 != 0) return B2S_OK;
+  s->uq_wpb = 0;
   s->osc_in_tail = want;
   try { build_layouts(s, s->ncg, s->hc_stride); } catch (const std::string& e) { return fail(B2S_ERR_MODEL, e); }
   int rc = choose_blocks(s);
@@ -829,7 +840,8 @@ template <typename R> static int enqueue_pipeline(b2s_sim* s, DState<R>& st, int
   return B2S_OK;
 }
 
-template <typename R> static int launch_pipeline_t(b2s_sim* s, DState<R>& st, int phases, int nsub, const R* action) {
+// global workspace rows + per-environment candidate tables / narrow-phase output slots (pipeline and unit-queue modes)
+template <typename R> static int ensure_ws(b2s_sim* s, DState<R>& st) {
   if (!st.wsg) {
     R* p = nullptr;
     if (cudaMalloc(&p, (size_t)s->n_env * s->lay[LAY_ROW].total * sizeof(R)) != cudaSuccess) return fail(B2S_ERR_CUDA, "cudaMalloc(pipeline workspace) failed");
@@ -861,6 +873,11 @@ template <typename R> static int launch_pipeline_t(b2s_sim* s, DState<R>& st, in
 #endif
     s->dirty = 1;
   }
+  return B2S_OK;
+}
+
+template <typename R> static int launch_pipeline_t(b2s_sim* s, DState<R>& st, int phases, int nsub, const R* action) {
+  { int rc0 = ensure_ws<R>(s, st); if (rc0 != B2S_OK) return rc0; }
 #ifdef B2S_INSTR
   cudaMemsetAsync(st.st_begin, 0xff, sizeof(unsigned long long) * 64 * 32 * 8, s->stream);
   cudaMemsetAsync(st.st_end, 0, sizeof(unsigned long long) * 64 * 32 * 8, s->stream);
@@ -976,6 +993,82 @@ static int launch_pipeline(b2s_sim* s, int phases, int nsub, const void* action)
                                  : launch_pipeline_t<double>(s, s->sd, phases, nsub, (const double*)action);
 }
 
+// ---- unit-queue mode: one persistent kernel per control step (b2s_unit.cuh)
+template <typename R> static int launch_unit_t(b2s_sim* s, DState<R>& st, int phases, int nsub, const R* action) {
+  { int rc0 = ensure_ws<R>(s, st); if (rc0 != B2S_OK) return rc0; }
+  { int rc2 = rebuild_layouts(s); if (rc2 != B2S_OK) return rc2; }
+  const int total = s->n_env * nsub;
+  if ((long long)s->n_env * nsub > (1ll << 30)) return fail(B2S_ERR_UNSUPPORTED, "unit-queue mode: n_env * nsub too large");
+  if (total > s->uq_cap) {
+    cudaStreamSynchronize(s->stream);
+    int* p = nullptr;
+    if (cudaMalloc(&p, sizeof(int) * (2 * (size_t)total + 8)) != cudaSuccess) return fail(B2S_ERR_CUDA, "cudaMalloc(unit ring) failed");
+    s->allocs.push_back(p);
+    s->uq_ring = p; s->uq_ovf = p + total; s->uq_ctr = p + 2 * (size_t)total; s->uq_cap = total;
+  }
+  if (s->uq_wpb == 0) {
+    // block shape: the warp's one workspace area holds phase 0's layout, then the EPA polytope + vertex staging, then the small tail tier
+    const size_t rsz = sizeof(R);
+    const bool tiered = s->mc_small < s->maxcon || s->me_small < s->maxefc;
+    int stride = std::max(std::max(s->lay[LAY_P0].total, s->lay[LAY_TS].total), EPA_PIPE_WORDS + 24 + 384);
+    stride = (stride + 3) & ~3;
+    int stride_l = (s->lay[LAY_TL].total + 3) & ~3;
+    CUDA_TRY(optin_max_smem(unit_kernel<R>, s->device));
+    int best_w = 0, best_b = 0, best = 0;
+    int wcap = B2S_LBU_THREADS / 32;
+    if (const char* v = getenv("B2S_UNIT_WPB")) { int x = atoi(v); if (x >= 1 && x <= wcap) wcap = x; }
+    for (int w = wcap; w >= 1; w--) {
+      size_t sm = std::max((size_t)w * stride, tiered ? (size_t)stride_l : 0) * rsz;
+      if (sm > 226 * 1024) continue;
+      int b = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, unit_kernel<R>, w * 32, sm) != cudaSuccess) { cudaGetLastError(); continue; }
+      if (w * b > best) { best = w * b; best_w = w; best_b = b; }
+    }
+    if (best == 0) return fail(B2S_ERR_UNSUPPORTED, "unit-queue mode: workspace does not fit shared memory");
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, s->device));
+    s->uq_wpb = best_w; s->uq_bps = best_b; s->uq_stride = stride; s->uq_stride_large = stride_l;
+    s->uq_smem = std::max((size_t)best_w * stride, tiered ? (size_t)stride_l : 0) * rsz;
+    s->uq_wpb_large = tiered ? std::min(best_w, (int)(s->uq_smem / rsz / stride_l)) : 0;
+    int slots = best_b * prop.multiProcessorCount;
+    int nl = 0;
+    if (tiered) {
+      nl = std::max(1, std::min(slots / 8, 12));
+      if (const char* v = getenv("B2S_UNIT_LARGE_BLOCKS")) { int x = atoi(v); if (x >= 1 && x < slots) nl = x; }
+    }
+    s->uq_nlarge = nl;
+    if (best_w > s->n_env) best_w = s->n_env;  // the lockstep rounds need n_env >= warps per block (b2s_unit.cuh)
+    s->uq_wpb = best_w;
+    int small_blocks = std::min(std::max(slots - nl, 1), (s->n_env + best_w - 1) / best_w);
+    if (const char* v = getenv("B2S_UNIT_BLOCKS")) { int x = atoi(v); if (x >= 1) small_blocks = x; }
+    s->uq_grid = nl + small_blocks;
+    if (getenv("B2S_VERBOSE"))
+      fprintf(stderr, "[b2s] unit-queue: %d warps/block x %d blocks/SM, %d words/warp (large role: %d words, %d warps/block, %d blocks), grid %d, smem %zu B\n",
+              best_w, best_b, stride, stride_l, s->uq_wpb_large, nl, s->uq_grid, s->uq_smem);
+  }
+  int rc = bind_constants(s);
+  if (rc != B2S_OK) return rc;
+  int ubar = 0;
+  if (const char* v = getenv("B2S_UNIT_BARRIERS")) ubar = atoi(v);
+  UnitQ q{s->uq_ring, s->uq_ovf, s->uq_ctr, total, s->uq_nlarge, s->uq_wpb_large, s->uq_stride, s->uq_stride_large, ubar};
+  unit_init_kernel<R><<<(total + 255) / 256, 256, 0, s->stream>>>(q, s->n_env);
+  unit_kernel<R><<<s->uq_grid, s->uq_wpb * 32, s->uq_smem, s->stream>>>(phases, nsub, action, s->slot, q);
+  s->launches += 2;
+  CUDA_TRY(cudaGetLastError());
+  if (getenv("B2S_UNIT_DEBUG")) {
+    int c[8];
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    CUDA_TRY(cudaMemcpy(c, s->uq_ctr, sizeof(c), cudaMemcpyDeviceToHost));
+    fprintf(stderr, "[b2s] unit ctr: head %d tail %d done %d ovf_head %d ovf_tail %d | watchdog ticket %d tail_then %d flag %d (total %d)\n", c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7], total);
+    if (c[7]) return fail(B2S_ERR_CUDA, "unit-queue watchdog: a ticket was never produced");
+  }
+  return B2S_OK;
+}
+static int launch_unit(b2s_sim* s, int phases, int nsub, const void* action) {
+  return s->precision == B2S_F32 ? launch_unit_t<float>(s, s->sf, phases, nsub, (const float*)action)
+                                 : launch_unit_t<double>(s, s->sd, phases, nsub, (const double*)action);
+}
+
 extern "C" {
 
 /* Host-only: the workspace layouts libb2s would build for a model of the given dimensions (no device needed).  out_words[5] receives
@@ -1004,7 +1097,7 @@ int b2s_debug_layouts(int nq, int nv, int nu, int nbody, int ncg, int nsite, int
 }
 
 int b2s_set_mode(b2s_sim* s, int mode) {
-  if (!s || (mode != 0 && mode != 1)) return fail(B2S_ERR_ARG, "b2s_set_mode: mode must be 0 (fused) or 1 (pipeline)");
+  if (!s || mode < 0 || mode > 2) return fail(B2S_ERR_ARG, "b2s_set_mode: mode must be 0 (fused), 1 (pipeline) or 2 (unit queue)");
   s->mode = mode;
   const char* eg = getenv("B2S_GROUPS");
   if (eg) { int v = atoi(eg); if (v >= 1 && v <= 64) s->ngroups = v; }
@@ -1043,6 +1136,7 @@ int b2s_step1(b2s_sim* s) { return s ? launch(s, PH_STEP1 | PH_EXPORT, 1) : fail
 int b2s_step2(b2s_sim* s) { return s ? launch(s, PH_STEP1 | PH_STEP2 | PH_EXPORT, 1) : fail(B2S_ERR_ARG, "null handle"); }
 int b2s_step(b2s_sim* s, int n) {
   if (!s || n < 1) return fail(B2S_ERR_ARG, "b2s_step: bad argument");
+  if (s->mode == 2) return launch_unit(s, PH_STEP1 | PH_STEP2, n, nullptr);
   if (s->mode == 1) return launch_pipeline(s, PH_STEP1 | PH_STEP2, n, nullptr);
   return launch(s, PH_STEP1 | PH_STEP2, n);
 }
@@ -1174,6 +1268,8 @@ int b2s_reset_envs(b2s_sim* s, const uint8_t* mask, const void* qpos_new) {
 
 int b2s_env_step(b2s_sim* s, const void* action, int nsub) {
   if (!s || !s->has_ctrl || !action || nsub < 1) return fail(B2S_ERR_ARG, "b2s_env_step: bad argument / controller not configured");
+  if (s->mode == 2 && !s->export_env_step && !s->profile)
+    return launch_unit(s, PH_STEP1 | PH_STEP2 | PH_CTRL | (s->has_obs ? PH_OBS : 0), nsub, action);
   if (s->mode == 1 && !s->export_env_step && !s->profile)
     return launch_pipeline(s, PH_STEP1 | PH_STEP2 | PH_CTRL | (s->has_obs ? PH_OBS : 0), nsub, action);
   return launch(s, PH_STEP1 | PH_STEP2 | PH_CTRL | (s->has_obs ? PH_OBS : 0) | (s->export_env_step ? PH_EXPORT : 0) | (s->profile ? PH_PROFILE : 0), nsub, action);
@@ -1191,6 +1287,7 @@ int b2s_obs_config(b2s_sim* s, int obs_dim, const int* op, const int* a, const i
     {
       std::vector<int> ones(s->n_env, 1);
       if (cudaMemcpy(fresh, ones.data(), sizeof(int) * s->n_env, cudaMemcpyHostToDevice) != cudaSuccess) throw std::string("obs_fresh upload failed");
+      cudaStreamSynchronize(cudaStreamLegacy);
     }
     if (s->precision == B2S_F32) { s->sf.obs = state_arr<float>(s, "obs", obs_dim); s->sf.task_out = state_arr<float>(s, "task_out", 8); s->sf.obs_fresh = fresh; }
     else { s->sd.obs = state_arr<double>(s, "obs", obs_dim); s->sd.task_out = state_arr<double>(s, "task_out", 8); s->sd.obs_fresh = fresh; }

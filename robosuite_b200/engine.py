@@ -256,7 +256,8 @@ class BatchedSim:
         self._check(self._L.b2s_set_export(self._h, int(bool(flag))))
 
     def set_mode(self, mode):
-        """0 = fused single kernel, 1 = pipelined phase kernels (identical results)"""
+        """0 = fused single kernel, 1 = pipelined phase kernels, 2 = unit queue (one persistent kernel per control step);
+        identical results"""
         self._check(self._L.b2s_set_mode(self._h, int(mode)))
 
     def timeline(self, enable=-1):

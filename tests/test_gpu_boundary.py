@@ -171,7 +171,7 @@ def test_two_handles_step_concurrently_and_bit_exactly():
             assert L.b2s_set_stream(h, C.c_void_p(stream.cuda_stream)) == 0
         c = _lift_osc_cfg(L, h)
         assert L.b2s_ctrl_config(h, C.byref(c)) == 0
-        assert L.b2s_set_export(h, 0) == 0 and L.b2s_set_mode(h, 1) == 0
+        assert L.b2s_set_export(h, 0) == 0 and L.b2s_set_mode(h, int(os.environ.get("B2S_TEST_MODE", "1"))) == 0
         with torch.cuda.stream(stream) if stream is not None else torch.cuda.stream(torch.cuda.current_stream()):
             _arr(L, h, "qpos").copy_(torch.as_tensor(q, dtype=torch.float32))
             assert L.b2s_forward(h) == 0 and L.b2s_ctrl_reset(h, None) == 0
@@ -185,8 +185,12 @@ def test_two_handles_step_concurrently_and_bit_exactly():
         for t in range(steps):  # interleaved enqueue: both handles' graphs are in flight at the same time
             with torch.cuda.stream(sa):
                 assert L.b2s_env_step(ha, C.c_void_p(acts_d[t].data_ptr()), 25) == 0, L.b2s_last_error()
+            if os.environ.get("B2S_TEST_SEQ"):
+                torch.cuda.synchronize()
             with torch.cuda.stream(sb):
                 assert L.b2s_env_step(hb, C.c_void_p(acts_d[t].data_ptr()), 25) == 0, L.b2s_last_error()
+            if os.environ.get("B2S_TEST_SEQ"):
+                torch.cuda.synchronize()
         torch.cuda.synchronize()
         qa, qb = _arr(L, ha, "qpos").clone(), _arr(L, hb, "qpos").clone()
         va, vb = _arr(L, ha, "qvel").clone(), _arr(L, hb, "qvel").clone()
