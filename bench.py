@@ -504,6 +504,11 @@ def run_gpu(args):
         "clocks": clk,
     }
     print(json.dumps(out))
+    for e in envs:
+        try:
+            e.close()
+        except Exception:
+            pass
     if world > 1:
         dist.destroy_process_group()
 

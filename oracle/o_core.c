@@ -150,7 +150,21 @@ void o_reset_data(const OModel* m, OData* d) {
 }
 
 /* ------------------------------------------------------------------------------------------------ kinematics */
+/* mj_checkPos / mj_checkVel / mj_checkAcc of the engine (first calls of mj_step, and after the solve): a non-finite or huge
+ * coordinate resets the data to the model defaults (warn bit 32) instead of integrating garbage */
+static int vec_bad(const double* x, int n) {
+  for (int i = 0; i < n; i++) if (!(fabs(x[i]) <= 1e10)) return 1;
+  return 0;
+}
+static void reset_defaults(const OModel* m, OData* d) {
+  memcpy(d->qpos, m->qpos0, sizeof(double) * m->nq);
+  for (int i = 0; i < m->nv; i++) { d->qvel[i] = 0; d->qacc[i] = 0; d->qacc_warmstart[i] = 0; }
+  d->time = 0;
+  d->warn_flags |= 32;
+}
+
 void o_kinematics(const OModel* m, OData* d) {
+  if (vec_bad(d->qpos, m->nq) || vec_bad(d->qvel, m->nv)) reset_defaults(m, d);
   /* world body */
   v3_set(d->xpos, 0, 0, 0);
   d->xquat[0] = 1; d->xquat[1] = d->xquat[2] = d->xquat[3] = 0;
@@ -513,6 +527,7 @@ void o_fwd_acceleration(const OModel* m, OData* d) {
 void o_euler(const OModel* m, OData* d) {
   int nv = m->nv;
   double h = m->timestep;
+  if (vec_bad(d->qacc, nv)) { reset_defaults(m, d); return; }
   double* qacc = (double*)malloc(sizeof(double) * nv);
   int damped = 0;
   for (int i = 0; i < nv; i++) damped |= m->dof_damping[i] > 0;

@@ -89,6 +89,7 @@ struct b2s_sim {
   int* uq_ring = nullptr; int* uq_ovf = nullptr; int* uq_ctr = nullptr; int uq_cap = 0;
   int uq_wpb = 0, uq_bps = 0, uq_stride = 0, uq_stride_large = 0, uq_wpb_large = 0, uq_nlarge = 0, uq_grid = 0;
   size_t uq_smem = 0;
+  unsigned long long* uq_prof = nullptr;
 };
 
 template <typename T> static T* dev_upload(b2s_sim* s, const std::vector<T>& h) {
@@ -670,6 +671,16 @@ int b2s_create(const void* blob_host, size_t nbytes, int n_env, int device, int 
 
 void b2s_destroy(b2s_sim* s) {
   if (!s) return;
+  if (s->uq_prof) {
+    unsigned long long h[16];
+    cudaSetDevice(s->device); cudaDeviceSynchronize();
+    if (cudaMemcpy(h, s->uq_prof, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess && h[15] > 0) {
+      static const char* nm[9] = {"take tickets", "ring slots", "phase 0", "narrow phase", "rows (gather, constraint)", "controller", "actuation + acceleration", "solve", "integrate, obs, publish"};
+      double tot = 0; for (int k = 0; k < 9; k++) tot += (double)h[k];
+      fprintf(stderr, "[b2s] unit-queue stage profile over %llu block rounds (mean cycles per round, share):\n", h[15]);
+      for (int k = 0; k < 9; k++) fprintf(stderr, "[b2s]   %-28s %9.0f  %5.1f %%\n", nm[k], (double)h[k] / (double)h[15], 100.0 * (double)h[k] / tot);
+    }
+  }
   if (s->slot >= 0 && g_slots[s->device & 63][s->slot] == s) g_slots[s->device & 63][s->slot] = nullptr;
   cudaSetDevice(s->device);
   cudaDeviceSynchronize();  // kernels of this handle may still be reading its buffers
@@ -1033,7 +1044,7 @@ template <typename R> static int launch_unit_t(b2s_sim* s, DState<R>& st, int ph
     int slots = best_b * prop.multiProcessorCount;
     int nl = 0;
     if (tiered) {
-      nl = std::max(1, std::min(slots / 8, 12));
+      nl = std::max(1, std::min(slots / 64, 12));  // a large-role block occupies a block slot (a whole SM at one block per SM)
       if (const char* v = getenv("B2S_UNIT_LARGE_BLOCKS")) { int x = atoi(v); if (x >= 1 && x < slots) nl = x; }
     }
     s->uq_nlarge = nl;
@@ -1048,9 +1059,10 @@ template <typename R> static int launch_unit_t(b2s_sim* s, DState<R>& st, int ph
   }
   int rc = bind_constants(s);
   if (rc != B2S_OK) return rc;
-  int ubar = 0;
+  if (getenv("B2S_UNIT_PROF") && !s->uq_prof) s->uq_prof = dev_zeros<unsigned long long>(s, 16);
+  int ubar = 4;
   if (const char* v = getenv("B2S_UNIT_BARRIERS")) ubar = atoi(v);
-  UnitQ q{s->uq_ring, s->uq_ovf, s->uq_ctr, total, s->uq_nlarge, s->uq_wpb_large, s->uq_stride, s->uq_stride_large, ubar};
+  UnitQ q{s->uq_ring, s->uq_ovf, s->uq_ctr, total, s->uq_nlarge, s->uq_wpb_large, s->uq_stride, s->uq_stride_large, s->uq_prof, ubar};
   unit_init_kernel<R><<<(total + 255) / 256, 256, 0, s->stream>>>(q, s->n_env);
   unit_kernel<R><<<s->uq_grid, s->uq_wpb * 32, s->uq_smem, s->stream>>>(phases, nsub, action, s->slot, q);
   s->launches += 2;

@@ -137,9 +137,25 @@ struct Eng {
   DEV int* pi(int off) const { return reinterpret_cast<int*>(ws + off); }
 
   // ------------------------------------------------------------------------------------------- kinematics
-  DEVN void kinematics() {
+  // mj_checkPos / mj_checkVel / mj_checkAcc of the reference engine (the first calls of mj_step, and after the solve): a non-finite
+  // or huge (> 1e10) coordinate means the simulation diverged; the engine warns and resets the data to the model defaults instead
+  // of integrating garbage (which here would also run every solver loop to its iteration cap).  Warp-uniform result.
+  DEV int vec_bad(const R* x, int n) const {
+    int b = 0;
+    for (int i = lane; i < n; i += 32) b |= !(r_abs(x[i]) <= R(1e10));
+    return warp_or_i(b);
+  }
+  // returns 32 when the state was reset (callers clear the rest of the per-environment data: acceleration, warm start, time)
+  DEVN int kinematics() {
     const DModel<R>& m = model(); const WSLayout& L = lay();
     R* xpos = p(L.xpos); R* xquat = p(L.xquat); R* xmat = p(L.xmat);
+    int was_reset = 0;
+    if (vec_bad(p(L.qpos), m.nq) | vec_bad(p(L.qvel), m.nv)) {
+      for (int i = lane; i < m.nq; i += 32) p(L.qpos)[i] = m.qpos0[i];
+      for (int i = lane; i < m.nv; i += 32) p(L.qvel)[i] = 0;
+      was_reset = 32;
+      __syncwarp();
+    }
     const R* qpos = p(L.qpos);
     // bodies welded to the world: constant pose
     for (int b = lane; b < m.nbody; b += 32)
@@ -283,6 +299,7 @@ struct Eng {
       q2mat(smat + 9 * s, q);
     }
     __syncwarp();
+    return was_reset;
   }
 
   // last dof on the kinematic chain ending at body b (-1 if none)
@@ -546,6 +563,13 @@ struct Eng {
     const DModel<R>& m = model(); const WSLayout& L = lay();
     int nv = m.nv;
     R h = m.timestep;
+    if (vec_bad(p(L.qacc), nv)) {  // mj_checkAcc: reset instead of integrating (returns bit 32; the clock restarts like mj_resetData's)
+      for (int i = lane; i < m.nq; i += 32) p(L.qpos)[i] = m.qpos0[i];
+      for (int i = lane; i < nv; i += 32) { p(L.qvel)[i] = 0; p(L.qacc)[i] = 0; p(L.qacc_ws)[i] = 0; }
+      if (time && lane == 0) *time = 0;
+      __syncwarp();
+      return 32;
+    }
     R* a = p(L.grad);  // reuse solver vector as the integration acceleration
     for (int i = lane; i < nv; i += 32) a[i] = p(L.qsmooth)[i] + p(L.qcon)[i];
     __syncwarp();

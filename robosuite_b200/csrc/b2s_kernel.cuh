@@ -135,7 +135,11 @@ __global__ void __launch_bounds__(512, 1) step_kernel(int phases, int nsub, cons
     if (prof) t0 = clock64();
     BAR(1, 11)
     if (phases & PH_STEP1) {
-      e.kinematics();
+      if (e.kinematics()) {  // diverged state reset to the model defaults (mj_checkPos / mj_checkVel)
+        for (int i = lane; i < m.nv; i += 32) { e.p(L.qacc)[i] = 0; e.p(L.qacc_ws)[i] = 0; }
+        time = 0; warn |= 32;
+        __syncwarp();
+      }
       TICK(0)
       e.velocity();
       e.crb();
@@ -162,7 +166,7 @@ __global__ void __launch_bounds__(512, 1) step_kernel(int phases, int nsub, cons
       if (ex) export_step2(e, env, nefc, niter);
       BAR(6, 11)
       if (!(phases & PH_NOINTEGRATE)) {
-        if (e.euler(&time)) warn |= 2;
+        { int eb = e.euler(&time); if (eb & 32) warn |= 32; else if (eb) warn |= 2; }
       }
       TICK(7)
     }

@@ -324,13 +324,19 @@ __global__ void __launch_bounds__(B2S_LB0_THREADS, B2S_LB0_BLOCKS) phase0_kernel
   load_row(e.p(L.qpos), s.qpos + E * m.nq, m.nq, lane);
   load_row(e.p(L.qvel), s.qvel + E * m.nv, m.nv, lane);
   __syncwarp();
-  e.kinematics();
+  const int was_reset = e.kinematics();
+  if (was_reset) {  // diverged state reset to the model defaults (mj_checkPos / mj_checkVel): the tail reads the state from global memory
+    for (int i = lane; i < m.nq; i += 32) s.qpos[E * m.nq + i] = e.p(L.qpos)[i];
+    for (int i = lane; i < m.nv; i += 32) { s.qvel[E * m.nv + i] = 0; s.qacc[E * m.nv + i] = 0; s.qacc_ws[E * m.nv + i] = 0; }
+    if (lane == 0) s.time[env] = 0;
+    __syncwarp();
+  }
   e.velocity();
   e.crb();
   // collision candidates of this environment -> global work lists (slots by warp-aggregated atomics)
   int* cand = reinterpret_cast<int*>(e.p(L.scratch));
   int* cand_g = cand + 96;
-  int na, ng, warn = 0;
+  int na, ng, warn = was_reset;
   cull_pairs(e, cand, cand_g, s.cl_maxa, s.cl_maxg, na, ng);
   if (na > s.cl_maxa) { na = s.cl_maxa; warn |= 4; }
   if (ng > s.cl_maxg) { ng = s.cl_maxg; warn |= 4; }
@@ -431,7 +437,7 @@ __global__ void __launch_bounds__(B2S_LB5_THREADS, B2S_LB5_BLOCKS) tail_kernel(i
     if (e.acceleration()) warn |= 1;
     solve(e, nefc, ncon, warn);
     if (!(phases & PH_NOINTEGRATE)) {
-      if (e.euler(&time)) warn |= 2;
+      { int eb = e.euler(&time); if (eb & 32) warn |= 32; else if (eb) warn |= 2; }
     }
     if ((phases & PH_OBS) && cc.obs_dim > 0 && sub == nsub - 1) {
       // The reference's observables sample on the LAST substep of a control step: reset()'s forced update already

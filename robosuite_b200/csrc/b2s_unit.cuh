@@ -25,6 +25,7 @@ struct UnitQ {
   int* ctr;       // [8]: 0 head ticket, 1 tail ticket, 2 finished units, 3 overflow head, 4 overflow tail
   int total, n_large, wpb_large;
   int stride, stride_large;  // words of shared memory per warp: small role / large role
+  unsigned long long* prof;  // B2S_UNIT_PROF: [16] clock64 cycles per stage summed over the blocks' rounds (thread 0 of every block), [15] = rounds
   int barriers;              // small role: -1 free-running warps, 0 the block starts its round of units together, 1..4 block
                              // barriers between the stages of a round as well (EXPERIMENTAL: stalls)
 };
@@ -41,7 +42,7 @@ template <typename R> __global__ void unit_init_kernel(UnitQ q, int n_env) {
 }
 
 // steps 1: kinematics, velocity stage + RNE bias, CRB -> M, broad phase; candidate table of the environment; poses etc. -> workspace row
-template <typename R> DEV int unit_phase0(R* area, int lane, int slot, int env) {
+template <typename R> DEVN int unit_phase0(R* area, int lane, int slot, int env) {
   const DModel<R>& m = cmodel<R>(slot);
   const DState<R>& s = cstate<R>(slot);
   const WSLayout& L = c_lay[slot][LAY_P0];
@@ -52,12 +53,18 @@ template <typename R> DEV int unit_phase0(R* area, int lane, int slot, int env) 
   load_row(e.p(L.qpos), s.qpos + E * m.nq, m.nq, lane);
   load_row(e.p(L.qvel), s.qvel + E * m.nv, m.nv, lane);
   __syncwarp();
-  e.kinematics();
+  const int was_reset = e.kinematics();
+  if (was_reset) {  // diverged state reset to the model defaults (mj_checkPos / mj_checkVel): the tail reads the state from global memory
+    for (int i = lane; i < m.nq; i += 32) s.qpos[E * m.nq + i] = e.p(L.qpos)[i];
+    for (int i = lane; i < m.nv; i += 32) { s.qvel[E * m.nv + i] = 0; s.qacc[E * m.nv + i] = 0; s.qacc_ws[E * m.nv + i] = 0; }
+    if (lane == 0) s.time[env] = 0;
+    __syncwarp();
+  }
   e.velocity();
   e.crb();
   int* cand = reinterpret_cast<int*>(e.p(L.scratch));
   int* cand_g = cand + 96;
-  int na, ng, warn = 0;
+  int na, ng, warn = was_reset;
   cull_pairs(e, cand, cand_g, s.cl_maxa, s.cl_maxg, na, ng);
   if (na > s.cl_maxa) { na = s.cl_maxa; warn |= 4; }
   if (ng > s.cl_maxg) { ng = s.cl_maxg; warn |= 4; }
@@ -74,7 +81,7 @@ template <typename R> DEV int unit_phase0(R* area, int lane, int slot, int env) 
 
 // narrow phase of ONE environment by its own warp: analytic pairs one per lane, convex pairs one after the other with the warp's whole
 // workspace area as EPA polytope + vertex staging scratch (phase 0's regions are in the global row by now)
-template <typename R> DEV void unit_narrow(R* area, int area_words, int lane, int slot, int env, int na, int ng) {
+template <typename R> DEVN void unit_narrow(R* area, int area_words, int lane, int slot, int env, int na, int ng) {
   const DModel<R>& m = cmodel<R>(slot);
   const DState<R>& s = cstate<R>(slot);
   const WSLayout& RL = c_lay[slot][LAY_ROW];
@@ -160,7 +167,7 @@ DEV int unit_tail(R* area, int lane, int slot, int lid, int env, int sub, int ns
   if (e.acceleration()) warn |= 1;
   solve(e, nefc, ncon, warn);
   if (!(phases & PH_NOINTEGRATE)) {
-    if (e.euler(&time)) warn |= 2;
+    { int eb = e.euler(&time); if (eb & 32) warn |= 32; else if (eb) warn |= 2; }
   }
   if ((phases & PH_OBS) && cc.obs_dim > 0 && sub == nsub - 1) {
     ws_load(e, row, io_late, bar, parity);
@@ -179,6 +186,89 @@ DEV int unit_tail(R* area, int lane, int slot, int lid, int env, int sub, int ns
   return 0;
 }
 
+// ---- the tail of a unit as separately compiled (noinline) stages: the lockstep rounds of the small role put block barriers between
+// them, and a kernel body that inlines all of it is the kind of function nvcc 12.9 has mis-allocated before
+// packed result of stage A: ncon (8 bits) | nefc (10 bits) << 8 | warn (8 bits) << 20 | does-not-fit-this-tier << 30
+template <typename R>
+DEVN int unit_tail_a(R* area, int lane, int slot, int env, unsigned long long* bar, unsigned& parity) {
+  const DModel<R>& m = cmodel<R>(slot);
+  const DState<R>& s = cstate<R>(slot);
+  const WSLayout& L = c_lay[slot][LAY_TS];
+  const WSLayout& RL = c_lay[slot][LAY_ROW];
+  Eng<R> e(area, lane, slot, LAY_TS);
+  const bool tiered = L.mc < m.maxcon || L.me < m.maxefc;
+  const size_t E = env;
+  const R* row = s.wsg + E * RL.total;
+  int warn = reinterpret_cast<const int*>(row + RL.hdr)[2];
+  ws_load(e, row, c_pio[slot][PIO_TS], bar, parity);
+  load_row(e.p(L.qpos), s.qpos + E * m.nq, m.nq, lane);
+  load_row(e.p(L.qvel), s.qvel + E * m.nv, m.nv, lane);
+  load_row(e.p(L.ctrl), s.ctrl + E * m.nu, m.nu, lane);
+  load_row(e.p(L.qacc_ws), s.qacc_ws + E * m.nv, m.nv, lane);
+  __syncwarp();
+  int wl = 0;
+  int ncon = gather_contacts(e, env, wl);
+  int nefc = (tiered && (wl & 4)) ? 0 : make_constraint(e, ncon, wl);
+  wl = warp_or_i(wl);
+  int ovf = (tiered && (wl & 12)) ? 1 : 0;
+  warn = warp_or_i(warn | wl) & 255;
+  return (ncon & 255) | ((nefc & 1023) << 8) | (warn << 20) | (ovf << 30);
+}
+template <typename R> DEVN void unit_tail_ctrl(R* area, int lane, int slot, int env, int sub, const R* action) {
+  const DModel<R>& m = cmodel<R>(slot);
+  const DState<R>& s = cstate<R>(slot);
+  const WSLayout& L = c_lay[slot][LAY_TS];
+  Eng<R> e(area, lane, slot, LAY_TS);
+  const size_t E = env;
+  CtrlState<R> cs;
+  ctrl_load(e, cs, env);
+  ctrl_run(e, cs, env, sub == 0 ? action : (const R*)nullptr);
+  for (int i = lane; i < m.nu; i += 32) s.ctrl[E * m.nu + i] = e.p(L.ctrl)[i];
+  if (sub == 0) ctrl_store(e, cs, env);
+  __syncwarp();
+}
+template <typename R> DEVN int unit_tail_acc(R* area, int lane, int slot) {
+  Eng<R> e(area, lane, slot, LAY_TS);
+  e.actuation((R*)nullptr);
+  int w = e.acceleration() ? 1 : 0;
+  return warp_or_i(w);
+}
+template <typename R> DEVN int unit_tail_solve(R* area, int lane, int slot, int nefc, int ncon) {
+  Eng<R> e(area, lane, slot, LAY_TS);
+  int warn = 0;
+  solve(e, nefc, ncon, warn);
+  return warp_or_i(warn);
+}
+template <typename R>
+DEVN void unit_tail_end(R* area, int lane, int slot, int env, int sub, int nsub, int phases, int ncon, int warn, unsigned long long* bar, unsigned& parity) {
+  const DModel<R>& m = cmodel<R>(slot);
+  const DState<R>& s = cstate<R>(slot);
+  const WSLayout& L = c_lay[slot][LAY_TS];
+  const WSLayout& RL = c_lay[slot][LAY_ROW];
+  const CtrlCfgDev& cc = c_cc[slot];
+  Eng<R> e(area, lane, slot, LAY_TS);
+  const size_t E = env;
+  const R* row = s.wsg + E * RL.total;
+  R time = s.time[env];
+  if (!(phases & PH_NOINTEGRATE)) {
+    { int eb = e.euler(&time); if (eb & 32) warn |= 32; else if (eb) warn |= 2; }
+  }
+  if ((phases & PH_OBS) && cc.obs_dim > 0 && sub == nsub - 1) {
+    ws_load(e, row, c_pio[slot][PIO_TS_LATE], bar, parity);
+    write_obs(e, env, (phases & PH_NOINTEGRATE) != 0);
+    write_task(e, env, ncon);
+  }
+  for (int i = lane; i < m.nq; i += 32) s.qpos[E * m.nq + i] = e.p(L.qpos)[i];
+  for (int i = lane; i < m.nv; i += 32) {
+    s.qvel[E * m.nv + i] = e.p(L.qvel)[i];
+    s.qacc[E * m.nv + i] = e.p(L.qacc)[i];
+    s.qacc_ws[E * m.nv + i] = e.p(L.qacc_ws)[i];
+  }
+  warn = warp_or_i(warn);
+  if (lane == 0) { s.time[env] = time; s.warn[env] |= warn; }
+  __syncwarp();
+}
+
 // the unit is finished: hand the environment to whoever takes the next ticket (or count it as done after its last substep)
 DEV void unit_finish(const UnitQ& q, int n_env, int env, int sub, int nsub, int lane) {
   __syncwarp();
@@ -194,9 +284,12 @@ DEV void unit_finish(const UnitQ& q, int n_env, int env, int sub, int nsub, int 
 }
 
 
+// One block of 16 warps per SM: what counts is that an SM executes ONE code region at a time (the hot code is ~10x the instruction
+// cache).  Measured on 4096 Lift environments (tools/run30.sh): 16 warps x 1 block 306 k env-steps/s, 8 warps x 2 blocks 248 k,
+// 8 warps x 1 block 210 k, 4 warps x 4 blocks 158 k, free-running warps 80 k.
 #ifndef B2S_LBU_THREADS
-#define B2S_LBU_THREADS 256
-#define B2S_LBU_BLOCKS 2
+#define B2S_LBU_THREADS 512
+#define B2S_LBU_BLOCKS 1
 #endif
 
 template <typename R>
@@ -242,26 +335,43 @@ __global__ void __launch_bounds__(B2S_LBU_THREADS, B2S_LBU_BLOCKS) unit_kernel(i
   // on nearly every fetch (measured: 1.1 ms per unit against ~0.2 ms of work); in lockstep an SM executes one or two code regions at
   // a time, like the phase kernels, and a stage costs the slowest of the block's 8 units (1.0-1.3x the mean) instead of the slowest
   // of a 512-environment launch (2.5x).
-  const DModel<R>& m = cmodel<R>(slot);
-  const WSLayout& L = c_lay[slot][LAY_TS];
-  const WSLayout& RL = c_lay[slot][LAY_ROW];
-  const PhaseIO& io = c_pio[slot][PIO_TS];
-  const PhaseIO& io_late = c_pio[slot][PIO_TS_LATE];
-  const CtrlCfgDev& cc = c_cc[slot];
-  const bool tiered = L.mc < m.maxcon || L.me < m.maxefc;
   const int wpb = blockDim.x >> 5;
-  __shared__ int sh_t0;
+  __shared__ int sh_t0, sh_k;
   R* area = smem + (size_t)warp * q.stride;
 #define UBAR(level) if (q.barriers >= (level)) __syncthreads();
+#define UTICK(k) if (q.prof != nullptr && threadIdx.x == 0) { long long tn_ = clock64(); atomicAdd(q.prof + (k), (unsigned long long)(tn_ - tprev)); tprev = tn_; }
+  long long tprev = clock64();
   for (;;) {
     int t;
     if (q.barriers >= 0) {
+      // the block takes up to `wpb` tickets that are ALREADY PRODUCED (head < tail): with stage barriers a unit whose ticket is still
+      // to come would hold the block's ready units hostage, and near the end of a control step, when the last tickets wait for the
+      // units in flight, the blocks would hold each other's producers (observed: every step stalled until the watchdog)
       __syncthreads();
-      if (threadIdx.x == 0) sh_t0 = ld_relaxed_gpu(q.ctr + 7) != 0 ? 0x7fffffff : atomicAdd(q.ctr, wpb);
+      if (threadIdx.x == 0) {
+        int t0v = 0x7fffffff, k = 0, spins = 0;
+        for (;;) {
+          if (ld_relaxed_gpu(q.ctr + 7) != 0) break;
+          const int H = ld_relaxed_gpu(q.ctr);
+          if (H >= q.total) break;
+          const int P = ld_acquire_gpu(q.ctr + 1);
+          if (H < P) {
+            k = min(wpb, P - H);
+            if (atomicCAS(q.ctr, H, H + k) == H) { t0v = H; break; }
+            k = 0;
+            continue;
+          }
+          __nanosleep(100);
+          if (++spins > (1 << 22)) { atomicCAS(q.ctr + 7, 0, 2); break; }
+        }
+        sh_t0 = t0v; sh_k = k;
+      }
       __syncthreads();
       const int t0 = sh_t0;
-      if (t0 >= q.total) break;
-      t = t0 + warp;
+      if (t0 == 0x7fffffff) break;
+      UTICK(0)
+      if (q.prof != nullptr && threadIdx.x == 0) atomicAdd(q.prof + 15, 1ull);
+      t = warp < sh_k ? t0 + warp : q.total;
     } else {  // free-running warps (no block synchronisation at all): one ticket per warp
       t = 0;
       if (lane == 0) t = ld_relaxed_gpu(q.ctr + 7) != 0 ? 0x7fffffff : atomicAdd(q.ctr, 1);
@@ -288,29 +398,20 @@ __global__ void __launch_bounds__(B2S_LBU_THREADS, B2S_LBU_BLOCKS) unit_kernel(i
       if (code < 0) { live = false; code = 0; }
     }
     const int env = code % n_env, sub = code / n_env;
-    const size_t E = env;
     UBAR(1)
+    UTICK(1)
     int nn = 0;
     if (live) nn = unit_phase0<R>(area, lane, slot, env);
     UBAR(2)
+    UTICK(2)
     if (live) unit_narrow<R>(area, q.stride, lane, slot, env, nn & 0xffff, nn >> 16);
     UBAR(1)
-    Eng<R> e(area, lane, slot, LAY_TS);
-    const R* row = s.wsg + E * RL.total;
+    UTICK(3)
     int warn = 0, ncon = 0, nefc = 0;
     if (live) {
-      warn = reinterpret_cast<const int*>(row + RL.hdr)[2];
-      ws_load(e, row, io, &mbar[warp], parity);
-      load_row(e.p(L.qpos), s.qpos + E * m.nq, m.nq, lane);
-      load_row(e.p(L.qvel), s.qvel + E * m.nv, m.nv, lane);
-      load_row(e.p(L.ctrl), s.ctrl + E * m.nu, m.nu, lane);
-      load_row(e.p(L.qacc_ws), s.qacc_ws + E * m.nv, m.nv, lane);
-      __syncwarp();
-      int wl = 0;
-      ncon = gather_contacts(e, env, wl);
-      nefc = (tiered && (wl & 4)) ? 0 : make_constraint(e, ncon, wl);
-      wl = warp_or_i(wl);
-      if (tiered && (wl & 12)) {  // does not fit the small tier: to the large-role warps, nothing of the state has been touched
+      const int pk = unit_tail_a<R>(area, lane, slot, env, &mbar[warp], parity);
+      ncon = pk & 255; nefc = (pk >> 8) & 1023; warn = (pk >> 20) & 255;
+      if (pk >> 30) {  // does not fit the small tier: to the large-role warps, nothing of the state has been touched
         if (lane == 0) {
           __threadfence();
           int p = atomicAdd(q.ctr + 4, 1);
@@ -319,46 +420,24 @@ __global__ void __launch_bounds__(B2S_LBU_THREADS, B2S_LBU_BLOCKS) unit_kernel(i
         __syncwarp();
         live = false;
       }
-      warn |= wl;
     }
     UBAR(3)
-    if (live && (phases & PH_CTRL)) {
-      CtrlState<R> cs;
-      ctrl_load(e, cs, env);
-      ctrl_run(e, cs, env, sub == 0 ? action : (const R*)nullptr);
-      for (int i = lane; i < m.nu; i += 32) s.ctrl[E * m.nu + i] = e.p(L.ctrl)[i];
-      if (sub == 0) ctrl_store(e, cs, env);
-      __syncwarp();
-    }
+    UTICK(4)
+    if (live && (phases & PH_CTRL)) unit_tail_ctrl<R>(area, lane, slot, env, sub, action);
     UBAR(3)
-    R time = 0;
-    if (live) {
-      time = s.time[env];
-      e.actuation((R*)nullptr);
-      if (e.acceleration()) warn |= 1;
-    }
+    UTICK(5)
+    if (live) warn |= unit_tail_acc<R>(area, lane, slot);
     UBAR(4)
-    if (live) solve(e, nefc, ncon, warn);
+    UTICK(6)
+    if (live) warn |= unit_tail_solve<R>(area, lane, slot, nefc, ncon);
     UBAR(4)
+    UTICK(7)
     if (live) {
-      if (!(phases & PH_NOINTEGRATE)) {
-        if (e.euler(&time)) warn |= 2;
-      }
-      if ((phases & PH_OBS) && cc.obs_dim > 0 && sub == nsub - 1) {
-        ws_load(e, row, io_late, &mbar[warp], parity);
-        write_obs(e, env, (phases & PH_NOINTEGRATE) != 0);
-        write_task(e, env, ncon);
-      }
-      for (int i = lane; i < m.nq; i += 32) s.qpos[E * m.nq + i] = e.p(L.qpos)[i];
-      for (int i = lane; i < m.nv; i += 32) {
-        s.qvel[E * m.nv + i] = e.p(L.qvel)[i];
-        s.qacc[E * m.nv + i] = e.p(L.qacc)[i];
-        s.qacc_ws[E * m.nv + i] = e.p(L.qacc_ws)[i];
-      }
-      warn = warp_or_i(warn);
-      if (lane == 0) { s.time[env] = time; s.warn[env] |= warn; }
+      unit_tail_end<R>(area, lane, slot, env, sub, nsub, phases, ncon, warn, &mbar[warp], parity);
       unit_finish(q, n_env, env, sub, nsub, lane);
     }
+    UTICK(8)
   }
 #undef UBAR
+#undef UTICK
 }

@@ -94,7 +94,8 @@ class ObsBuilder:
 
 # bits of sim.warn / info["sim_warn"] (robosuite_b200/csrc: b2s_kernel.cuh, b2s_collide.cuh, b2s_solver.cuh)
 SIM_WARN_BITS = {1: "singular mass matrix", 2: "non-finite state in the integrator", 4: "contact capacity overflow (maxcon)",
-                 8: "constraint-row capacity overflow (maxefc)", 16: "singular Newton Hessian"}
+                 8: "constraint-row capacity overflow (maxefc)", 16: "singular Newton Hessian",
+                 32: "diverged state (non-finite / huge qpos, qvel or qacc): data reset to the model defaults, as mj_checkPos/Vel/Acc do"}
 
 
 class BatchedMujocoEnv:
@@ -376,6 +377,9 @@ class BatchedMujocoEnv:
         self.cur_time += self.control_timestep
         reward = self.reward(action)
         self.done = (self.timestep >= self.horizon) & (not self.ignore_done)
+        if not self.ignore_done:
+            # the engine reset a diverged environment to the model defaults (mj_resetData after mj_checkPos/Vel/Acc): its episode is over
+            self.done = self.done | ((self.sim.warn & 32) != 0)
         # per-environment engine flags since the last reset, as a device tensor (no host sync here; see SIM_WARN_BITS): a non-zero entry means
         # the episode is no longer a faithful MuJoCo rollout (capacity overflow, singular mass matrix / Hessian, diverged state)
         return self._get_observations(), reward, self.done, {"sim_warn": self.sim.warn}

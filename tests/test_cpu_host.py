@@ -330,3 +330,26 @@ def test_error_classes_follow_the_reference_names():
         compile_mjcf("<mujoco><worldbody>")
     with pytest.raises(XMLError):
         compile_mjcf("<robot/>")
+
+
+def test_oracle_resets_diverged_state_like_mj_check():
+    """mj_checkPos / mj_checkVel / mj_checkAcc: a non-finite or huge coordinate resets the data to the model defaults (time 0, warn bit
+    32) instead of integrating garbage; the device engine mirrors this (tests/test_gpu_engine.py)"""
+    model = load("Lift_Panda")
+    q, _ = lift_states(model, 1, seed=5)
+    o = _oracle(model)
+    o.qpos[:] = q[0]
+    for _ in range(3):
+        o.step()
+    assert o.time > 0 and o.geti("warn_flags") == 0
+    o.qvel[2] = np.nan
+    o.step()
+    assert o.geti("warn_flags") & 32
+    assert np.isfinite(o.qpos).all() and np.isfinite(o.qvel).all()
+    assert abs(o.time - model.opt_timestep) < 1e-12  # the clock restarted, then one step was integrated from qpos0
+    o2 = _oracle(model)
+    o2.step()
+    assert np.array_equal(o.qpos, o2.qpos)
+    o.qvel[0] = 1e12  # huge, finite
+    o.step()
+    assert np.abs(o.qvel).max() < 1e3

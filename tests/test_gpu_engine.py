@@ -408,3 +408,43 @@ def test_engine_parity_other_task_models(name):
         max(errs) if errs else float("nan"), len(errs), n, worst))
     assert worst < (1e-4 if len(errs) == n else 2e-3)
     sim.close()
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_diverged_environment_is_reset_not_integrated(mode):
+    """mj_checkPos / mj_checkVel / mj_checkAcc (the first calls of mj_step in the reference's engine): an environment whose state is
+    non-finite or huge is reset to the model defaults and flagged (warn bit 32); its neighbours are untouched, in every schedule"""
+    import torch
+
+    from robosuite_b200 import controller_config as cc
+    from robosuite_b200.engine import BatchedSim, CtrlCfg
+
+    model = load("Lift_Panda")
+    n = 8
+    q, _ = lift_states(model, n, seed=2)
+    outs = []
+    for poison in (False, True):
+        sim = BatchedSim(model, n, precision="f32")
+        sim.ctrl_config(cc.resolve(model, cc.default_composite_config(), CtrlCfg))
+        sim.set_export(False)
+        sim.set_mode(mode)
+        sim.qpos.copy_(torch.as_tensor(q, dtype=torch.float32))
+        sim.forward()
+        sim.ctrl_reset()
+        act = torch.zeros((n, 7), dtype=torch.float32, device=sim.torch_device)
+        sim.env_step(act, 5)
+        if poison:
+            sim.qvel[3, 2] = float("nan")
+            sim.qpos[5, 0] = 3e12
+        sim.env_step(act, 5)
+        torch.cuda.synchronize()
+        outs.append((sim.qpos.clone(), sim.qvel.clone(), sim.warn.clone(), sim.time.clone()))
+        sim.close()
+    (qa, va, wa, ta), (qb, vb, wb, tb) = outs
+    assert torch.isfinite(qb).all() and torch.isfinite(vb).all()
+    assert int(wa.abs().max()) == 0
+    assert (wb[[3, 5]] & 32).bool().all() and int(wb[[0, 1, 2, 4, 6, 7]].abs().max()) == 0
+    keep = [0, 1, 2, 4, 6, 7]
+    assert torch.equal(qa[keep], qb[keep]) and torch.equal(va[keep], vb[keep])
+    assert float(tb[3]) < float(ta[3]) and float(tb[3]) > 0  # the clock restarted, then ran on
+    assert (qb[[3, 5], :7] - torch.as_tensor(np.asarray(model.qpos0)[:7], dtype=torch.float32, device=qb.device)).abs().max() < 0.05

@@ -301,3 +301,41 @@ def test_device_joint_velocity_replays_reference_class_golden():
     assert worst_q < 1e-6 and worst_v < 1e-4 and worst_u < 1e-3
     assert int(env.sim.warn.abs().max()) == 0
     env.close()
+
+
+@pytest.mark.parametrize("task,robot,ctrl", [("Stack", "Sawyer", "JOINT_VELOCITY"), ("Door", "Panda", "OSC_POSE"),
+                                             ("PickPlace", "Panda", "OSC_POSE"), ("NutAssemblyRound", "Panda", "OSC_POSE")])
+def test_unit_queue_mode_matches_pipeline_on_task_envs(task, robot, ctrl):
+    """mode 2 (persistent unit-queue kernel) against mode 1 (phase pipeline) through the env API on the other BASELINE tasks: tiered
+    layouts (Door, PickPlace), the JOINT_VELOCITY controller, a 33-dof model.  Same device functions, same per-environment data ->
+    bit-identical states and observations (OSC evaluated inside the tail in both, B2S_CTRL_SPLIT=0: the thread-per-environment
+    controller kernel of the pipeline orders its fp64 sums differently)"""
+    import torch
+
+    import robosuite_b200 as suite
+    from robosuite_b200 import controller_config as cc
+
+    n, steps = 24, 5
+    kw = {}
+    if ctrl != "OSC_POSE":
+        kw["controller_configs"] = cc.refactor_composite_controller_config(cc.load_part_controller_config(ctrl), robot, ["right"])
+    out = []
+    os.environ["B2S_CTRL_SPLIT"] = "0"
+    try:
+        for mode in (1, 2):
+            env = suite.make(task, robots=robot, num_envs=n, seed=5, horizon=10 ** 6, **kw)
+            env.sim.set_mode(mode)
+            gen = torch.Generator(device=env.device)
+            gen.manual_seed(9)
+            for t in range(steps):
+                act = torch.rand((n, env.action_dim), generator=gen, device=env.device, dtype=env.dtype) * 2 - 1
+                act[: n // 2, 2] = -1.0  # half of the arms push down: contacts, EPA, large-tier environments
+                env.step(act)
+            torch.cuda.synchronize()
+            assert int(env.sim.warn.abs().max()) == 0
+            out.append((env.sim.qpos.clone(), env.sim.qvel.clone(), env.flat_obs().clone()))
+            env.close()
+    finally:
+        os.environ.pop("B2S_CTRL_SPLIT", None)
+    for a, b in zip(out[0], out[1]):
+        assert torch.isfinite(b).all() and torch.equal(a, b)
