@@ -594,7 +594,11 @@ DEVN int gjk(const Shape<R>& A, const Shape<R>& B, R* sx, int& ns, R& dist, R* w
     if (vw0 > 0 && vw0 * vw0 > cutoff * cutoff * vv0) { dist = cutoff + 1; ns = 1; return 0; }
   }
   v3copy(v, w.w);
-  for (int it = 0; it < 64; it++) {
+  // iteration cap: 64 in fp64 (the oracle's); the fp32 build stops at 32 - its relative convergence test (1e-6) sits at the edge of
+  // fp32 resolution, so touching / grazing pairs of curved shapes never pass it and churned through all 64 iterations at their
+  // rounding floor (the 300-400 us work items that set the length of half of the narrow-phase launches: profiles/r02_summary.md)
+  const int max_it = sizeof(R) == 4 ? 32 : 64;
+  for (int it = 0; it < max_it; it++) {
     R vv = v3dot(v, v);
     if (vv < tol_vv) { ns = n; if (cache && lane == 0) { cache[0] = 0; cache[1] = 0; cache[2] = 0; } return 1; }
     v3scl(nv, v, R(-1));
@@ -841,7 +845,16 @@ DEVN int convex_convex(const Shape<R>& A0, const Shape<R>& B0, R* out, int maxn,
   Shape<R> A = A0, B = B0;
   R ra = shape_radius(A), rb = shape_radius(B);
   if (stage != nullptr) {
-    if (cache != nullptr) {  // gjk()'s own first test, made here so that dismissed pairs (the common case) never pay for staging
+    // the two poses first (24 reals, one load per lane): support_w reads them on every call - through pointers into the global
+    // workspace row that is four dependent L2 latencies per support pair (ncu: long-scoreboard stalls on the first use of `mat` and
+    // on `pos` were ~45 % of support_w's samples), and the dismissal test below is one support pair
+    __syncwarp();
+    if (lane < 12) stage[lane] = lane < 3 ? A.pos[lane] : A.mat[lane - 3];
+    else if (lane < 24) stage[lane] = lane < 15 ? B.pos[lane - 12] : B.mat[lane - 15];
+    A.pos = stage; A.mat = stage + 3; B.pos = stage + 12; B.mat = stage + 15;
+    stage += 24; stage_cap -= 24;
+    __syncwarp();
+    if (cache != nullptr) {  // gjk()'s own first test, made here so that dismissed pairs (the common case) never pay for staging the hulls
       R cv[3] = {cache[0], cache[1], cache[2]};
       if (v3dot(cv, cv) > R(1e-12)) {
         R nv[3] = {-cv[0], -cv[1], -cv[2]};
@@ -851,12 +864,7 @@ DEVN int convex_convex(const Shape<R>& A0, const Shape<R>& B0, R* out, int maxn,
         if (vw0 > 0 && vw0 * vw0 > cut * cut * vv0) return 0;
       }
     }
-    // the two poses first (24 reals): support_w reads them on every call, through pointers into the global workspace row otherwise
     __syncwarp();
-    if (lane < 12) stage[lane] = lane < 3 ? A.pos[lane] : A.mat[lane - 3];
-    else if (lane < 24) stage[lane] = lane < 15 ? B.pos[lane - 12] : B.mat[lane - 15];
-    A.pos = stage; A.mat = stage + 3; B.pos = stage + 12; B.mat = stage + 15;
-    stage += 24; stage_cap -= 24;
     int used = 0;
     if (A.nvert > 0 && 3 * A.nvert <= stage_cap) {
       for (int i = lane; i < 3 * A.nvert; i += 32) stage[i] = A.vert[i];
