@@ -430,6 +430,8 @@ def run_gpu(args):
         for e in envs[1:]:
             e.close()
         tl = device_timeline(parts[0], groups)
+    if args.mode == 2:
+        kernel = "unit_kernel<float> (persistent: every environment-substep of the control step as units on a ticket ring)"
     if args.mode == 1:
         envs_per_launch = env0.num_envs // groups
         kernel = "tail_kernel<float> (contact gather, constraint rows, Newton solve, integrate; small tier)"

@@ -377,9 +377,8 @@ class BatchedMujocoEnv:
         self.cur_time += self.control_timestep
         reward = self.reward(action)
         self.done = (self.timestep >= self.horizon) & (not self.ignore_done)
-        if not self.ignore_done:
-            # the engine reset a diverged environment to the model defaults (mj_resetData after mj_checkPos/Vel/Acc): its episode is over
-            self.done = self.done | ((self.sim.warn & 32) != 0)
+        # (an environment whose state diverged was reset to the model defaults by the engine, like mj_resetData after mj_checkPos / Vel / Acc;
+        # as in the reference the episode simply continues from there - info["sim_warn"] bit 32 tells the caller)
         # per-environment engine flags since the last reset, as a device tensor (no host sync here; see SIM_WARN_BITS): a non-zero entry means
         # the episode is no longer a faithful MuJoCo rollout (capacity overflow, singular mass matrix / Hessian, diverged state)
         return self._get_observations(), reward, self.done, {"sim_warn": self.sim.warn}
