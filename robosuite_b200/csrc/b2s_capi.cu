@@ -596,6 +596,8 @@ int b2s_create(const void* blob_host, size_t nbytes, int n_env, int device, int 
   if (!blob_host || !out || n_env <= 0) return fail(B2S_ERR_ARG, "b2s_create: bad argument");
   if (nbytes < 16 || memcmp(blob_host, "B2SMODEL", 8) != 0) return fail(B2S_ERR_MODEL, "b2s_create: not a model blob");
   if (precision != B2S_F32 && precision != B2S_F64) return fail(B2S_ERR_ARG, "b2s_create: precision must be B2S_F32 or B2S_F64");
+  // work-list entries pack (env << 12 | pair) into an int, unit-queue tickets env + n_env * substep
+  if (n_env >= (1 << 19)) return fail(B2S_ERR_UNSUPPORTED, "b2s_create: n_env must be below 524288 per handle (create several handles)");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(B2S_ERR_CUDA, "b2s_create: no CUDA device available (this library has no CPU fallback)");
