@@ -111,6 +111,14 @@ int b2s_env_step(b2s_sim* sim, const void* action, int n_substeps);
  * auto-reset can be enqueued after every step. */
 int b2s_reset_envs(b2s_sim* sim, const uint8_t* env_mask, const void* qpos_new);
 
+/* Per-environment world pose of a body welded to the world.  The reference writes sampled placements into the MODEL per reset
+ * (Door: `sim.model.body_pos[door_body_id] = door_pos; body_quat = door_quat`, environments/manipulation/door.py:417-427); a batch shares
+ * its model constants, so such poses are per-environment DATA here.  After the call the arrays "body_xpos_ov:<id>" [n_env, 3] and
+ * "body_xquat_ov:<id>" [n_env, 4] (initialised to the model's pose; fetch them with b2s_array and write them like any state array)
+ * replace the constant world pose of that body in every kinematics pass.  Bodies welded to an overridden body keep THEIR constant world
+ * pose: override them too (pose = parent pose * local pose).  At most 4 bodies per handle. */
+int b2s_body_pose_override(b2s_sim* sim, int body_id);
+
 /* Observation program = MujocoEnv._get_observations flattened (environments/base.py:429-465): one (op, a, b) entry
  * per output scalar (ops: enum OB_* in csrc/b2s_types.cuh; OB_REL_*_LAG entries read the previous sample, as the reference's
  * sensor ordering does: manipulation_env.py:268-329).  Creates the device arrays "obs" [n_env, obs_dim] and "obs_fresh" [n_env]

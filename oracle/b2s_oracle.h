@@ -119,6 +119,7 @@ void o_step2(const OModel* m, OData* d);
 void o_step(const OModel* m, OData* d);
 
 /* stages (exposed for tests) */
+void o_model_set_body_pose(OModel* m, int body, const double* pos, const double* quat);
 void o_kinematics(const OModel* m, OData* d);
 void o_crb(const OModel* m, OData* d);
 void o_factor_m(const OModel* m, OData* d);

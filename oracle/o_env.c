@@ -42,3 +42,11 @@ const int* o_efc_int(const OData* d, const char* name) {
   return 0;
 }
 void o_set_time(OData* d, double t) { d->time = t; }
+
+/* what the reference does per reset for the Door: sim.model.body_pos[id] = pos; body_quat[id] = quat (door.py:417-427).  The model owns a
+ * private copy of its blob, so the constants are writable. */
+void o_model_set_body_pose(OModel* m, int body, const double* pos, const double* quat) {
+  double* bp = (double*)m->body_pos + 3 * body; double* bq = (double*)m->body_quat + 4 * body;
+  for (int k = 0; k < 3; k++) bp[k] = pos[k];
+  for (int k = 0; k < 4; k++) bq[k] = quat[k];
+}

@@ -27,6 +27,7 @@ def lib():
         L.o_model_load.restype = C.c_void_p
         L.o_model_load.argtypes = [C.c_char_p, C.c_size_t]
         L.o_model_free.argtypes = [C.c_void_p]
+        L.o_model_set_body_pose.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.o_data_new.restype = C.c_void_p
         L.o_data_new.argtypes = [C.c_void_p]
         L.o_data_free.argtypes = [C.c_void_p]
@@ -122,6 +123,11 @@ class Oracle:
             self._L.o_model_free(self.m)
         except Exception:
             pass
+
+    def set_body_pose(self, body, pos, quat):
+        """model.body_pos[body] = pos; model.body_quat[body] = quat (what the reference does per reset for the Door)"""
+        p = (C.c_double * 3)(*[float(x) for x in pos]); q = (C.c_double * 4)(*[float(x) for x in quat])
+        self._L.o_model_set_body_pose(self.m, int(body), p, q)
 
     # scalars
     @property

@@ -90,6 +90,8 @@ struct b2s_sim {
   int uq_wpb = 0, uq_bps = 0, uq_stride = 0, uq_stride_large = 0, uq_wpb_large = 0, uq_nlarge = 0, uq_grid = 0;
   size_t uq_smem = 0;
   unsigned long long* uq_prof = nullptr;
+  std::vector<double> xpos0_h, xquat0_h;  // world poses of the bodies welded to the world (model constants)
+  std::vector<int> body_weldid_h;
 };
 
 template <typename T> static T* dev_upload(b2s_sim* s, const std::vector<T>& h) {
@@ -257,6 +259,8 @@ template <typename R> static void build_model(b2s_sim* s, const Blob& b, DModel<
   m.body_iquat = up_f<R>(s, b, "body_iquat"); m.body_mass = up_f<R>(s, b, "body_mass"); m.body_inertia = up_f<R>(s, b, "body_inertia");
   m.body_invweight0 = up_f<R>(s, b, "body_invweight0");
   m.body_xpos0 = up_vec<R>(s, xpos0); m.body_xquat0 = up_vec<R>(s, xquat0);
+  s->xpos0_h = xpos0; s->xquat0_h = xquat0;
+  { const int* wd = b.i32("body_weldid"); s->body_weldid_h.assign(wd, wd + nb); }
   m.jnt_type = up_i(s, b, "jnt_type"); m.jnt_qposadr = up_i(s, b, "jnt_qposadr"); m.jnt_dofadr = up_i(s, b, "jnt_dofadr");
   m.jnt_bodyid = up_i(s, b, "jnt_bodyid"); m.jnt_limited = up_i(s, b, "jnt_limited");
   m.jnt_pos = up_f<R>(s, b, "jnt_pos"); m.jnt_axis = up_f<R>(s, b, "jnt_axis"); m.jnt_range = up_f<R>(s, b, "jnt_range");
@@ -1278,6 +1282,33 @@ int b2s_reset_envs(b2s_sim* s, const uint8_t* mask, const void* qpos_new) {
   if (s->has_ctrl) return b2s_ctrl_reset(s, mask);
   clear_warm_start(s, mask);
   return B2S_OK;
+}
+
+}  // extern "C"
+template <typename R> static int body_pose_override_t(b2s_sim* s, DState<R>& st, int body) {
+  for (int k = 0; k < st.n_ov; k++) if (st.ov_body[k] == body) return B2S_OK;
+  if (st.n_ov >= 4) return fail(B2S_ERR_UNSUPPORTED, "b2s_body_pose_override: at most 4 bodies per handle");
+  std::vector<R> hp((size_t)s->n_env * 3), hq((size_t)s->n_env * 4);
+  for (int e = 0; e < s->n_env; e++) {
+    for (int k = 0; k < 3; k++) hp[(size_t)e * 3 + k] = (R)s->xpos0_h[3 * body + k];
+    for (int k = 0; k < 4; k++) hq[(size_t)e * 4 + k] = (R)s->xquat0_h[4 * body + k];
+  }
+  const int k = st.n_ov;
+  try { st.ov_pos[k] = dev_upload(s, hp); st.ov_quat[k] = dev_upload(s, hq); } catch (const std::string& e) { return fail(B2S_ERR_CUDA, e); }
+  st.ov_body[k] = body;
+  st.n_ov = k + 1;
+  const int code = s->precision == B2S_F32 ? B2S_F32 : B2S_F64;
+  s->arrays["body_xpos_ov:" + std::to_string(body)] = ArrayInfo{st.ov_pos[k], code, 2, {s->n_env, 3, 0, 0}};
+  s->arrays["body_xquat_ov:" + std::to_string(body)] = ArrayInfo{st.ov_quat[k], code, 2, {s->n_env, 4, 0, 0}};
+  s->dirty = 1;
+  return B2S_OK;
+}
+extern "C" {
+int b2s_body_pose_override(b2s_sim* s, int body_id) {
+  if (!s || body_id <= 0 || body_id >= s->nbody) return fail(B2S_ERR_ARG, "b2s_body_pose_override: bad argument");
+  if (s->body_weldid_h[body_id] != 0) return fail(B2S_ERR_UNSUPPORTED, "b2s_body_pose_override: the body is not welded to the world (move it through qpos)");
+  CUDA_TRY(cudaSetDevice(s->device));
+  return s->precision == B2S_F32 ? body_pose_override_t<float>(s, s->sf, body_id) : body_pose_override_t<double>(s, s->sd, body_id);
 }
 
 int b2s_env_step(b2s_sim* s, const void* action, int nsub) {

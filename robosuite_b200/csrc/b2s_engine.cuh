@@ -127,6 +127,7 @@ struct Eng {
   R* ws;  // this warp's workspace
   int lane;
   int slot, lid;  // descriptor slot of the owning handle, workspace layout of the running kernel (LAY_*)
+  int env = 0;    // environment index (set by the kernels that run kinematics: per-environment poses of world-welded bodies)
 
   DEV Eng(R* ws_, int lane_, int slot_, int lid_) : ws(ws_), lane(lane_), slot(slot_), lid(lid_) {}
   DEV const DModel<R>& model() const { return cmodel<R>(slot); }
@@ -160,8 +161,12 @@ struct Eng {
     // bodies welded to the world: constant pose
     for (int b = lane; b < m.nbody; b += 32)
       if (m.body_weldid[b] == 0) {
-        R q[4] = {m.body_xquat0[4 * b], m.body_xquat0[4 * b + 1], m.body_xquat0[4 * b + 2], m.body_xquat0[4 * b + 3]};
-        xpos[3 * b] = m.body_xpos0[3 * b]; xpos[3 * b + 1] = m.body_xpos0[3 * b + 1]; xpos[3 * b + 2] = m.body_xpos0[3 * b + 2];
+        const R* px = m.body_xpos0 + 3 * b; const R* pq = m.body_xquat0 + 4 * b;
+        const DState<R>& st = state();
+        for (int k = 0; k < st.n_ov; k++)
+          if (st.ov_body[k] == b) { px = st.ov_pos[k] + 3 * (size_t)env; pq = st.ov_quat[k] + 4 * (size_t)env; }
+        R q[4] = {pq[0], pq[1], pq[2], pq[3]};
+        xpos[3 * b] = px[0]; xpos[3 * b + 1] = px[1]; xpos[3 * b + 2] = px[2];
         xquat[4 * b] = q[0]; xquat[4 * b + 1] = q[1]; xquat[4 * b + 2] = q[2]; xquat[4 * b + 3] = q[3];
         q2mat(xmat + 9 * b, q);
       }

@@ -110,6 +110,7 @@ __global__ void __launch_bounds__(512, 1) step_kernel(int phases, int nsub, cons
     if (!live) env = pick;
   }
   Eng<R> e(smem + (size_t)warp * L.fused_stride, lane, slot, LAY_FULL);
+  e.env = env;
   size_t E = env;
   load_row(e.p(L.qpos), s.qpos + E * m.nq, m.nq, lane);
   load_row(e.p(L.qvel), s.qvel + E * m.nv, m.nv, lane);

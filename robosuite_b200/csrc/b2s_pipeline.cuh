@@ -315,6 +315,7 @@ __global__ void __launch_bounds__(B2S_LB0_THREADS, B2S_LB0_BLOCKS) phase0_kernel
   if (env >= g.nenv) return;
   env += g.env0;
   Eng<R> e(smem + (size_t)warp * L.total, lane, g.slot, LAY_P0);
+  e.env = env;
 #ifdef B2S_ZERO_SMEM
   for (int i = lane; i < L.total; i += 32) e.ws[i] = 0;
   __syncwarp();

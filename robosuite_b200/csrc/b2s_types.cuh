@@ -93,6 +93,11 @@ struct DState {
   R* gjk_cache;    // [n_env][npair][3] last separating direction of each convex pair (GJK warm start)
   int* cl_env;     // [n_env][2 + 2 * (cl_maxa + cl_maxg)] na, ng, then (pair, slot) of each candidate
   int* obs_fresh;  // [n_env] 1 = observation cache empty (set at reset, cleared by the first sample)
+  // per-environment world poses of bodies welded to the world (the reference writes sampled placements into model.body_pos /
+  // body_quat per reset, e.g. the Door: door.py:417-427; model constants are shared by a batch here, so these are DATA): up to 4 bodies
+  int n_ov, ov_body[4];
+  R* ov_pos[4];    // [n_env, 3]
+  R* ov_quat[4];   // [n_env, 4]
   R* task_vec;     // [n_env, task_dim] task table values after the last substep
   R* task_out;     // [n_env, 8]: body height, |grip site - body|, grasp flag, horizontal |body - body2|, obj-obj2 contact flag
   // -DB2S_INSTR builds only (measurement aid, see b2s_instr in b2s_pipeline.cuh): device timeline of the graph replay and

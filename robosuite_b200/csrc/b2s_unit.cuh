@@ -48,6 +48,7 @@ template <typename R> DEVN int unit_phase0(R* area, int lane, int slot, int env)
   const WSLayout& L = c_lay[slot][LAY_P0];
   const WSLayout& RL = c_lay[slot][LAY_ROW];
   Eng<R> e(area, lane, slot, LAY_P0);
+  e.env = env;
   size_t E = env;
   R* row = s.wsg + E * RL.total;
   load_row(e.p(L.qpos), s.qpos + E * m.nq, m.nq, lane);

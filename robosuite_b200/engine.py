@@ -67,6 +67,7 @@ def lib():
         L.b2s_ctrl_reset.argtypes = [C.c_void_p, C.c_void_p]
         L.b2s_env_step.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.b2s_reset_envs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.b2s_body_pose_override.argtypes = [C.c_void_p, C.c_int]
         L.b2s_obs_config.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.b2s_task_config.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.b2s_task_config2.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
@@ -218,6 +219,12 @@ class BatchedSim:
             assert qpos.is_cuda and qpos.dtype == self.dtype and qpos.is_contiguous() and qpos.shape == (self.n_env, self.model.nq)
         self._check(self._L.b2s_reset_envs(self._h, None if mask is None else C.c_void_p(mask.data_ptr()),
                                            None if qpos is None else C.c_void_p(qpos.data_ptr())))
+
+    def body_pose_override(self, body_id):
+        """(pos [n_env, 3], quat [n_env, 4]) tensors that replace the constant world pose of a world-welded body per environment
+        (b2s_body_pose_override; the reference writes model.body_pos / body_quat per reset, door.py:417-427)"""
+        self._check(self._L.b2s_body_pose_override(self._h, int(body_id)))
+        return self.array("body_xpos_ov:%d" % body_id), self.array("body_xquat_ov:%d" % body_id)
 
     def ctrl_reset(self, mask=None):
         self._check(self._L.b2s_ctrl_reset(self._h, None if mask is None else C.c_void_p(mask.data_ptr())))

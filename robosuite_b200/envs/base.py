@@ -249,6 +249,9 @@ class BatchedMujocoEnv:
     def _sample_reset_state(self, n):
         raise NotImplementedError
 
+    def _randomize_model(self, mask):
+        """per-reset placements the reference writes into MODEL constants (Door: door.py:417-427); mask: bool [N] on the device or None"""
+
     def reward(self, action=None):
         raise NotImplementedError
 
@@ -290,6 +293,7 @@ class BatchedMujocoEnv:
         import torch
 
         q = self._sample_reset_state(self.num_envs).to(self.dtype).contiguous()
+        self._randomize_model(None if mask is None else mask.to(device=self.device).bool())
         if mask is None:
             self.timestep.zero_()
             self.done.zero_()

@@ -77,8 +77,30 @@ class OracleSim:
     def close(self): pass
 
     # ---- state exchange with the oracles
+    def body_pose_override(self, body_id):
+        """same surface as BatchedSim.body_pose_override; only bodies attached to the world directly reach the oracle (its
+        kinematics composes welded children from their parents, so their overrides are redundant there)"""
+        m = self.model
+        b = int(body_id)
+        chain, k = [], b
+        while k > 0:
+            chain.append(k); k = int(m.body_parentid[k])
+        pos, quat = np.zeros(3), np.array([1.0, 0, 0, 0])
+        for k in reversed(chain):
+            pos = pos + _q2m(quat) @ np.asarray(m.body_pos[k], dtype=float)
+            a, c = quat, np.asarray(m.body_quat[k], dtype=float)
+            quat = np.array([a[0] * c[0] - a[1:] @ c[1:], *(a[0] * c[1:] + c[0] * a[1:] + np.cross(a[1:], c[1:]))])
+        P = torch.as_tensor(np.tile(pos, (self.n_env, 1))); Q = torch.as_tensor(np.tile(quat, (self.n_env, 1)))
+        if not hasattr(self, "_ov"):
+            self._ov = {}
+        self._ov[b] = (P, Q, int(m.body_parentid[b]) == 0)
+        return P, Q
+
     def _push(self, e):
         o = self.o[e]
+        for b, (P, Q, direct) in getattr(self, "_ov", {}).items():
+            if direct:
+                o.set_body_pose(b, P[e].numpy(), Q[e].numpy())
         o.qpos[:] = self.qpos[e].numpy(); o.qvel[:] = self.qvel[e].numpy(); o.ctrl[:] = self.ctrl[e].numpy()
         o.qacc_warmstart[:] = self.qacc_warmstart[e].numpy(); o.time = float(self.time[e])
 

@@ -316,3 +316,36 @@ def test_reset_distribution_matches_reference_stack(task):
     assert np.abs(q[:, var].mean(0) - mean[var]).max() < 0.25 * std[var].max() + 0.15 * span[var].max(), task
     ratio = q[:, var].std(0) / std[var]
     assert np.all(ratio > 0.7) and np.all(ratio < 1.4), (task, ratio)
+
+
+def test_door_placement_is_drawn_per_environment_and_reset():
+    """door.py:303-318, 417-427: x in [0.07, 0.09], y in [-0.01, 0.01], yaw in [-pi/2 - 0.25, -pi/2] relative to table_offset, redrawn at
+    every reset of the environment; a masked reset leaves the other environments' doors where they are; the welded frame body follows"""
+    import torch
+
+    import robosuite_b200 as suite
+    from tests.oracle_sim import OracleSim
+
+    n = 64
+    env = suite.make("Door", robots="Panda", num_envs=n, seed=7, sim_cls=OracleSim)
+    env.reset()
+    P, Q = (t.clone() for t in env.door_pose)
+    tx, ty, tz = env.table_offset
+    x, y = P[:, 0] - tx, P[:, 1] - ty
+    yaw = 2 * torch.atan2(Q[:, 3], Q[:, 0])
+    assert float(x.min()) >= 0.07 - 1e-9 and float(x.max()) <= 0.09 + 1e-9 and float(x.std()) > 0.003
+    assert float(y.min()) >= -0.01 - 1e-9 and float(y.max()) <= 0.01 + 1e-9 and float(y.std()) > 0.003
+    assert float(yaw.min()) >= -np.pi / 2 - 0.25 - 1e-9 and float(yaw.max()) <= -np.pi / 2 + 1e-9 and float(yaw.std()) > 0.04
+    assert torch.allclose(P[:, 2], torch.full((n,), tz + 0.3, dtype=P.dtype)) and float(Q[:, 1:3].abs().max()) == 0
+    obs = env._get_observations()
+    bn = env.model.names["body"]
+    off = obs["door_pos"] - P  # Door_door sits at a fixed offset in the (rotated) frame: |offset| is the same everywhere
+    assert float((off.norm(dim=1) - off.norm(dim=1)[0]).abs().max()) < 1e-9 and float((off[0] - off[1]).abs().max()) > 1e-4
+    mask = torch.zeros(n, dtype=torch.bool); mask[::2] = True
+    env.reset(mask=mask, host_mask=mask.numpy())
+    P2, _ = env.door_pose
+    assert torch.equal(P2[1::2], P[1::2]) and float((P2[::2] - P[::2]).abs().max()) > 1e-4
+    env.close()
+    pinned = suite.make("Door", robots="Panda", num_envs=2, seed=7, sim_cls=OracleSim, door_placement=(0.08, 0.0, -np.pi / 2 - 0.125))
+    assert pinned.door_pose is None
+    pinned.close()

@@ -207,8 +207,14 @@ def test_other_task_envs_obs_and_reward(task, obs_dim):
     for e in range(n):
         o = Oracle(pack_model(model))
         o.ctrl_setup(cc.resolve(model, cc.default_composite_config(), OCfg))
+        if task == "Door":  # the door pose is drawn per environment and reset (door.py:417-427): the oracle gets it as model constants
+            assert env.door_pose is not None
+            P, Q = (t.cpu().numpy().astype(np.float64) for t in env.door_pose)
+            o.set_body_pose(model.names["body"].index("Door_main"), P[e], Q[e])
         o.qpos[:] = q0[e]; o.forward(); o.ctrl_reset()
         oracles.append(o); caches.append({})
+    if task == "Door":
+        assert np.abs(P[0] - P[1]).max() > 1e-4  # really per environment
     flat = env.flat_obs().cpu().numpy().astype(np.float64)
     for e in range(n):
         exp = _object_obs(env, oracles[e], caches[e], task)
