@@ -9,6 +9,42 @@ device-side launch sequence (`b2s_reset_envs`)."""
 import numpy as np
 
 
+class _Box:
+    """duck-typed stand-in for gymnasium.spaces.Box (bounds, shape, dtype, contains, sample) when gymnasium is not installed"""
+
+    def __init__(self, low, high, dtype=np.float32):
+        self.low, self.high = np.asarray(low, dtype=dtype), np.asarray(high, dtype=dtype)
+        self.shape, self.dtype = self.low.shape, np.dtype(dtype)
+
+    def contains(self, x):
+        x = np.asarray(x)
+        return x.shape == self.shape and bool(np.all(x >= self.low) and np.all(x <= self.high))
+
+    def sample(self, rng=None):
+        rng = rng or np.random.default_rng()
+        lo, hi = np.where(np.isfinite(self.low), self.low, -1.0), np.where(np.isfinite(self.high), self.high, 1.0)
+        return rng.uniform(lo, hi).astype(self.dtype)
+
+    def __repr__(self):
+        return f"Box({self.low.min()}, {self.high.max()}, {self.shape}, {self.dtype})"
+
+
+def _make_spaces(obs_dim, act_low, act_high, num_envs):
+    """(single_observation_space, single_action_space, observation_space, action_space) as in gym_wrapper.py:70-85, batched like a
+    gymnasium VectorEnv; real gymnasium spaces when the package is importable"""
+    hi = np.full((obs_dim,), np.inf, dtype=np.float32)
+    try:
+        from gymnasium import spaces
+        from gymnasium.vector.utils import batch_space
+
+        so, sa = spaces.Box(-hi, hi, dtype=np.float32), spaces.Box(act_low, act_high, dtype=np.float32)
+        return so, sa, batch_space(so, num_envs), batch_space(sa, num_envs)
+    except ImportError:
+        so, sa = _Box(-hi, hi), _Box(act_low, act_high)
+        rep = lambda b: _Box(np.tile(b.low, (num_envs, 1)), np.tile(b.high, (num_envs, 1)))
+        return so, sa, rep(so), rep(sa)
+
+
 class BatchedGymWrapper:
     def __init__(self, env, keys=None, flatten_obs=True, auto_reset=True):
         self.env = env
@@ -29,6 +65,10 @@ class BatchedGymWrapper:
         self.action_low, self.action_high = np.asarray(low, dtype=np.float32), np.asarray(high, dtype=np.float32)
         self.single_observation_shape = (self.obs_dim,)
         self.single_action_shape = self.action_low.shape
+        # gymnasium VectorEnv surface (gym_wrapper.py:70-85 per environment, batched along the leading axis)
+        (self.single_observation_space, self.single_action_space, self.observation_space,
+         self.action_space) = _make_spaces(self.obs_dim, self.action_low, self.action_high, self.num_envs)
+        self.metadata, self.render_mode, self.spec = {"autoreset_mode": "same_step"}, None, None
 
     def _flatten_obs(self, obs_dict):
         import torch

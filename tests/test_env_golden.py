@@ -275,6 +275,12 @@ def test_batched_gym_wrapper_autoreset_on_cpu():
     assert torch.equal(obs[:, :10], d["object-state"]) and torch.equal(obs[:, 10:], d["robot0_proprio-state"])
     low, high = env.action_low, env.action_high
     assert low.shape == (7,) and np.all(low == -1) and np.all(high == 1)
+    # VectorEnv surface: per-environment spaces as gym_wrapper.py:70-85 builds them, batched along the leading axis
+    assert env.single_observation_space.shape == (60,) and env.single_action_space.shape == (7,)
+    assert env.observation_space.shape == (n, 60) and env.action_space.shape == (n, 7)
+    assert np.all(np.isinf(env.single_observation_space.high)) and np.all(env.single_action_space.low == -1)
+    assert env.single_action_space.contains(np.zeros(7, dtype=np.float32)) and not env.single_action_space.contains(np.full(7, 2.0, dtype=np.float32))
+    assert env.action_space.contains(env.action_space.sample())
     obs, rew, term, trunc, info = env.step(torch.zeros((n, 7)))
     assert not bool(term.any()) and "final_observation" not in info
     obs, rew, term, trunc, info = env.step(torch.zeros((n, 7)))
