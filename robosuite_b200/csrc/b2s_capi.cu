@@ -1071,7 +1071,8 @@ template <typename R> static int launch_unit_t(b2s_sim* s, DState<R>& st, int ph
   UnitQ q{s->uq_ring, s->uq_ovf, s->uq_ctr, total, s->uq_nlarge, s->uq_wpb_large, s->uq_stride, s->uq_stride_large, s->uq_prof, ubar};
   unit_init_kernel<R><<<(total + 255) / 256, 256, 0, s->stream>>>(q, s->n_env);
   unit_kernel<R><<<s->uq_grid, s->uq_wpb * 32, s->uq_smem, s->stream>>>(phases, nsub, action, s->slot, q);
-  s->launches += 2;
+  unit_check_kernel<R><<<8, 256, 0, s->stream>>>(q, s->slot);
+  s->launches += 3;
   CUDA_TRY(cudaGetLastError());
   if (getenv("B2S_UNIT_DEBUG")) {
     int c[8];

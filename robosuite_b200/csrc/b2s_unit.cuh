@@ -41,6 +41,14 @@ template <typename R> __global__ void unit_init_kernel(UnitQ q, int n_env) {
   if (i < 8) q.ctr[i] = i == 1 ? n_env : 0;
 }
 
+// after the persistent kernel: a watchdog event (ctr[7] != 0: a ticket never arrived, the blocks drained) means the control step is
+// INCOMPLETE - flag every environment (warn bit 64) so that the caller sees it in info["sim_warn"] without a host sync
+template <typename R> __global__ void unit_check_kernel(UnitQ q, int slot) {
+  const DState<R>& s = cstate<R>(slot);
+  if (q.ctr[7] == 0) return;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < s.n_env; i += gridDim.x * blockDim.x) s.warn[i] |= 64;
+}
+
 // steps 1: kinematics, velocity stage + RNE bias, CRB -> M, broad phase; candidate table of the environment; poses etc. -> workspace row
 template <typename R> DEVN int unit_phase0(R* area, int lane, int slot, int env) {
   const DModel<R>& m = cmodel<R>(slot);
@@ -345,9 +353,9 @@ __global__ void __launch_bounds__(B2S_LBU_THREADS, B2S_LBU_BLOCKS) unit_kernel(i
   for (;;) {
     int t;
     if (q.barriers >= 0) {
-      // the block takes up to `wpb` tickets that are ALREADY PRODUCED (head < tail): with stage barriers a unit whose ticket is still
-      // to come would hold the block's ready units hostage, and near the end of a control step, when the last tickets wait for the
-      // units in flight, the blocks would hold each other's producers (observed: every step stalled until the watchdog)
+      // the block takes up to `wpb` tickets that are ALREADY PRODUCED (head < tail).  The first lockstep version took `wpb` tickets
+      // whether they existed or not and waited for the missing ones in front of the first stage barrier: every control step stalled until
+      // the watchdog on the GPU (the ticket arithmetic itself terminates: tests/test_unit_queue_protocol.py).  No wait inside a round now.
       __syncthreads();
       if (threadIdx.x == 0) {
         int t0v = 0x7fffffff, k = 0, spins = 0;

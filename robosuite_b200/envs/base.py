@@ -95,7 +95,8 @@ class ObsBuilder:
 # bits of sim.warn / info["sim_warn"] (robosuite_b200/csrc: b2s_kernel.cuh, b2s_collide.cuh, b2s_solver.cuh)
 SIM_WARN_BITS = {1: "singular mass matrix", 2: "non-finite state in the integrator", 4: "contact capacity overflow (maxcon)",
                  8: "constraint-row capacity overflow (maxefc)", 16: "singular Newton Hessian",
-                 32: "diverged state (non-finite / huge qpos, qvel or qacc): data reset to the model defaults, as mj_checkPos/Vel/Acc do"}
+                 32: "diverged state (non-finite / huge qpos, qvel or qacc): data reset to the model defaults, as mj_checkPos/Vel/Acc do",
+                 64: "unit-queue watchdog fired: the control step is incomplete (mode 2 only; a library bug, please report)"}
 
 
 class BatchedMujocoEnv:
