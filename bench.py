@@ -2,9 +2,10 @@
 """bench.py - env-steps/sec of the batched engine on BASELINE.json's configurations.
 
 One "step" = one control step of every environment on the GPU = 25 x {step1, controller, step2} per environment
-(robosuite/environments/base.py:467-521), replayed as ONE CUDA graph per task handle (phase-kernel pipeline, DESIGN.md
-section 4).  Device-timed with CUDA events around each step on the launch stream, L2 flushed between timed iterations, max
-over ranks.
+(robosuite/environments/base.py:467-521): by default the phase-kernel pipeline, one CUDA graph of 25 x 4 kernel nodes per
+environment group (8 groups per task handle, each on its own stream); --mode 2 = one persistent unit-queue kernel per handle
+(DESIGN.md section 4).  Device-timed with CUDA events around each step on the launch stream, L2 flushed between timed
+iterations, max over ranks; the e2e leg times the public API with host buffers.
 
   python bench.py --gpus N --steps K --warmup W [--config 2|3|4|5]   # this repo's CUDA path
   python bench.py --impl reference --gpus N --steps K ...            # CPU arm: the oracle port of the same path on host cores
