@@ -4,7 +4,8 @@ the reference's own acceptance criteria: bit-identical open-loop playback (test_
 close on a cube and lift it (test_panda_gripper.py, test_rethink_gripper.py, test_robotiq_*.py, test_jaco_threefinger.py,
 test_all_grippers.py), and - slow, opt-in with B2S_REF_SLOW=1 - the
 variable-impedance and linear-interpolator trajectory tests of the reference's OSC stack (test_variable_impedance.py,
-test_linear_interpolator.py; 60 s each; they passed when last run)."""
+test_linear_interpolator.py; 60 s each) and test_composite_controllers.py on the five fixed-base single arms (Panda, Sawyer, IIWA, UR5e,
+Kinova3 x {None, BASIC}; 50 s); they passed when last run)."""
 import os
 import subprocess
 import sys
@@ -33,5 +34,5 @@ def test_reference_playback_and_gripper_tests_pass_on_the_oracle():
 
 @pytest.mark.skipif(not os.environ.get("B2S_REF_SLOW"), reason="2 minutes: set B2S_REF_SLOW=1")
 def test_reference_controller_trajectory_tests_pass_on_the_oracle():
-    lines = _run(["variable_impedance", "linear_interpolator"], 1200)
-    assert len(lines) == 2
+    lines = _run(["variable_impedance", "linear_interpolator", "composite_controllers"], 1800)
+    assert len(lines) == 12

@@ -21,6 +21,7 @@ TESTS = {
     "robotiq_three": ("test_grippers/test_robotiq_threefinger.py", None),
     "jaco_three": ("test_grippers/test_jaco_threefinger.py", None),
     "all_robots": ("test_robots/test_all_robots.py", None),
+    "composite_controllers": ("test_controllers/test_composite_controllers.py", None),
     "variable_impedance": ("test_controllers/test_variable_impedance.py", None),
     "linear_interpolator": ("test_controllers/test_linear_interpolator.py", None),
 }
@@ -33,9 +34,28 @@ def load(path):
     return mod
 
 
+def composite(results):
+    """test_composite_controllers.py is parametrised over every robot of the reference; the fixed-base single arms are this repo's scope"""
+    mod = load("test_controllers/test_composite_controllers.py")
+    for robot in ("Panda", "Sawyer", "IIWA", "UR5e", "Kinova3"):
+        for ctrl in (None, "BASIC"):
+            key = "composite_controllers::test_basic_controller_predefined_robots[%s-%s]" % (robot, ctrl)
+            t0 = time.time()
+            try:
+                mod.test_basic_controller_predefined_robots.__wrapped__(robot, ctrl) if hasattr(mod.test_basic_controller_predefined_robots, "__wrapped__") \
+                    else mod.test_basic_controller_predefined_robots(robot, ctrl)
+                results[key] = ("passed", time.time() - t0)
+            except Exception as e:  # noqa: BLE001
+                traceback.print_exc()
+                results[key] = ("FAILED %r" % (e,), time.time() - t0)
+
+
 def main(names):
     results = {}
     for nm in names:
+        if nm == "composite_controllers":
+            composite(results)
+            continue
         path, fn = TESTS[nm]
         mod = load(path)
         fns = [fn] if fn else [k for k in dir(mod) if k.startswith("test_")]
